@@ -1,0 +1,401 @@
+// Fused LoRA projection GEMM for sm_100a: persistent, warp-specialised, TMA -> 128B-swizzled smem ring ->
+// tcgen05.mma (M=128 x N=BN x K=16, fp32 accumulators double-buffered in TMEM) -> epilogue warps (tcgen05.ld).
+//
+// Replaces the reference's `peft` LoRA Linear forward / backward-dgrad on the MMDiT block projections
+// (/root/reference/src/qflux/models/transformer_qwenimage.py:286-293,348-352 and FeedForward :408,418; LoRA injected
+// at /root/reference/src/qflux/trainer/base_trainer.py:929-941).  The low-rank term is appended to the K loop of the
+// same contraction as extra 64-wide k-blocks taken from a second pair of tensor maps, so each projection is ONE
+// tensor-core contraction:   acc = X.W^T + (s X A^T).B^T   (forward)   |   acc = dY.W + (s dY B).A   (dgrad).
+//
+// Roles (256 threads, 1 CTA / SM): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31 = output rows).
+#include "../../include/qfx.h"
+#include "host_common.h"
+#include "sm100.cuh"
+#include <string.h>
+
+namespace qfx {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+
+struct GemmProb {
+  CUtensorMap tmA, tmB, tmA2, tmB2;
+  int M, kb2, a2_col0, rows_per_batch;
+  const bf16* bias;
+  bf16* out;
+  bf16* out2;
+  const bf16* resid;
+  const bf16* gate;
+  const bf16* aux;
+  int64_t ldo, ldo2, ldr, ldg, ldaux;
+};
+
+struct GemmParams {
+  GemmProb p[QFX_MAX_PROBLEMS];
+  int nprob, N, K, lora_group_n;
+  int tiles_m0, tiles_m_total, tiles_n, total_tiles;
+  float alpha;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : BN == 192 ? 5 : BN == 128 ? 6 : 8;
+  static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool TRANS_B, int EPI>
+__global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ GemmParams P) {
+  using C = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < P.nprob; ++i) {
+      tma_prefetch_desc(&P.p[i].tmA);
+      tma_prefetch_desc(&P.p[i].tmB);
+      if (P.p[i].kb2) {
+        tma_prefetch_desc(&P.p[i].tmA2);
+        tma_prefetch_desc(&P.p[i].tmB2);
+      }
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int nkb = P.K / BK;
+
+  auto decode = [&](int tile, int& prob, int& m0, int& n0) {
+    int n_blk = tile / P.tiles_m_total;
+    int mm = tile - n_blk * P.tiles_m_total;
+    prob = mm >= P.tiles_m0 ? 1 : 0;
+    m0 = (prob ? mm - P.tiles_m0 : mm) * BM;
+    n0 = n_blk * BN;
+  };
+
+  if (warp == 0) {
+    // =============================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        int prob, m0, n0;
+        decode(tile, prob, m0, n0);
+        const GemmProb& q = P.p[prob];
+        const int kb_total = nkb + q.kb2;
+        const int grp = (!TRANS_B && P.lora_group_n > 0) ? n0 / P.lora_group_n : 0;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + C::A_BYTES;
+          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          if (kb < nkb) {
+            tma_load_2d(a_dst, &q.tmA, full_bar(stage), kb * BK, m0);
+            if (!TRANS_B) {
+              tma_load_2d(b_dst, &q.tmB, full_bar(stage), kb * BK, n0);
+            } else {
+#pragma unroll
+              for (int a = 0; a < BN / 64; ++a) tma_load_2d(b_dst + a * 8192, &q.tmB, full_bar(stage), n0 + a * 64, kb * BK);
+            }
+          } else {
+            const int j = kb - nkb;
+            tma_load_2d(a_dst, &q.tmA2, full_bar(stage), q.a2_col0 + (grp * q.kb2 + j) * 64, m0);
+            if (!TRANS_B) {
+              tma_load_2d(b_dst, &q.tmB2, full_bar(stage), j * 64, n0);
+            } else {
+#pragma unroll
+              for (int a = 0; a < BN / 64; ++a) tma_load_2d(b_dst + a * 8192, &q.tmB2, full_bar(stage), n0 + a * 64, j * 64);
+            }
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(BM, BN, 0, TRANS_B ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+        int prob, m0, n0;
+        decode(tile, prob, m0, n0);
+        const int kb_total = nkb + P.p[prob].kb2;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = sdesc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = TRANS_B ? sdesc_sw128(b_addr + k * 2048, 8192, 1024) : sdesc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================================================== epilogue
+    const int q4 = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      int prob, m0, n0;
+      decode(tile, prob, m0, n0);
+      const GemmProb& q = P.p[prob];
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m0 + q4 * 32 + lane;
+      const bool row_ok = row < q.M;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * BN;
+      const bf16* gate_row = nullptr;
+      if (EPI == QFX_EPI_RESID_GATE && row_ok) gate_row = q.gate + (int64_t)(row / q.rows_per_batch) * q.ldg;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c, r);
+        tmem_ld_wait();
+        const int n = n0 + c;
+        uint32_t o[16];
+        uint4 bias4[4];
+        if (q.bias != nullptr) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) bias4[v] = __ldg(reinterpret_cast<const uint4*>(q.bias + n) + v);
+        } else {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) bias4[v] = make_uint4(0, 0, 0, 0);
+        }
+        const uint32_t* bw = reinterpret_cast<const uint32_t*>(bias4);
+        if (EPI == QFX_EPI_BIAS) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float v0 = __uint_as_float(r[2 * i]) * P.alpha + bf16_lo(bw[i]);
+            float v1 = __uint_as_float(r[2 * i + 1]) * P.alpha + bf16_hi(bw[i]);
+            o[i] = pack_bf16(v0, v1);
+          }
+        } else if (EPI == QFX_EPI_GELU) {
+          uint32_t u[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            u[i] = pack_bf16(__uint_as_float(r[2 * i]) + bf16_lo(bw[i]), __uint_as_float(r[2 * i + 1]) + bf16_hi(bw[i]));
+            o[i] = pack_bf16(gelu_tanh(bf16_lo(u[i])), gelu_tanh(bf16_hi(u[i])));
+          }
+          if (row_ok) {
+            uint4* dst2 = reinterpret_cast<uint4*>(q.out2 + (int64_t)row * q.ldo2 + n);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) dst2[v] = make_uint4(u[4 * v], u[4 * v + 1], u[4 * v + 2], u[4 * v + 3]);
+          }
+        } else if (EPI == QFX_EPI_RESID_GATE) {
+          if (row_ok) {
+            const uint4* rs = reinterpret_cast<const uint4*>(q.resid + (int64_t)row * q.ldr + n);
+            const uint4* gs = reinterpret_cast<const uint4*>(gate_row + n);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              uint4 rr = rs[v];
+              uint4 gg = __ldg(gs + v);
+              const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rr);
+              const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gg);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = 4 * v + e;
+                // eager bf16 rounding points of the reference: y=Linear(x) -> gate*y -> resid + (.)
+                float y0 = round_bf16(__uint_as_float(r[2 * i]) + bf16_lo(bw[i]));
+                float y1 = round_bf16(__uint_as_float(r[2 * i + 1]) + bf16_hi(bw[i]));
+                float z0 = round_bf16(bf16_lo(gw[e]) * y0);
+                float z1 = round_bf16(bf16_hi(gw[e]) * y1);
+                o[i] = pack_bf16(bf16_lo(rw[e]) + z0, bf16_hi(rw[e]) + z1);
+              }
+            }
+          }
+        } else if (EPI == QFX_EPI_DGELU) {
+          if (row_ok) {
+            const uint4* us = reinterpret_cast<const uint4*>(q.aux + (int64_t)row * q.ldaux + n);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              uint4 uu = us[v];
+              const uint32_t* uw = reinterpret_cast<const uint32_t*>(&uu);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = 4 * v + e;
+                float g0 = round_bf16(__uint_as_float(r[2 * i]) * P.alpha);
+                float g1 = round_bf16(__uint_as_float(r[2 * i + 1]) * P.alpha);
+                o[i] = pack_bf16(g0 * gelu_tanh_grad(bf16_lo(uw[e])), g1 * gelu_tanh_grad(bf16_hi(uw[e])));
+              }
+            }
+          }
+        }
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(q.out + (int64_t)row * q.ldo + n);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) dst[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------ host
+static int make_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, int64_t ld_elems, uint32_t box_inner,
+                   uint32_t box_outer) {
+  uint64_t dims[2] = {inner, outer};
+  uint64_t strides[1] = {(uint64_t)ld_elems * 2};
+  uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap_bf16(m, base, 2, dims, strides, box);
+}
+
+template <int BN, bool TRANS_B, int EPI>
+static int launch(const GemmParams& P, cudaStream_t stream) {
+  using C = GemmCfg<BN>;
+  auto kern = gemm_kernel<BN, TRANS_B, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    QFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
+  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(P);
+  QFX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int dispatch(const GemmParams& P, int trans_b, int epi, cudaStream_t s) {
+  if (!trans_b) {
+    switch (epi) {
+      case QFX_EPI_BIAS: return launch<BN, false, QFX_EPI_BIAS>(P, s);
+      case QFX_EPI_GELU: return launch<BN, false, QFX_EPI_GELU>(P, s);
+      case QFX_EPI_RESID_GATE: return launch<BN, false, QFX_EPI_RESID_GATE>(P, s);
+    }
+  } else {
+    switch (epi) {
+      case QFX_EPI_BIAS: return launch<BN, true, QFX_EPI_BIAS>(P, s);
+      case QFX_EPI_DGELU: return launch<BN, true, QFX_EPI_DGELU>(P, s);
+    }
+  }
+  set_error("qfx_gemm_bf16: unsupported (trans_b=%d, epilogue=%d)", trans_b, epi);
+  return -1;
+}
+
+}  // namespace qfx
+
+using namespace qfx;
+
+extern "C" int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, int K, int trans_b, int epilogue, float alpha,
+                             int lora_group_n, int block_n, void* stream) {
+  QFX_CHECK_ARG(nprob >= 1 && nprob <= QFX_MAX_PROBLEMS, "qfx_gemm_bf16: nprob=%d", nprob);
+  QFX_CHECK_ARG(K > 0 && K % BK == 0, "qfx_gemm_bf16: K=%d must be a positive multiple of 64", K);
+  int bn = block_n;
+  if (bn == 0) bn = N % 256 == 0 ? 256 : N % 192 == 0 ? 192 : N % 128 == 0 ? 128 : 64;
+  QFX_CHECK_ARG((bn == 64 || bn == 128 || bn == 192 || bn == 256) && N % bn == 0, "qfx_gemm_bf16: N=%d block_n=%d", N, bn);
+  QFX_CHECK_ARG(!(trans_b && lora_group_n), "qfx_gemm_bf16: lora_group_n only with trans_b=0");
+  QFX_CHECK_ARG(lora_group_n == 0 || lora_group_n % bn == 0, "qfx_gemm_bf16: lora_group_n %% block_n != 0");
+
+  GemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.nprob = nprob;
+  P.N = N;
+  P.K = K;
+  P.lora_group_n = lora_group_n;
+  P.alpha = alpha;
+  P.tiles_n = N / bn;
+  int tiles_m_total = 0;
+  for (int i = 0; i < nprob; ++i) {
+    const qfx_gemm_problem& s = probs[i];
+    GemmProb& d = P.p[i];
+    QFX_CHECK_ARG(s.M > 0 && s.A && s.B && s.out, "qfx_gemm_bf16: problem %d has null/empty operands", i);
+    QFX_CHECK_ARG(s.lda % 8 == 0 && s.ldb % 8 == 0 && s.ldo % 8 == 0, "qfx_gemm_bf16: leading dims must be multiples of 8");
+    int rc = make_2d(&d.tmA, s.A, (uint64_t)K, (uint64_t)s.M, s.lda, BK, BM);
+    if (rc) return rc;
+    if (!trans_b)
+      rc = make_2d(&d.tmB, s.B, (uint64_t)K, (uint64_t)N, s.ldb, BK, (uint32_t)bn);
+    else
+      rc = make_2d(&d.tmB, s.B, (uint64_t)N, (uint64_t)K, s.ldb, 64, BK);
+    if (rc) return rc;
+    d.kb2 = s.kb2;
+    d.a2_col0 = s.a2_col0;
+    if (s.kb2 > 0) {
+      QFX_CHECK_ARG(s.A2 && s.B2 && s.lda2 % 8 == 0 && s.ldb2 % 8 == 0, "qfx_gemm_bf16: bad LoRA operands");
+      const int groups = lora_group_n ? N / lora_group_n : 1;
+      rc = make_2d(&d.tmA2, s.A2, (uint64_t)(s.a2_col0 + 64 * s.kb2 * groups), (uint64_t)s.M, s.lda2, BK, BM);
+      if (rc) return rc;
+      if (!trans_b)
+        rc = make_2d(&d.tmB2, s.B2, (uint64_t)(64 * s.kb2), (uint64_t)N, s.ldb2, BK, (uint32_t)bn);
+      else
+        rc = make_2d(&d.tmB2, s.B2, (uint64_t)N, (uint64_t)(64 * s.kb2), s.ldb2, 64, BK);
+      if (rc) return rc;
+    }
+    d.M = s.M;
+    d.rows_per_batch = s.rows_per_batch > 0 ? s.rows_per_batch : s.M;
+    d.bias = (const bf16*)s.bias;
+    d.out = (bf16*)s.out;
+    d.out2 = (bf16*)s.out2;
+    d.resid = (const bf16*)s.resid;
+    d.gate = (const bf16*)s.gate;
+    d.aux = (const bf16*)s.aux;
+    d.ldo = s.ldo; d.ldo2 = s.ldo2; d.ldr = s.ldr; d.ldg = s.ldg; d.ldaux = s.ldaux;
+    if (epilogue == QFX_EPI_GELU) QFX_CHECK_ARG(s.out2 && s.ldo2 % 8 == 0, "qfx_gemm_bf16: GELU epilogue needs out2");
+    if (epilogue == QFX_EPI_RESID_GATE) QFX_CHECK_ARG(s.resid && s.gate && s.ldr % 8 == 0 && s.ldg % 8 == 0, "qfx_gemm_bf16: RESID_GATE epilogue needs resid+gate");
+    if (epilogue == QFX_EPI_DGELU) QFX_CHECK_ARG(s.aux && s.ldaux % 8 == 0, "qfx_gemm_bf16: DGELU epilogue needs aux");
+    int tm = (s.M + BM - 1) / BM;
+    if (i == 0) P.tiles_m0 = tm;
+    tiles_m_total += tm;
+  }
+  P.tiles_m_total = tiles_m_total;
+  P.total_tiles = tiles_m_total * P.tiles_n;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (bn) {
+    case 64: return dispatch<64>(P, trans_b, epilogue, st);
+    case 128: return dispatch<128>(P, trans_b, epilogue, st);
+    case 192: return dispatch<192>(P, trans_b, epilogue, st);
+    default: return dispatch<256>(P, trans_b, epilogue, st);
+  }
+}

@@ -1,0 +1,152 @@
+"""GPU check of qfx_gemm_bf16 against torch fp32 matmul (run under gpurun)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from harness import main, rel_l2, time_cuda  # noqa: E402
+
+import torch  # noqa: E402
+
+
+def _mk(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).bfloat16()
+
+
+def _gelu_grad(u):
+    u = u.detach().float().requires_grad_(True)
+    torch.nn.functional.gelu(u, approximate="tanh").sum().backward()
+    return u.grad
+
+
+def basic(trans_b, bn, M=300, N=768, K=256, bias=True, alpha=1.0):
+    from qflux_b200 import lib
+    A = _mk(M, K, seed=1)
+    W = _mk(K, N, seed=2) if trans_b else _mk(N, K, seed=2)
+    b = _mk(N, seed=3) if bias else None
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    lib.gemm([lib.gemm_problem(A, W, out, bias=b)], N, K, trans_b=trans_b, alpha=alpha, block_n=bn)
+    torch.cuda.synchronize()
+    ref = alpha * (A.float() @ (W.float() if trans_b else W.float().t()))
+    if bias:
+        ref = ref + b.float()
+    return dict(err=rel_l2(out.float(), ref))
+
+
+def lora(trans_b, bn, M=520, N=768, K=512, kb2=1, groups=1):
+    """acc = A.B(^T) + A2[:, slice].B2(^T) ; groups>1 => fused q|k|v (trans_b=0 only)."""
+    from qflux_b200 import lib
+    A = _mk(M, K, seed=1)
+    W = _mk(K, N, seed=2) if trans_b else _mk(N, K, seed=2)
+    r = 64 * kb2
+    a2c = 0
+    A2 = _mk(M, r * groups, seed=4)
+    B2 = _mk(r, N, seed=5) if trans_b else _mk(N, r, seed=5)
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    gn = N // groups if groups > 1 else 0
+    lib.gemm([lib.gemm_problem(A, W, out, A2=A2, B2=B2, kb2=kb2, a2_col0=a2c)], N, K, trans_b=trans_b, lora_group_n=gn,
+             block_n=bn)
+    torch.cuda.synchronize()
+    ref = A.float() @ (W.float() if trans_b else W.float().t())
+    if trans_b:
+        ref = ref + A2.float() @ B2.float()
+    else:
+        for g in range(groups):
+            n0, n1 = g * (N // groups), (g + 1) * (N // groups)
+            ref[:, n0:n1] += A2[:, g * r:(g + 1) * r].float() @ B2[n0:n1].float().t()
+    return dict(err=rel_l2(out.float(), ref))
+
+
+def epilogues(bn):
+    from qflux_b200 import lib
+    M, N, K, Bsz = 384, 512, 256, 3
+    A, W, b = _mk(M, K, seed=1), _mk(N, K, seed=2, scale=0.1), _mk(N, seed=3)
+    res = {}
+    # GELU
+    out, u = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16), torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    lib.gemm([lib.gemm_problem(A, W, out, bias=b, out2=u)], N, K, epilogue=lib.EPI_GELU, block_n=bn)
+    ref_u = A.float() @ W.float().t() + b.float()
+    res["gelu_u"] = rel_l2(u.float(), ref_u)
+    res["gelu"] = rel_l2(out.float(), torch.nn.functional.gelu(ref_u, approximate="tanh"))
+    # RESID_GATE
+    resid, gate = _mk(M, N, seed=6), _mk(Bsz, N, seed=7)
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    lib.gemm([lib.gemm_problem(A, W, out, bias=b, resid=resid, gate=gate, rows_per_batch=M // Bsz)], N, K,
+             epilogue=lib.EPI_RESID_GATE, block_n=bn)
+    ref = resid.float() + gate.float().repeat_interleave(M // Bsz, 0) * ref_u
+    res["resid_gate"] = rel_l2(out.float(), ref)
+    # DGELU (trans_b)
+    Wt = _mk(K, N, seed=8, scale=0.1)
+    aux = _mk(M, N, seed=9)
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    lib.gemm([lib.gemm_problem(A, Wt, out, aux=aux)], N, K, trans_b=True, epilogue=lib.EPI_DGELU, block_n=bn)
+    ref = (A.float() @ Wt.float()) * _gelu_grad(aux)
+    res["dgelu"] = rel_l2(out.float(), ref)
+    torch.cuda.synchronize()
+    res["err"] = max(res.values())
+    return res
+
+
+def grouped(trans_b, bn):
+    from qflux_b200 import lib
+    N, K = 768, 512
+    M0, M1 = 700, 130
+    A0, A1 = _mk(M0, K, seed=1), _mk(M1, K, seed=2)
+    W0 = _mk(K, N, seed=3) if trans_b else _mk(N, K, seed=3)
+    W1 = _mk(K, N, seed=4) if trans_b else _mk(N, K, seed=4)
+    A2 = _mk(M0, 64, seed=5)
+    B2 = _mk(64, N, seed=6) if trans_b else _mk(N, 64, seed=6)
+    o0 = torch.zeros(M0, N, device="cuda", dtype=torch.bfloat16)
+    o1 = torch.zeros(M1, N, device="cuda", dtype=torch.bfloat16)
+    lib.gemm([lib.gemm_problem(A0, W0, o0, A2=A2, B2=B2, kb2=1), lib.gemm_problem(A1, W1, o1)], N, K, trans_b=trans_b,
+             block_n=bn)
+    torch.cuda.synchronize()
+    f = (lambda a, w: a.float() @ w.float()) if trans_b else (lambda a, w: a.float() @ w.float().t())
+    r0 = f(A0, W0) + f(A2, B2)
+    return dict(err=max(rel_l2(o0.float(), r0), rel_l2(o1.float(), f(A1, W1))))
+
+
+def perf(trans_b, bn, M0=8192, M1=1408, N=3072, K=3072):
+    from qflux_b200 import lib
+    A0, A1 = _mk(M0, K, seed=1), _mk(M1, K, seed=2)
+    W0 = _mk(K, N, seed=3, scale=0.02) if trans_b else _mk(N, K, seed=3, scale=0.02)
+    W1 = _mk(K, N, seed=4, scale=0.02) if trans_b else _mk(N, K, seed=4, scale=0.02)
+    o0 = torch.zeros(M0, N, device="cuda", dtype=torch.bfloat16)
+    o1 = torch.zeros(M1, N, device="cuda", dtype=torch.bfloat16)
+    probs = [lib.gemm_problem(A0, W0, o0), lib.gemm_problem(A1, W1, o1)]
+    flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
+    ms = time_cuda(lambda: lib.gemm(probs, N, K, trans_b=trans_b, block_n=bn), flush=flush)
+    fl = 2.0 * (M0 + M1) * N * K
+    f = (lambda a, w: a @ w) if trans_b else (lambda a, w: a @ w.t())
+    ms_t = time_cuda(lambda: (f(A0, W0), f(A1, W1)), flush=flush)
+    err = rel_l2(o0.float(), f(A0.float(), W0.float()))
+    return dict(ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1), torch_ms=round(ms_t, 4), torch_tflops=round(fl / ms_t / 1e9, 1),
+                err=err)
+
+
+CASES = {}
+for bn in (64, 128, 192, 256):
+    CASES[f"basic_nt_bn{bn}"] = (lambda bn=bn: basic(False, bn))
+    CASES[f"basic_nn_bn{bn}"] = (lambda bn=bn: basic(True, bn))
+CASES["basic_nt_alpha_nobias"] = lambda: basic(False, 0, M=128, N=64, K=64, bias=False, alpha=0.5)
+CASES["basic_nt_big"] = lambda: basic(False, 0, M=2400, N=3072, K=3072)
+CASES["basic_nn_big"] = lambda: basic(True, 0, M=2400, N=3072, K=12288)
+for bn in (128, 256):
+    CASES[f"lora_nt_bn{bn}"] = (lambda bn=bn: lora(False, bn))
+    CASES[f"lora_nn_bn{bn}"] = (lambda bn=bn: lora(True, bn))
+CASES["lora_nt_groups3"] = lambda: lora(False, 128, N=768, groups=3)
+CASES["lora_nt_kb2"] = lambda: lora(False, 192, kb2=2)
+CASES["lora_nn_kb3"] = lambda: lora(True, 192, kb2=3)
+CASES["epilogues_bn128"] = lambda: epilogues(128)
+CASES["epilogues_bn256"] = lambda: epilogues(256)
+CASES["grouped_nt"] = lambda: grouped(False, 256)
+CASES["grouped_nn"] = lambda: grouped(True, 192)
+for bn in (128, 192, 256):
+    CASES[f"perf_nt_bn{bn}"] = (lambda bn=bn: perf(False, bn))
+    CASES[f"perf_nn_bn{bn}"] = (lambda bn=bn: perf(True, bn))
+CASES["perf_nt_mlp_up"] = lambda: perf(False, 256, N=12288, K=3072)
+CASES["perf_nt_mlp_down"] = lambda: perf(False, 256, N=3072, K=12288)
+CASES["perf_nn_mlp_down"] = lambda: perf(True, 256, N=12288, K=3072)
+
+if __name__ == "__main__":
+    main(CASES, os.path.abspath(__file__), "gemm_check.log")
