@@ -1,0 +1,290 @@
+// Joint (text+image) non-causal attention forward for sm_100a, head_dim 128, bf16 in / fp32 softmax.
+// Replaces `dispatch_attention_fn` -> F.scaled_dot_product_attention on the concatenated [txt; img] sequence
+// (/root/reference/src/qflux/models/transformer_qwenimage.py:322-345, transformer_flux.py:149-156).
+//
+// One CTA per (128-query tile, batch*head).  Roles: warp 0 = TMEM alloc + TMA producer, warp 1 = MMA issuer,
+// warps 2-5 = softmax (thread == query row == TMEM lane).  Per 128-key tile j:
+//     S[j%2] = Q K_j^T            tcgen05.mma SS, both operands K-major (d contiguous), accumulator in TMEM
+//     P      = exp2(S*c - m)      softmax warps: tcgen05.ld, row max / sum in registers, bf16 P -> swizzled smem
+//     O     += P V_j              tcgen05.mma SS, A = P (K-major), B = V (MN-major: d contiguous), accumulate in TMEM
+// QK^T of tile j+1 is issued before P V of tile j so the tensor pipe works while the softmax warps run.
+// O is rescaled in TMEM only when the running max grows by more than 2^8 (warp-uniform decision), as the final
+// normalisation by the running sum makes a stale max exact.
+#include <string.h>
+
+#include "../../include/qfx.h"
+#include "host_common.h"
+#include "sm100.cuh"
+
+namespace qfx {
+
+constexpr int ATT_D = 128;
+constexpr int ATT_BQ = 128;
+constexpr int ATT_BK = 128;
+constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KB: two 64-wide 128B-swizzle atoms of [128 rows x 128 B]
+constexpr int ATOM_BYTES = 128 * 128;      // 16 KB
+
+struct AttnFwdParams {
+  CUtensorMap tmQ, tmK, tmV;  // [B*H, S, 128] bf16, box {64, 128, 1}
+  bf16* out0;                 // rows with joint position s < split  -> out0[(b*rows0 + s) * ld0 + h*128 ..]
+  bf16* out1;                 // rows with s >= split               -> out1[(b*rows1 + s - split) * ld1 + h*128 ..]
+  int64_t ld0, ld1;
+  int rows0, rows1, split;
+  float* lse;          // [B*H, S] log2-domain logsumexp:  m + log2(l)
+  const int* kv_len;   // [B] valid joint length per sample (NULL: S)
+  int S, H;
+  float scale_log2;    // (1/sqrt(d)) * log2(e)
+};
+
+constexpr int ATT_SMEM = 7 * TILE_BYTES + 1024 + 256;  // Q, K x2, V x2, P x2
+
+__global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base;
+  auto sK = [&](int s) { return smem_base + TILE_BYTES * (1 + s); };
+  auto sV = [&](int s) { return smem_base + TILE_BYTES * (3 + s); };
+  auto sP = [&](int s) { return smem_base + TILE_BYTES * (5 + s); };
+  const uint32_t bar_base = smem_base + 7 * TILE_BYTES;
+  const uint32_t q_full = bar_base;
+  auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto v_full = [&](int s) { return bar_base + 8u * (3 + s); };
+  auto s_full = [&](int s) { return bar_base + 8u * (5 + s); };
+  auto p_full = [&](int s) { return bar_base + 8u * (7 + s); };
+  auto pv_done = [&](int s) { return bar_base + 8u * (9 + s); };
+  const uint32_t o_full = bar_base + 8u * 11;
+  const uint32_t tmem_slot = bar_base + 8u * 12;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BQ;
+  const int bh = blockIdx.y;
+  const int b = bh / P.H, h = bh - b * P.H;
+  const int kv_len = P.kv_len ? P.kv_len[b] : P.S;
+  const int n_tiles = (kv_len + ATT_BK - 1) / ATT_BK;
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full(s), 1);
+      mbar_init(v_full(s), 1);
+      mbar_init(s_full(s), 1);
+      mbar_init(p_full(s), 4);
+      mbar_init(pv_done(s), 1);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  const uint32_t tS0 = tmem_base, tO = tmem_base + 256;
+
+  if (warp == 0) {
+    // ================================================================= TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&P.tmQ);
+      tma_prefetch_desc(&P.tmK);
+      tma_prefetch_desc(&P.tmV);
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(sQ, &P.tmQ, q_full, 0, q0, bh);
+      tma_load_3d(sQ + ATOM_BYTES, &P.tmQ, q_full, 64, q0, bh);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        if (j >= 2) mbar_wait(pv_done(s), ((j - 2) >> 1) & 1);  // P V of tile j-2 finished reading K/V stage s
+        mbar_expect_tx(k_full(s), TILE_BYTES);
+        tma_load_3d(sK(s), &P.tmK, k_full(s), 0, j * ATT_BK, bh);
+        tma_load_3d(sK(s) + ATOM_BYTES, &P.tmK, k_full(s), 64, j * ATT_BK, bh);
+        mbar_expect_tx(v_full(s), TILE_BYTES);
+        tma_load_3d(sV(s), &P.tmV, v_full(s), 0, j * ATT_BK, bh);
+        tma_load_3d(sV(s) + ATOM_BYTES, &P.tmV, v_full(s), 64, j * ATT_BK, bh);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = idesc_bf16(128, 128, 0, 1);
+      mbar_wait(q_full, 0);
+      auto issue_pv = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(p_full(s), (j >> 1) & 1);
+        mbar_wait(v_full(s), (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t ad = sdesc_sw128(sP(s) + (k >> 2) * ATOM_BYTES + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = sdesc_sw128(sV(s) + k * 2048, ATOM_BYTES, 1024);
+          umma_bf16(tO, ad, bd, idesc_pv, (j | k) != 0);
+        }
+        umma_commit(pv_done(s));
+      };
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        mbar_wait(k_full(s), (j >> 1) & 1);
+        tc_fence_after();
+        // S[s] is free: p_full(s) of tile j-2 (== softmax finished reading S[s]) was waited before P V (j-2) was issued
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t ad = sdesc_sw128(sQ + (k >> 2) * ATOM_BYTES + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = sdesc_sw128(sK(s) + (k >> 2) * ATOM_BYTES + (k & 3) * 32, 16, 1024);
+          umma_bf16(tS0 + s * 128, ad, bd, idesc_qk, k != 0);
+        }
+        umma_commit(s_full(s));
+        if (j > 0) issue_pv(j - 1);
+      }
+      issue_pv(n_tiles - 1);
+      umma_commit(o_full);
+    }
+  } else {
+    // ================================================================= softmax warps (thread = query row)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j & 1;
+      const int valid = kv_len - j * ATT_BK;  // columns >= valid are masked
+      mbar_wait(s_full(s), (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tS = tS0 + s * 128 + lane_off;
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tS + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      const float m_new = fmaxf(m_used, mx * P.scale_log2);
+      // warp-uniform lazy rescale of the TMEM accumulator
+      const bool need = (j == 0) || (m_new > m_used + 8.f);
+      if (__any_sync(0xffffffffu, need)) {
+        if (j > 0) {
+          mbar_wait(pv_done((j - 1) & 1), ((j - 1) >> 1) & 1);  // all earlier P V MMAs have landed in O
+          tc_fence_after();
+          const float alpha = exp2f(m_used - m_new);
+#pragma unroll 1
+          for (int c = 0; c < 128; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(tO + lane_off + c, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st32(tO + lane_off + c, r);
+          }
+          tmem_st_wait();
+          l *= alpha;
+        }
+        m_used = m_new;
+      }
+      if (j >= 2) mbar_wait(pv_done(s), ((j - 2) >> 1) & 1);  // P buffer s no longer read by the tensor core
+      const uint32_t p_row = sP(s) + row * 128;
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tS + c, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = (c + 2 * i < valid) ? exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used) : 0.f;
+          float p1 = (c + 2 * i + 1 < valid) ? exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used) : 0.f;
+          pk[i] = pack_bf16(p0, p1);
+          // the row sum uses the bf16-rounded probabilities, i.e. exactly what the tensor core multiplies with V
+          lsum += bf16_lo(pk[i]) + bf16_hi(pk[i]);
+        }
+        // columns c..c+31 = 16-byte chunks (c/8 .. c/8+3) of atom c/64, XOR-swizzled by (row & 7)
+        const uint32_t atom = p_row + (c >> 6) * ATOM_BYTES;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const uint32_t chunk = (uint32_t)(((c & 63) >> 3) + v) ^ (uint32_t)(row & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom + chunk * 16), "r"(pk[4 * v]), "r"(pk[4 * v + 1]),
+                       "r"(pk[4 * v + 2]), "r"(pk[4 * v + 3])
+                       : "memory");
+        }
+      }
+      l += lsum;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(s));
+    }
+    // ----------------------------------------------------------------- epilogue: O / l -> bf16, token-major
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int sq = q0 + row;
+    const bool ok = sq < P.S;
+    const float inv = 1.f / l;
+    bf16* dst = nullptr;
+    if (ok) {
+      dst = sq < P.split ? P.out0 + ((int64_t)b * P.rows0 + sq) * P.ld0 + h * ATT_D
+                         : P.out1 + ((int64_t)b * P.rows1 + (sq - P.split)) * P.ld1 + h * ATT_D;
+      if (P.lse) P.lse[(int64_t)bh * P.S + sq] = m_used + log2f(l);
+    }
+#pragma unroll 1
+    for (int c = 0; c < 128; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(tO + lane_off + c, r);
+      tmem_ld_wait();
+      if (ok) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c);
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          d4[v] = make_uint4(pack_bf16(__uint_as_float(r[8 * v]) * inv, __uint_as_float(r[8 * v + 1]) * inv),
+                             pack_bf16(__uint_as_float(r[8 * v + 2]) * inv, __uint_as_float(r[8 * v + 3]) * inv),
+                             pack_bf16(__uint_as_float(r[8 * v + 4]) * inv, __uint_as_float(r[8 * v + 5]) * inv),
+                             pack_bf16(__uint_as_float(r[8 * v + 6]) * inv, __uint_as_float(r[8 * v + 7]) * inv));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int make_qkv_tmap(CUtensorMap* m, const void* base, int BH, int S) {
+  uint64_t dims[3] = {128, (uint64_t)S, (uint64_t)BH};
+  uint64_t strides[2] = {128 * 2, (uint64_t)S * 128 * 2};
+  uint32_t box[3] = {64, 128, 1};
+  return make_tmap_bf16(m, base, 3, dims, strides, box);
+}
+
+}  // namespace qfx
+
+using namespace qfx;
+
+/* Q,K,V: [B, H, S, 128] bf16 (head-major joint sequence, text tokens first).  Output is written token-major into two
+ * row groups (text rows -> out0, image rows -> out1) so the output projections consume it without a split/copy. */
+extern "C" int qfx_attn_fwd(const void* Q, const void* K, const void* V, void* out0, int64_t ld0, int rows0, void* out1,
+                            int64_t ld1, int rows1, int split, float* lse, const int* kv_len, int B, int H, int S,
+                            float softmax_scale, void* stream) {
+  QFX_CHECK_ARG(B > 0 && H > 0 && S > 0 && out0 && (split >= S || out1), "qfx_attn_fwd: bad arguments");
+  AttnFwdParams P;
+  memset(&P, 0, sizeof(P));
+  int rc;
+  if ((rc = make_qkv_tmap(&P.tmQ, Q, B * H, S))) return rc;
+  if ((rc = make_qkv_tmap(&P.tmK, K, B * H, S))) return rc;
+  if ((rc = make_qkv_tmap(&P.tmV, V, B * H, S))) return rc;
+  P.out0 = (bf16*)out0; P.out1 = (bf16*)out1;
+  P.ld0 = ld0; P.ld1 = ld1; P.rows0 = rows0; P.rows1 = rows1; P.split = split;
+  P.lse = lse; P.kv_len = kv_len; P.S = S; P.H = H;
+  P.scale_log2 = softmax_scale * 1.4426950408889634f;
+  static bool attr_done = false;
+  if (!attr_done) {
+    QFX_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    attr_done = true;
+  }
+  dim3 grid((S + ATT_BQ - 1) / ATT_BQ, B * H);
+  attn_fwd_kernel<<<grid, 192, ATT_SMEM, (cudaStream_t)stream>>>(P);
+  QFX_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,654 @@
+// HBM-bound glue kernels of the MMDiT training step (everything that is not a tensor-core contraction).
+// One warp per row, 16-byte vector accesses, fp32 math, bf16 rounding at the reference's eager rounding points.
+//
+// Reference call sites (paths under /root/reference/src/qflux/models/):
+//   ln_modulate_*      transformer_qwenimage.py:420-423,443-448,477-484  (LayerNorm(no affine, eps 1e-6) + AdaLN modulate)
+//   qk_norm_rope_*     transformer_qwenimage.py:296-326,93-140           (per-head RMSNorm, complex RoPE, [txt;img] concat)
+//   gemv_act           transformer_qwenimage.py:143-156,389-392,435-436   (SiLU -> Linear on the [B, D] conditioning vector)
+//   rmsnorm_rows       transformer_qwenimage.py:549,625                   (txt_norm)
+//   flow_* / loss      trainer/qwen_image_edit_trainer.py:796-812,839-847 ; losses/mse_loss.py:68-82
+//   lora_wgrad         peft LoRA Linear autograd: dB = dY^T (s X A^T),  dA = (s dY B)^T X
+#include <string.h>
+#include <type_traits>
+
+#include "../../include/qfx.h"
+#include "host_common.h"
+#include "sm100.cuh"
+
+namespace qfx {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = bf16_lo(w[i]);
+    f[2 * i + 1] = bf16_hi(w[i]);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+// ============================================================================================ LayerNorm + modulate
+// y = bf16( bf16( bf16(LN(x)) * bf16(1 + scale[b]) ) + shift[b] ),   b = row / rows_per_batch.   NV = D / 256.
+template <int NV>
+__global__ void __launch_bounds__(256) ln_modulate_fwd_kernel(const bf16* __restrict__ x, int64_t ldx, bf16* __restrict__ y,
+                                                              int64_t ldy, const bf16* __restrict__ shift,
+                                                              const bf16* __restrict__ scale, int64_t ldmod,
+                                                              int rows_per_batch, float* __restrict__ mean_out,
+                                                              float* __restrict__ rstd_out, int M, float eps) {
+  constexpr int D = NV * 256;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float v[NV][8];
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * ldx);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    unpack8(xr[i * 32 + lane], v[i]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += v[i][e];
+  }
+  const float mean = warp_sum(s) * (1.f / D);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float d = v[i][e] - mean;
+      ss += d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.f / D) + eps);
+  if (lane == 0 && mean_out) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+  const int b = row / rows_per_batch;
+  const uint4* sh = reinterpret_cast<const uint4*>(shift + (int64_t)b * ldmod);
+  const uint4* sc = reinterpret_cast<const uint4*>(scale + (int64_t)b * ldmod);
+  uint4* yr = reinterpret_cast<uint4*>(y + (int64_t)row * ldy);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float fs[8], fc[8], o[8];
+    unpack8(__ldg(sh + i * 32 + lane), fs);
+    unpack8(__ldg(sc + i * 32 + lane), fc);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float n = round_bf16((v[i][e] - mean) * rstd);
+      float m = round_bf16(n * round_bf16(1.f + fc[e]));
+      o[e] = m + fs[e];
+    }
+    yr[i * 32 + lane] = pack8(o);
+  }
+}
+
+// dx = dres + LN_bwd( dy * (1 + scale[b]) );  optional second output dx_gated = dx * gate[b]  (feeds the next dgrad GEMM)
+template <int NV>
+__global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const bf16* __restrict__ dy, int64_t lddy,
+                                                              const bf16* __restrict__ x, int64_t ldx,
+                                                              const float* __restrict__ mean_in,
+                                                              const float* __restrict__ rstd_in,
+                                                              const bf16* __restrict__ scale, int64_t ldmod,
+                                                              int rows_per_batch, const bf16* __restrict__ dres,
+                                                              int64_t lddres, bf16* __restrict__ dx, int64_t lddx,
+                                                              const bf16* __restrict__ gate, int64_t ldgate,
+                                                              bf16* __restrict__ dx_gated, int64_t lddxg, int M) {
+  constexpr int D = NV * 256;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int b = row / rows_per_batch;
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  const uint4* dyr = reinterpret_cast<const uint4*>(dy + (int64_t)row * lddy);
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * ldx);
+  const uint4* sc = reinterpret_cast<const uint4*>(scale + (int64_t)b * ldmod);
+  float g[NV][8], xh[NV][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float fd[8], fx[8], fc[8];
+    unpack8(dyr[i * 32 + lane], fd);
+    unpack8(xr[i * 32 + lane], fx);
+    unpack8(__ldg(sc + i * 32 + lane), fc);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      g[i][e] = round_bf16(fd[e] * round_bf16(1.f + fc[e]));  // autograd: grad wrt LN output, bf16
+      xh[i][e] = (fx[e] - mean) * rstd;
+      s1 += g[i][e];
+      s2 += g[i][e] * xh[i][e];
+    }
+  }
+  s1 = warp_sum(s1) * (1.f / D);
+  s2 = warp_sum(s2) * (1.f / D);
+  const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + (int64_t)row * lddres) : nullptr;
+  uint4* dxr = reinterpret_cast<uint4*>(dx + (int64_t)row * lddx);
+  const uint4* gt = dx_gated ? reinterpret_cast<const uint4*>(gate + (int64_t)b * ldgate) : nullptr;
+  uint4* dxg = dx_gated ? reinterpret_cast<uint4*>(dx_gated + (int64_t)row * lddxg) : nullptr;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float o[8], fr[8];
+    if (rr) unpack8(rr[i * 32 + lane], fr);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float d = round_bf16(rstd * (g[i][e] - s1 - xh[i][e] * s2));
+      o[e] = rr ? round_bf16(fr[e] + d) : d;
+    }
+    dxr[i * 32 + lane] = pack8(o);
+    if (dxg) {
+      float fg[8], og[8];
+      unpack8(__ldg(gt + i * 32 + lane), fg);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) og[e] = o[e] * fg[e];
+      dxg[i * 32 + lane] = pack8(og);
+    }
+  }
+}
+
+// out = a * gate[b]   (backward of the gated residual branch when no LN-bwd kernel precedes it)
+__global__ void __launch_bounds__(256) gate_mul_kernel(const bf16* __restrict__ a, int64_t lda, const bf16* __restrict__ gate,
+                                                       int64_t ldg, int rows_per_batch, bf16* __restrict__ out, int64_t ldo,
+                                                       int M, int D) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int b = row / rows_per_batch;
+  const uint4* ar = reinterpret_cast<const uint4*>(a + (int64_t)row * lda);
+  const uint4* gr = reinterpret_cast<const uint4*>(gate + (int64_t)b * ldg);
+  uint4* orow = reinterpret_cast<uint4*>(out + (int64_t)row * ldo);
+  for (int i = lane; i < D / 8; i += 32) {
+    float fa[8], fg[8], o[8];
+    unpack8(ar[i], fa);
+    unpack8(__ldg(gr + i), fg);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = fa[e] * fg[e];
+    orow[i] = pack8(o);
+  }
+}
+
+// ============================================================================================ RMSNorm over rows (txt_norm)
+// diffusers RMSNorm: y = bf16( bf16(x * rsqrt(mean(x^2)+eps)) * w )
+__global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* __restrict__ w,
+                                                           bf16* __restrict__ y, int64_t ldy, int M, int D, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * ldx);
+  float ss = 0.f;
+  for (int i = lane; i < D / 8; i += 32) {
+    float f[8];
+    unpack8(xr[i], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss += f[e] * f[e];
+  }
+  const float r = rsqrtf(warp_sum(ss) / D + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + (int64_t)row * ldy);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  for (int i = lane; i < D / 8; i += 32) {
+    float f[8], fw[8], o[8];
+    unpack8(xr[i], f);
+    unpack8(__ldg(wr + i), fw);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = round_bf16(f[e] * r) * fw[e];
+    yr[i] = pack8(o);
+  }
+}
+
+// ============================================================================================ q/k RMSNorm + RoPE + layout
+// Token-major projections qkv[tok, q|k|v, H, 128]  ->  head-major joint tensors Q/K/V[B, H, S, 128] at joint position
+// s = s_offset + (tok % tokens_per_sample).  rope[(b*rope_bstride) + s][64] = (cos, sin) fp32 pairs; pair i rotates
+// elements (2i, 2i+1).  One warp per (token, head); lane owns 4 consecutive elements.
+template <bool ROUND_MID>
+__global__ void __launch_bounds__(256) qk_norm_rope_fwd_kernel(const bf16* __restrict__ qkv, int64_t ldqkv,
+                                                               const bf16* __restrict__ wq, const bf16* __restrict__ wk,
+                                                               const float2* __restrict__ rope, int64_t rope_bstride,
+                                                               bf16* __restrict__ Q, bf16* __restrict__ K, bf16* __restrict__ V,
+                                                               int tokens, int tokens_per_sample, int s_offset, int S, int H,
+                                                               float eps) {
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= tokens * H) return;
+  const int tok = gw / H, h = gw - tok * H;
+  const int b = tok / tokens_per_sample, s = s_offset + tok - b * tokens_per_sample;
+  const int D = H * 128;
+  const bf16* base = qkv + (int64_t)tok * ldqkv + h * 128 + lane * 4;
+  const int64_t dst = (((int64_t)b * H + h) * S + s) * 128 + lane * 4;
+  const float4 cs = *reinterpret_cast<const float4*>(rope + ((int64_t)b * rope_bstride + s) * 64 + lane * 2);
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(base + which * D);
+    float f[4] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y)};
+    float ss = warp_sum(f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3]);
+    const float r = rsqrtf(ss * (1.f / 128) + eps);
+    const uint2 wr = __ldg(reinterpret_cast<const uint2*>((which ? wk : wq) + lane * 4));
+    const float w[4] = {bf16_lo(wr.x), bf16_hi(wr.x), bf16_lo(wr.y), bf16_hi(wr.y)};
+    float n[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) n[e] = ROUND_MID ? round_bf16(round_bf16(f[e] * r) * w[e]) : round_bf16(f[e] * r * w[e]);
+    float o[4];
+    o[0] = n[0] * cs.x - n[1] * cs.y;
+    o[1] = n[0] * cs.y + n[1] * cs.x;
+    o[2] = n[2] * cs.z - n[3] * cs.w;
+    o[3] = n[2] * cs.w + n[3] * cs.z;
+    *reinterpret_cast<uint2*>((which ? K : Q) + dst) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+  }
+  *reinterpret_cast<uint2*>(V + dst) = *reinterpret_cast<const uint2*>(base + 2 * D);
+}
+
+// Backward: dQ/dK/dV[B,H,S,128] (bf16) + saved pre-norm qkv  ->  dqkv[tok, 3D].
+template <bool ROUND_MID>
+__global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(const bf16* __restrict__ dQ, const bf16* __restrict__ dK,
+                                                               const bf16* __restrict__ dV, const bf16* __restrict__ qkv,
+                                                               int64_t ldqkv, const bf16* __restrict__ wq,
+                                                               const bf16* __restrict__ wk, const float2* __restrict__ rope,
+                                                               int64_t rope_bstride, bf16* __restrict__ dqkv, int64_t lddqkv,
+                                                               int tokens, int tokens_per_sample, int s_offset, int S, int H,
+                                                               float eps) {
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= tokens * H) return;
+  const int tok = gw / H, h = gw - tok * H;
+  const int b = tok / tokens_per_sample, s = s_offset + tok - b * tokens_per_sample;
+  const int D = H * 128;
+  const bf16* base = qkv + (int64_t)tok * ldqkv + h * 128 + lane * 4;
+  bf16* obase = dqkv + (int64_t)tok * lddqkv + h * 128 + lane * 4;
+  const int64_t src = (((int64_t)b * H + h) * S + s) * 128 + lane * 4;
+  const float4 cs = *reinterpret_cast<const float4*>(rope + ((int64_t)b * rope_bstride + s) * 64 + lane * 2);
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const uint2 graw = *reinterpret_cast<const uint2*>((which ? dK : dQ) + src);
+    const float go[4] = {bf16_lo(graw.x), bf16_hi(graw.x), bf16_lo(graw.y), bf16_hi(graw.y)};
+    // rotate back by the conjugate angle (RoPE is orthogonal)
+    float gn[4];
+    gn[0] = round_bf16(go[0] * cs.x + go[1] * cs.y);
+    gn[1] = round_bf16(-go[0] * cs.y + go[1] * cs.x);
+    gn[2] = round_bf16(go[2] * cs.z + go[3] * cs.w);
+    gn[3] = round_bf16(-go[2] * cs.w + go[3] * cs.z);
+    const uint2 raw = *reinterpret_cast<const uint2*>(base + which * D);
+    const float f[4] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y)};
+    const uint2 wr = __ldg(reinterpret_cast<const uint2*>((which ? wk : wq) + lane * 4));
+    const float w[4] = {bf16_lo(wr.x), bf16_hi(wr.x), bf16_lo(wr.y), bf16_hi(wr.y)};
+    const float ss = warp_sum(f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3]);
+    const float r = rsqrtf(ss * (1.f / 128) + eps);
+    float gw4[4], dot = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      gw4[e] = gn[e] * w[e];
+      dot += gw4[e] * f[e];
+    }
+    dot = warp_sum(dot) * (1.f / 128) * r * r * r;
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = r * gw4[e] - f[e] * dot;
+    *reinterpret_cast<uint2*>(obase + which * D) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+  }
+  *reinterpret_cast<uint2*>(obase + 2 * D) = *reinterpret_cast<const uint2*>(dV + src);
+}
+
+// ============================================================================================ conditioning GEMV
+// y[b, n] = bf16( sum_k act(x[b,k]) * W[n,k] + bias[n] ),  b < 8.  act: 0 none, 1 SiLU (rounded to bf16 like eager).
+// One warp per output row n; W streamed once (13.6 GB for all 60 Qwen blocks' modulation linears).
+template <int NB>
+__global__ void __launch_bounds__(256) gemv_act_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* __restrict__ W,
+                                                       int64_t ldw, const bf16* __restrict__ bias, bf16* __restrict__ y,
+                                                       int64_t ldy, int N, int K, int act) {
+  extern __shared__ float xs[];  // [NB][K]
+  for (int i = threadIdx.x; i < NB * K; i += blockDim.x) {
+    int b = i / K, k = i - b * K;
+    float v = __bfloat162float(x[(int64_t)b * ldx + k]);
+    if (act == 1) v = round_bf16(v / (1.f + __expf(-v)));
+    xs[i] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int n = blockIdx.x * 8 + (threadIdx.x >> 5); n < N; n += gridDim.x * 8) {
+    const uint4* wr = reinterpret_cast<const uint4*>(W + (int64_t)n * ldw);
+    float acc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+    for (int i = lane; i < K / 8; i += 32) {
+      float fw[8];
+      unpack8(__ldg(wr + i), fw);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float* xb = xs + b * K + i * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[b] += fw[e] * xb[e];
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float v = warp_sum(acc[b]);
+      if (lane == 0) y[(int64_t)b * ldy + n] = __float2bfloat16_rn(v + (bias ? __bfloat162float(bias[n]) : 0.f));
+    }
+  }
+}
+
+// sinusoidal timestep embedding, diffusers Timesteps(256, flip_sin_to_cos=True, shift=0, scale): out[b] = [cos | sin]
+__global__ void timestep_sinusoid_kernel(const float* __restrict__ t, float scale, bf16* __restrict__ out, int B, int dim) {
+  const int half = dim / 2;
+  for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < B * half; i += blockDim.x * gridDim.x) {
+    int b = i / half, j = i - b * half;
+    // timestep has been rounded to bf16 by the model (transformer_qwenimage.py:624) — the caller passes that value
+    float freq = expf(-9.210340371976184f * (float)j / (float)half);
+    float arg = scale * (t[b] * freq);
+    out[(int64_t)b * dim + j] = __float2bfloat16_rn(cosf(arg));
+    out[(int64_t)b * dim + half + j] = __float2bfloat16_rn(sinf(arg));
+  }
+}
+
+// ============================================================================================ flow matching
+// packed[b, 0:L] = bf16( bf16((1-sigma_b)*x0) + bf16(sigma_b*noise) ) ; packed[b, L:L+Lc] = control
+__global__ void flow_noisy_input_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ noise,
+                                        const bf16* __restrict__ control, const float* __restrict__ sigma,
+                                        bf16* __restrict__ packed, int B, int L, int Lc, int Cc) {
+  const int64_t per = (int64_t)(L + Lc) * Cc;
+  const int64_t total = (int64_t)B * per;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / per);
+    int64_t r = i - (int64_t)b * per;
+    if (r < (int64_t)L * Cc) {
+      float sg = round_bf16(sigma[b]);
+      float one_m = round_bf16(1.f - sg);
+      float a = round_bf16(one_m * __bfloat162float(x0[(int64_t)b * L * Cc + r]));
+      float c = round_bf16(sg * __bfloat162float(noise[(int64_t)b * L * Cc + r]));
+      packed[i] = __float2bfloat16_rn(a + c);
+    } else {
+      packed[i] = control[(int64_t)b * Lc * Cc + (r - (int64_t)L * Cc)];
+    }
+  }
+}
+
+// loss += norm * sum w[b,t] * (pred - (noise - x0))^2 ;  dpred = 2 * norm * w * (pred - target) * loss_scale  (bf16),
+// zero for the control tokens.  pred is [B, Ltot, C]; only the first L tokens carry loss (trainer :839).
+__global__ void __launch_bounds__(256) flow_loss_kernel(const bf16* __restrict__ pred, const bf16* __restrict__ x0,
+                                                        const bf16* __restrict__ noise, const float* __restrict__ w,
+                                                        float norm, float grad_scale, float* __restrict__ loss,
+                                                        bf16* __restrict__ dpred, int B, int L, int Ltot, int Cc) {
+  const int64_t total = (int64_t)B * Ltot * Cc;
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t bt = i / Cc;
+    int c = (int)(i - bt * Cc);
+    int b = (int)(bt / Ltot), t = (int)(bt - (int64_t)b * Ltot);
+    float g = 0.f;
+    if (t < L) {
+      int64_t j = ((int64_t)b * L + t) * Cc + c;
+      float target = round_bf16(__bfloat162float(noise[j]) - __bfloat162float(x0[j]));
+      float d = __bfloat162float(pred[i]) - target;
+      float wt = w ? w[(int64_t)b * L + t] : 1.f;
+      acc += wt * d * d;
+      g = 2.f * norm * wt * d * grad_scale;
+    }
+    if (dpred) dpred[i] = __float2bfloat16_rn(g);
+  }
+  acc = warp_sum(acc);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    atomicAdd(loss, s * norm);
+  }
+}
+
+// ============================================================================================ LoRA weight gradients
+// G[i, j] += sum_m P[m, i] * Q[m, j]   (i < Dp, j < r <= 64), fp32 atomics into G with strides (gs_i, gs_j) so the same
+// kernel writes dB[out, r] (P = dY, Q = s X A^T) and dA[r, in] (P = X, Q = s dY B; transposed store).
+// Block: 128 columns of P x a chunk of rows; thread = one column i, r fp32 accumulators; Q rows broadcast from smem.
+template <int R>
+__global__ void __launch_bounds__(128) lora_wgrad_kernel(const bf16* __restrict__ P, int64_t ldp, const bf16* __restrict__ Q,
+                                                         int64_t ldq, float* __restrict__ G, int64_t gs_i, int64_t gs_j, int M,
+                                                         int Dp, int rows_per_block) {
+  __shared__ float qs[64][R];
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  const int m_begin = blockIdx.y * rows_per_block;
+  const int m_end = min(M, m_begin + rows_per_block);
+  float acc[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) acc[j] = 0.f;
+  for (int m0 = m_begin; m0 < m_end; m0 += 64) {
+    const int nrows = min(64, m_end - m0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < 64 * R; e += 128) {
+      int rr = e / R, j = e - rr * R;
+      qs[rr][j] = rr < nrows ? __bfloat162float(Q[(int64_t)(m0 + rr) * ldq + j]) : 0.f;
+    }
+    __syncthreads();
+    if (i < Dp) {
+#pragma unroll 4
+      for (int rr = 0; rr < nrows; ++rr) {
+        const float p = __bfloat162float(P[(int64_t)(m0 + rr) * ldp + i]);
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[j] += p * qs[rr][j];
+      }
+    }
+  }
+  if (i < Dp) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) atomicAdd(G + (int64_t)i * gs_i + (int64_t)j * gs_j, acc[j]);
+  }
+}
+
+// delta[b,h,s] = sum_d dO * O over one head (token-major [tokens, H*128] operands) — softmax-backward row term.
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ O, int64_t ldo, const bf16* __restrict__ dO,
+                                                         int64_t lddo, float* __restrict__ delta, int tokens,
+                                                         int tokens_per_sample, int s_offset, int S, int H) {
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= tokens * H) return;
+  const int tok = gw / H, h = gw - tok * H;
+  const int b = tok / tokens_per_sample, s = s_offset + tok - b * tokens_per_sample;
+  const uint2 a = *reinterpret_cast<const uint2*>(O + (int64_t)tok * ldo + h * 128 + lane * 4);
+  const uint2 g = *reinterpret_cast<const uint2*>(dO + (int64_t)tok * lddo + h * 128 + lane * 4);
+  float d = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) + bf16_hi(a.y) * bf16_hi(g.y);
+  d = warp_sum(d);
+  if (lane == 0) delta[((int64_t)b * H + h) * S + s] = d;
+}
+
+// grads(fp32 accumulators) -> scale (1/world, clip) -> bf16 ; sumsq of the scaled-by-inv_world grads accumulated first
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, float pre_scale, float* __restrict__ out) {
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = g[i] * pre_scale;
+    acc += v * v;
+  }
+  acc = warp_sum(acc);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    atomicAdd(out, s);
+  }
+}
+// out_bf16 = g * pre_scale * min(1, max_norm / (sqrt(sumsq) + 1e-6))     (torch.nn.utils.clip_grad_norm_ semantics)
+__global__ void __launch_bounds__(256) clip_cast_kernel(const float* __restrict__ g, int64_t n, float pre_scale,
+                                                        const float* __restrict__ sumsq, float max_norm, bf16* __restrict__ out) {
+  float coef = 1.f;
+  if (max_norm > 0.f) {
+    float c = max_norm / (sqrtf(*sumsq) + 1e-6f);
+    coef = c < 1.f ? c : 1.f;
+  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(g[i] * pre_scale * coef);
+}
+
+}  // namespace qfx
+
+using namespace qfx;
+
+#define LAUNCH_OK()              \
+  QFX_CUDA(cudaGetLastError()); \
+  return 0
+
+template <typename F>
+static int dispatch_nv(int D, F&& f) {
+  switch (D / 256) {
+    case 1: return f(std::integral_constant<int, 1>());
+    case 2: return f(std::integral_constant<int, 2>());
+    case 4: return f(std::integral_constant<int, 4>());
+    case 8: return f(std::integral_constant<int, 8>());
+    case 12: return f(std::integral_constant<int, 12>());
+    case 16: return f(std::integral_constant<int, 16>());
+  }
+  set_error("hidden size %d unsupported (need 256*{1,2,4,8,12,16})", D);
+  return -1;
+}
+
+extern "C" int qfx_ln_modulate_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, const void* shift, const void* scale,
+                                   int64_t ldmod, int rows_per_batch, float* mean, float* rstd, int M, int D, float eps,
+                                   void* stream) {
+  QFX_CHECK_ARG(D % 256 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldmod % 8 == 0, "qfx_ln_modulate_fwd: bad dims");
+  return dispatch_nv(D, [&](auto nv) {
+    ln_modulate_fwd_kernel<decltype(nv)::value><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)shift, (const bf16*)scale, ldmod, rows_per_batch, mean, rstd, M, eps);
+    LAUNCH_OK();
+  });
+}
+
+extern "C" int qfx_ln_modulate_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* mean,
+                                   const float* rstd, const void* scale, int64_t ldmod, int rows_per_batch, const void* dres,
+                                   int64_t lddres, void* dx, int64_t lddx, const void* gate, int64_t ldgate, void* dx_gated,
+                                   int64_t lddxg, int M, int D, void* stream) {
+  QFX_CHECK_ARG(D % 256 == 0, "qfx_ln_modulate_bwd: bad dims");
+  return dispatch_nv(D, [&](auto nv) {
+    ln_modulate_bwd_kernel<decltype(nv)::value><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)dy, lddy, (const bf16*)x, ldx, mean, rstd, (const bf16*)scale, ldmod, rows_per_batch, (const bf16*)dres,
+        lddres, (bf16*)dx, lddx, (const bf16*)gate, ldgate, (bf16*)dx_gated, lddxg, M);
+    LAUNCH_OK();
+  });
+}
+
+extern "C" int qfx_gate_mul(const void* a, int64_t lda, const void* gate, int64_t ldg, int rows_per_batch, void* out,
+                            int64_t ldo, int M, int D, void* stream) {
+  QFX_CHECK_ARG(D % 8 == 0, "qfx_gate_mul: D %% 8");
+  gate_mul_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, lda, (const bf16*)gate, ldg, rows_per_batch,
+                                                                 (bf16*)out, ldo, M, D);
+  LAUNCH_OK();
+}
+
+extern "C" int qfx_rmsnorm_rows(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int M, int D, float eps,
+                                void* stream) {
+  QFX_CHECK_ARG(D % 8 == 0, "qfx_rmsnorm_rows: D %% 8");
+  rmsnorm_rows_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)w, (bf16*)y, ldy, M, D, eps);
+  LAUNCH_OK();
+}
+
+extern "C" int qfx_qk_norm_rope_fwd(const void* qkv, int64_t ldqkv, const void* wq, const void* wk, const float* rope,
+                                    int64_t rope_bstride, void* Q, void* K, void* V, int tokens, int tokens_per_sample,
+                                    int s_offset, int S, int H, float eps, int round_mid, void* stream) {
+  const int blocks = (tokens * H + 7) / 8;
+  if (round_mid)
+    qk_norm_rope_fwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk, (const float2*)rope, rope_bstride, (bf16*)Q, (bf16*)K, (bf16*)V,
+        tokens, tokens_per_sample, s_offset, S, H, eps);
+  else
+    qk_norm_rope_fwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk, (const float2*)rope, rope_bstride, (bf16*)Q, (bf16*)K, (bf16*)V,
+        tokens, tokens_per_sample, s_offset, S, H, eps);
+  LAUNCH_OK();
+}
+
+extern "C" int qfx_qk_norm_rope_bwd(const void* dQ, const void* dK, const void* dV, const void* qkv, int64_t ldqkv,
+                                    const void* wq, const void* wk, const float* rope, int64_t rope_bstride, void* dqkv,
+                                    int64_t lddqkv, int tokens, int tokens_per_sample, int s_offset, int S, int H, float eps,
+                                    int round_mid, void* stream) {
+  const int blocks = (tokens * H + 7) / 8;
+  if (round_mid)
+    qk_norm_rope_bwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)dQ, (const bf16*)dK, (const bf16*)dV, (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk,
+        (const float2*)rope, rope_bstride, (bf16*)dqkv, lddqkv, tokens, tokens_per_sample, s_offset, S, H, eps);
+  else
+    qk_norm_rope_bwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)dQ, (const bf16*)dK, (const bf16*)dV, (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk,
+        (const float2*)rope, rope_bstride, (bf16*)dqkv, lddqkv, tokens, tokens_per_sample, s_offset, S, H, eps);
+  LAUNCH_OK();
+}
+
+extern "C" int qfx_gemv_act(const void* x, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* y, int64_t ldy,
+                            int B, int N, int K, int act, void* stream) {
+  QFX_CHECK_ARG(B >= 1 && B <= 8 && K % 8 == 0 && ldw % 8 == 0, "qfx_gemv_act: B=%d K=%d", B, K);
+  int grid = (N + 7) / 8;
+  if (grid > 148 * 8) grid = 148 * 8;
+  size_t sm = (size_t)B * K * sizeof(float);
+  QFX_CHECK_ARG(sm <= 200 * 1024, "qfx_gemv_act: K too large");
+#define GEMV(NB)                                                                                                             \
+  case NB: {                                                                                                                 \
+    static bool done = false;                                                                                                \
+    if (!done) {                                                                                                             \
+      QFX_CUDA(cudaFuncSetAttribute(gemv_act_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));          \
+      done = true;                                                                                                           \
+    }                                                                                                                        \
+    gemv_act_kernel<NB><<<grid, 256, sm, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)W, ldw, (const bf16*)bias, \
+                                                                 (bf16*)y, ldy, N, K, act);                                 \
+  } break;
+  switch (B) {
+    GEMV(1) GEMV(2) GEMV(3) GEMV(4) GEMV(5) GEMV(6) GEMV(7) GEMV(8)
+  }
+#undef GEMV
+  LAUNCH_OK();
+}
+
+extern "C" int qfx_timestep_sinusoid(const float* t, float scale, void* out, int B, int dim, void* stream) {
+  timestep_sinusoid_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(t, scale, (bf16*)out, B, dim);
+  LAUNCH_OK();
+}
+
+extern "C" int qfx_flow_noisy_input(const void* x0, const void* noise, const void* control, const float* sigma, void* packed,
+                                    int B, int L, int Lc, int C, void* stream) {
+  flow_noisy_input_kernel<<<296, 256, 0, (cudaStream_t)stream>>>((const bf16*)x0, (const bf16*)noise, (const bf16*)control, sigma,
+                                                                 (bf16*)packed, B, L, Lc, C);
+  LAUNCH_OK();
+}
+
+extern "C" int qfx_flow_loss(const void* pred, const void* x0, const void* noise, const float* w, float norm, float grad_scale,
+                             float* loss, void* dpred, int B, int L, int Ltot, int C, void* stream) {
+  QFX_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
+  flow_loss_kernel<<<296, 256, 0, (cudaStream_t)stream>>>((const bf16*)pred, (const bf16*)x0, (const bf16*)noise, w, norm,
+                                                          grad_scale, loss, (bf16*)dpred, B, L, Ltot, C);
+  LAUNCH_OK();
+}
+
+extern "C" int qfx_lora_wgrad(const void* P, int64_t ldp, const void* Q, int64_t ldq, float* G, int64_t gs_i, int64_t gs_j,
+                              int M, int Dp, int r, void* stream) {
+  int splits = (M + 511) / 512;
+  int rows = ((M + splits - 1) / splits + 63) / 64 * 64;
+  dim3 grid((Dp + 127) / 128, (M + rows - 1) / rows);
+#define WG(R)                                                                                                                  \
+  case R:                                                                                                                      \
+    lora_wgrad_kernel<R><<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)P, ldp, (const bf16*)Q, ldq, G, gs_i, gs_j, M, Dp, \
+                                                                 rows);                                                        \
+    break;
+  switch (r) {
+    WG(4) WG(8) WG(16) WG(32) WG(64)
+    default:
+      set_error("qfx_lora_wgrad: rank %d unsupported (4/8/16/32/64)", r);
+      return -1;
+  }
+#undef WG
+  LAUNCH_OK();
+}
+
+extern "C" int qfx_attn_delta(const void* O, int64_t ldo, const void* dO, int64_t lddo, float* delta, int tokens,
+                              int tokens_per_sample, int s_offset, int S, int H, void* stream) {
+  attn_delta_kernel<<<(tokens * H + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const bf16*)O, ldo, (const bf16*)dO, lddo, delta,
+                                                                            tokens, tokens_per_sample, s_offset, S, H);
+  LAUNCH_OK();
+}
+
+extern "C" int qfx_grad_finalize(const float* g, int64_t n, float pre_scale, float max_norm, float* sumsq, void* out_bf16,
+                                 void* stream) {
+  QFX_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float), (cudaStream_t)stream));
+  sumsq_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(g, n, pre_scale, sumsq);
+  clip_cast_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(g, n, pre_scale, sumsq, max_norm, (bf16*)out_bf16);
+  LAUNCH_OK();
+}

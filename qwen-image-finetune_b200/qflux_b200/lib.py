@@ -90,3 +90,130 @@ def gemm(problems, N, K, *, trans_b=False, epilogue=EPI_BIAS, alpha=1.0, lora_gr
     arr = (GemmProblem * len(problems))(*problems)
     check(_lib.qfx_gemm_bf16(arr, len(problems), N, K, int(trans_b), epilogue, float(alpha), lora_group_n, block_n,
                              cur_stream()), "qfx_gemm_bf16")
+
+
+# ---------------------------------------------------------------------------------------------------- elementwise
+def _sig(name, *argtypes):
+    f = getattr(_lib, name)
+    f.argtypes = list(argtypes)
+    f.restype = C.c_int
+    return f
+
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_ln_fwd = _sig("qfx_ln_modulate_fwd", _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _vp, _vp, _i, _i, _f, _vp)
+_ln_bwd = _sig("qfx_ln_modulate_bwd", _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp, _i64, _vp, _i64, _vp, _i64, _vp,
+               _i64, _i, _i, _vp)
+_gate_mul = _sig("qfx_gate_mul", _vp, _i64, _vp, _i64, _i, _vp, _i64, _i, _i, _vp)
+_rms_rows = _sig("qfx_rmsnorm_rows", _vp, _i64, _vp, _vp, _i64, _i, _i, _f, _vp)
+_qknr_fwd = _sig("qfx_qk_norm_rope_fwd", _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp)
+_qknr_bwd = _sig("qfx_qk_norm_rope_bwd", _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _f, _i,
+                 _vp)
+_gemv = _sig("qfx_gemv_act", _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp)
+_tsin = _sig("qfx_timestep_sinusoid", _vp, _f, _vp, _i, _i, _vp)
+_noisy = _sig("qfx_flow_noisy_input", _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp)
+_floss = _sig("qfx_flow_loss", _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _i, _i, _i, _i, _vp)
+_wgrad = _sig("qfx_lora_wgrad", _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp)
+_delta = _sig("qfx_attn_delta", _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp)
+_gfin = _sig("qfx_grad_finalize", _vp, _i64, _f, _f, _vp, _vp, _vp)
+_attn_fwd = _sig("qfx_attn_fwd", _vp, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _vp, _vp, _i, _i, _i, _f, _vp)
+
+
+def ln_modulate_fwd(x, y, shift, scale, rows_per_batch, mean=None, rstd=None, eps=1e-6):
+    """shift/scale: [B, D] views (row stride = stride(0)) of the modulation tensor."""
+    require_cuda(x, y, shift, scale)
+    assert shift.stride(0) == scale.stride(0)
+    check(_ln_fwd(ptr(x), x.stride(0), ptr(y), y.stride(0), ptr(shift), ptr(scale), shift.stride(0), rows_per_batch,
+                  ptr(mean), ptr(rstd), x.shape[0], x.shape[1], eps, cur_stream()), "qfx_ln_modulate_fwd")
+
+
+def ln_modulate_bwd(dy, x, mean, rstd, scale, rows_per_batch, dx, dres=None, gate=None, dx_gated=None):
+    require_cuda(dy, x, mean, rstd, scale, dx)
+    check(_ln_bwd(ptr(dy), dy.stride(0), ptr(x), x.stride(0), ptr(mean), ptr(rstd), ptr(scale), scale.stride(0),
+                  rows_per_batch, ptr(dres), _ld(dres), ptr(dx), dx.stride(0), ptr(gate), _ld(gate), ptr(dx_gated),
+                  _ld(dx_gated), x.shape[0], x.shape[1], cur_stream()), "qfx_ln_modulate_bwd")
+
+
+def gate_mul(a, gate, rows_per_batch, out):
+    require_cuda(a, gate, out)
+    check(_gate_mul(ptr(a), a.stride(0), ptr(gate), gate.stride(0), rows_per_batch, ptr(out), out.stride(0), a.shape[0],
+                    a.shape[1], cur_stream()), "qfx_gate_mul")
+
+
+def rmsnorm_rows(x, w, y, eps=1e-6):
+    require_cuda(x, w, y)
+    check(_rms_rows(ptr(x), x.stride(0), ptr(w), ptr(y), y.stride(0), x.shape[0], x.shape[1], eps, cur_stream()),
+          "qfx_rmsnorm_rows")
+
+
+def qk_norm_rope_fwd(qkv, wq, wk, rope, Q, K, V, tokens_per_sample, s_offset, eps=1e-6, round_mid=True):
+    """qkv [tokens, 3*H*128]; rope fp32 [S,64,2] (shared) or [B,S,64,2]; Q/K/V [B,H,S,128]."""
+    require_cuda(qkv, wq, wk, rope, Q, K, V)
+    B, H, S, _ = Q.shape
+    bstride = 0 if rope.dim() == 3 else S
+    check(_qknr_fwd(ptr(qkv), qkv.stride(0), ptr(wq), ptr(wk), ptr(rope), bstride, ptr(Q), ptr(K), ptr(V), qkv.shape[0],
+                    tokens_per_sample, s_offset, S, H, eps, int(round_mid), cur_stream()), "qfx_qk_norm_rope_fwd")
+
+
+def qk_norm_rope_bwd(dQ, dK, dV, qkv, wq, wk, rope, dqkv, tokens_per_sample, s_offset, eps=1e-6, round_mid=True):
+    require_cuda(dQ, dK, dV, qkv, wq, wk, rope, dqkv)
+    B, H, S, _ = dK.shape
+    bstride = 0 if rope.dim() == 3 else S
+    check(_qknr_bwd(ptr(dQ), ptr(dK), ptr(dV), ptr(qkv), qkv.stride(0), ptr(wq), ptr(wk), ptr(rope), bstride, ptr(dqkv),
+                    dqkv.stride(0), qkv.shape[0], tokens_per_sample, s_offset, S, H, eps, int(round_mid), cur_stream()),
+          "qfx_qk_norm_rope_bwd")
+
+
+def gemv_act(x, W, bias, y, act=0):
+    """y[b, :] = act_in(x[b]) @ W^T + bias ; act: 0 none, 1 SiLU.  x [B<=8, K], W [N, K]."""
+    require_cuda(x, W, bias, y)
+    check(_gemv(ptr(x), x.stride(0), ptr(W), W.stride(0), ptr(bias), ptr(y), y.stride(0), x.shape[0], W.shape[0], W.shape[1],
+                act, cur_stream()), "qfx_gemv_act")
+
+
+def timestep_sinusoid(t_f32, scale, out):
+    require_cuda(t_f32, out)
+    check(_tsin(ptr(t_f32), scale, ptr(out), out.shape[0], out.shape[1], cur_stream()), "qfx_timestep_sinusoid")
+
+
+def flow_noisy_input(x0, noise, control, sigma_f32, packed):
+    require_cuda(x0, noise, control, sigma_f32, packed)
+    B, L, Cc = x0.shape
+    check(_noisy(ptr(x0), ptr(noise), ptr(control), ptr(sigma_f32), ptr(packed), B, L, control.shape[1], Cc, cur_stream()),
+          "qfx_flow_noisy_input")
+
+
+def flow_loss(pred, x0, noise, w, norm, loss, dpred=None, grad_scale=1.0):
+    require_cuda(pred, x0, noise, w, loss, dpred)
+    B, L, Cc = x0.shape
+    check(_floss(ptr(pred), ptr(x0), ptr(noise), ptr(w), norm, grad_scale, ptr(loss), ptr(dpred), B, L, pred.shape[1], Cc,
+                 cur_stream()), "qfx_flow_loss")
+
+
+def lora_wgrad(P, Q, G, gs_i, gs_j, r):
+    """G[i*gs_i + j*gs_j] += sum_m P[m,i] Q[m,j], j < r.  G fp32."""
+    require_cuda(P, Q, G)
+    check(_wgrad(ptr(P), P.stride(0), ptr(Q), Q.stride(0), ptr(G), gs_i, gs_j, P.shape[0], P.shape[1], r, cur_stream()),
+          "qfx_lora_wgrad")
+
+
+def attn_delta(O, dO, delta, tokens_per_sample, s_offset):
+    require_cuda(O, dO, delta)
+    B, H, S = delta.shape
+    check(_delta(ptr(O), O.stride(0), ptr(dO), dO.stride(0), ptr(delta), O.shape[0], tokens_per_sample, s_offset, S, H,
+                 cur_stream()), "qfx_attn_delta")
+
+
+def grad_finalize(g_f32, pre_scale, max_norm, sumsq, out_bf16):
+    require_cuda(g_f32, sumsq, out_bf16)
+    check(_gfin(ptr(g_f32), g_f32.numel(), pre_scale, max_norm, ptr(sumsq), ptr(out_bf16), cur_stream()), "qfx_grad_finalize")
+
+
+def attn_fwd(Q, K, V, out_txt, out_img, split, lse=None, kv_len=None, scale=None):
+    """Q/K/V [B,H,S,128]; rows s<split of sample b -> out_txt[b*split + s], others -> out_img[b*(S-split) + s-split]."""
+    require_cuda(Q, K, V, out_txt, out_img, lse, kv_len)
+    B, H, S, d = Q.shape
+    assert d == 128 and Q.is_contiguous() and K.is_contiguous() and V.is_contiguous()
+    scale = scale if scale is not None else d ** -0.5
+    check(_attn_fwd(ptr(Q), ptr(K), ptr(V), ptr(out_txt), _ld(out_txt), split, ptr(out_img), _ld(out_img), S - split, split,
+                    ptr(lse), ptr(kv_len), B, H, S, scale, cur_stream()), "qfx_attn_fwd")

@@ -1,0 +1,223 @@
+"""GPU check of the elementwise / attention entry points against fp32 torch references (run under gpurun)."""
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from harness import main, rel_l2, time_cuda  # noqa: E402
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+BF = torch.bfloat16
+
+
+def _mk(*shape, scale=1.0, seed=0, dtype=BF):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(dtype)
+
+
+def ln_mod(D=3072, M=1000, Bsz=4):
+    from qflux_b200 import lib
+    x = _mk(M, D, seed=1, scale=2.0) + 0.5
+    mod = _mk(Bsz, 6 * D, seed=2, scale=0.3)
+    shift, scale, gate = mod[:, :D], mod[:, D:2 * D], mod[:, 2 * D:3 * D]
+    rpb = M // Bsz
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(M, device="cuda"), torch.empty(M, device="cuda")
+    lib.ln_modulate_fwd(x, y, shift, scale, rpb, mean, rstd)
+    xf = x.float().requires_grad_(True)
+    sc = scale.float().repeat_interleave(rpb, 0)
+    sh = shift.float().repeat_interleave(rpb, 0)
+    ref = F.layer_norm(xf, (D,), eps=1e-6) * (1 + sc) + sh
+    res = dict(fwd=rel_l2(y.float(), ref), mean=rel_l2(mean, x.float().mean(1)))
+    dy = _mk(M, D, seed=3)
+    dres = _mk(M, D, seed=4)
+    ref.backward(dy.float())
+    dx, dxg = torch.empty_like(x), torch.empty_like(x)
+    lib.ln_modulate_bwd(dy, x, mean, rstd, scale, rpb, dx, dres=dres, gate=gate, dx_gated=dxg)
+    ref_dx = dres.float() + xf.grad
+    res["bwd"] = rel_l2(dx.float(), ref_dx)
+    res["bwd_gated"] = rel_l2(dxg.float(), ref_dx * gate.float().repeat_interleave(rpb, 0))
+    out = torch.empty_like(x)
+    lib.gate_mul(dy, gate, rpb, out)
+    res["gate_mul"] = rel_l2(out.float(), dy.float() * gate.float().repeat_interleave(rpb, 0))
+    torch.cuda.synchronize()
+    res["err"] = max(res.values())
+    return res
+
+
+def rms_rows():
+    from qflux_b200 import lib
+    from oracle.mmdit_oracle import diffusers_rms_norm
+    x, w = _mk(700, 3584, seed=1, scale=3.0), (_mk(3584, seed=2, scale=0.2) + 1)
+    y = torch.empty_like(x)
+    lib.rmsnorm_rows(x, w, y)
+    return dict(err=rel_l2(y.float(), diffusers_rms_norm(x.float(), w.float(), 1e-6)),
+                err_bf16=rel_l2(y.float(), diffusers_rms_norm(x, w, 1e-6).float()))
+
+
+def _rope_table(S, seed=5):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    ang = torch.rand(S, 64, device="cuda", generator=g) * 6.28
+    return torch.stack([ang.cos(), ang.sin()], -1).contiguous()  # [S,64,2]
+
+
+def qk_norm_rope(H=24, Bsz=2, T=40, L=260):
+    from qflux_b200 import lib
+    from oracle.mmdit_oracle import apply_rotary_emb_qwen, diffusers_rms_norm
+    D, S = H * 128, T + L
+    rope = _rope_table(S)
+    fc = torch.complex(rope[..., 0], rope[..., 1])
+    wq, wk = _mk(128, seed=1, scale=0.2) + 1, _mk(128, seed=2, scale=0.2) + 1
+    Q, K, V = (torch.zeros(Bsz, H, S, 128, device="cuda", dtype=BF) for _ in range(3))
+    res = {}
+    streams = {}
+    for name, n, off in (("txt", T, 0), ("img", L, T)):
+        qkv = _mk(Bsz * n, 3 * D, seed=10 + off)
+        lib.qk_norm_rope_fwd(qkv, wq, wk, rope, Q, K, V, n, off)
+        streams[name] = (qkv, n, off)
+    refs = {}
+    for name, (qkv, n, off) in streams.items():
+        x = qkv.float().view(Bsz, n, 3, H, 128).requires_grad_(True)
+        q = apply_rotary_emb_qwen(diffusers_rms_norm(x[:, :, 0], wq.float(), 1e-6), fc[off:off + n])
+        k = apply_rotary_emb_qwen(diffusers_rms_norm(x[:, :, 1], wk.float(), 1e-6), fc[off:off + n])
+        refs[name] = (x, q, k, x[:, :, 2])
+        res[f"q_{name}"] = rel_l2(Q[:, :, off:off + n].float(), q.permute(0, 2, 1, 3))
+        res[f"k_{name}"] = rel_l2(K[:, :, off:off + n].float(), k.permute(0, 2, 1, 3))
+        res[f"v_{name}"] = rel_l2(V[:, :, off:off + n].float(), x[:, :, 2].permute(0, 2, 1, 3))
+    dQ = _mk(Bsz, H, S, 128, seed=20, dtype=torch.float32)
+    dK, dV = _mk(Bsz, H, S, 128, seed=21), _mk(Bsz, H, S, 128, seed=22)
+    for name, (qkv, n, off) in streams.items():
+        dqkv = torch.empty_like(qkv)
+        lib.qk_norm_rope_bwd(dQ, dK, dV, qkv, wq, wk, rope, dqkv, n, off)
+        x, q, k, v = refs[name]
+        sl = slice(off, off + n)
+        loss = (q * dQ[:, :, sl].permute(0, 2, 1, 3)).sum() + (k * dK[:, :, sl].float().permute(0, 2, 1, 3)).sum() + \
+               (v * dV[:, :, sl].float().permute(0, 2, 1, 3)).sum()
+        (g,) = torch.autograd.grad(loss, x)
+        res[f"bwd_{name}"] = rel_l2(dqkv.float(), g.reshape(Bsz * n, 3 * D))
+    torch.cuda.synchronize()
+    res["err"] = max(res.values())
+    return res
+
+
+def gemv():
+    from qflux_b200 import lib
+    res = {}
+    for (Bsz, N, K, act) in ((4, 18432 * 2, 3072, 1), (1, 3072, 256, 0), (8, 512, 3072, 1)):
+        x, W, b = _mk(Bsz, K, seed=1), _mk(N, K, seed=2, scale=0.02), _mk(N, seed=3)
+        y = torch.empty(Bsz, N, device="cuda", dtype=BF)
+        lib.gemv_act(x, W, b, y, act)
+        xin = F.silu(x.float()).to(BF).float() if act else x.float()
+        res[f"B{Bsz}_N{N}"] = rel_l2(y.float(), xin @ W.float().t() + b.float())
+    torch.cuda.synchronize()
+    res["err"] = max(res.values())
+    return res
+
+
+def flow():
+    from qflux_b200 import lib
+    from oracle.mmdit_oracle import timestep_sinusoid
+    Bsz, L, Cc = 4, 1024, 64
+    x0, noise, ctrl = _mk(Bsz, L, Cc, seed=1), _mk(Bsz, L, Cc, seed=2), _mk(Bsz, L, Cc, seed=3)
+    sigma = torch.tensor([0.999, 0.5, 0.123, 0.001], device="cuda")
+    packed = torch.empty(Bsz, 2 * L, Cc, device="cuda", dtype=BF)
+    lib.flow_noisy_input(x0, noise, ctrl, sigma, packed)
+    sg = sigma.to(BF).view(Bsz, 1, 1)
+    ref = torch.cat([(1.0 - sg) * x0 + sg * noise, ctrl], 1)
+    res = dict(noisy=rel_l2(packed.float(), ref.float()))
+    pred = _mk(Bsz, 2 * L, Cc, seed=4)
+    w = torch.rand(Bsz, L, device="cuda") + 0.5
+    norm = 1.0 / (Bsz * L * Cc)
+    loss, dpred = torch.zeros(1, device="cuda"), torch.empty_like(pred)
+    lib.flow_loss(pred, x0, noise, w, norm, loss, dpred)
+    pf = pred.float().requires_grad_(True)
+    tgt = (noise - x0).float()
+    ref_loss = (w[..., None] * (pf[:, :L] - tgt) ** 2).sum() * norm
+    ref_loss.backward()
+    res["loss"] = abs(loss.item() - ref_loss.item()) / ref_loss.item()
+    res["dpred"] = rel_l2(dpred.float(), pf.grad)
+    t = sigma.to(BF).float()
+    out = torch.empty(Bsz, 256, device="cuda", dtype=BF)
+    lib.timestep_sinusoid(t, 1000.0, out)
+    res["sinusoid"] = rel_l2(out.float(), timestep_sinusoid(t, 256, 1000.0).to(BF).float())
+    torch.cuda.synchronize()
+    res["err"] = max(res.values())
+    return res
+
+
+def wgrad():
+    from qflux_b200 import lib
+    M, Dp, res = 2500, 3072, {}
+    for r in (4, 16, 64):
+        Pm, Q = _mk(M, Dp, seed=1), _mk(M, 64, seed=2)
+        G = torch.zeros(Dp, r, device="cuda")
+        lib.lora_wgrad(Pm, Q, G, r, 1, r)
+        ref = Pm.float().t() @ Q.float()[:, :r]
+        res[f"r{r}"] = rel_l2(G, ref)
+        GT = torch.zeros(r, Dp, device="cuda")
+        lib.lora_wgrad(Pm, Q, GT, 1, Dp, r)
+        res[f"r{r}_T"] = rel_l2(GT, ref.t())
+    n = 1 << 20
+    g = _mk(n, seed=3, dtype=torch.float32)
+    ss, out = torch.zeros(1, device="cuda"), torch.empty(n, device="cuda", dtype=BF)
+    lib.grad_finalize(g, 0.5, 1.0, ss, out)
+    gn = (g * 0.5).norm()
+    res["sumsq"] = abs(ss.item() ** 0.5 - gn.item()) / gn.item()
+    res["clip"] = rel_l2(out.float(), g * 0.5 * min(1.0, 1.0 / (gn.item() + 1e-6)))
+    torch.cuda.synchronize()
+    res["err"] = max(res.values())
+    return res
+
+
+def attn(Bsz=2, H=3, S=300, split=44, ragged=False, perf=False):
+    from qflux_b200 import lib
+    Q, K, V = (_mk(Bsz, H, S, 128, seed=i, scale=1.0) for i in (1, 2, 3))
+    Q = Q * 2.0  # sharper softmax so the running-max logic is exercised
+    T, L = split, S - split
+    ot = torch.zeros(Bsz * T, H * 128, device="cuda", dtype=BF)
+    oi = torch.zeros(Bsz * L, H * 128, device="cuda", dtype=BF)
+    lse = torch.zeros(Bsz, H, S, device="cuda")
+    kv_len = None
+    if ragged:
+        kv_len = torch.tensor([S - 37 * i for i in range(Bsz)], device="cuda", dtype=torch.int32)
+    lib.attn_fwd(Q, K, V, ot, oi, split, lse, kv_len)
+    torch.cuda.synchronize()
+    mask = None
+    if ragged:
+        mask = (torch.arange(S, device="cuda")[None, :] < kv_len[:, None])[:, None, None, :]
+    ref = F.scaled_dot_product_attention(Q.float(), K.float(), V.float(), attn_mask=mask)  # [B,H,S,d]
+    out = torch.cat([ot.view(Bsz, T, H, 128), oi.view(Bsz, L, H, 128)], 1).permute(0, 2, 1, 3).float()
+    sc = Q.float() @ K.float().transpose(-1, -2) / math.sqrt(128)
+    if mask is not None:
+        sc = sc.masked_fill(~mask, float("-inf"))
+    ref_lse = torch.logsumexp(sc, -1) * 1.4426950408889634
+    res = dict(err=rel_l2(out, ref), lse=rel_l2(lse, ref_lse))
+    if perf:
+        flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
+        ms = time_cuda(lambda: lib.attn_fwd(Q, K, V, ot, oi, split, lse, kv_len), flush=flush)
+        fl = 4.0 * Bsz * H * S * S * 128
+        ms_t = time_cuda(lambda: F.scaled_dot_product_attention(Q, K, V), flush=flush)
+        res.update(ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1), torch_ms=round(ms_t, 4), torch_tflops=round(fl / ms_t / 1e9, 1))
+    return res
+
+
+CASES = {
+    "ln_mod_3072": lambda: ln_mod(3072),
+    "ln_mod_256": lambda: ln_mod(256, M=96, Bsz=3),
+    "rms_rows": rms_rows,
+    "qk_norm_rope": qk_norm_rope,
+    "qk_norm_rope_h2": lambda: qk_norm_rope(H=2, Bsz=3, T=7, L=33),
+    "gemv": gemv,
+    "flow": flow,
+    "wgrad": wgrad,
+    "attn_small": lambda: attn(1, 2, 128, 32),
+    "attn_300": lambda: attn(2, 3, 300, 44),
+    "attn_1tile_tail": lambda: attn(1, 1, 70, 10),
+    "attn_ragged": lambda: attn(3, 2, 700, 100, ragged=True),
+    "attn_qwen_perf": lambda: attn(4, 24, 2400, 352, perf=True),
+}
+
+if __name__ == "__main__":
+    main(CASES, os.path.abspath(__file__), "ops_check.log")
