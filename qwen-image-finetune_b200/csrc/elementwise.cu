@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) qk_norm_rope_fwd_kernel(const bf16* __res
 
 // Backward: dQ/dK/dV[B,H,S,128] (bf16) + saved pre-norm qkv  ->  dqkv[tok, 3D].
 template <bool ROUND_MID>
-__global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(const bf16* __restrict__ dQ, const bf16* __restrict__ dK,
+__global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(const float* __restrict__ dQ, const bf16* __restrict__ dK,
                                                                const bf16* __restrict__ dV, const bf16* __restrict__ qkv,
                                                                int64_t ldqkv, const bf16* __restrict__ wq,
                                                                const bf16* __restrict__ wk, const float2* __restrict__ rope,
@@ -262,8 +262,14 @@ __global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(const bf16* __res
   const float4 cs = *reinterpret_cast<const float4*>(rope + ((int64_t)b * rope_bstride + s) * 64 + lane * 2);
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
-    const uint2 graw = *reinterpret_cast<const uint2*>((which ? dK : dQ) + src);
-    const float go[4] = {bf16_lo(graw.x), bf16_hi(graw.x), bf16_lo(graw.y), bf16_hi(graw.y)};
+    float go[4];
+    if (which) {
+      const uint2 graw = *reinterpret_cast<const uint2*>(dK + src);
+      go[0] = bf16_lo(graw.x); go[1] = bf16_hi(graw.x); go[2] = bf16_lo(graw.y); go[3] = bf16_hi(graw.y);
+    } else {  // dQ is the fp32 TMA-reduce accumulator of the attention backward; autograd would hold it in bf16
+      const float4 gq = *reinterpret_cast<const float4*>(dQ + src);
+      go[0] = round_bf16(gq.x); go[1] = round_bf16(gq.y); go[2] = round_bf16(gq.z); go[3] = round_bf16(gq.w);
+    }
     // rotate back by the conjugate angle (RoPE is orthogonal)
     float gn[4];
     gn[0] = round_bf16(go[0] * cs.x + go[1] * cs.y);
@@ -439,8 +445,8 @@ __global__ void __launch_bounds__(128) lora_wgrad_kernel(const bf16* __restrict_
 
 // delta[b,h,s] = sum_d dO * O over one head (token-major [tokens, H*128] operands) — softmax-backward row term.
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ O, int64_t ldo, const bf16* __restrict__ dO,
-                                                         int64_t lddo, float* __restrict__ delta, int tokens,
-                                                         int tokens_per_sample, int s_offset, int S, int H) {
+                                                         int64_t lddo, float* __restrict__ delta, bf16* __restrict__ dOj,
+                                                         int tokens, int tokens_per_sample, int s_offset, int S, int H) {
   const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (gw >= tokens * H) return;
@@ -451,6 +457,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   float d = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) + bf16_hi(a.y) * bf16_hi(g.y);
   d = warp_sum(d);
   if (lane == 0) delta[((int64_t)b * H + h) * S + s] = d;
+  if (dOj) *reinterpret_cast<uint2*>(dOj + (((int64_t)b * H + h) * S + s) * 128 + lane * 4) = g;
 }
 
 // grads(fp32 accumulators) -> scale (1/world, clip) -> bf16 ; sumsq of the scaled-by-inv_world grads accumulated first
@@ -565,11 +572,11 @@ extern "C" int qfx_qk_norm_rope_bwd(const void* dQ, const void* dK, const void* 
   const int blocks = (tokens * H + 7) / 8;
   if (round_mid)
     qk_norm_rope_bwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)dQ, (const bf16*)dK, (const bf16*)dV, (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk,
+        (const float*)dQ, (const bf16*)dK, (const bf16*)dV, (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk,
         (const float2*)rope, rope_bstride, (bf16*)dqkv, lddqkv, tokens, tokens_per_sample, s_offset, S, H, eps);
   else
     qk_norm_rope_bwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)dQ, (const bf16*)dK, (const bf16*)dV, (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk,
+        (const float*)dQ, (const bf16*)dK, (const bf16*)dV, (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk,
         (const float2*)rope, rope_bstride, (bf16*)dqkv, lddqkv, tokens, tokens_per_sample, s_offset, S, H, eps);
   LAUNCH_OK();
 }
@@ -638,10 +645,11 @@ extern "C" int qfx_lora_wgrad(const void* P, int64_t ldp, const void* Q, int64_t
   LAUNCH_OK();
 }
 
-extern "C" int qfx_attn_delta(const void* O, int64_t ldo, const void* dO, int64_t lddo, float* delta, int tokens,
-                              int tokens_per_sample, int s_offset, int S, int H, void* stream) {
+extern "C" int qfx_attn_delta(const void* O, int64_t ldo, const void* dO, int64_t lddo, float* delta, void* dO_joint,
+                              int tokens, int tokens_per_sample, int s_offset, int S, int H, void* stream) {
   attn_delta_kernel<<<(tokens * H + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const bf16*)O, ldo, (const bf16*)dO, lddo, delta,
-                                                                            tokens, tokens_per_sample, s_offset, S, H);
+                                                                            (bf16*)dO_joint, tokens, tokens_per_sample, s_offset,
+                                                                            S, H);
   LAUNCH_OK();
 }
 

@@ -30,6 +30,9 @@ void set_error(const char* fmt, ...);
 // Returns 0 on success.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
+// same, fp32 elements (used for TMA reduce-add of fp32 tiles)
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
 
 int num_sms();
 

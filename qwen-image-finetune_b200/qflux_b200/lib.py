@@ -114,7 +114,8 @@ _tsin = _sig("qfx_timestep_sinusoid", _vp, _f, _vp, _i, _i, _vp)
 _noisy = _sig("qfx_flow_noisy_input", _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp)
 _floss = _sig("qfx_flow_loss", _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _i, _i, _i, _i, _vp)
 _wgrad = _sig("qfx_lora_wgrad", _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp)
-_delta = _sig("qfx_attn_delta", _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp)
+_delta = _sig("qfx_attn_delta", _vp, _i64, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp)
+_attn_bwd = _sig("qfx_attn_bwd", _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp)
 _gfin = _sig("qfx_grad_finalize", _vp, _i64, _f, _f, _vp, _vp, _vp)
 _attn_fwd = _sig("qfx_attn_fwd", _vp, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _vp, _vp, _i, _i, _i, _f, _vp)
 
@@ -197,11 +198,22 @@ def lora_wgrad(P, Q, G, gs_i, gs_j, r):
           "qfx_lora_wgrad")
 
 
-def attn_delta(O, dO, delta, tokens_per_sample, s_offset):
-    require_cuda(O, dO, delta)
+def attn_delta(O, dO, delta, tokens_per_sample, s_offset, dO_joint=None):
+    """delta[b,h,s] = sum_d O*dO for token-major O/dO rows; optionally scatters dO into the joint [B,H,S,128] layout."""
+    require_cuda(O, dO, delta, dO_joint)
     B, H, S = delta.shape
-    check(_delta(ptr(O), O.stride(0), ptr(dO), dO.stride(0), ptr(delta), O.shape[0], tokens_per_sample, s_offset, S, H,
-                 cur_stream()), "qfx_attn_delta")
+    check(_delta(ptr(O), O.stride(0), ptr(dO), dO.stride(0), ptr(delta), ptr(dO_joint), O.shape[0], tokens_per_sample,
+                 s_offset, S, H, cur_stream()), "qfx_attn_delta")
+
+
+def attn_bwd(Q, K, V, dO, lse, delta, dQ_accum, dK, dV, kv_len=None, scale=None):
+    """All [B,H,S,128]; dQ_accum fp32 and zeroed by the caller; lse/delta [B,H,S] fp32."""
+    require_cuda(Q, K, V, dO, lse, delta, dQ_accum, dK, dV, kv_len)
+    B, H, S, d = Q.shape
+    assert d == 128 and dQ_accum.dtype == torch.float32
+    scale = scale if scale is not None else d ** -0.5
+    check(_attn_bwd(ptr(Q), ptr(K), ptr(V), ptr(dO), ptr(lse), ptr(delta), ptr(dQ_accum), ptr(dK), ptr(dV), ptr(kv_len), B, H,
+                    S, scale, cur_stream()), "qfx_attn_bwd")
 
 
 def grad_finalize(g_f32, pre_scale, max_norm, sumsq, out_bf16):

@@ -203,6 +203,52 @@ def attn(Bsz=2, H=3, S=300, split=44, ragged=False, perf=False):
     return res
 
 
+def attn_bwd(Bsz=2, H=3, S=300, split=44, ragged=False, perf=False):
+    from qflux_b200 import lib
+    Q, K, V = (_mk(Bsz, H, S, 128, seed=i) for i in (1, 2, 3))
+    Q = Q * 2.0
+    T, L = split, S - split
+    ot = torch.zeros(Bsz * T, H * 128, device="cuda", dtype=BF)
+    oi = torch.zeros(Bsz * L, H * 128, device="cuda", dtype=BF)
+    lse = torch.zeros(Bsz, H, S, device="cuda")
+    kv_len = torch.tensor([S - 37 * i for i in range(Bsz)], device="cuda", dtype=torch.int32) if ragged else None
+    lib.attn_fwd(Q, K, V, ot, oi, split, lse, kv_len)
+    dot, doi = _mk(Bsz * T, H * 128, seed=7), _mk(Bsz * L, H * 128, seed=8)
+    if ragged:  # padded query rows carry no gradient
+        for b in range(Bsz):
+            doi.view(Bsz, L, -1)[b, int(kv_len[b]) - T:] = 0
+    delta = torch.zeros(Bsz, H, S, device="cuda")
+    dOj = torch.zeros(Bsz, H, S, 128, device="cuda", dtype=BF)
+    lib.attn_delta(ot, dot, delta, T, 0, dOj)
+    lib.attn_delta(oi, doi, delta, L, T, dOj)
+    dQ = torch.zeros(Bsz, H, S, 128, device="cuda")
+    dK, dV = torch.empty_like(K), torch.empty_like(V)
+    lib.attn_bwd(Q, K, V, dOj, lse, delta, dQ, dK, dV, kv_len)
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (Q, K, V))
+    mask = None
+    if ragged:
+        mask = (torch.arange(S, device="cuda")[None, :] < kv_len[:, None])[:, None, None, :]
+    ref = F.scaled_dot_product_attention(qf, kf, vf, attn_mask=mask)
+    dO_ref = torch.cat([dot.view(Bsz, T, H, 128), doi.view(Bsz, L, H, 128)], 1).permute(0, 2, 1, 3).float()
+    ref.backward(dO_ref)
+    res = dict(dOj=rel_l2(dOj.float(), dO_ref), delta=rel_l2(delta, (ref.detach() * dO_ref).sum(-1)),
+               dQ=rel_l2(dQ, qf.grad), dK=rel_l2(dK.float(), kf.grad), dV=rel_l2(dV.float(), vf.grad))
+    if ragged:
+        res.pop("delta")  # padded rows differ by construction
+    res["err"] = max(res.values())
+    if perf:
+        flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
+
+        def run():
+            dQ.zero_()
+            lib.attn_bwd(Q, K, V, dOj, lse, delta, dQ, dK, dV, kv_len)
+        ms = time_cuda(run, flush=flush)
+        fl = 10.0 * Bsz * H * S * S * 128
+        res.update(ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1))
+    return res
+
+
 CASES = {
     "ln_mod_3072": lambda: ln_mod(3072),
     "ln_mod_256": lambda: ln_mod(256, M=96, Bsz=3),
@@ -217,6 +263,11 @@ CASES = {
     "attn_1tile_tail": lambda: attn(1, 1, 70, 10),
     "attn_ragged": lambda: attn(3, 2, 700, 100, ragged=True),
     "attn_qwen_perf": lambda: attn(4, 24, 2400, 352, perf=True),
+    "attn_bwd_small": lambda: attn_bwd(1, 2, 128, 32),
+    "attn_bwd_300": lambda: attn_bwd(2, 3, 300, 44),
+    "attn_bwd_tail": lambda: attn_bwd(1, 1, 70, 10),
+    "attn_bwd_ragged": lambda: attn_bwd(3, 2, 700, 100, ragged=True),
+    "attn_bwd_qwen_perf": lambda: attn_bwd(4, 24, 2400, 352, perf=True),
 }
 
 if __name__ == "__main__":
