@@ -60,15 +60,16 @@ class LoraLinear(nn.Module):
         self.lora_B = nn.ModuleDict()
         self.scaling = 0.0
         self.r = 0
+        self._register_state_dict_hook(LoraLinear._sd_hook)
 
-    # expose diffusers names when no adapter is attached
-    def _save_to_state_dict(self, destination, prefix, keep_vars):
-        if self.r == 0:
-            destination[prefix + "weight"] = self.base_layer.weight if keep_vars else self.base_layer.weight.detach()
-            if self.base_layer.bias is not None:
-                destination[prefix + "bias"] = self.base_layer.bias if keep_vars else self.base_layer.bias.detach()
-        else:
-            super()._save_to_state_dict(destination, prefix, keep_vars)
+    # expose diffusers names (`weight`, `bias`) when no adapter is attached
+    @staticmethod
+    def _sd_hook(module, state_dict, prefix, local_metadata):
+        if module.r == 0:
+            for n in ("weight", "bias"):
+                k = prefix + "base_layer." + n
+                if k in state_dict:
+                    state_dict[prefix + n] = state_dict.pop(k)
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
         for n in ("weight", "bias"):

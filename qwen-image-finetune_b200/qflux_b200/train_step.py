@@ -1,0 +1,137 @@
+"""Training-step recipes on top of the fused model — mirrors of the reference trainers' `_compute_loss`.
+
+  QwenImageEditStep.compute_loss   <- /root/reference/src/qflux/trainer/qwen_image_edit_trainer.py:777-849 (+ _get_sigmas :851-861)
+  loss kinds                       <- /root/reference/src/qflux/losses/{mse_loss,edit_mask_loss,attention_mask_loss}.py
+  gradient sync / clip             <- /root/reference/src/qflux/trainer/base_trainer.py:383-388 (DDP over the LoRA params), :449-455
+
+Differences that are deliberate (SURVEY.md §5 caveat):
+  * the per-step `deepcopy(scheduler)` + `.nonzero().item()` host syncs are gone: sigma = (1000 - idx)/1000 is computed on
+    the host from the CPU uniform draw (same RNG stream as the reference) and uploaded asynchronously;
+  * LoRA gradients are mean-all-reduced explicitly every optimizer step (one NCCL all-reduce over one flat fp32 buffer).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import lib
+from .qwen_model import BF, QwenImageB200
+
+
+def token_weights_and_norm(kind, B, L, C, weighting=None, attention_mask=None, edit_mask=None, fg=2.0, bg=1.0, eps=1e-12):
+    """(w [B, L] fp32 on host or device, norm) with  loss = norm * sum w * (pred - target)^2  for reduction='mean'.
+    kind: "mse" (MseLoss), "mask_edit" (MaskEditLoss), "attention_mask" (AttentionMaskMseLoss)."""
+    dev = None
+    for t in (weighting, attention_mask, edit_mask):
+        if t is not None:
+            dev = t.device
+    w = torch.ones(B, L, dtype=torch.float32, device=dev)
+    if weighting is not None:
+        w = w * weighting.float().reshape(B, -1)[:, :1]
+    if kind == "mse":
+        return w, 1.0 / (B * L * C)
+    if kind == "mask_edit":
+        w = w * ((edit_mask.float() * fg + (1 - edit_mask.float()) * bg) if edit_mask is not None else fg)
+        return w, 1.0 / (B * L * C)
+    if kind == "attention_mask":
+        if edit_mask is not None:
+            w = w * (edit_mask.float() * fg + (1 - edit_mask.float()) * bg)
+        if attention_mask is None:
+            return w, 1.0 / (C * (B * L + eps))
+        w = w * attention_mask.float()
+        return w, None  # norm needs the valid-token count: computed on device by the caller
+    raise ValueError(f"unknown loss kind {kind!r}")
+
+
+class _StepFn(torch.autograd.Function):
+    """loss = fused(forward -> flow loss -> backward); autograd backward only scales the already computed gradients."""
+
+    @staticmethod
+    def forward(ctx, step, args, *params):
+        loss = step._run(*args)
+        ctx.step = step
+        return loss.clone().reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        m = ctx.step.dit
+        flat = (m.G32 * g).to(BF)
+        r, grads = m.lora_rank, []
+        offs = {}
+        for site in m.sites.values():
+            for slot, (full, pA, pB, ga, gb, d_in, d_out) in site.members.items():
+                offs[full + ".lora_A.default.weight"] = flat[ga: ga + r * d_in].view(r, d_in)
+                offs[full + ".lora_B.default.weight"] = flat[gb: gb + d_out * r].view(d_out, r)
+        grads = tuple(offs[k] for k in m._lora_params)
+        return (None, None) + grads
+
+
+class QwenImageEditStep:
+    def __init__(self, dit: QwenImageB200, loss_kind: str = "mse", fg: float = 2.0, bg: float = 1.0,
+                 num_train_timesteps: int = 1000, max_grad_norm: float = 1.0):
+        self.dit, self.loss_kind, self.fg, self.bg = dit, loss_kind, fg, bg
+        self.num_train_timesteps, self.max_grad_norm = num_train_timesteps, max_grad_norm
+        self._ones = {}
+
+    # --------------------------------------------------------------------------------------------- internals
+    def _sigmas(self, B, u=None):
+        if u is None:
+            u = torch.rand(B)  # compute_density_for_timestep_sampling("none"): global CPU RNG, like the reference
+        idx = (u * self.num_train_timesteps).long()
+        timesteps = (self.num_train_timesteps - idx).float()  # scheduler.timesteps = linspace(1, 1000, 1000)[::-1]
+        return (timesteps / self.num_train_timesteps)
+
+    def _run(self, image_latents, control_latents, prompt_embeds, img_shapes, noise, sigma, w, norm):
+        m = self.dit
+        B, L, C = image_latents.shape
+        packed = torch.empty(B, L + control_latents.shape[1], C, device=m.dev, dtype=BF)
+        lib.flow_noisy_input(image_latents, noise, control_latents, sigma, packed)
+        pred = m._forward_impl(packed, prompt_embeds, sigma, img_shapes, train=True)
+        ws = m._ws
+        lib.flow_loss(pred, image_latents, noise, w, norm, ws["loss"], ws["dpred"])
+        m.G32.zero_()
+        m._backward_impl(ws["dpred"])
+        return ws["loss"]
+
+    def _prepare(self, embeddings, noise, u):
+        m = self.dit
+        dev = m.dev
+        x0 = embeddings["image_latents"].to(dev, BF, non_blocking=True).contiguous()
+        ctrl = embeddings["control_latents"].to(dev, BF, non_blocking=True).contiguous()
+        pe = embeddings["prompt_embeds"].to(dev, BF, non_blocking=True).contiguous()
+        B, L, C = x0.shape
+        if noise is None:
+            noise = torch.randn(x0.shape, device=dev, dtype=BF)
+        sigma = self._sigmas(B, u).to(dev, non_blocking=True)
+        edit_mask = embeddings.get("edit_mask")
+        if self.loss_kind == "mse" and edit_mask is None:
+            key = (B, L)
+            if key not in self._ones:
+                self._ones[key] = torch.ones(B, L, device=dev)
+            w, norm = self._ones[key], 1.0 / (B * L * C)
+        else:
+            w, norm = token_weights_and_norm(self.loss_kind, B, L, C, None, None,
+                                             None if edit_mask is None else edit_mask.to(dev), self.fg, self.bg)
+            w = w.to(dev).contiguous()
+        return (x0, ctrl, pe, embeddings["img_shapes"], noise.to(dev, BF), sigma, w, norm)
+
+    # --------------------------------------------------------------------------------------------- public
+    def compute_loss(self, embeddings: dict, noise=None, u=None) -> torch.Tensor:
+        """Drop-in for `Trainer._compute_loss(embeddings)`: scalar loss whose `.backward()` fills the LoRA `.grad`s."""
+        args = self._prepare(embeddings, noise, u)
+        return _StepFn.apply(self, args, *self.dit._lora_params.values())
+
+    @torch.no_grad()
+    def train_step(self, embeddings: dict, optimizer=None, noise=None, u=None):
+        """Fast path (no autograd graph): fused fwd/loss/bwd -> NCCL mean all-reduce of the flat LoRA gradient ->
+        clip -> bf16 grads -> optimizer.step().  Returns the (device) loss tensor; nothing here syncs with the host."""
+        args = self._prepare(embeddings, noise, u)
+        loss = self._run(*args)
+        world = 1
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            world = dist.get_world_size()
+            dist.all_reduce(self.dit.G32)
+        self.dit.finalize_grads(world, self.max_grad_norm)
+        if optimizer is not None:
+            optimizer.step()
+        return loss

@@ -1,0 +1,130 @@
+"""GPU parity of the fused Qwen-Image training step against the pure-torch oracle (run under gpurun).
+
+The oracle runs on the same GPU in fp32 (reference numerics) and in bf16 (the reference's eager working dtype); the
+B200 path is compared with both using the reference's own metric, relative L2 (tests/src/models/test_qwen_custom.py:550).
+"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from harness import main, rel_l2  # noqa: E402
+
+import torch  # noqa: E402
+
+
+def build_pair(H, L, J, r, targets, seed=0, b_std=0.05, w_std=0.05):
+    from oracle import mmdit_oracle as mo
+    from qflux_b200.qwen_model import QwenB200Config, QwenImageB200
+    cfg = mo.QwenConfig(num_layers=L, attention_head_dim=128, num_attention_heads=H, joint_attention_dim=J)
+    orc = mo.init_synthetic_(mo.QwenImageOracle(cfg), seed=1234 + seed, std=w_std)
+    # make norm weights / biases non-trivial so the parity test exercises them
+    g = torch.Generator().manual_seed(99)
+    with torch.no_grad():
+        for n, p in orc.named_parameters():
+            if n.endswith("bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+            elif p.ndim == 1:
+                p.copy_(1 + torch.randn(p.shape, generator=g) * 0.1)
+    if r:
+        mo.add_lora_adapter(orc, r=r, alpha=r, target_modules=targets, seed=seed, b_std=b_std)
+    orc = orc.cuda()
+    # quantise every parameter to bf16 once so that fp32-oracle, bf16-oracle and the B200 model share identical weights
+    with torch.no_grad():
+        for p in orc.parameters():
+            p.copy_(p.bfloat16().float())
+    m = QwenImageB200(QwenB200Config(num_layers=L, num_attention_heads=H, joint_attention_dim=J))
+    if r:
+        m.add_adapter(r, r, target_modules=targets)
+    missing, unexpected = m.load_state_dict(orc.state_dict(), strict=True)
+    assert not unexpected and not missing, (missing, unexpected)
+    return orc, m
+
+
+def inputs(B, hw, T, J, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    L = hw * hw
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()
+    return dict(image_latents=rn(B, L, 64), control_latents=rn(B, L, 64), prompt_embeds=rn(B, T, J) * 3,
+                prompt_embeds_mask=torch.ones(B, T, dtype=torch.int64, device="cuda"),
+                img_shapes=[[(1, hw, hw), (1, hw, hw)]] * B, noise=rn(B, L, 64),
+                u=torch.tensor([0.9371, 0.4312, 0.0521, 0.7613][:B]))
+
+
+def step_parity(H=2, L=2, J=128, B=2, hw=4, T=24, r=4, targets=("to_q", "to_k", "to_v", "to_out.0"), bf16_oracle=True):
+    from oracle import mmdit_oracle as mo
+    from qflux_b200.train_step import QwenImageEditStep
+    orc, m = build_pair(H, L, J, r, targets)
+    x = inputs(B, hw, T, J)
+    res = {}
+    # ---- fp32 oracle
+    xf = {k: (v.float() if torch.is_tensor(v) and v.is_floating_point() and k != "u" else v) for k, v in x.items()}
+    loss_o, pred_o = mo.qwen_compute_loss(orc, **xf)
+    loss_o.backward()
+    g_o = {n: p.grad.clone() for n, p in orc.named_parameters() if p.requires_grad}
+    # ---- B200
+    step = QwenImageEditStep(m)
+    emb = {k: x[k] for k in ("image_latents", "control_latents", "prompt_embeds", "img_shapes")}
+    loss_b = step.compute_loss(emb, noise=x["noise"], u=x["u"])
+    pred_b = m._ws["pred"].view(B, -1, 64)[:, : hw * hw].float().clone()
+    loss_b.backward()
+    torch.cuda.synchronize()
+    res["pred_vs_fp32"] = rel_l2(pred_b, pred_o)
+    res["loss_abs"] = abs(loss_b.item() - loss_o.item())
+    gb = {n: p.grad.float() for n, p in m.named_parameters()}
+    assert set(gb) == set(g_o), (set(gb) ^ set(g_o))
+    num = sum(((gb[n] - g_o[n]).double() ** 2).sum() for n in g_o)
+    den = sum((g_o[n].double() ** 2).sum() for n in g_o)
+    res["grad_vs_fp32"] = float((num / den).sqrt())
+    res["grad_worst"] = max(rel_l2(gb[n], g_o[n]) for n in g_o)
+    # fast path must give the same gradients as the autograd path
+    step.train_step(emb, noise=x["noise"], u=x["u"])
+    gv = m.lora_grad_views()
+    res["fast_vs_autograd"] = max(rel_l2(gv[n], gb[n]) for n in gb)
+    # ---- bf16 oracle (what the reference actually runs on a GPU)
+    if bf16_oracle:
+        orc.zero_grad()
+        orc16 = orc.bfloat16()
+        loss_h, pred_h = mo.qwen_compute_loss(orc16, **x)
+        loss_h.backward()
+        g_h = {n: p.grad.float() for n, p in orc16.named_parameters() if p.requires_grad}
+        res["bf16oracle_pred_vs_fp32"] = rel_l2(pred_h.float(), pred_o)
+        res["pred_vs_bf16oracle"] = rel_l2(pred_b, pred_h.float())
+        num = sum(((g_h[n] - g_o[n]).double() ** 2).sum() for n in g_o)
+        res["bf16oracle_grad_vs_fp32"] = float((num / den).sqrt())
+    res["err"] = max(res["pred_vs_fp32"], res["grad_vs_fp32"])
+    return res
+
+
+def inference_parity():
+    """no-grad forward through the public module signature (the `dit(...)` call of the trainer)."""
+    orc, m = build_pair(2, 2, 128, 0, None)
+    x = inputs(2, 4, 24, 128)
+    packed = torch.cat([x["image_latents"], x["control_latents"]], 1)
+    t = torch.tensor([0.7, 0.2], device="cuda")
+    with torch.no_grad():
+        po = orc(hidden_states=packed.float(), timestep=t, encoder_hidden_states=x["prompt_embeds"].float(),
+                 encoder_hidden_states_mask=x["prompt_embeds_mask"], img_shapes=x["img_shapes"], txt_seq_lens=[24, 24])[0]
+        pb = m(hidden_states=packed, timestep=t, guidance=None, encoder_hidden_states_mask=x["prompt_embeds_mask"],
+               encoder_hidden_states=x["prompt_embeds"], img_shapes=x["img_shapes"], txt_seq_lens=[24, 24], return_dict=False)[0]
+    return dict(err=rel_l2(pb.float(), po))
+
+
+def full_width_block():
+    """One full-width Qwen block (D=3072, H=24) at the benchmark sequence shape, B=1."""
+    t0 = time.time()
+    r = step_parity(H=24, L=1, J=3584, B=1, hw=32, T=352, r=16, bf16_oracle=True)
+    r["secs"] = round(time.time() - t0, 1)
+    return r
+
+
+CASES = {
+    "inference_tiny": inference_parity,
+    "step_tiny": lambda: step_parity(),
+    "step_tiny_nolora_targets_all_attn": lambda: step_parity(targets=("to_q", "to_k", "to_v", "to_out.0", "add_q_proj", "add_k_proj", "add_v_proj", "to_add_out", "net.0.proj"), r=8),
+    "step_mid": lambda: step_parity(H=4, L=3, J=256, B=2, hw=16, T=40, r=16),
+    "step_full_width_1blk": full_width_block,
+}
+
+if __name__ == "__main__":
+    main(CASES, os.path.abspath(__file__), "model_check.log")
