@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py — training images/sec of the Qwen-Image-Edit LoRA step (BASELINE.json metric, configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+b200 arm     : one "step" = noisy-input -> fused MMDiT forward -> flow-matching loss -> fused backward -> NCCL all-reduce of
+               the flat LoRA gradient -> clip -> AdamW step, Qwen-Image-Edit dims (60 blocks, D=3072, H=24), LoRA r=16,
+               bf16, 512x512 (1024+1024 image tokens, 352 text tokens), batch 4 per GPU, synthetic cached embeddings,
+               random-init weights.  `value` = device-timed (inputs resident in HBM), `e2e` = through the public
+               `QwenImageEditStep.train_step` with pinned HOST inputs (H2D inside the timed region, loss read back).
+reference arm: the reference's eager PyTorch path restated in oracle/mmdit_oracle.py (diffusers/peft are not installable
+               offline — DESIGN.md), timed on the box's host cores; a step is a bounded sample (full-width depth-1 and
+               depth-2 models at B=1, fwd+loss+bwd) extrapolated linearly in depth to the 60-block model.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "qwen-image-finetune_b200"))
+
+METRIC = "training images/sec (Qwen-Image-Edit LoRA r=16 bf16, 512x512, cached embeds)"
+CFG = dict(layers=60, heads=24, joint=3584, T=352, hw=32, B=4, r=16)
+# algorithmic train FLOPs per image: N_blocks * (2 * F_gemm + 3.5 * F_attn)
+S_TOK = CFG["T"] + 2 * CFG["hw"] ** 2
+FLOP_PER_IMAGE = CFG["layers"] * (2 * S_TOK * 226.49e6 + 3.5 * 4 * S_TOK ** 2 * 3072)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+
+
+# ====================================================================================================== reference arm
+def cpu_block_times(reps=1, threads=None):
+    """fwd+loss+bwd wall time of full-width depth-1 / depth-2 oracle models at B=1 on the host cores (bf16 weights)."""
+    import torch
+    from oracle import mmdit_oracle as mo
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(1234)
+    L, T, hw = CFG["hw"] ** 2, CFG["T"], CFG["hw"]
+    x = dict(image_latents=torch.randn(1, L, 64, generator=g).bfloat16(), control_latents=torch.randn(1, L, 64, generator=g).bfloat16(),
+             prompt_embeds=(torch.randn(1, T, CFG["joint"], generator=g) * 3).bfloat16(),
+             prompt_embeds_mask=torch.ones(1, T, dtype=torch.int64), img_shapes=[[(1, hw, hw), (1, hw, hw)]],
+             noise=torch.randn(1, L, 64, generator=g).bfloat16(), u=torch.tensor([0.5]))
+    out = {}
+    for depth in (1, 2):
+        cfg = mo.QwenConfig(num_layers=depth)
+        m = mo.init_synthetic_(mo.QwenImageOracle(cfg))
+        mo.add_lora_adapter(m, r=CFG["r"], alpha=CFG["r"], b_std=0.02)
+        m = m.bfloat16()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            loss, _ = mo.qwen_compute_loss(m, **x)
+            loss.backward()
+            ts.append(time.perf_counter() - t0)
+            m.zero_grad()
+        out[depth] = min(ts)
+        del m
+    per_block = max(out[2] - out[1], 1e-9)
+    fixed = max(out[1] - per_block, 0.0)
+    full = fixed + CFG["layers"] * per_block
+    return dict(t1=out[1], t2=out[2], per_block_s=per_block, full_step_s=full, images_per_s=1.0 / full, cores=threads)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_block_times()
+        if i >= args.warmup:
+            vals.append(r)
+    v = statistics.median([r["images_per_s"] for r in vals])
+    ms = 1e3 / v
+    sample = "B=1 full-width (D=3072) depth-1 and depth-2 oracle models, fwd+loss+bwd, bf16 weights, linear extrapolation to 60 blocks"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "Qwen-Image-Edit LoRA r=16, 512x512 cached embeds (CPU path, extrapolated)", "global_batch": 1},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": vals[-1]["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ====================================================================================================== B200 arm
+def build_model(dev, layers):
+    import torch
+    from qflux_b200.qwen_model import QwenB200Config, QwenImageB200
+    m = QwenImageB200(QwenB200Config(num_layers=layers, num_attention_heads=CFG["heads"], joint_attention_dim=CFG["joint"]), device=dev)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    for k, t in m.w.items():  # N(0, 0.02^2) weights, zero biases, unit norm weights (SURVEY.md §8d cfg 2)
+        if k.endswith("_w") and t.ndim >= 2 and "norm" not in k or k in ("norm_out_w",):
+            t.normal_(0.0, 0.02, generator=g)
+    m.add_adapter(CFG["r"], CFG["r"], b_std=0.02)
+    return m
+
+
+def gemm_roofline(dev):
+    """dominant kernel = gemm_kernel<256,...>: time the block's largest grouped projection stand-alone with CUDA events."""
+    import torch
+    from qflux_b200 import lib
+    Mi, Mt, N, K = CFG["B"] * 2 * CFG["hw"] ** 2, CFG["B"] * CFG["T"], 12288, 3072
+    A0, A1 = torch.randn(Mi, K, device=dev).bfloat16(), torch.randn(Mt, K, device=dev).bfloat16()
+    W0, W1 = torch.randn(N, K, device=dev).bfloat16() * 0.02, torch.randn(N, K, device=dev).bfloat16() * 0.02
+    o0, o1 = torch.empty(Mi, N, device=dev, dtype=torch.bfloat16), torch.empty(Mt, N, device=dev, dtype=torch.bfloat16)
+    probs = [lib.gemm_problem(A0, W0, o0), lib.gemm_problem(A1, W1, o1)]
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    for _ in range(3):
+        lib.gemm(probs, N, K)
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib.gemm(probs, N, K)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = statistics.median(ts)
+    return 2.0 * (Mi + Mt) * N * K / ms / 1e9, ms
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from qflux_b200 import lib
+    from qflux_b200.train_step import QwenImageEditStep
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234 + rank)
+    m = build_model(dev, args.layers)
+    step = QwenImageEditStep(m, "mse", max_grad_norm=1.0)
+    opt = torch.optim.AdamW(list(m.parameters()), lr=1e-4, foreach=True)
+    B, L, T, hw = CFG["B"], CFG["hw"] ** 2, CFG["T"], CFG["hw"]
+    host = dict(image_latents=torch.randn(B, L, 64).half().pin_memory(), control_latents=torch.randn(B, L, 64).half().pin_memory(),
+                prompt_embeds=(torch.randn(B, T, CFG["joint"]) * 3).bfloat16().pin_memory(),
+                img_shapes=[[(1, hw, hw), (1, hw, hw)]] * B)
+    devd = {k: (v.to(dev, torch.bfloat16) if torch.is_tensor(v) else v) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v)) + 4 * B
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident arm
+    for _ in range(args.warmup):
+        step.train_step(devd, opt)
+    sync()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step.train_step(devd, opt)
+    e1.record()
+    sync()
+    launches = lib.LAUNCHES - n0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = ms.item() / args.steps
+    clk = clocks.stop() if rank == 0 else None
+    loss_val = float(loss.item())
+    # ---------------- end-to-end arm: pinned host inputs, loss read back every step
+    step.train_step(host, opt)
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lv = step.train_step(host, opt).item()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_ips = B * world * args.steps / dt.item()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = B * world / (ms_step / 1e3)
+    scale = args.layers / CFG["layers"]
+    burst, sustained, which = peaks()
+    g_tf, g_ms = gemm_roofline(dev)
+    step_tf = FLOP_PER_IMAGE * scale * value / world / 1e12
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        c = cpu_block_times()
+        cpu = {"value": c["images_per_s"], "unit": "images/s", "cores": c["cores"], "kind": "port",
+               "sample": f"B=1 full-width depth-1 ({c['t1']:.2f}s) and depth-2 ({c['t2']:.2f}s) oracle fwd+loss+bwd, extrapolated to 60 blocks"}
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"Qwen-Image-Edit LoRA r=16 bf16 512x512 cached embeds, {args.layers} blocks D=3072 H=24, "
+                                   f"S=352 txt + 2x1024 img tokens", "global_batch": B * world, "batch_per_gpu": B,
+                       "parallelism": f"dp{world}", "l2": "inputs > L2: 41 GB weights + 35 GB activations stream through 126 MB L2",
+                       "optimizer": "torch AdamW(foreach) on LoRA params", "loss": loss_val},
+            "clocks": clk, "gpu_launches": launches,
+            "e2e": {"value": e2e_ips, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "roofline": {"bound": "tensor", "kernel": "gemm_kernel<256,false,GELU> grouped img+txt MLP-up [8192+1408,3072]x[12288,3072]",
+                         "achieved": g_tf, "peak": burst, "unit": "TFLOP/s", "frac": g_tf / burst, "traffic": None,
+                         "peak_source": f"{which} MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)", "kernel_ms": g_ms,
+                         "step_algorithmic_tflops_per_gpu": step_tf, "step_frac_of_sustained": step_tf / sustained},
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--layers", type=int, default=CFG["layers"], help="debug only: fewer blocks (INVALID as a bench value)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

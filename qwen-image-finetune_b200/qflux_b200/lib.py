@@ -23,7 +23,13 @@ class QfxError(RuntimeError):
     pass
 
 
+LAUNCHES = 0  # kernels of THIS library launched so far (bench.py reports the per-step delta as gpu_launches)
+_KERNELS_PER_CALL = {"qfx_grad_finalize": 2}
+
+
 def check(rc: int, what: str):
+    global LAUNCHES
+    LAUNCHES += _KERNELS_PER_CALL.get(what, 1)
     if rc != 0:
         raise QfxError(f"{what} failed (rc={rc}): {_lib.qfx_last_error().decode()}")
 

@@ -292,9 +292,9 @@ class QwenImageB200(nn.Module):
         ws["hn"] = e(Mi, D)
         ws["pred"] = e(Mi, self.C_out)
         # LoRA forward intermediates  T = s * X A^T  (kept for the dB gradient)
-        ws["T"] = {}
+        ws["loraT"] = {}
         for (l, grp, s), site in self.sites.items():
-            ws["T"][(l, grp, s)] = torch.zeros((Mi if s == 0 else Mt), site.n * PAD, device=self.dev, dtype=BF)
+            ws["loraT"][(l, grp, s)] = torch.zeros((Mi if s == 0 else Mt), site.n * PAD, device=self.dev, dtype=BF)
         if train:
             ws["dX"] = e(2, M, D)
             ws["dY"] = e(M, D)
@@ -336,7 +336,7 @@ class QwenImageB200(nn.Module):
         site = self._site(l, grp, s)
         if site is None:
             return None, None
-        Tb = ws["T"][(l, grp, s)]
+        Tb = ws["loraT"][(l, grp, s)]
         lib.gemm([lib.gemm_problem(X, site.A_pad, Tb)], site.n * PAD, X.shape[1], alpha=self.lora_scaling)
         return site, Tb
 
@@ -420,7 +420,7 @@ class QwenImageB200(nn.Module):
         site = self._site(l, grp, s)
         if site is None:
             return None
-        r, Tb = site.r, ws["T"][(l, grp, s)]
+        r, Tb = site.r, ws["loraT"][(l, grp, s)]
         U = self._rows(ws, ws["U"], s)[:, : site.n * PAD]
         for g in range(site.n):
             dYg = dY[:, g * n_out_each:(g + 1) * n_out_each]

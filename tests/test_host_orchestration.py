@@ -1,0 +1,133 @@
+"""Host-side logic of the B200 model (launch sequencing, operand wiring, LoRA registry, gradient offsets) on CPU:
+`qflux_b200.lib` is replaced by the plain-PyTorch emulation in tests/emu_lib.py and the result is compared with the oracle.
+(The CUDA kernels themselves are covered by the `-m gpu` tests.)"""
+import pytest
+import torch
+
+import emu_lib
+from oracle import mmdit_oracle as mo
+
+
+@pytest.fixture()
+def emu():
+    from qflux_b200 import lib
+    restore = emu_lib.install(lib)
+    yield lib
+    restore()
+
+
+def _pair(H, L, J, r, targets):
+    from qflux_b200.qwen_model import QwenB200Config, QwenImageB200
+    cfg = mo.QwenConfig(num_layers=L, attention_head_dim=128, num_attention_heads=H, joint_attention_dim=J)
+    orc = mo.init_synthetic_(mo.QwenImageOracle(cfg), std=0.05)
+    g = torch.Generator().manual_seed(99)
+    with torch.no_grad():
+        for n, p in orc.named_parameters():
+            if n.endswith("bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+            elif p.ndim == 1:
+                p.copy_(1 + torch.randn(p.shape, generator=g) * 0.1)
+    if r:
+        mo.add_lora_adapter(orc, r=r, alpha=2 * r, target_modules=targets, b_std=0.05)
+    with torch.no_grad():
+        for p in orc.parameters():
+            p.copy_(p.bfloat16().float())
+    m = QwenImageB200(QwenB200Config(num_layers=L, num_attention_heads=H, joint_attention_dim=J), device="cpu", _host_only=True)
+    if r:
+        m.add_adapter(r, 2 * r, target_modules=targets)
+    missing, unexpected = m.load_state_dict(orc.state_dict(), strict=True)
+    assert not missing and not unexpected
+    return orc, m
+
+
+def _inputs(B, hw, T, J):
+    g = torch.Generator().manual_seed(0)
+    rn = lambda *s: torch.randn(*s, generator=g).bfloat16()
+    return dict(image_latents=rn(B, hw * hw, 64), control_latents=rn(B, hw * hw, 64), prompt_embeds=rn(B, T, J) * 3,
+                prompt_embeds_mask=torch.ones(B, T, dtype=torch.int64), img_shapes=[[(1, hw, hw), (1, hw, hw)]] * B,
+                noise=rn(B, hw * hw, 64), u=torch.tensor([0.5, 0.25, 0.125][:B]))  # sigma = .5, .75, .875: exact in bf16 (the model rounds t to bf16, :624)
+
+
+@pytest.mark.parametrize("targets,r", [(("to_q", "to_k", "to_v", "to_out.0"), 4),
+                                       (("to_q", "to_v", "add_k_proj", "to_add_out", "net.0.proj"), 8)])
+def test_step_matches_oracle_on_cpu(emu, targets, r):
+    from qflux_b200.train_step import QwenImageEditStep
+    orc, m = _pair(2, 2, 128, r, targets)
+    x = _inputs(2, 4, 24, 128)
+    xf = {k: (v.float() if torch.is_tensor(v) and v.is_floating_point() and k != "u" else v) for k, v in x.items()}
+    loss_o, pred_o = mo.qwen_compute_loss(orc, **xf)
+    loss_o.backward()
+    step = QwenImageEditStep(m)
+    emb = {k: x[k] for k in ("image_latents", "control_latents", "prompt_embeds", "img_shapes")}
+    loss_b = step.compute_loss(emb, noise=x["noise"], u=x["u"])
+    pred_b = m._ws["pred"].view(2, -1, 64)[:, :16].float().clone()
+    loss_b.backward()
+    rel = ((pred_b - pred_o).norm() / pred_o.norm()).item()
+    assert rel < 1e-2, rel                                  # bf16 storage vs fp32 oracle
+    assert abs(loss_b.item() - loss_o.item()) < 1e-2
+    go = {n: (p.grad if p.grad is not None else torch.zeros_like(p)) for n, p in orc.named_parameters() if p.requires_grad}
+    gb = {n: p.grad.float() for n, p in m.named_parameters()}
+    assert set(go) == set(gb)
+    num = sum(((gb[n] - go[n]) ** 2).sum() for n in go)
+    den = sum((go[n] ** 2).sum() for n in go)
+    assert float((num / den).sqrt()) < 2e-2
+    # the no-autograd fast path produces the same gradients, clipped to max_grad_norm = 1
+    step.train_step(emb, noise=x["noise"], u=x["u"])
+    gnorm = float(den.sqrt())
+    for n, p in m.named_parameters():
+        ref = go[n] * min(1.0, 1.0 / (gnorm + 1e-6))
+        if ref.abs().max() > 0:
+            assert ((p.grad.float() - ref).norm() / ref.norm()).item() < 3e-2, n
+
+
+def test_module_forward_signature_no_grad(emu):
+    orc, m = _pair(2, 1, 128, 0, None)
+    x = _inputs(2, 4, 24, 128)
+    packed = torch.cat([x["image_latents"], x["control_latents"]], 1)
+    t = torch.tensor([0.75, 0.25])
+    with torch.no_grad():
+        po = orc(hidden_states=packed.float(), timestep=t, encoder_hidden_states=x["prompt_embeds"].float(),
+                 encoder_hidden_states_mask=x["prompt_embeds_mask"], img_shapes=x["img_shapes"], txt_seq_lens=[24, 24])[0]
+        pb = m(hidden_states=packed, timestep=t, guidance=None, encoder_hidden_states_mask=x["prompt_embeds_mask"],
+               encoder_hidden_states=x["prompt_embeds"], img_shapes=x["img_shapes"], txt_seq_lens=[24, 24], return_dict=False)[0]
+    assert pb.shape == po.shape
+    assert ((pb.float() - po).norm() / po.norm()).item() < 1e-2
+
+
+def test_module_forward_autograd_bridge(emu):
+    """`dit(...)` under grad mode carries autograd history to the LoRA parameters (drop-in for arbitrary losses)."""
+    orc, m = _pair(2, 1, 128, 4, ("to_q", "to_k", "to_v", "to_out.0"))
+    x = _inputs(1, 4, 24, 128)
+    packed = torch.cat([x["image_latents"], x["control_latents"]], 1)
+    t = torch.tensor([0.625])
+    kw = dict(timestep=t, encoder_hidden_states_mask=x["prompt_embeds_mask"], img_shapes=x["img_shapes"], txt_seq_lens=[24])
+    po = orc(hidden_states=packed.float(), encoder_hidden_states=x["prompt_embeds"].float(), **kw)[0]
+    po.pow(2).mean().backward()
+    pb = m(hidden_states=packed, encoder_hidden_states=x["prompt_embeds"], **kw)[0]
+    pb.float().pow(2).mean().backward()
+    go = {n: p.grad for n, p in orc.named_parameters() if p.requires_grad}
+    num = sum(((p.grad.float() - go[n]) ** 2).sum() for n, p in m.named_parameters())
+    den = sum((v ** 2).sum() for v in go.values())
+    assert float((num / den).sqrt()) < 2e-2
+
+
+def test_lora_registry_and_errors():
+    from qflux_b200.qwen_model import QwenB200Config, QwenImageB200
+    m = QwenImageB200(QwenB200Config(num_layers=2, num_attention_heads=2, joint_attention_dim=128), device="cpu", _host_only=True)
+    with pytest.raises(NotImplementedError):
+        m.add_adapter(4, 4, target_modules=("net.2",))
+    m = QwenImageB200(QwenB200Config(num_layers=2, num_attention_heads=2, joint_attention_dim=128), device="cpu", _host_only=True)
+    with pytest.raises(NotImplementedError):
+        m.add_adapter(4, 4, target_modules=r".*(img_mod\.1|attn\.to_q)")
+    m = QwenImageB200(QwenB200Config(num_layers=2, num_attention_heads=2, joint_attention_dim=128), device="cpu", _host_only=True)
+    m.add_adapter(16, 16)
+    names = [n for n, _ in m.named_parameters()]
+    assert len(names) == 2 * 4 * 2 and all("lora" in n for n in names)
+    assert m.G32.numel() == sum(p.numel() for p in m.parameters())
+    # padded storage stays zero outside the adapter's rank
+    site = m.sites[(0, "qkv", 0)]
+    assert site.A_pad[16:64].abs().sum() == 0 and site.B_pad[:, 16:].abs().sum() == 0
+    # ops refuse CPU tensors (no fallback)
+    from qflux_b200 import lib
+    with pytest.raises(lib.QfxError):
+        lib.rmsnorm_rows(torch.zeros(8, 64, dtype=torch.bfloat16), torch.ones(64, dtype=torch.bfloat16), torch.zeros(8, 64, dtype=torch.bfloat16))

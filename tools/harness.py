@@ -51,7 +51,7 @@ def main(cases: dict, script: str, out_name: str):
             out = r.stdout + r.stderr
             res = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
             status = "ok" if (r.returncode == 0 and res) else f"FAIL rc={r.returncode}"
-            tail = res[-1][7:] if res else out[-1500:]
+            tail = res[-1][7:] if res else " | ".join(out.strip().splitlines()[-4:])[-700:]
         except subprocess.TimeoutExpired:
             status, tail = "TIMEOUT", ""
         ok_all &= status == "ok"
