@@ -72,46 +72,50 @@ class ClockSampler:
 
 
 # ====================================================================================================== reference arm
-def cpu_block_times(reps=1, threads=None):
-    """fwd+loss+bwd wall time of full-width depth-1 / depth-2 oracle models at B=1 on the host cores (bf16 weights)."""
-    import torch
-    from oracle import mmdit_oracle as mo
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
-    g = torch.Generator().manual_seed(1234)
-    L, T, hw = CFG["hw"] ** 2, CFG["T"], CFG["hw"]
-    x = dict(image_latents=torch.randn(1, L, 64, generator=g).bfloat16(), control_latents=torch.randn(1, L, 64, generator=g).bfloat16(),
-             prompt_embeds=(torch.randn(1, T, CFG["joint"], generator=g) * 3).bfloat16(),
-             prompt_embeds_mask=torch.ones(1, T, dtype=torch.int64), img_shapes=[[(1, hw, hw), (1, hw, hw)]],
-             noise=torch.randn(1, L, 64, generator=g).bfloat16(), u=torch.tensor([0.5]))
-    out = {}
-    for depth in (1, 2):
-        cfg = mo.QwenConfig(num_layers=depth)
-        m = mo.init_synthetic_(mo.QwenImageOracle(cfg))
-        mo.add_lora_adapter(m, r=CFG["r"], alpha=CFG["r"], b_std=0.02)
-        m = m.bfloat16()
-        ts = []
-        for _ in range(reps):
+class CpuReference:
+    """The reference's eager path (oracle restatement) on the host cores: full-width depth-1 and depth-2 models at B=1,
+    bf16 weights, fwd + loss + bwd; linear extrapolation in depth to the 60-block model."""
+
+    def __init__(self, threads=None):
+        import torch
+        from oracle import mmdit_oracle as mo
+        self.mo, self.torch = mo, torch
+        self.threads = threads or os.cpu_count()
+        torch.set_num_threads(self.threads)
+        g = torch.Generator().manual_seed(1234)
+        L, T, hw = CFG["hw"] ** 2, CFG["T"], CFG["hw"]
+        self.x = dict(image_latents=torch.randn(1, L, 64, generator=g).bfloat16(), control_latents=torch.randn(1, L, 64, generator=g).bfloat16(),
+                      prompt_embeds=(torch.randn(1, T, CFG["joint"], generator=g) * 3).bfloat16(),
+                      prompt_embeds_mask=torch.ones(1, T, dtype=torch.int64), img_shapes=[[(1, hw, hw), (1, hw, hw)]],
+                      noise=torch.randn(1, L, 64, generator=g).bfloat16(), u=torch.tensor([0.5]))
+        self.models = {}
+        for depth in (1, 2):
+            m = mo.init_synthetic_(mo.QwenImageOracle(mo.QwenConfig(num_layers=depth)))
+            mo.add_lora_adapter(m, r=CFG["r"], alpha=CFG["r"], b_std=0.02)
+            self.models[depth] = m.bfloat16()
+
+    def step(self):
+        out = {}
+        for depth, m in self.models.items():
             t0 = time.perf_counter()
-            loss, _ = mo.qwen_compute_loss(m, **x)
+            loss, _ = self.mo.qwen_compute_loss(m, **self.x)
             loss.backward()
-            ts.append(time.perf_counter() - t0)
+            out[depth] = time.perf_counter() - t0
             m.zero_grad()
-        out[depth] = min(ts)
-        del m
-    per_block = max(out[2] - out[1], 1e-9)
-    fixed = max(out[1] - per_block, 0.0)
-    full = fixed + CFG["layers"] * per_block
-    return dict(t1=out[1], t2=out[2], per_block_s=per_block, full_step_s=full, images_per_s=1.0 / full, cores=threads)
+        per_block = max(out[2] - out[1], 1e-9)
+        fixed = max(out[1] - per_block, 0.0)
+        full = fixed + CFG["layers"] * per_block
+        return dict(t1=out[1], t2=out[2], per_block_s=per_block, full_step_s=full, images_per_s=1.0 / full, cores=self.threads)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    ref = CpuReference()
     vals = []
     for i in range(args.warmup + args.steps):
-        r = cpu_block_times()
+        r = ref.step()
         if i >= args.warmup:
             vals.append(r)
     v = statistics.median([r["images_per_s"] for r in vals])
@@ -234,7 +238,9 @@ def run_b200(args):
     step_tf = FLOP_PER_IMAGE * scale * value / world / 1e12
     cpu = None
     if world == 1 and not args.no_cpu:
-        c = cpu_block_times()
+        ref = CpuReference()
+        ref.step()
+        c = ref.step()
         cpu = {"value": c["images_per_s"], "unit": "images/s", "cores": c["cores"], "kind": "port",
                "sample": f"B=1 full-width depth-1 ({c['t1']:.2f}s) and depth-2 ({c['t2']:.2f}s) oracle fwd+loss+bwd, extrapolated to 60 blocks"}
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

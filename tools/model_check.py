@@ -71,6 +71,8 @@ def step_parity(H=2, L=2, J=128, B=2, hw=4, T=24, r=4, targets=("to_q", "to_k", 
     torch.cuda.synchronize()
     res["pred_vs_fp32"] = rel_l2(pred_b, pred_o)
     res["loss_abs"] = abs(loss_b.item() - loss_o.item())
+    res["loss"] = loss_o.item()
+    res["loss_rel"] = res["loss_abs"] / max(1.0, abs(loss_o.item()))
     gb = {n: p.grad.float() for n, p in m.named_parameters()}
     assert set(gb) == set(g_o), (set(gb) ^ set(g_o))
     num = sum(((gb[n] - g_o[n]).double() ** 2).sum() for n in g_o)
