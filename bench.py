@@ -80,7 +80,7 @@ class CpuReference:
         import torch
         from oracle import mmdit_oracle as mo
         self.mo, self.torch = mo, torch
-        self.threads = threads or os.cpu_count()
+        self.threads = threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
         torch.set_num_threads(self.threads)
         g = torch.Generator().manual_seed(1234)
         L, T, hw = CFG["hw"] ** 2, CFG["T"], CFG["hw"]

@@ -65,6 +65,68 @@ typedef struct {
 int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, int K, int trans_b, int epilogue, float alpha,
                   int lora_group_n, int block_n, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Joint text+image attention (head_dim 128), tcgen05.  Q/K/V/dO/dK/dV: [B, H, S, 128] bf16 head-major, text positions
+ * first.  Replaces dispatch_attention_fn -> F.scaled_dot_product_attention on the concatenated sequence and its autograd
+ * backward (transformer_qwenimage.py:322-345; transformer_flux.py:149-156).  kv_len (int32 [B], may be NULL) masks keys
+ * >= kv_len[b] (pad-to-max multi-resolution batches: transformer_qwen_custom.py:444-553).
+ * Forward writes O token-major into two row groups: rows with joint position s < split of sample b go to
+ * out0[(b*rows0 + s)*ld0 + h*128 ..], the others to out1[(b*rows1 + s - split)*ld1 + h*128 ..]; lse is the log2-domain
+ * log-sum-exp [B,H,S].  Backward: dQ_accum is fp32 [B,H,S,128], zeroed by the caller (target of TMA reduce-adds);
+ * delta = rowsum(dO * O) [B,H,S]. */
+int qfx_attn_fwd(const void* Q, const void* K, const void* V, void* out0, int64_t ld0, int rows0, void* out1, int64_t ld1,
+                 int rows1, int split, float* lse, const int* kv_len, int B, int H, int S, float softmax_scale, void* stream);
+int qfx_attn_bwd(const void* Q, const void* K, const void* V, const void* dO, const float* lse, const float* delta,
+                 float* dQ_accum, void* dK, void* dV, const int* kv_len, int B, int H, int S, float softmax_scale, void* stream);
+/* delta[b,h,s] = sum_d O*dO from token-major rows (tokens_per_sample rows per sample at joint offset s_offset);
+ * optionally scatters dO into the head-major layout the backward kernel loads with TMA. */
+int qfx_attn_delta(const void* O, int64_t ldo, const void* dO, int64_t lddo, float* delta, void* dO_joint, int tokens,
+                   int tokens_per_sample, int s_offset, int S, int H, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * HBM-bound glue (one warp per row, 16-byte accesses, fp32 math, bf16 rounding at the reference's eager rounding points).
+ * Row -> sample: b = row / rows_per_batch; per-sample vectors (shift/scale/gate) have row stride ldmod / ldg. */
+/* y = LN(x; no affine, eps) * (1 + scale[b]) + shift[b]   (transformer_qwenimage.py:420-423,443-448; AdaLayerNormContinuous) */
+int qfx_ln_modulate_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, const void* shift, const void* scale, int64_t ldmod,
+                        int rows_per_batch, float* mean, float* rstd, int M, int D, float eps, void* stream);
+/* dx = dres + LN_bwd(dy * (1 + scale[b])) ; optional dx_gated = dx * gate[b] (input of the next dgrad GEMM) */
+int qfx_ln_modulate_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* mean, const float* rstd,
+                        const void* scale, int64_t ldmod, int rows_per_batch, const void* dres, int64_t lddres, void* dx,
+                        int64_t lddx, const void* gate, int64_t ldgate, void* dx_gated, int64_t lddxg, int M, int D, void* stream);
+int qfx_gate_mul(const void* a, int64_t lda, const void* gate, int64_t ldg, int rows_per_batch, void* out, int64_t ldo, int M,
+                 int D, void* stream);
+/* diffusers RMSNorm over rows (txt_norm, transformer_qwenimage.py:549,625) */
+int qfx_rmsnorm_rows(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int M, int D, float eps, void* stream);
+/* per-head RMSNorm(q,k) + RoPE + token-major [tok, q|k|v, H, 128] -> head-major Q/K/V[B,H,S,128] at joint position
+ * s_offset + tok % tokens_per_sample (transformer_qwenimage.py:296-326).  rope: fp32 (cos,sin) pairs [S,64,2] when
+ * rope_bstride = 0, else per sample [B,S,64,2] with rope_bstride = S.  round_mid = 1 reproduces diffusers' RMSNorm
+ * (cast before the weight multiply), 0 = torch.nn.RMSNorm (FLUX).  The backward takes dQ as the fp32 accumulator. */
+int qfx_qk_norm_rope_fwd(const void* qkv, int64_t ldqkv, const void* wq, const void* wk, const float* rope, int64_t rope_bstride,
+                         void* Q, void* K, void* V, int tokens, int tokens_per_sample, int s_offset, int S, int H, float eps,
+                         int round_mid, void* stream);
+int qfx_qk_norm_rope_bwd(const void* dQ, const void* dK, const void* dV, const void* qkv, int64_t ldqkv, const void* wq,
+                         const void* wk, const float* rope, int64_t rope_bstride, void* dqkv, int64_t lddqkv, int tokens,
+                         int tokens_per_sample, int s_offset, int S, int H, float eps, int round_mid, void* stream);
+/* y[b,:] = act(x[b,:]) . W^T + bias, b < 8; act 0 none / 1 SiLU  (timestep MLP, img_mod/txt_mod, norm_out.linear) */
+int qfx_gemv_act(const void* x, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* y, int64_t ldy, int B, int N,
+                 int K, int act, void* stream);
+/* diffusers Timesteps(dim, flip_sin_to_cos=True, shift 0, scale): out[b] = [cos(scale*t*f) | sin(scale*t*f)] */
+int qfx_timestep_sinusoid(const float* t, float scale, void* out, int B, int dim, void* stream);
+/* packed[b] = [ (1-sigma_b) x0 + sigma_b noise | control ]   (qwen_image_edit_trainer.py:811-812) */
+int qfx_flow_noisy_input(const void* x0, const void* noise, const void* control, const float* sigma, void* packed, int B, int L,
+                         int Lc, int C, void* stream);
+/* loss = norm * sum_{b,t<L,c} w[b,t] (pred - (noise - x0))^2 ; dpred = d loss / d pred * grad_scale (zeros for t >= L)
+ * — covers MseLoss / MaskEditLoss / AttentionMaskMseLoss (losses/*.py) through (w, norm). */
+int qfx_flow_loss(const void* pred, const void* x0, const void* noise, const float* w, float norm, float grad_scale, float* loss,
+                  void* dpred, int B, int L, int Ltot, int C, void* stream);
+/* G[i*gs_i + j*gs_j] += sum_m P[m,i] Q[m,j], j < r  (LoRA dB = dY^T (sXA^T), dA = (s dY B)^T X); fp32 atomics */
+int qfx_lora_wgrad(const void* P, int64_t ldp, const void* Q, int64_t ldq, float* G, int64_t gs_i, int64_t gs_j, int M, int Dp,
+                   int r, void* stream);
+/* out = bf16(g * pre_scale * min(1, max_norm / (||g * pre_scale|| + 1e-6)))  (clip_grad_norm_, base_trainer.py:449-455);
+ * sumsq receives ||g*pre_scale||^2.  max_norm <= 0 disables clipping. */
+int qfx_grad_finalize(const float* g, int64_t n, float pre_scale, float max_norm, float* sumsq, void* out_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
