@@ -44,7 +44,7 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t
                : "memory");
 }
 
-__global__ void __launch_bounds__(192, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams P) {
+__global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = smem_base, sV = smem_base + BW_TILE, sQ = smem_base + 2 * BW_TILE, sdO = smem_base + 3 * BW_TILE;
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_kernel(const __grid_constant_
     mbar_init(qdo_full, 1);
     mbar_init(qdo_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(pds_full, 4);
+    mbar_init(pds_full, 8);
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 1);
     mbar_init(acc_full, 1);
@@ -130,11 +130,14 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_kernel(const __grid_constant_
       umma_commit(acc_full);
     }
   } else {
-    // ================================================================= compute warps (thread = query row)
+    // ================================================================= compute warps: 2 per TMEM lane quadrant,
+    // thread = query row x 64 of the 128 key columns (and 64 of the 128 head-dim columns when draining dQ / dK / dV)
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int c0 = half * 64;
     const int row = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    const int tid = threadIdx.x - 64;  // 0..127
+    const int tid = threadIdx.x - 64;  // 0..255
     if (active) {
       const int valid = kv_len - kv0;  // key columns >= valid are masked
       for (int i = 0; i < n_q; ++i) {
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_kernel(const __grid_constant_
         mbar_wait(s_full, i & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
+        for (int c = c0; c < c0 + 64; c += 32) {
           uint32_t rs[32], rp[32];
           tmem_ld32(tS + lane_off + c, rs);
           tmem_ld32(tdP + lane_off + c, rp);
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_kernel(const __grid_constant_
         mbar_wait(dq_full, i & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
+        for (int c = c0; c < c0 + 64; c += 32) {
           uint32_t r[32];
           tmem_ld32(tS + lane_off + c, r);
           tmem_ld_wait();
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_kernel(const __grid_constant_
         }
         fence_proxy_async_smem();
         tc_fence_before();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (tid == 0) {
 #pragma unroll
           for (int sl = 0; sl < 4; ++sl) tma_reduce_add_3d(&P.tmdQ, sP + sl * BW_ATOM, sl * 32, i * 128, bh);
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_kernel(const __grid_constant_
         bf16* dst = (which ? P.dK : P.dV) + ((int64_t)bh * P.S + kv) * 128;
         const uint32_t t = (which ? tdK : tdV) + lane_off;
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
+        for (int c = c0; c < c0 + 64; c += 32) {
           uint32_t r[32];
           if (active) {
             tmem_ld32(t + c, r);
@@ -280,7 +283,7 @@ extern "C" int qfx_attn_bwd(const void* Q, const void* K, const void* V, const v
     attr_done = true;
   }
   dim3 grid((S + 127) / 128, B * H);
-  attn_bwd_kernel<<<grid, 192, BW_SMEM, (cudaStream_t)stream>>>(P);
+  attn_bwd_kernel<<<grid, 320, BW_SMEM, (cudaStream_t)stream>>>(P);
   QFX_CUDA(cudaGetLastError());
   return 0;
 }

@@ -3,7 +3,8 @@
 // (/root/reference/src/qflux/models/transformer_qwenimage.py:322-345, transformer_flux.py:149-156).
 //
 // One CTA per (128-query tile, batch*head).  Roles: warp 0 = TMEM alloc + TMA producer, warp 1 = MMA issuer,
-// warps 2-5 = softmax (thread == query row == TMEM lane).  Per 128-key tile j:
+// warps 2-9 = softmax: two warps per TMEM lane quadrant, each thread owns one query row x 64 of the 128 key columns
+// (row max / row sum are combined across the pair through shared memory).  Per 128-key tile j:
 //     S[j%2] = Q K_j^T            tcgen05.mma SS, both operands K-major (d contiguous), accumulator in TMEM
 //     P      = exp2(S*c - m)      softmax warps: tcgen05.ld, row max / sum in registers, bf16 P -> swizzled smem
 //     O     += P V_j              tcgen05.mma SS, A = P (K-major), B = V (MN-major: d contiguous), accumulate in TMEM
@@ -36,11 +37,12 @@ struct AttnFwdParams {
   float scale_log2;    // (1/sqrt(d)) * log2(e)
 };
 
-constexpr int ATT_SMEM = 7 * TILE_BYTES + 1024 + 256;  // Q, K x2, V x2, P x2
+constexpr int ATT_SMEM = 7 * TILE_BYTES + 256 + 2 * 2 * 128 * 4;  // Q, K x2, V x2, P x2, barriers, row-max exchange
 
-__global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdParams P) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+__global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];  // 128B-swizzle atoms need 1024 B alignment (no slack left to round up)
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
   const uint32_t sQ = smem_base;
   auto sK = [&](int s) { return smem_base + TILE_BYTES * (1 + s); };
   auto sV = [&](int s) { return smem_base + TILE_BYTES * (3 + s); };
@@ -54,6 +56,7 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
   auto pv_done = [&](int s) { return bar_base + 8u * (9 + s); };
   const uint32_t o_full = bar_base + 8u * 11;
   const uint32_t tmem_slot = bar_base + 8u * 12;
+  const uint32_t red_base = bar_base + 256;  // float red[2 (tile parity)][2 (half)][128 rows]
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
       mbar_init(k_full(s), 1);
       mbar_init(v_full(s), 1);
       mbar_init(s_full(s), 1);
-      mbar_init(p_full(s), 4);
+      mbar_init(p_full(s), 8);
       mbar_init(pv_done(s), 1);
     }
     mbar_init(o_full, 1);
@@ -139,29 +142,36 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
       umma_commit(o_full);
     }
   } else {
-    // ================================================================= softmax warps (thread = query row)
+    // ================================================================= softmax warps (thread = query row x 64 key columns)
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;  // 0: columns 0..63, 1: columns 64..127 of every tile (and of O in the epilogue)
     const int row = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const int c0 = half * 64;
+    float* red = reinterpret_cast<float*>(smem_gen + (red_base - smem_base));
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
     float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
       const int s = j & 1;
       const int valid = kv_len - j * ATT_BK;  // columns >= valid are masked
       mbar_wait(s_full(s), (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t tS = tS0 + s * 128 + lane_off;
+      const uint32_t tS = tS0 + s * 128 + lane_off + c0;
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
+      for (int c = 0; c < 64; c += 32) {
         uint32_t r[32];
         tmem_ld32(tS + c, r);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (c + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+          if (c0 + c + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
       }
+      red[(s * 2 + half) * 128 + row] = mx;
+      pair_sync();
+      mx = fmaxf(mx, red[(s * 2 + (half ^ 1)) * 128 + row]);
       const float m_new = fmaxf(m_used, mx * P.scale_log2);
-      // warp-uniform lazy rescale of the TMEM accumulator
+      // warp-uniform lazy rescale of the TMEM accumulator (both warps of a pair see the same rows -> same decision)
       const bool need = (j == 0) || (m_new > m_used + 8.f);
       if (__any_sync(0xffffffffu, need)) {
         if (j > 0) {
@@ -169,13 +179,13 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
           tc_fence_after();
           const float alpha = exp2f(m_used - m_new);
 #pragma unroll 1
-          for (int c = 0; c < 128; c += 32) {
+          for (int c = 0; c < 64; c += 32) {
             uint32_t r[32];
-            tmem_ld32(tO + lane_off + c, r);
+            tmem_ld32(tO + lane_off + c0 + c, r);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st32(tO + lane_off + c, r);
+            tmem_st32(tO + lane_off + c0 + c, r);
           }
           tmem_st_wait();
           l *= alpha;
@@ -183,28 +193,26 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
         m_used = m_new;
       }
       if (j >= 2) mbar_wait(pv_done(s), ((j - 2) >> 1) & 1);  // P buffer s no longer read by the tensor core
-      const uint32_t p_row = sP(s) + row * 128;
+      const uint32_t p_row = sP(s) + half * ATOM_BYTES + row * 128;  // this thread's 64 columns = one swizzle atom row
       float lsum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
+      for (int c = 0; c < 64; c += 32) {
         uint32_t r[32];
         tmem_ld32(tS + c, r);
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float p0 = (c + 2 * i < valid) ? exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used) : 0.f;
-          float p1 = (c + 2 * i + 1 < valid) ? exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used) : 0.f;
+          float p0 = (c0 + c + 2 * i < valid) ? exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used) : 0.f;
+          float p1 = (c0 + c + 2 * i + 1 < valid) ? exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used) : 0.f;
           pk[i] = pack_bf16(p0, p1);
           // the row sum uses the bf16-rounded probabilities, i.e. exactly what the tensor core multiplies with V
           lsum += bf16_lo(pk[i]) + bf16_hi(pk[i]);
         }
-        // columns c..c+31 = 16-byte chunks (c/8 .. c/8+3) of atom c/64, XOR-swizzled by (row & 7)
-        const uint32_t atom = p_row + (c >> 6) * ATOM_BYTES;
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-          const uint32_t chunk = (uint32_t)(((c & 63) >> 3) + v) ^ (uint32_t)(row & 7);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom + chunk * 16), "r"(pk[4 * v]), "r"(pk[4 * v + 1]),
+          const uint32_t chunk = (uint32_t)((c >> 3) + v) ^ (uint32_t)(row & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16), "r"(pk[4 * v]), "r"(pk[4 * v + 1]),
                        "r"(pk[4 * v + 2]), "r"(pk[4 * v + 3])
                        : "memory");
         }
@@ -216,6 +224,10 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
       if (lane == 0) mbar_arrive(p_full(s));
     }
     // ----------------------------------------------------------------- epilogue: O / l -> bf16, token-major
+    pair_sync();  // everyone is done with the row-max slots: reuse slot 0 for the partial row sums
+    red[half * 128 + row] = l;
+    pair_sync();
+    l += red[(half ^ 1) * 128 + row];
     mbar_wait(o_full, 0);
     tc_fence_after();
     const int sq = q0 + row;
@@ -223,14 +235,14 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
     const float inv = 1.f / l;
     bf16* dst = nullptr;
     if (ok) {
-      dst = sq < P.split ? P.out0 + ((int64_t)b * P.rows0 + sq) * P.ld0 + h * ATT_D
-                         : P.out1 + ((int64_t)b * P.rows1 + (sq - P.split)) * P.ld1 + h * ATT_D;
-      if (P.lse) P.lse[(int64_t)bh * P.S + sq] = m_used + log2f(l);
+      dst = (sq < P.split ? P.out0 + ((int64_t)b * P.rows0 + sq) * P.ld0 + h * ATT_D
+                          : P.out1 + ((int64_t)b * P.rows1 + (sq - P.split)) * P.ld1 + h * ATT_D) + c0;
+      if (P.lse && half == 0) P.lse[(int64_t)bh * P.S + sq] = m_used + log2f(l);
     }
 #pragma unroll 1
-    for (int c = 0; c < 128; c += 32) {
+    for (int c = 0; c < 64; c += 32) {
       uint32_t r[32];
-      tmem_ld32(tO + lane_off + c, r);
+      tmem_ld32(tO + lane_off + c0 + c, r);
       tmem_ld_wait();
       if (ok) {
         uint4* d4 = reinterpret_cast<uint4*>(dst + c);
@@ -284,7 +296,7 @@ extern "C" int qfx_attn_fwd(const void* Q, const void* K, const void* V, void* o
     attr_done = true;
   }
   dim3 grid((S + ATT_BQ - 1) / ATT_BQ, B * H);
-  attn_fwd_kernel<<<grid, 192, ATT_SMEM, (cudaStream_t)stream>>>(P);
+  attn_fwd_kernel<<<grid, 320, ATT_SMEM, (cudaStream_t)stream>>>(P);
   QFX_CUDA(cudaGetLastError());
   return 0;
 }

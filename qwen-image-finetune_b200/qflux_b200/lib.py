@@ -204,6 +204,19 @@ def lora_wgrad(P, Q, G, gs_i, gs_j, r):
           "qfx_lora_wgrad")
 
 
+_wgrad_tc = _sig("qfx_lora_wgrad_tc", _vp, _i64, _i, _vp, _i64, _i, _i, _i, _i, C.POINTER(C.c_void_p), _i64, _i64, _i, _vp)
+
+
+def lora_wgrad_tc(A, B, G_list, gs_i, gs_j, r, mode=0, Dg=0):
+    """tcgen05 LoRA weight gradient: G_g += A^T B_g over rows.  A [M, Na], B [M, 64*G] bf16; G_list: fp32 tensors (one per
+    group).  mode 0: all A columns pair with every group; mode 1: A columns [g*Dg, (g+1)*Dg) pair with group g only."""
+    require_cuda(A, B, *G_list)
+    n = len(G_list)
+    arr = (C.c_void_p * n)(*[g.data_ptr() for g in G_list])
+    check(_wgrad_tc(ptr(A), A.stride(0), A.shape[1], ptr(B), B.stride(0), n, A.shape[0], mode, Dg, arr, gs_i, gs_j, r,
+                    cur_stream()), "qfx_lora_wgrad_tc")
+
+
 def attn_delta(O, dO, delta, tokens_per_sample, s_offset, dO_joint=None):
     """delta[b,h,s] = sum_d O*dO for token-major O/dO rows; optionally scatters dO into the joint [B,H,S,128] layout."""
     require_cuda(O, dO, delta, dO_joint)

@@ -242,6 +242,7 @@ class QwenImageB200(nn.Module):
         self.G32 = torch.zeros(off, device=self.dev, dtype=torch.float32)
         self.G16 = torch.zeros(off, device=self.dev, dtype=BF)
         self._gnorm_sq = torch.zeros(1, device=self.dev, dtype=torch.float32)
+        self._gscratch = torch.zeros(4 * D * PAD, device=self.dev, dtype=torch.float32)
         return self
 
     def bind_param_grads(self):
@@ -426,10 +427,18 @@ class QwenImageB200(nn.Module):
             dYg = dY[:, g * n_out_each:(g + 1) * n_out_each]
             Bg = site.B_pad[g * n_out_each:(g + 1) * n_out_each]
             lib.gemm([lib.gemm_problem(dYg, Bg, U[:, g * PAD:(g + 1) * PAD])], PAD, n_out_each, trans_b=True, alpha=self.lora_scaling)
-        for g, (full, pA, pB, ga, gb, d_in, d_out) in site.members.items():
-            dYg = dY[:, g * n_out_each:(g + 1) * n_out_each]
-            lib.lora_wgrad(dYg, Tb[:, g * PAD:], self.G32[gb:], r, 1, r)          # dB[out, r] += dY_g^T T_g
-            lib.lora_wgrad(Xsaved, U[:, g * PAD:], self.G32[ga:], 1, d_in, r)     # dA[r, in]  += U_g^T X
+        # weight gradients on the tensor cores: dB_g[out, r] += dY_g^T T_g  (grouped-diagonal), dA_g[r, in] += U_g^T X
+        gB, gA = [], []
+        for g in range(site.n):
+            if g in site.members:
+                full, pA, pB, ga, gb, d_in, d_out = site.members[g]
+                gB.append(self.G32[gb:])
+                gA.append(self.G32[ga:])
+            else:  # slot without an adapter (e.g. LoRA on to_q/to_v only): its zero factors produce zeros -> scratch
+                gB.append(self._gscratch)
+                gA.append(self._gscratch)
+        lib.lora_wgrad_tc(dY, Tb, gB, r, 1, r, mode=1 if site.n > 1 else 0, Dg=n_out_each if site.n > 1 else 0)
+        lib.lora_wgrad_tc(Xsaved, U, gA, 1, Xsaved.shape[1], r, mode=0)
         return U, site.A_pad, site.n
 
     def _dgrad_grouped(self, ws, l, grp, dY, dXout, N, K, n_out_each, Xsaved, epilogue=lib.EPI_BIAS, aux=None):

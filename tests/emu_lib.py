@@ -184,6 +184,17 @@ def lora_wgrad(P, Q, G, gs_i, gs_j, r):
     view += res
 
 
+def lora_wgrad_tc(A, B, G_list, gs_i, gs_j, r, mode=0, Dg=0):
+    Af, Bf = A.float(), B.float()
+    for g, G in enumerate(G_list):
+        if mode == 1:
+            res = Af[:, g * Dg:(g + 1) * Dg].t() @ Bf[:, g * 64: g * 64 + r]
+        else:
+            res = Af.t() @ Bf[:, g * 64: g * 64 + r]
+        view = torch.as_strided(G, (res.shape[0], r), (gs_i, gs_j))
+        view += res
+
+
 def attn_delta(O, dO, delta, tokens_per_sample, s_offset, dO_joint=None):
     B, H, S = delta.shape
     n = tokens_per_sample
@@ -240,7 +251,7 @@ def require_cuda(*tensors):
 
 
 _NAMES = ["gemm_problem", "gemm", "ln_modulate_fwd", "ln_modulate_bwd", "gate_mul", "rmsnorm_rows", "qk_norm_rope_fwd",
-          "qk_norm_rope_bwd", "gemv_act", "timestep_sinusoid", "flow_noisy_input", "flow_loss", "lora_wgrad", "attn_delta",
+          "qk_norm_rope_bwd", "gemv_act", "timestep_sinusoid", "flow_noisy_input", "flow_loss", "lora_wgrad", "lora_wgrad_tc", "attn_delta",
           "attn_fwd", "attn_bwd", "grad_finalize", "require_cuda"]
 
 

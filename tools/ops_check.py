@@ -171,6 +171,41 @@ def wgrad():
     return res
 
 
+def wgrad_tc(perf=False):
+    from qflux_b200 import lib
+    res = {}
+    M, D = (8192, 3072) if perf else (1000, 512)
+    for r in (4, 16, 64):
+        # mode 0, three groups (dA of a fused q|k|v site): A = X [M, D], B = U [M, 192]
+        X, U = _mk(M, D, seed=1), _mk(M, 192, seed=2)
+        Gs = [torch.zeros(r, D, device="cuda") for _ in range(3)]
+        lib.lora_wgrad_tc(X, U, Gs, 1, D, r, mode=0)
+        for g in range(3):
+            res[f"dA_r{r}_g{g}"] = rel_l2(Gs[g], (X.float().t() @ U.float()[:, g * 64:g * 64 + r]).t())
+        # mode 1 (dB of a fused site): A = dY [M, 3D], B = T [M, 192]
+        dY, T = _mk(M, 3 * D, seed=3), _mk(M, 192, seed=4)
+        Gb = [torch.zeros(D, r, device="cuda") for _ in range(3)]
+        lib.lora_wgrad_tc(dY, T, Gb, r, 1, r, mode=1, Dg=D)
+        for g in range(3):
+            res[f"dB_r{r}_g{g}"] = rel_l2(Gb[g], dY.float()[:, g * D:(g + 1) * D].t() @ T.float()[:, g * 64:g * 64 + r])
+    # single group, ragged M
+    X, U = _mk(777, 256, seed=5), _mk(777, 64, seed=6)
+    G1 = torch.zeros(256, 16, device="cuda")
+    lib.lora_wgrad_tc(X, U, [G1], 16, 1, 16)
+    res["single"] = rel_l2(G1, X.float().t() @ U.float()[:, :16])
+    torch.cuda.synchronize()
+    res["err"] = max(res.values())
+    if perf:
+        flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
+        X8, U8 = _mk(8192, 3072, seed=1), _mk(8192, 192, seed=2)
+        Gs8 = [torch.zeros(16, 3072, device="cuda") for _ in range(3)]
+        res["ms_dA3"] = round(time_cuda(lambda: lib.lora_wgrad_tc(X8, U8, Gs8, 1, 3072, 16, mode=0), flush=flush), 4)
+        dY8 = _mk(8192, 9216, seed=3)
+        Gb8 = [torch.zeros(3072, 16, device="cuda") for _ in range(3)]
+        res["ms_dB3"] = round(time_cuda(lambda: lib.lora_wgrad_tc(dY8, U8, Gb8, 16, 1, 16, mode=1, Dg=3072), flush=flush), 4)
+    return res
+
+
 def attn(Bsz=2, H=3, S=300, split=44, ragged=False, perf=False):
     from qflux_b200 import lib
     Q, K, V = (_mk(Bsz, H, S, 128, seed=i, scale=1.0) for i in (1, 2, 3))
@@ -258,6 +293,8 @@ CASES = {
     "gemv": gemv,
     "flow": flow,
     "wgrad": wgrad,
+    "wgrad_tc": wgrad_tc,
+    "wgrad_tc_perf": lambda: wgrad_tc(perf=True),
     "attn_small": lambda: attn(1, 2, 128, 32),
     "attn_300": lambda: attn(2, 3, 300, 44),
     "attn_1tile_tail": lambda: attn(1, 1, 70, 10),
