@@ -253,7 +253,8 @@ def run_b200(args):
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_ips, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel<256,false,GELU> grouped img+txt MLP-up [8192+1408,3072]x[12288,3072]",
-                         "achieved": g_tf, "peak": burst, "unit": "TFLOP/s", "frac": g_tf / burst, "traffic": None,
+                         "achieved": g_tf, "peak": burst, "unit": "TFLOP/s", "frac": g_tf / burst, "traffic": 1.363e9,
+                         "traffic_source": "dram__bytes_read+write per launch, profiles/r01_ncu_full_gemm_kernel.md (algorithmic 0.68e9)",
                          "peak_source": f"{which} MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)", "kernel_ms": g_ms,
                          "step_algorithmic_tflops_per_gpu": step_tf, "step_frac_of_sustained": step_tf / sustained},
             "cpu_baseline": cpu}

@@ -1,0 +1,429 @@
+"""Shared host-side machinery of the fused B200 MMDiT models (Qwen-Image, FLUX): HBM layout, LoRA registry, the
+double-stream block forward/backward launch sequences and the autograd bridge.  All arithmetic is in libqfx_b200.so.
+
+Layout conventions:
+  * tokens are stream-major: rows [0, B*T) text (stream index 1), rows [B*T, B*T + B*L) image (stream index 0);
+  * frozen weights are plain device tensors in `self.w`, layer-stacked and fused (q|k|v concatenated per stream);
+  * a "site" is one (block, weight group, stream) that may carry LoRA factors, zero-padded to 64 (`A_pad [64*n, in]`,
+    `B_pad [n*out, 64]`, n = 3 for a fused q|k|v site); the trainable nn.Parameters are views into those buffers;
+  * LoRA gradients accumulate in one flat fp32 buffer `G32` (the all-reduce payload); `G16` holds the bf16 grads.
+"""
+from __future__ import annotations
+
+import math
+import re
+
+import torch
+import torch.nn as nn
+
+from . import lib
+
+BF = torch.bfloat16
+PAD = 64  # LoRA rank is padded to one 64-wide k-block
+DEFAULT_TARGETS = ("to_q", "to_k", "to_v", "to_out.0")  # /root/reference/src/qflux/data/config.py:315
+
+
+class LoraSite:
+    """LoRA factors of one (block, group): padded buffers shared by its 1 or 3 member modules (and, for FLUX single
+    blocks, by both streams)."""
+
+    def __init__(self, n_slots, d_in, d_out_each, device):
+        self.n = n_slots
+        self.A_pad = torch.zeros(n_slots * PAD, d_in, device=device, dtype=BF)        # rows g*64.. = A of slot g
+        self.B_pad = torch.zeros(n_slots * d_out_each, PAD, device=device, dtype=BF)  # rows g*out.. = B of slot g
+        self.members = {}  # slot -> (name, A_param, B_param, gA_off, gB_off, d_in, d_out)
+        self.r = 0
+
+
+class FusedMMDiTBase(nn.Module):
+    # subclasses fill these -------------------------------------------------------------------------------------------
+    round_mid = True  # diffusers RMSNorm (Qwen) rounds before the weight multiply; torch.nn.RMSNorm (FLUX) does not
+
+    def _weight_views(self) -> dict:
+        raise NotImplementedError
+
+    def _linear_table(self) -> dict:
+        """full module name -> (site_key=(l, grp), streams tuple, slot, d_in, d_out, n_slots)"""
+        raise NotImplementedError
+
+    def _wb(self, l, grp, s):
+        return self.w[grp + "_w"][l, s], self.w[grp + "_b"][l, s]
+
+    # -----------------------------------------------------------------------------------------------------------------
+    def _init_common(self, device, host_only):
+        if not host_only and not torch.cuda.is_available():
+            raise lib.QfxError(f"{type(self).__name__} needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.dev = torch.device(device)
+        self.sites = {}          # (l, grp, s) -> LoraSite
+        self._lora_params = {}   # PEFT name -> nn.Parameter
+        self.lora_scaling, self.lora_rank = 0.0, 0
+        self.G32 = self.G16 = None
+        self._ws = self._ws_key = None
+        self._rope_cache = {}
+        self.gradient_checkpointing = False  # accepted for interface compatibility; HBM holds the activations
+
+    @property
+    def device(self):
+        return self.dev
+
+    @property
+    def dtype(self):
+        return BF
+
+    def enable_gradient_checkpointing(self):
+        self.gradient_checkpointing = True
+
+    # ------------------------------------------------------------------------------------------------ state dict
+    def state_dict(self, *args, **kwargs):
+        """diffusers / PEFT key names; LoRA'd modules expose `base_layer.*` and `lora_{A,B}.default.weight`."""
+        lora_mods = {n.rsplit(".lora_", 1)[0] for n in self._lora_params}
+        sd = {}
+        for k, v in self._weight_views().items():
+            mod, leaf = k.rsplit(".", 1)
+            sd[(mod + ".base_layer." + leaf) if mod in lora_mods else k] = v
+        for k, p in self._lora_params.items():
+            sd[k] = p.detach()
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, sd, strict=True, assign=False):
+        views = self._weight_views()
+        unexpected, seen = [], set()
+        for k, v in sd.items():
+            kk = k.replace(".base_layer.", ".")
+            if kk in views:
+                views[kk].copy_(v.to(self.dev, BF))
+                seen.add(kk)
+            elif k in self._lora_params:
+                self._lora_params[k].copy_(v.to(self.dev, BF))
+                seen.add(k)
+            else:
+                unexpected.append(k)
+        missing = [k for k in list(views) + list(self._lora_params) if k not in seen]
+        if strict and (unexpected or [m for m in missing if "lora" not in m]):
+            raise KeyError(f"load_state_dict: missing {missing[:5]}..., unexpected {unexpected[:5]}...")
+        return missing, unexpected
+
+    def named_parameters(self, prefix="", recurse=True, remove_duplicate=True):
+        for k, p in self._lora_params.items():
+            yield (prefix + ("." if prefix else "") + k, p)
+
+    def parameters(self, recurse=True):
+        for _, p in self.named_parameters():
+            yield p
+
+    # ------------------------------------------------------------------------------------------------ LoRA registry
+    def add_adapter(self, r: int, lora_alpha: float, target_modules=DEFAULT_TARGETS, init_lora_weights="gaussian",
+                    seed: int = 0, b_std: float = 0.0):
+        """PEFT-equivalent of `dit.add_adapter(LoraConfig(...))` (/root/reference/src/qflux/trainer/base_trainer.py:929-941).
+        target_modules: list of name suffixes or one full regex (PEFT matching rules)."""
+        if r not in (4, 8, 16, 32, 64):
+            raise NotImplementedError(f"LoRA rank {r}: the fused kernels take r in (4, 8, 16, 32, 64)")
+        if self._lora_params:
+            raise lib.QfxError("an adapter is already attached")
+        table = self._linear_table()
+
+        def match(full):
+            if isinstance(target_modules, str):
+                return re.fullmatch(target_modules, full) is not None
+            return any(full == t or full.endswith("." + t) for t in target_modules)
+
+        wanted = [full for full in table if match(full)]
+        for k in self._weight_views():  # modules PEFT would adapt but the fused path cannot: fail loudly
+            mod = k.rsplit(".", 1)[0]
+            if k.endswith(".weight") and self._weight_views()[k].ndim == 2 and mod not in table and match(mod):
+                raise NotImplementedError(f"LoRA on `{mod}` is outside the fused hot path (SURVEY.md §8a a12)")
+        if not wanted:
+            raise lib.QfxError(f"no LoRA-capable module matches target_modules={target_modules!r}")
+        self.lora_rank, self.lora_scaling = r, float(lora_alpha) / r
+        g = torch.Generator(device=self.dev).manual_seed(seed)
+        off = 0
+        for full in wanted:
+            (l, grp), streams, slot, d_in, d_out, n_slots = table[full]
+            if grp in self._no_lora_groups():
+                raise NotImplementedError(f"LoRA on `{full}`: the backward does not regenerate this linear's input yet")
+            site = self.sites.get((l, grp, streams[0]))
+            if site is None:
+                site = LoraSite(n_slots, d_in, d_out, self.dev)
+                for s in streams:
+                    self.sites[(l, grp, s)] = site
+            site.r = r
+            A_view = site.A_pad[slot * PAD: slot * PAD + r]            # [r, in]  contiguous
+            B_view = site.B_pad[slot * d_out:(slot + 1) * d_out, :r]   # [out, r] strided view
+            if init_lora_weights == "gaussian":
+                A_view.copy_(torch.randn(r, d_in, device=self.dev, generator=g) / r)
+            else:
+                A_view.copy_((torch.rand(r, d_in, device=self.dev, generator=g) * 2 - 1) / math.sqrt(d_in))
+            if b_std > 0:
+                B_view.copy_(torch.randn(d_out, r, device=self.dev, generator=g) * b_std)
+            pA, pB = nn.Parameter(A_view), nn.Parameter(B_view)
+            gA_off, gB_off = off, off + r * d_in
+            off = gB_off + d_out * r
+            site.members[slot] = (full, pA, pB, gA_off, gB_off, d_in, d_out)
+            self._lora_params[full + ".lora_A.default.weight"] = pA
+            self._lora_params[full + ".lora_B.default.weight"] = pB
+        self.G32 = torch.zeros(off, device=self.dev, dtype=torch.float32)
+        self.G16 = torch.zeros(off, device=self.dev, dtype=BF)
+        self._gnorm_sq = torch.zeros(1, device=self.dev, dtype=torch.float32)
+        self._gscratch = torch.zeros(4 * self.D * PAD, device=self.dev, dtype=torch.float32)
+        return self
+
+    def _no_lora_groups(self):
+        return ("down",)
+
+    def _unique_sites(self):
+        seen = set()
+        for site in self.sites.values():
+            if id(site) not in seen:
+                seen.add(id(site))
+                yield site
+
+    def bind_param_grads(self):
+        """Point every LoRA `param.grad` at its slice of the flat bf16 gradient buffer (no copies)."""
+        r = self.lora_rank
+        for site in self._unique_sites():
+            for slot, (full, pA, pB, ga, gb, d_in, d_out) in site.members.items():
+                pA.grad = self.G16[ga: ga + r * d_in].view(r, d_in)
+                pB.grad = self.G16[gb: gb + d_out * r].view(d_out, r)
+
+    def lora_grad_views(self, flat=None):
+        """{param name: view into a flat gradient buffer (default: the fp32 accumulator)}."""
+        flat = self.G32 if flat is None else flat
+        out, r = {}, self.lora_rank
+        for site in self._unique_sites():
+            for slot, (full, pA, pB, ga, gb, d_in, d_out) in site.members.items():
+                out[full + ".lora_A.default.weight"] = flat[ga: ga + r * d_in].view(r, d_in)
+                out[full + ".lora_B.default.weight"] = flat[gb: gb + d_out * r].view(d_out, r)
+        return out
+
+    def zero_lora_grads(self):
+        self.G32.zero_()
+
+    def finalize_grads(self, world_size: int = 1, max_norm: float = 0.0):
+        """fp32 accumulator (already all-reduced by the caller) -> mean over ranks -> clip -> bf16 `param.grad`."""
+        lib.grad_finalize(self.G32, 1.0 / world_size, max_norm, self._gnorm_sq, self.G16)
+        self.bind_param_grads()
+        return self._gnorm_sq
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def _rows(self, ws, t, s):
+        """rows of a stream-major [M, *] tensor: s=1 text, s=0 image."""
+        return t[: ws["Mt"]] if s == 1 else t[ws["Mt"]:]
+
+    def _rpb(self, ws, s):
+        return ws["Limg"] if s == 0 else ws["T"]
+
+    def _site(self, l, grp, s):
+        return self.sites.get((l, grp, s))
+
+    def _alloc_lora_T(self, ws):
+        ws["loraT"] = {}
+        for (l, grp, s), site in self.sites.items():
+            ws["loraT"][(l, grp, s)] = torch.zeros(ws["Mi"] if s == 0 else ws["Mt"], site.n * PAD, device=self.dev, dtype=BF)
+
+    def _lora_T(self, ws, l, grp, s, X):
+        """T = scaling * X @ A_pad^T  for the site (None if the site has no adapter)."""
+        site = self._site(l, grp, s)
+        if site is None:
+            return None, None
+        Tb = ws["loraT"][(l, grp, s)]
+        lib.gemm([lib.gemm_problem(X, site.A_pad, Tb)], site.n * PAD, X.shape[1], alpha=self.lora_scaling)
+        return site, Tb
+
+    def _grouped(self, ws, l, grp, src, dst, N, K, epilogue, **epi):
+        """One grouped GEMM over (image, text) rows of block l for weight group `grp` with optional fused LoRA."""
+        probs = []
+        for s in (0, 1):
+            A = self._rows(ws, src, s)
+            site, Tb = self._lora_T(ws, l, grp, s, A)
+            kw = {}
+            if site is not None:
+                kw = dict(A2=Tb, B2=site.B_pad, kb2=1)
+            for k, v in epi.items():
+                if v is None:
+                    continue
+                if k == "gate":
+                    kw["gate"], kw["rows_per_batch"] = v[s], self._rpb(ws, s)
+                else:
+                    kw[k] = self._rows(ws, v, s)
+            W, b = self._wb(l, grp, s)
+            probs.append(lib.gemm_problem(A, W, self._rows(ws, dst, s), bias=b, **kw))
+        fused3 = any(p.kb2 for p in probs) and self._site_n(l, grp) == 3
+        lib.gemm(probs, N, K, epilogue=epilogue, lora_group_n=(N // 3 if fused3 else 0))
+
+    def _site_n(self, l, grp):
+        for s in (0, 1):
+            site = self._site(l, grp, s)
+            if site is not None:
+                return site.n
+        return 0
+
+    def _lora_bwd(self, ws, l, grp, s, dY, Xsaved, n_out_each):
+        """LoRA part of a linear's backward for one site: U = s*dY.B (for the fused dgrad) and the weight gradients.
+        dY [M_s, n_slots*out]; Xsaved [M_s, in] is the linear's input (for dA)."""
+        site = self._site(l, grp, s)
+        if site is None:
+            return None
+        r, Tb = site.r, ws["loraT"][(l, grp, s)]
+        U = self._rows(ws, ws["U"], s)[:, : site.n * PAD]
+        for g in range(site.n):
+            dYg = dY[:, g * n_out_each:(g + 1) * n_out_each]
+            Bg = site.B_pad[g * n_out_each:(g + 1) * n_out_each]
+            lib.gemm([lib.gemm_problem(dYg, Bg, U[:, g * PAD:(g + 1) * PAD])], PAD, n_out_each, trans_b=True, alpha=self.lora_scaling)
+        # weight gradients on the tensor cores: dB_g[out, r] += dY_g^T T_g  (grouped-diagonal), dA_g[r, in] += U_g^T X
+        gB, gA = [], []
+        for g in range(site.n):
+            if g in site.members:
+                full, pA, pB, ga, gb, d_in, d_out = site.members[g]
+                gB.append(self.G32[gb:])
+                gA.append(self.G32[ga:])
+            else:  # slot without an adapter (e.g. LoRA on to_q/to_v only): its zero factors produce zeros -> scratch
+                gB.append(self._gscratch)
+                gA.append(self._gscratch)
+        lib.lora_wgrad_tc(dY, Tb, gB, r, 1, r, mode=1 if site.n > 1 else 0, Dg=n_out_each if site.n > 1 else 0)
+        lib.lora_wgrad_tc(Xsaved, U, gA, 1, Xsaved.shape[1], r, mode=0)
+        return U, site.A_pad, site.n
+
+    def _dgrad_grouped(self, ws, l, grp, dY, dXout, N, K, n_out_each, Xsaved, epilogue=lib.EPI_BIAS, aux=None, resid=None):
+        """dX = dY . W (+ U . A) for both streams of weight group `grp` (W stored [out, in] = [K_red, N])."""
+        probs = []
+        for s in (0, 1):
+            dYs = self._rows(ws, dY, s)
+            lb = self._lora_bwd(ws, l, grp, s, dYs, self._rows(ws, Xsaved, s) if Xsaved is not None else None, n_out_each)
+            kw = {}
+            if lb is not None:
+                kw = dict(A2=lb[0], B2=lb[1], kb2=lb[2])
+            if aux is not None:
+                kw["aux"] = self._rows(ws, aux, s)
+            if resid is not None:
+                kw["resid"] = self._rows(ws, resid, s)
+            probs.append(lib.gemm_problem(dYs, self._wb(l, grp, s)[0], self._rows(ws, dXout, s), **kw))
+        lib.gemm(probs, N, K, trans_b=True, epilogue=epilogue)
+
+    # ------------------------------------------------------------------------------------------------ double-stream block
+    # mods(j): j-th D-wide chunk (shift1, scale1, gate1, shift2, scale2, gate2) -> (img view, txt view), each [B, D]
+    def _double_fwd(self, ws, l, Xin, Xout, save, mods):
+        D = self.D
+        T, Limg, Mt = ws["T"], ws["Limg"], ws["Mt"]
+        st, qkv, O, xmid, u = save["stats"], save["qkv"], save["O"], save["xmid"], save["u"]
+        w = self.w
+        for s in (0, 1):
+            lib.ln_modulate_fwd(self._rows(ws, Xin, s), self._rows(ws, ws["xm"], s), mods(0)[s], mods(1)[s], self._rpb(ws, s),
+                                self._rows(ws, st[0], s), self._rows(ws, st[1], s))
+        self._grouped(ws, l, "qkv", ws["xm"], qkv, 3 * D, D, lib.EPI_BIAS)
+        for s in (0, 1):
+            lib.qk_norm_rope_fwd(self._rows(ws, qkv, s), w["qknorm_w"][l, 2 * s], w["qknorm_w"][l, 2 * s + 1], ws["rope"], ws["Q"],
+                                 ws["K"], ws["V"], self._rpb(ws, s), T if s == 0 else 0, round_mid=self.round_mid)
+        lib.attn_fwd(ws["Q"], ws["K"], ws["V"], O[:Mt], O[Mt:], T, save["lse"])
+        self._grouped(ws, l, "out", O, xmid, D, D, lib.EPI_RESID_GATE, resid=Xin, gate=mods(2))
+        for s in (0, 1):
+            lib.ln_modulate_fwd(self._rows(ws, xmid, s), self._rows(ws, ws["xm"], s), mods(3)[s], mods(4)[s], self._rpb(ws, s),
+                                self._rows(ws, st[2], s), self._rows(ws, st[3], s))
+        self._grouped(ws, l, "up", ws["xm"], ws["h"], 4 * D, D, lib.EPI_GELU, out2=u)
+        self._grouped(ws, l, "down", ws["h"], Xout, D, 4 * D, lib.EPI_RESID_GATE, resid=xmid, gate=mods(5))
+
+    def _attn_bwd_core(self, ws, qkv, O, lse, wq_wk):
+        """dO (token-major, ws['dO']) -> dqkv (ws['dqkv']); wq_wk(s) -> (wq, wk) norm weights of stream s."""
+        T = ws["T"]
+        for s in (0, 1):
+            wq, wk = wq_wk(s)
+            lib.attn_delta(self._rows(ws, O, s), self._rows(ws, ws["dO"], s), ws["delta"], self._rpb(ws, s), T if s == 0 else 0,
+                           ws["dOj"])
+            lib.qk_norm_rope_fwd(self._rows(ws, qkv, s), wq, wk, ws["rope"], ws["Q"], ws["K"], ws["V"], self._rpb(ws, s),
+                                 T if s == 0 else 0, round_mid=self.round_mid)
+        ws["dQ"].zero_()
+        lib.attn_bwd(ws["Q"], ws["K"], ws["V"], ws["dOj"], lse, ws["delta"], ws["dQ"], ws["dK"], ws["dV"])
+        for s in (0, 1):
+            wq, wk = wq_wk(s)
+            lib.qk_norm_rope_bwd(ws["dQ"], ws["dK"], ws["dV"], self._rows(ws, qkv, s), wq, wk, ws["rope"],
+                                 self._rows(ws, ws["dqkv"], s), self._rpb(ws, s), T if s == 0 else 0, round_mid=self.round_mid)
+
+    def _double_bwd(self, ws, l, Xin, dX, dXn, save, mods, prev_gate):
+        """dX: grad wrt the block output (ws['dY'] already holds dX * gate2).  Writes the grad wrt the block input to dXn
+        and, when prev_gate is given, dXn * prev_gate to ws['dY'] for the block before."""
+        D = self.D
+        st, qkv, O, xmid, u = save["stats"], save["qkv"], save["O"], save["xmid"], save["u"]
+        w = self.w
+        # ---- MLP branch
+        self._dgrad_grouped(ws, l, "down", ws["dY"], ws["dbig"], 4 * D, D, D, None, epilogue=lib.EPI_DGELU, aux=u)
+        if self._site(l, "up", 0) or self._site(l, "up", 1):  # LoRA input = xm2, recomputed from the statistics
+            for s in (0, 1):
+                lib.ln_modulate_fwd(self._rows(ws, xmid, s), self._rows(ws, ws["xm"], s), mods(3)[s], mods(4)[s], self._rpb(ws, s))
+        self._dgrad_grouped(ws, l, "up", ws["dbig"], ws["dxm"], D, 4 * D, 4 * D, ws["xm"])
+        # ---- norm2 backward: dXmid = dX + LN_bwd ; also emit dXmid * gate1 for the attention out-projection
+        for s in (0, 1):
+            lib.ln_modulate_bwd(self._rows(ws, ws["dxm"], s), self._rows(ws, xmid, s), self._rows(ws, st[2], s),
+                                self._rows(ws, st[3], s), mods(4)[s], self._rpb(ws, s), self._rows(ws, dX, s),
+                                dres=self._rows(ws, dX, s), gate=mods(2)[s], dx_gated=self._rows(ws, ws["dY"], s))
+        # ---- attention output projection (LoRA input = O), attention, q|k|v projection (LoRA input = xm1, recomputed)
+        self._dgrad_grouped(ws, l, "out", ws["dY"], ws["dO"], D, D, D, O)
+        self._attn_bwd_core(ws, qkv, O, save["lse"], lambda s: (w["qknorm_w"][l, 2 * s], w["qknorm_w"][l, 2 * s + 1]))
+        if self._site(l, "qkv", 0) or self._site(l, "qkv", 1):
+            for s in (0, 1):
+                lib.ln_modulate_fwd(self._rows(ws, Xin, s), self._rows(ws, ws["xm"], s), mods(0)[s], mods(1)[s], self._rpb(ws, s))
+        self._dgrad_grouped(ws, l, "qkv", ws["dqkv"], ws["dxm"], D, 3 * D, D, ws["xm"])
+        # ---- norm1 backward: dXin = dXmid + LN_bwd ; emit dXin * (gate of the block before)
+        for s in (0, 1):
+            lib.ln_modulate_bwd(self._rows(ws, ws["dxm"], s), self._rows(ws, Xin, s), self._rows(ws, st[0], s),
+                                self._rows(ws, st[1], s), mods(1)[s], self._rpb(ws, s), self._rows(ws, dXn, s),
+                                dres=self._rows(ws, dX, s), gate=prev_gate[s] if prev_gate else None,
+                                dx_gated=self._rows(ws, ws["dY"], s) if prev_gate else None)
+
+    # ------------------------------------------------------------------------------------------------ workspace pieces
+    def _alloc_common(self, ws, B, T, Limg, train, n_double, n_single=0):
+        D, H = self.D, self.H
+        Mt, Mi = B * T, B * Limg
+        M, S = Mt + Mi, T + Limg
+        e = lambda *s, dt=BF: torch.empty(*s, device=self.dev, dtype=dt)
+        ws.update(B=B, T=T, Limg=Limg, S=S, Mt=Mt, Mi=Mi, M=M)
+        nblk = n_double + n_single
+        ws["X"] = e(nblk + 1 if train else 2, M, D)
+        ws["xm"], ws["h"] = e(M, D), e(M, 4 * D)
+        ws["Q"], ws["K"], ws["V"] = e(B, H, S, 128), e(B, H, S, 128), e(B, H, S, 128)
+        nd = n_double if train else min(1, n_double)
+        ns = n_single if train else min(1, n_single)
+        ws["dbl"] = [dict(stats=e(4, M, dt=torch.float32), qkv=e(M, 3 * D), O=e(M, D), lse=e(B, H, S, dt=torch.float32),
+                          xmid=e(M, D), u=e(M, 4 * D)) for _ in range(nd)]
+        ws["sgl"] = [dict(stats=e(2, M, dt=torch.float32), qkv=e(M, 3 * D), O=e(M, D), lse=e(B, H, S, dt=torch.float32),
+                          u=e(M, 4 * D)) for _ in range(ns)]
+        ws["hn"], ws["pred"] = e(Mi, D), e(Mi, self.C_out)
+        ws["fstats"] = e(2, Mi, dt=torch.float32)
+        self._alloc_lora_T(ws)
+        if train:
+            ws["dX"] = e(2, M, D)
+            ws["dY"], ws["dbig"], ws["dqkv"], ws["dxm"], ws["dO"] = e(M, D), e(M, 4 * D), e(M, 3 * D), e(M, D), e(M, D)
+            ws["dOj"], ws["dK"], ws["dV"] = e(B, H, S, 128), e(B, H, S, 128), e(B, H, S, 128)
+            ws["dQ"] = e(B, H, S, 128, dt=torch.float32)
+            ws["delta"] = e(B, H, S, dt=torch.float32)
+            ws["U"] = e(M, 3 * PAD)
+            ws["dhn"], ws["dpred"] = e(Mi, D), e(Mi, self.C_out)
+            ws["loss"] = torch.zeros(1, device=self.dev, dtype=torch.float32)
+        return ws
+
+    def _get_workspace(self, key, build):
+        if self._ws_key == key:
+            return self._ws
+        self._ws = None
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+        self._ws = build()
+        self._ws_key = key
+        return self._ws
+
+
+class ModelFn(torch.autograd.Function):
+    """Autograd bridge for `dit(...)`: forward = fused kernels (activations kept in the model workspace), backward = fused
+    kernels writing LoRA gradients into the flat accumulator; the returned per-parameter grads are views of it."""
+
+    @staticmethod
+    def forward(ctx, model, fwd_args, *params):
+        ctx.model = model
+        return model._forward_impl(*fwd_args, train=True).clone()
+
+    @staticmethod
+    def backward(ctx, dpred):
+        m = ctx.model
+        m.G32.zero_()
+        m._backward_impl(dpred.to(BF).reshape(-1, m.C_out).contiguous())
+        views = m.lora_grad_views(m.G32.to(BF))
+        return (None, None) + tuple(views[k] for k in m._lora_params)

@@ -55,14 +55,8 @@ class _StepFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         m = ctx.step.dit
-        flat = (m.G32 * g).to(BF)
-        r, grads = m.lora_rank, []
-        offs = {}
-        for site in m.sites.values():
-            for slot, (full, pA, pB, ga, gb, d_in, d_out) in site.members.items():
-                offs[full + ".lora_A.default.weight"] = flat[ga: ga + r * d_in].view(r, d_in)
-                offs[full + ".lora_B.default.weight"] = flat[gb: gb + d_out * r].view(d_out, r)
-        grads = tuple(offs[k] for k in m._lora_params)
+        views = m.lora_grad_views((m.G32 * g).to(BF))
+        grads = tuple(views[k] for k in m._lora_params)
         return (None, None) + grads
 
 
