@@ -41,7 +41,8 @@ enum qfx_epilogue {
   QFX_EPI_BIAS = 0,       /* out = alpha*acc + bias                                                  (nn.Linear)            */
   QFX_EPI_GELU = 1,       /* out2 = u = acc + bias ; out = gelu_tanh(u)        (FeedForward "gelu-approximate" net.0)       */
   QFX_EPI_RESID_GATE = 2, /* out = resid + gate[row / rows_per_batch, :] * (acc + bias)   (transformer_qwenimage.py:473,480) */
-  QFX_EPI_DGELU = 3       /* out = acc * gelu_tanh'(aux)                                   (autograd of net.0's GELU)        */
+  QFX_EPI_DGELU = 3,      /* out = acc * gelu_tanh'(aux)                                   (autograd of net.0's GELU)        */
+  QFX_EPI_ADD = 4         /* out = resid + alpha*acc   (trans_b=1: sum of two dgrads, FLUX single block qkv + proj_mlp)      */
 };
 
 typedef struct {
@@ -96,6 +97,8 @@ int qfx_ln_modulate_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx
                         int64_t lddx, const void* gate, int64_t ldgate, void* dx_gated, int64_t lddxg, int M, int D, void* stream);
 int qfx_gate_mul(const void* a, int64_t lda, const void* gate, int64_t ldg, int rows_per_batch, void* out, int64_t ldo, int M,
                  int D, void* stream);
+/* out = bf16(a + b), n elements (sums of the [B, D] conditioning embeddings, transformer_flux.py time_text_embed) */
+int qfx_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 /* diffusers RMSNorm over rows (txt_norm, transformer_qwenimage.py:549,625) */
 int qfx_rmsnorm_rows(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int M, int D, float eps, void* stream);
 /* per-head RMSNorm(q,k) + RoPE + token-major [tok, q|k|v, H, 128] -> head-major Q/K/V[B,H,S,128] at joint position

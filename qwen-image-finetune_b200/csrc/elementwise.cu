@@ -172,6 +172,11 @@ __global__ void __launch_bounds__(256) gate_mul_kernel(const bf16* __restrict__ 
   }
 }
 
+__global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(__bfloat162float(a[i]) + __bfloat162float(b[i]));
+}
+
 // ============================================================================================ RMSNorm over rows (txt_norm)
 // diffusers RMSNorm: y = bf16( bf16(x * rsqrt(mean(x^2)+eps)) * w )
 __global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* __restrict__ w,
@@ -540,6 +545,11 @@ extern "C" int qfx_gate_mul(const void* a, int64_t lda, const void* gate, int64_
   QFX_CHECK_ARG(D % 8 == 0, "qfx_gate_mul: D %% 8");
   gate_mul_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, lda, (const bf16*)gate, ldg, rows_per_batch,
                                                                  (bf16*)out, ldo, M, D);
+  LAUNCH_OK();
+}
+
+extern "C" int qfx_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream) {
+  add_bf16_kernel<<<64, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n);
   LAUNCH_OK();
 }
 

@@ -246,6 +246,21 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
               }
             }
           }
+        } else if (EPI == QFX_EPI_ADD) {
+          if (row_ok) {
+            const uint4* rs = reinterpret_cast<const uint4*>(q.resid + (int64_t)row * q.ldr + n);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              uint4 rr = rs[v];
+              const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rr);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = 4 * v + e;
+                o[i] = pack_bf16(bf16_lo(rw[e]) + round_bf16(__uint_as_float(r[2 * i]) * P.alpha),
+                                 bf16_hi(rw[e]) + round_bf16(__uint_as_float(r[2 * i + 1]) * P.alpha));
+              }
+            }
+          }
         } else if (EPI == QFX_EPI_DGELU) {
           if (row_ok) {
             const uint4* us = reinterpret_cast<const uint4*>(q.aux + (int64_t)row * q.ldaux + n);
@@ -319,6 +334,7 @@ static int dispatch(const GemmParams& P, int trans_b, int epi, cudaStream_t s) {
     switch (epi) {
       case QFX_EPI_BIAS: return launch<BN, true, QFX_EPI_BIAS>(P, s);
       case QFX_EPI_DGELU: return launch<BN, true, QFX_EPI_DGELU>(P, s);
+      case QFX_EPI_ADD: return launch<BN, true, QFX_EPI_ADD>(P, s);
     }
   }
   set_error("qfx_gemm_bf16: unsupported (trans_b=%d, epilogue=%d)", trans_b, epi);
@@ -384,6 +400,7 @@ extern "C" int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, in
     d.ldo = s.ldo; d.ldo2 = s.ldo2; d.ldr = s.ldr; d.ldg = s.ldg; d.ldaux = s.ldaux;
     if (epilogue == QFX_EPI_GELU) QFX_CHECK_ARG(s.out2 && s.ldo2 % 8 == 0, "qfx_gemm_bf16: GELU epilogue needs out2");
     if (epilogue == QFX_EPI_RESID_GATE) QFX_CHECK_ARG(s.resid && s.gate && s.ldr % 8 == 0 && s.ldg % 8 == 0, "qfx_gemm_bf16: RESID_GATE epilogue needs resid+gate");
+    if (epilogue == QFX_EPI_ADD) QFX_CHECK_ARG(s.resid && s.ldr % 8 == 0, "qfx_gemm_bf16: ADD epilogue needs resid");
     if (epilogue == QFX_EPI_DGELU) QFX_CHECK_ARG(s.aux && s.ldaux % 8 == 0, "qfx_gemm_bf16: DGELU epilogue needs aux");
     int tm = (s.M + BM - 1) / BM;
     if (i == 0) P.tiles_m0 = tm;

@@ -49,7 +49,7 @@ def cur_stream():
 
 
 # ---------------------------------------------------------------------------------------------------- GEMM
-EPI_BIAS, EPI_GELU, EPI_RESID_GATE, EPI_DGELU = 0, 1, 2, 3
+EPI_BIAS, EPI_GELU, EPI_RESID_GATE, EPI_DGELU, EPI_ADD = 0, 1, 2, 3, 4
 
 
 class GemmProblem(C.Structure):
@@ -145,6 +145,15 @@ def gate_mul(a, gate, rows_per_batch, out):
     require_cuda(a, gate, out)
     check(_gate_mul(ptr(a), a.stride(0), ptr(gate), gate.stride(0), rows_per_batch, ptr(out), out.stride(0), a.shape[0],
                     a.shape[1], cur_stream()), "qfx_gate_mul")
+
+
+_add = _sig("qfx_add_bf16", _vp, _vp, _vp, _i64, _vp)
+
+
+def add_bf16(a, b, out):
+    require_cuda(a, b, out)
+    assert a.is_contiguous() and b.is_contiguous() and out.is_contiguous()
+    check(_add(ptr(a), ptr(b), ptr(out), a.numel(), cur_stream()), "qfx_add_bf16")
 
 
 def rmsnorm_rows(x, w, y, eps=1e-6):

@@ -129,9 +129,9 @@ class FusedMMDiTBase(nn.Module):
             return any(full == t or full.endswith("." + t) for t in target_modules)
 
         wanted = [full for full in table if match(full)]
-        for k in self._weight_views():  # modules PEFT would adapt but the fused path cannot: fail loudly
+        for k, v in self._weight_views().items():  # modules PEFT would adapt but the fused path cannot: fail loudly
             mod = k.rsplit(".", 1)[0]
-            if k.endswith(".weight") and self._weight_views()[k].ndim == 2 and mod not in table and match(mod):
+            if k.endswith(".weight") and v.ndim == 2 and mod not in table and match(mod):
                 raise NotImplementedError(f"LoRA on `{mod}` is outside the fused hot path (SURVEY.md §8a a12)")
         if not wanted:
             raise lib.QfxError(f"no LoRA-capable module matches target_modules={target_modules!r}")

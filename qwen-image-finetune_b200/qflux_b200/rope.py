@@ -39,6 +39,7 @@ def qwen_rope_table(img_shapes, txt_len: int, axes_dim=(16, 56, 56), theta: floa
 
 def flux_rope_table(ids: torch.Tensor, axes_dim=(16, 56, 56), theta: float = 10000.0) -> torch.Tensor:
     """ids: [S, n_axes] (text ids first, as the model concatenates them). Returns [S, sum(axes)/2, 2]."""
-    pos = ids.detach().cpu().double()
-    ang = torch.cat([torch.outer(pos[:, i], _axis_freqs(d, theta, torch.float64)) for i, d in enumerate(axes_dim)], dim=-1)
+    pos = ids.detach().double()  # stays on the ids' device: no host synchronisation inside the training step
+    ang = torch.cat([torch.outer(pos[:, i], _axis_freqs(d, theta, torch.float64).to(pos.device)) for i, d in enumerate(axes_dim)],
+                    dim=-1)
     return torch.stack([ang.cos().float(), ang.sin().float()], dim=-1).contiguous()

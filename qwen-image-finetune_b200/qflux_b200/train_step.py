@@ -129,3 +129,76 @@ class QwenImageEditStep:
         if optimizer is not None:
             optimizer.step()
         return loss
+
+
+class FluxKontextStep:
+    """Mirror of `FluxKontextLoraTrainer._compute_loss_shared_mode`
+    (/root/reference/src/qflux/trainer/flux_kontext_trainer.py:494-577): t ~ U(0,1) in bf16 on the device, x_t = (1-t) x0 + t eps,
+    ids = [target ids ; control ids], guidance = 1 when the model has guidance embeddings, target = eps - x0, MSE."""
+
+    def __init__(self, dit, loss_kind: str = "mse", fg: float = 2.0, bg: float = 1.0, max_grad_norm: float = 1.0):
+        self.dit, self.loss_kind, self.fg, self.bg, self.max_grad_norm = dit, loss_kind, fg, bg, max_grad_norm
+        self._ones = {}
+
+    @staticmethod
+    def latent_image_ids(h2, w2, device, first=0.0):
+        """_prepare_latent_image_ids (flux_kontext_trainer.py:869-883): [h2*w2, 3] = (first, row, col)."""
+        ids = torch.zeros(h2, w2, 3, device=device)
+        ids[..., 0] = first
+        ids[..., 1] = ids[..., 1] + torch.arange(h2, device=device)[:, None]
+        ids[..., 2] = ids[..., 2] + torch.arange(w2, device=device)[None, :]
+        return ids.reshape(h2 * w2, 3)
+
+    def _prepare(self, embeddings, noise, t):
+        m = self.dit
+        dev = m.dev
+        x0 = embeddings["image_latents"].to(dev, BF, non_blocking=True).contiguous()
+        ctrl = embeddings["control_latents"].to(dev, BF, non_blocking=True).contiguous()
+        pe = embeddings["prompt_embeds"].to(dev, BF, non_blocking=True).contiguous()
+        pooled = embeddings["pooled_prompt_embeds"].to(dev, BF, non_blocking=True).contiguous()
+        B, L, C = x0.shape
+        if noise is None:
+            noise = embeddings["noise"] if "noise" in embeddings else torch.randn(x0.shape, device=dev, dtype=BF)
+        if t is None:
+            t = embeddings["timestep"] if "timestep" in embeddings else torch.rand((B,), device=dev, dtype=BF)
+        t = t.to(dev, BF)
+        ids = torch.cat([embeddings["image_ids"].to(dev), embeddings["control_ids"].to(dev)], dim=0)
+        edit_mask = embeddings.get("edit_mask")
+        if self.loss_kind == "mse" and edit_mask is None:
+            if (B, L) not in self._ones:
+                self._ones[(B, L)] = torch.ones(B, L, device=dev)
+            w, norm = self._ones[(B, L)], 1.0 / (B * L * C)
+        else:
+            w, norm = token_weights_and_norm(self.loss_kind, B, L, C, None, None, None if edit_mask is None else edit_mask.to(dev),
+                                             self.fg, self.bg)
+            w = w.to(dev).contiguous()
+        guidance = torch.ones(B, device=dev) if m.config.guidance_embeds else None
+        return (x0, ctrl, pe, pooled, embeddings["text_ids"].to(dev), ids, noise.to(dev, BF), t, guidance, w, norm)
+
+    def _run(self, x0, ctrl, pe, pooled, text_ids, ids, noise, t, guidance, w, norm):
+        m = self.dit
+        B, L, C = x0.shape
+        packed = torch.empty(B, L + ctrl.shape[1], C, device=m.dev, dtype=BF)
+        lib.flow_noisy_input(x0, noise, ctrl, t.float().contiguous(), packed)
+        pred = m._forward_impl(packed, pe, pooled, t, ids, text_ids, guidance, train=True)
+        ws = m._ws
+        lib.flow_loss(pred, x0, noise, w, norm, ws["loss"], ws["dpred"])
+        m.G32.zero_()
+        m._backward_impl(ws["dpred"])
+        return ws["loss"]
+
+    def compute_loss(self, embeddings: dict, noise=None, t=None) -> torch.Tensor:
+        args = self._prepare(embeddings, noise, t)
+        return _StepFn.apply(self, args, *self.dit._lora_params.values())
+
+    @torch.no_grad()
+    def train_step(self, embeddings: dict, optimizer=None, noise=None, t=None):
+        loss = self._run(*self._prepare(embeddings, noise, t))
+        world = 1
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            world = dist.get_world_size()
+            dist.all_reduce(self.dit.G32)
+        self.dit.finalize_grads(world, self.max_grad_norm)
+        if optimizer is not None:
+            optimizer.step()
+        return loss

@@ -15,7 +15,7 @@ import torch
 import torch.nn.functional as F
 
 BF = torch.bfloat16
-EPI_BIAS, EPI_GELU, EPI_RESID_GATE, EPI_DGELU = 0, 1, 2, 3
+EPI_BIAS, EPI_GELU, EPI_RESID_GATE, EPI_DGELU, EPI_ADD = 0, 1, 2, 3, 4
 
 
 def _f(t):
@@ -60,6 +60,8 @@ def gemm(problems, N, K, *, trans_b=False, epilogue=EPI_BIAS, alpha=1.0, lora_gr
             rpb = p.rows_per_batch or A.shape[0]
             g = p.gate.float().repeat_interleave(rpb, 0)
             p.out.copy_((p.resid.float() + (g * y).to(BF).float()).to(BF))
+        elif epilogue == EPI_ADD:
+            p.out.copy_((p.resid.float() + (acc * alpha).to(BF).float()).to(BF))
         elif epilogue == EPI_DGELU:
             p.out.copy_(((acc * alpha).to(BF).float() * _gelu_grad(p.aux.float())).to(BF))
         else:
@@ -92,6 +94,10 @@ def ln_modulate_bwd(dy, x, mean, rstd, scale, rows_per_batch, dx, dres=None, gat
 
 def gate_mul(a, gate, rows_per_batch, out):
     out.copy_((a.float() * gate.float().repeat_interleave(rows_per_batch, 0)).to(BF))
+
+
+def add_bf16(a, b, out):
+    out.copy_((a.float() + b.float()).to(BF))
 
 
 def rmsnorm_rows(x, w, y, eps=1e-6):
@@ -250,7 +256,7 @@ def require_cuda(*tensors):
     return None
 
 
-_NAMES = ["gemm_problem", "gemm", "ln_modulate_fwd", "ln_modulate_bwd", "gate_mul", "rmsnorm_rows", "qk_norm_rope_fwd",
+_NAMES = ["gemm_problem", "gemm", "ln_modulate_fwd", "ln_modulate_bwd", "gate_mul", "add_bf16", "rmsnorm_rows", "qk_norm_rope_fwd",
           "qk_norm_rope_bwd", "gemv_act", "timestep_sinusoid", "flow_noisy_input", "flow_loss", "lora_wgrad", "lora_wgrad_tc", "attn_delta",
           "attn_fwd", "attn_bwd", "grad_finalize", "require_cuda"]
 

@@ -48,7 +48,7 @@ def test_attention_full_size_properties():
 
 
 @pytest.mark.parametrize("name", ["inference_tiny", "step_tiny", "step_tiny_nolora_targets_all_attn", "step_mid",
-                                  "step_full_width_1blk"])
+                                  "step_full_width_1blk", "flux_tiny", "flux_tiny_regex_noguidance", "flux_full_width_1p1"])
 def test_fused_step_vs_oracle(name):
     r = _cases("model_check")[name]()
     if "pred_vs_fp32" not in r:

@@ -131,3 +131,70 @@ def test_lora_registry_and_errors():
     from qflux_b200 import lib
     with pytest.raises(lib.QfxError):
         lib.rmsnorm_rows(torch.zeros(8, 64, dtype=torch.bfloat16), torch.ones(64, dtype=torch.bfloat16), torch.zeros(8, 64, dtype=torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------------------------ FLUX
+def _flux_pair(r, targets, guidance=True):
+    from qflux_b200.flux_model import FluxB200, FluxB200Config
+    kw = dict(num_layers=2, num_single_layers=2, attention_head_dim=128, num_attention_heads=2, joint_attention_dim=64,
+              pooled_projection_dim=64, guidance_embeds=guidance)
+    orc = mo.init_synthetic_(mo.FluxOracle(mo.FluxConfig(**kw)), std=0.05)
+    g = torch.Generator().manual_seed(98)
+    with torch.no_grad():
+        for n, p in orc.named_parameters():
+            if n.endswith("bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+            elif p.ndim == 1:
+                p.copy_(1 + torch.randn(p.shape, generator=g) * 0.1)
+    if r:
+        mo.add_lora_adapter(orc, r=r, alpha=r, target_modules=targets, b_std=0.05)
+    with torch.no_grad():
+        for p in orc.parameters():
+            p.copy_(p.bfloat16().float())
+    m = FluxB200(FluxB200Config(**kw), device="cpu", _host_only=True)
+    if r:
+        m.add_adapter(r, r, target_modules=targets)
+    missing, unexpected = m.load_state_dict(orc.state_dict(), strict=True)
+    assert not missing and not unexpected, (missing, unexpected)
+    assert set(m.state_dict()) == set(orc.state_dict())
+    return orc, m
+
+
+@pytest.mark.parametrize("targets", [("to_q", "to_k", "to_v", "to_out.0"),
+                                     r".*(attn\.(to_[qkv]|add_[qkv]_proj|to_add_out)|proj_mlp|ff\.net\.0\.proj)"])
+def test_flux_step_matches_oracle_on_cpu(emu, targets):
+    """BASELINE config 3 family (FLUX-Kontext shared-resolution recipe) at tiny size: 2 double + 2 single blocks."""
+    from qflux_b200.train_step import FluxKontextStep
+    orc, m = _flux_pair(4, targets)
+    g = torch.Generator().manual_seed(3)
+    rn = lambda *s: torch.randn(*s, generator=g).bfloat16()
+    B, hw, T = 2, 4, 8
+    L = hw * hw
+    emb = dict(image_latents=rn(B, L, 64), control_latents=rn(B, L, 64), pooled_prompt_embeds=rn(B, 64), prompt_embeds=rn(B, T, 64),
+               text_ids=torch.zeros(T, 3), image_ids=FluxKontextStep.latent_image_ids(hw, hw, "cpu", 0.0),
+               control_ids=FluxKontextStep.latent_image_ids(hw, hw, "cpu", 1.0))
+    noise, t = rn(B, L, 64), torch.tensor([0.5, 0.25])
+    loss_o, pred_o = mo.flux_compute_loss_shared(orc, emb["image_latents"].float(), emb["control_latents"].float(),
+                                                 emb["pooled_prompt_embeds"].float(), emb["prompt_embeds"].float(), emb["text_ids"],
+                                                 emb["image_ids"], emb["control_ids"], noise=noise.float(), t=t)
+    loss_o.backward()
+    step = FluxKontextStep(m)
+    loss_b = step.compute_loss(emb, noise=noise, t=t)
+    pred_b = m._ws["pred"].view(B, -1, 64)[:, :L].float().clone()
+    loss_b.backward()
+    assert ((pred_b - pred_o).norm() / pred_o.norm()).item() < 1e-2
+    assert abs(loss_b.item() - loss_o.item()) < 1e-2
+    go = {n: (p.grad if p.grad is not None else torch.zeros_like(p)) for n, p in orc.named_parameters() if p.requires_grad}
+    gb = {n: p.grad.float() for n, p in m.named_parameters()}
+    assert set(go) == set(gb)
+    num = sum(((gb[n] - go[n]) ** 2).sum() for n in go)
+    den = sum((go[n] ** 2).sum() for n in go)
+    assert float((num / den).sqrt()) < 2e-2
+
+
+def test_flux_rope_table_matches_oracle():
+    from qflux_b200.rope import flux_rope_table
+    ids = torch.tensor([[0., 0, 0], [0, 1, 2], [1, 3, 0], [0, 0, 5]])
+    cos, sin = mo.flux_rope(ids, (16, 56, 56))
+    tab = flux_rope_table(ids)
+    assert torch.equal(tab[..., 0], cos[:, 0::2]) and torch.equal(tab[..., 1], sin[:, 0::2])

@@ -120,12 +120,77 @@ def full_width_block():
     return r
 
 
+def flux_step_parity(H=2, L=2, Ls=2, J=64, Pp=64, B=2, hw=4, T=8, r=4,
+                     targets=("to_q", "to_k", "to_v", "to_out.0"), guidance=True):
+    """FLUX-Kontext shared-resolution recipe (flux_kontext_trainer.py:494-577) vs the oracle."""
+    from oracle import mmdit_oracle as mo
+    from qflux_b200.flux_model import FluxB200, FluxB200Config
+    from qflux_b200.train_step import FluxKontextStep
+    kw = dict(num_layers=L, num_single_layers=Ls, attention_head_dim=128, num_attention_heads=H, joint_attention_dim=J,
+              pooled_projection_dim=Pp, guidance_embeds=guidance)
+    orc = mo.init_synthetic_(mo.FluxOracle(mo.FluxConfig(**kw)), std=0.05 if H < 8 else 0.02)
+    g = torch.Generator().manual_seed(98)
+    with torch.no_grad():
+        for n, p in orc.named_parameters():
+            if n.endswith("bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+            elif p.ndim == 1:
+                p.copy_(1 + torch.randn(p.shape, generator=g) * 0.1)
+    mo.add_lora_adapter(orc, r=r, alpha=r, target_modules=targets, b_std=0.05)
+    orc = orc.cuda()
+    with torch.no_grad():
+        for p in orc.parameters():
+            p.copy_(p.bfloat16().float())
+    m = FluxB200(FluxB200Config(**kw)).add_adapter(r, r, target_modules=targets)
+    missing, unexpected = m.load_state_dict(orc.state_dict(), strict=True)
+    assert not missing and not unexpected
+    gg = torch.Generator(device="cuda").manual_seed(3)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=gg).bfloat16()
+    Lt = hw * hw
+    emb = dict(image_latents=rn(B, Lt, 64), control_latents=rn(B, Lt, 64), pooled_prompt_embeds=rn(B, Pp), prompt_embeds=rn(B, T, J),
+               text_ids=torch.zeros(T, 3, device="cuda"), image_ids=FluxKontextStep.latent_image_ids(hw, hw, "cuda", 0.0),
+               control_ids=FluxKontextStep.latent_image_ids(hw, hw, "cuda", 1.0))
+    noise, t = rn(B, Lt, 64), torch.tensor([0.5, 0.25, 0.75, 0.125][:B], device="cuda")
+    f = lambda k: emb[k].float()
+    loss_o, pred_o = mo.flux_compute_loss_shared(orc, f("image_latents"), f("control_latents"), f("pooled_prompt_embeds"),
+                                                 f("prompt_embeds"), emb["text_ids"], emb["image_ids"], emb["control_ids"],
+                                                 noise=noise.float(), t=t)
+    loss_o.backward()
+    g_o = {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in orc.named_parameters() if p.requires_grad}
+    step = FluxKontextStep(m)
+    loss_b = step.compute_loss(emb, noise=noise, t=t)
+    pred_b = m._ws["pred"].view(B, -1, 64)[:, :Lt].float().clone()
+    loss_b.backward()
+    torch.cuda.synchronize()
+    res = dict(pred_vs_fp32=rel_l2(pred_b, pred_o), loss=loss_o.item(), loss_abs=abs(loss_b.item() - loss_o.item()))
+    res["loss_rel"] = res["loss_abs"] / max(1.0, abs(loss_o.item()))
+    gb = {n: p.grad.float() for n, p in m.named_parameters()}
+    num = sum(((gb[n] - g_o[n]).double() ** 2).sum() for n in g_o)
+    den = sum((g_o[n].double() ** 2).sum() for n in g_o)
+    res["grad_vs_fp32"] = float((num / den).sqrt())
+    step.train_step(emb, noise=noise, t=t)
+    gv = m.lora_grad_views()
+    res["fast_vs_autograd"] = max(rel_l2(gv[n], gb[n]) for n in gb if gb[n].abs().max() > 0)
+    orc.zero_grad()
+    orc16 = orc.bfloat16()
+    _, pred_h = mo.flux_compute_loss_shared(orc16, emb["image_latents"], emb["control_latents"], emb["pooled_prompt_embeds"],
+                                            emb["prompt_embeds"], emb["text_ids"], emb["image_ids"], emb["control_ids"], noise=noise,
+                                            t=t.bfloat16())
+    res["bf16oracle_pred_vs_fp32"] = rel_l2(pred_h.float(), pred_o)
+    res["err"] = max(res["pred_vs_fp32"], res["grad_vs_fp32"])
+    return res
+
+
 CASES = {
     "inference_tiny": inference_parity,
     "step_tiny": lambda: step_parity(),
     "step_tiny_nolora_targets_all_attn": lambda: step_parity(targets=("to_q", "to_k", "to_v", "to_out.0", "add_q_proj", "add_k_proj", "add_v_proj", "to_add_out", "net.0.proj"), r=8),
     "step_mid": lambda: step_parity(H=4, L=3, J=256, B=2, hw=16, T=40, r=16),
     "step_full_width_1blk": full_width_block,
+    "flux_tiny": lambda: flux_step_parity(),
+    "flux_tiny_regex_noguidance": lambda: flux_step_parity(guidance=False, r=8,
+                                                           targets=r".*(attn\.(to_[qkv]|add_[qkv]_proj|to_add_out)|proj_mlp|ff\.net\.0\.proj)"),
+    "flux_full_width_1p1": lambda: flux_step_parity(H=24, L=1, Ls=1, J=4096, Pp=768, B=1, hw=32, T=512, r=16),
 }
 
 if __name__ == "__main__":
