@@ -154,14 +154,23 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
           tmem_ld32(tdP + lane_off + c, rp);
           tmem_ld_wait();
           uint32_t pk[16], dk[16];
+          const float dls = dl * P.scale;
+          if (valid >= 128) {  // warp-uniform fast path: no key masking
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            float p0 = (c + 2 * e < valid) ? exp2f(__uint_as_float(rs[2 * e]) * P.scale_log2 - L) : 0.f;
-            float p1 = (c + 2 * e + 1 < valid) ? exp2f(__uint_as_float(rs[2 * e + 1]) * P.scale_log2 - L) : 0.f;
-            float d0 = p0 * (__uint_as_float(rp[2 * e]) - dl) * P.scale;
-            float d1 = p1 * (__uint_as_float(rp[2 * e + 1]) - dl) * P.scale;
-            pk[e] = pack_bf16(p0, p1);
-            dk[e] = pack_bf16(d0, d1);
+            for (int e = 0; e < 16; ++e) {
+              const float p0 = exp2f(__uint_as_float(rs[2 * e]) * P.scale_log2 - L);
+              const float p1 = exp2f(__uint_as_float(rs[2 * e + 1]) * P.scale_log2 - L);
+              pk[e] = pack_bf16(p0, p1);
+              dk[e] = pack_bf16(p0 * (__uint_as_float(rp[2 * e]) * P.scale - dls), p1 * (__uint_as_float(rp[2 * e + 1]) * P.scale - dls));
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float p0 = (c + 2 * e < valid) ? exp2f(__uint_as_float(rs[2 * e]) * P.scale_log2 - L) : 0.f;
+              const float p1 = (c + 2 * e + 1 < valid) ? exp2f(__uint_as_float(rs[2 * e + 1]) * P.scale_log2 - L) : 0.f;
+              pk[e] = pack_bf16(p0, p1);
+              dk[e] = pack_bf16(p0 * (__uint_as_float(rp[2 * e]) * P.scale - dls), p1 * (__uint_as_float(rp[2 * e + 1]) * P.scale - dls));
+            }
           }
           const uint32_t off = (uint32_t)row * 128 + (c >> 6) * BW_ATOM;
 #pragma unroll

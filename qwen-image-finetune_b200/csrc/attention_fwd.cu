@@ -158,14 +158,20 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
       tc_fence_after();
       const uint32_t tS = tS0 + s * 128 + lane_off + c0;
       float mx = -INFINITY;
+      const bool full_tile = valid >= ATT_BK;  // warp-uniform: no key masking needed (all tiles but the last)
 #pragma unroll 1
       for (int c = 0; c < 64; c += 32) {
         uint32_t r[32];
         tmem_ld32(tS + c, r);
         tmem_ld_wait();
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c0 + c + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + c + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
       }
       red[(s * 2 + half) * 128 + row] = mx;
       pair_sync();
@@ -201,13 +207,22 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
         tmem_ld32(tS + c, r);
         tmem_ld_wait();
         uint32_t pk[16];
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = (c0 + c + 2 * i < valid) ? exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used) : 0.f;
-          float p1 = (c0 + c + 2 * i + 1 < valid) ? exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used) : 0.f;
-          pk[i] = pack_bf16(p0, p1);
-          // the row sum uses the bf16-rounded probabilities, i.e. exactly what the tensor core multiplies with V
-          lsum += bf16_lo(pk[i]) + bf16_hi(pk[i]);
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used);
+            const float p1 = exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used);
+            pk[i] = pack_bf16(p0, p1);
+            lsum += p0 + p1;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = (c0 + c + 2 * i < valid) ? exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used) : 0.f;
+            const float p1 = (c0 + c + 2 * i + 1 < valid) ? exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used) : 0.f;
+            pk[i] = pack_bf16(p0, p1);
+            lsum += p0 + p1;
+          }
         }
 #pragma unroll
         for (int v = 0; v < 4; ++v) {

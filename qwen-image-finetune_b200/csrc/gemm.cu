@@ -48,6 +48,108 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// Epilogue of one [128 x BN] accumulator tile: thread = output row (TMEM lane), 32 columns per tcgen05.ld.
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmProb& q, const GemmParams& P, uint32_t t_row, int row, bool row_ok, int n0) {
+    const bf16* gate_row = nullptr;
+    if (EPI == QFX_EPI_RESID_GATE && row_ok) gate_row = q.gate + (int64_t)(row / q.rows_per_batch) * q.ldg;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(t_row + c, r);
+      tmem_ld_wait();
+      const int n = n0 + c;
+      uint32_t o[16];
+      uint4 bias4[4];
+      if (q.bias != nullptr) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) bias4[v] = __ldg(reinterpret_cast<const uint4*>(q.bias + n) + v);
+      } else {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) bias4[v] = make_uint4(0, 0, 0, 0);
+      }
+      const uint32_t* bw = reinterpret_cast<const uint32_t*>(bias4);
+      if (EPI == QFX_EPI_BIAS) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float v0 = __uint_as_float(r[2 * i]) * P.alpha + bf16_lo(bw[i]);
+          float v1 = __uint_as_float(r[2 * i + 1]) * P.alpha + bf16_hi(bw[i]);
+          o[i] = pack_bf16(v0, v1);
+        }
+      } else if (EPI == QFX_EPI_GELU) {
+        uint32_t u[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          u[i] = pack_bf16(__uint_as_float(r[2 * i]) + bf16_lo(bw[i]), __uint_as_float(r[2 * i + 1]) + bf16_hi(bw[i]));
+          o[i] = pack_bf16(gelu_tanh(bf16_lo(u[i])), gelu_tanh(bf16_hi(u[i])));
+        }
+        if (row_ok) {
+          uint4* dst2 = reinterpret_cast<uint4*>(q.out2 + (int64_t)row * q.ldo2 + n);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) dst2[v] = make_uint4(u[4 * v], u[4 * v + 1], u[4 * v + 2], u[4 * v + 3]);
+        }
+      } else if (EPI == QFX_EPI_RESID_GATE) {
+        if (row_ok) {
+          const uint4* rs = reinterpret_cast<const uint4*>(q.resid + (int64_t)row * q.ldr + n);
+          const uint4* gs = reinterpret_cast<const uint4*>(gate_row + n);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint4 rr = rs[v];
+            uint4 gg = __ldg(gs + v);
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rr);
+            const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gg);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * v + e;
+              // eager bf16 rounding points of the reference: y=Linear(x) -> gate*y -> resid + (.)
+              float y0 = round_bf16(__uint_as_float(r[2 * i]) + bf16_lo(bw[i]));
+              float y1 = round_bf16(__uint_as_float(r[2 * i + 1]) + bf16_hi(bw[i]));
+              float z0 = round_bf16(bf16_lo(gw[e]) * y0);
+              float z1 = round_bf16(bf16_hi(gw[e]) * y1);
+              o[i] = pack_bf16(bf16_lo(rw[e]) + z0, bf16_hi(rw[e]) + z1);
+            }
+          }
+        }
+      } else if (EPI == QFX_EPI_ADD) {
+        if (row_ok) {
+          const uint4* rs = reinterpret_cast<const uint4*>(q.resid + (int64_t)row * q.ldr + n);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint4 rr = rs[v];
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rr);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * v + e;
+              o[i] = pack_bf16(bf16_lo(rw[e]) + round_bf16(__uint_as_float(r[2 * i]) * P.alpha),
+                               bf16_hi(rw[e]) + round_bf16(__uint_as_float(r[2 * i + 1]) * P.alpha));
+            }
+          }
+        }
+      } else if (EPI == QFX_EPI_DGELU) {
+        if (row_ok) {
+          const uint4* us = reinterpret_cast<const uint4*>(q.aux + (int64_t)row * q.ldaux + n);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint4 uu = us[v];
+            const uint32_t* uw = reinterpret_cast<const uint32_t*>(&uu);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * v + e;
+              float g0 = round_bf16(__uint_as_float(r[2 * i]) * P.alpha);
+              float g1 = round_bf16(__uint_as_float(r[2 * i + 1]) * P.alpha);
+              o[i] = pack_bf16(g0 * gelu_tanh_grad(bf16_lo(uw[e])), g1 * gelu_tanh_grad(bf16_hi(uw[e])));
+            }
+          }
+        }
+      }
+      if (row_ok) {
+        uint4* dst = reinterpret_cast<uint4*>(q.out + (int64_t)row * q.ldo + n);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) dst[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+      }
+    }
+}
+
 template <int BN, bool TRANS_B, int EPI>
 __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ GemmParams P) {
   using C = GemmCfg<BN>;
@@ -187,103 +289,7 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
       const int row = m0 + q4 * 32 + lane;
       const bool row_ok = row < q.M;
       const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * BN;
-      const bf16* gate_row = nullptr;
-      if (EPI == QFX_EPI_RESID_GATE && row_ok) gate_row = q.gate + (int64_t)(row / q.rows_per_batch) * q.ldg;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_row + c, r);
-        tmem_ld_wait();
-        const int n = n0 + c;
-        uint32_t o[16];
-        uint4 bias4[4];
-        if (q.bias != nullptr) {
-#pragma unroll
-          for (int v = 0; v < 4; ++v) bias4[v] = __ldg(reinterpret_cast<const uint4*>(q.bias + n) + v);
-        } else {
-#pragma unroll
-          for (int v = 0; v < 4; ++v) bias4[v] = make_uint4(0, 0, 0, 0);
-        }
-        const uint32_t* bw = reinterpret_cast<const uint32_t*>(bias4);
-        if (EPI == QFX_EPI_BIAS) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float v0 = __uint_as_float(r[2 * i]) * P.alpha + bf16_lo(bw[i]);
-            float v1 = __uint_as_float(r[2 * i + 1]) * P.alpha + bf16_hi(bw[i]);
-            o[i] = pack_bf16(v0, v1);
-          }
-        } else if (EPI == QFX_EPI_GELU) {
-          uint32_t u[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            u[i] = pack_bf16(__uint_as_float(r[2 * i]) + bf16_lo(bw[i]), __uint_as_float(r[2 * i + 1]) + bf16_hi(bw[i]));
-            o[i] = pack_bf16(gelu_tanh(bf16_lo(u[i])), gelu_tanh(bf16_hi(u[i])));
-          }
-          if (row_ok) {
-            uint4* dst2 = reinterpret_cast<uint4*>(q.out2 + (int64_t)row * q.ldo2 + n);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) dst2[v] = make_uint4(u[4 * v], u[4 * v + 1], u[4 * v + 2], u[4 * v + 3]);
-          }
-        } else if (EPI == QFX_EPI_RESID_GATE) {
-          if (row_ok) {
-            const uint4* rs = reinterpret_cast<const uint4*>(q.resid + (int64_t)row * q.ldr + n);
-            const uint4* gs = reinterpret_cast<const uint4*>(gate_row + n);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              uint4 rr = rs[v];
-              uint4 gg = __ldg(gs + v);
-              const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rr);
-              const uint32_t* gw = reinterpret_cast<const uint32_t*>(&gg);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int i = 4 * v + e;
-                // eager bf16 rounding points of the reference: y=Linear(x) -> gate*y -> resid + (.)
-                float y0 = round_bf16(__uint_as_float(r[2 * i]) + bf16_lo(bw[i]));
-                float y1 = round_bf16(__uint_as_float(r[2 * i + 1]) + bf16_hi(bw[i]));
-                float z0 = round_bf16(bf16_lo(gw[e]) * y0);
-                float z1 = round_bf16(bf16_hi(gw[e]) * y1);
-                o[i] = pack_bf16(bf16_lo(rw[e]) + z0, bf16_hi(rw[e]) + z1);
-              }
-            }
-          }
-        } else if (EPI == QFX_EPI_ADD) {
-          if (row_ok) {
-            const uint4* rs = reinterpret_cast<const uint4*>(q.resid + (int64_t)row * q.ldr + n);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              uint4 rr = rs[v];
-              const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rr);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int i = 4 * v + e;
-                o[i] = pack_bf16(bf16_lo(rw[e]) + round_bf16(__uint_as_float(r[2 * i]) * P.alpha),
-                                 bf16_hi(rw[e]) + round_bf16(__uint_as_float(r[2 * i + 1]) * P.alpha));
-              }
-            }
-          }
-        } else if (EPI == QFX_EPI_DGELU) {
-          if (row_ok) {
-            const uint4* us = reinterpret_cast<const uint4*>(q.aux + (int64_t)row * q.ldaux + n);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              uint4 uu = us[v];
-              const uint32_t* uw = reinterpret_cast<const uint32_t*>(&uu);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int i = 4 * v + e;
-                float g0 = round_bf16(__uint_as_float(r[2 * i]) * P.alpha);
-                float g1 = round_bf16(__uint_as_float(r[2 * i + 1]) * P.alpha);
-                o[i] = pack_bf16(g0 * gelu_tanh_grad(bf16_lo(uw[e])), g1 * gelu_tanh_grad(bf16_hi(uw[e])));
-              }
-            }
-          }
-        }
-        if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(q.out + (int64_t)row * q.ldo + n);
-#pragma unroll
-          for (int v = 0; v < 4; ++v) dst[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
-        }
-      }
+      epilogue_tile<BN, EPI>(q, P, t_row, row, row_ok, n0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -295,6 +301,171 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// =====================================================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x BN tile.  Each CTA stages its own 128 rows of A and
+// HALF of the B tile, so per-SM shared-memory traffic drops by a third and the ring holds 6 stages instead of 4 for the
+// same 192 KB; the leader CTA issues tcgen05.mma.cta_group::2 (M = 256), completion is multicast to both CTAs' barriers.
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 6 : 8;
+  static constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN, bool TRANS_B, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm2_kernel(const __grid_constant__ GemmParams P) {
+  using C = Gemm2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 2);   // leader: own arrive.expect_tx + the peer's remote arrive
+      mbar_init(empty_bar(s), 1);  // multicast tcgen05.commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);   // multicast tcgen05.commit
+      mbar_init(tempty_bar(s), 8);  // leader: 4 epilogue warps of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int nkb = P.K / BK;
+  auto decode = [&](int tile, int& prob, int& m0, int& n0) {  // tiles are 256 rows tall here
+    int n_blk = tile / P.tiles_m_total;
+    int mm = tile - n_blk * P.tiles_m_total;
+    prob = mm >= P.tiles_m0 ? 1 : 0;
+    m0 = (prob ? mm - P.tiles_m0 : mm) * 256 + (int)rank * BM;
+    n0 = n_blk * BN;
+  };
+
+  if (warp == 0) {
+    // =============================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < P.total_tiles; tile += n_clusters) {
+        int prob, m0, n0;
+        decode(tile, prob, m0, n0);
+        const GemmProb& q = P.p[prob];
+        const int kb_total = nkb + q.kb2;
+        const int grp = (!TRANS_B && P.lora_group_n > 0) ? n0 / P.lora_group_n : 0;
+        const int nh = n0 + (int)rank * (BN / 2);  // this CTA's half of the B columns
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + C::A_BYTES;
+          const uint32_t fb = full_bar(stage);
+          if (leader) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);
+          else mbar_arrive_remote(fb, 0);
+          if (kb < nkb) {
+            tma_load_2d_2sm(a_dst, &q.tmA, fb, kb * BK, m0);
+            if (!TRANS_B) {
+              tma_load_2d_2sm(b_dst, &q.tmB, fb, kb * BK, nh);
+            } else {
+#pragma unroll
+              for (int a = 0; a < BN / 128; ++a) tma_load_2d_2sm(b_dst + a * 8192, &q.tmB, fb, nh + a * 64, kb * BK);
+            }
+          } else {
+            const int j = kb - nkb;
+            tma_load_2d_2sm(a_dst, &q.tmA2, fb, q.a2_col0 + (grp * q.kb2 + j) * 64, m0);
+            if (!TRANS_B) {
+              tma_load_2d_2sm(b_dst, &q.tmB2, fb, j * 64, nh);
+            } else {
+#pragma unroll
+              for (int a = 0; a < BN / 128; ++a) tma_load_2d_2sm(b_dst + a * 8192, &q.tmB2, fb, nh + a * 64, j * 64);
+            }
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================================================== MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = idesc_bf16(256, BN, 0, TRANS_B ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < P.total_tiles; tile += n_clusters, ++it) {
+        int prob, m0, n0;
+        decode(tile, prob, m0, n0);
+        const int kb_total = nkb + P.p[prob].kb2;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = sdesc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = TRANS_B ? sdesc_sw128(b_addr + k * 2048, 8192, 1024) : sdesc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb | k) != 0);
+          }
+          umma_commit_2sm(empty_bar(stage), 3);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(tfull_bar(acc), 3);
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================================================== epilogue (both CTAs, own 128 rows)
+    const int q4 = warp & 3;
+    int it = 0;
+    for (int tile = cluster_id; tile < P.total_tiles; tile += n_clusters, ++it) {
+      int prob, m0, n0;
+      decode(tile, prob, m0, n0);
+      const GemmProb& q = P.p[prob];
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m0 + q4 * 32 + lane;
+      const bool row_ok = row < q.M;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * BN;
+      epilogue_tile<BN, EPI>(q, P, t_row, row, row_ok, n0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_remote(tempty_bar(acc), 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -320,6 +491,41 @@ static int launch(const GemmParams& P, cudaStream_t stream) {
   kern<<<grid, 256, C::SMEM_BYTES, stream>>>(P);
   QFX_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int BN, bool TRANS_B, int EPI>
+static int launch2(const GemmParams& P, cudaStream_t stream) {
+  using C = Gemm2Cfg<BN>;
+  auto kern = gemm2_kernel<BN, TRANS_B, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    QFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  int clusters = num_sms() / 2;
+  if (P.total_tiles < clusters) clusters = P.total_tiles;
+  kern<<<2 * clusters, 256, C::SMEM_BYTES, stream>>>(P);
+  QFX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int dispatch2(const GemmParams& P, int trans_b, int epi, cudaStream_t s) {
+  if (!trans_b) {
+    switch (epi) {
+      case QFX_EPI_BIAS: return launch2<BN, false, QFX_EPI_BIAS>(P, s);
+      case QFX_EPI_GELU: return launch2<BN, false, QFX_EPI_GELU>(P, s);
+      case QFX_EPI_RESID_GATE: return launch2<BN, false, QFX_EPI_RESID_GATE>(P, s);
+    }
+  } else {
+    switch (epi) {
+      case QFX_EPI_BIAS: return launch2<BN, true, QFX_EPI_BIAS>(P, s);
+      case QFX_EPI_DGELU: return launch2<BN, true, QFX_EPI_DGELU>(P, s);
+      case QFX_EPI_ADD: return launch2<BN, true, QFX_EPI_ADD>(P, s);
+    }
+  }
+  set_error("qfx_gemm_bf16: unsupported (trans_b=%d, epilogue=%d)", trans_b, epi);
+  return -1;
 }
 
 template <int BN>
@@ -349,9 +555,12 @@ extern "C" int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, in
                              int lora_group_n, int block_n, void* stream) {
   QFX_CHECK_ARG(nprob >= 1 && nprob <= QFX_MAX_PROBLEMS, "qfx_gemm_bf16: nprob=%d", nprob);
   QFX_CHECK_ARG(K > 0 && K % BK == 0, "qfx_gemm_bf16: K=%d must be a positive multiple of 64", K);
+  const bool two_cta = block_n >= 1000;  // block_n = 1000 + {128, 256}: CTA-pair (cta_group::2) kernel, 256-row tiles
+  if (two_cta) block_n -= 1000;
   int bn = block_n;
   if (bn == 0) bn = N % 256 == 0 ? 256 : N % 192 == 0 ? 192 : N % 128 == 0 ? 128 : 64;
   QFX_CHECK_ARG((bn == 64 || bn == 128 || bn == 192 || bn == 256) && N % bn == 0, "qfx_gemm_bf16: N=%d block_n=%d", N, bn);
+  QFX_CHECK_ARG(!two_cta || bn == 128 || bn == 256, "qfx_gemm_bf16: the 2-CTA kernel takes block_n 128 or 256");
   QFX_CHECK_ARG(!(trans_b && lora_group_n), "qfx_gemm_bf16: lora_group_n only with trans_b=0");
   QFX_CHECK_ARG(lora_group_n == 0 || lora_group_n % bn == 0, "qfx_gemm_bf16: lora_group_n %% block_n != 0");
 
@@ -372,7 +581,7 @@ extern "C" int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, in
     int rc = make_2d(&d.tmA, s.A, (uint64_t)K, (uint64_t)s.M, s.lda, BK, BM);
     if (rc) return rc;
     if (!trans_b)
-      rc = make_2d(&d.tmB, s.B, (uint64_t)K, (uint64_t)N, s.ldb, BK, (uint32_t)bn);
+      rc = make_2d(&d.tmB, s.B, (uint64_t)K, (uint64_t)N, s.ldb, BK, (uint32_t)(two_cta ? bn / 2 : bn));
     else
       rc = make_2d(&d.tmB, s.B, (uint64_t)N, (uint64_t)K, s.ldb, 64, BK);
     if (rc) return rc;
@@ -384,7 +593,7 @@ extern "C" int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, in
       rc = make_2d(&d.tmA2, s.A2, (uint64_t)(s.a2_col0 + 64 * s.kb2 * groups), (uint64_t)s.M, s.lda2, BK, BM);
       if (rc) return rc;
       if (!trans_b)
-        rc = make_2d(&d.tmB2, s.B2, (uint64_t)(64 * s.kb2), (uint64_t)N, s.ldb2, BK, (uint32_t)bn);
+        rc = make_2d(&d.tmB2, s.B2, (uint64_t)(64 * s.kb2), (uint64_t)N, s.ldb2, BK, (uint32_t)(two_cta ? bn / 2 : bn));
       else
         rc = make_2d(&d.tmB2, s.B2, (uint64_t)N, (uint64_t)(64 * s.kb2), s.ldb2, 64, BK);
       if (rc) return rc;
@@ -402,13 +611,14 @@ extern "C" int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, in
     if (epilogue == QFX_EPI_RESID_GATE) QFX_CHECK_ARG(s.resid && s.gate && s.ldr % 8 == 0 && s.ldg % 8 == 0, "qfx_gemm_bf16: RESID_GATE epilogue needs resid+gate");
     if (epilogue == QFX_EPI_ADD) QFX_CHECK_ARG(s.resid && s.ldr % 8 == 0, "qfx_gemm_bf16: ADD epilogue needs resid");
     if (epilogue == QFX_EPI_DGELU) QFX_CHECK_ARG(s.aux && s.ldaux % 8 == 0, "qfx_gemm_bf16: DGELU epilogue needs aux");
-    int tm = (s.M + BM - 1) / BM;
+    int tm = two_cta ? (s.M + 255) / 256 : (s.M + BM - 1) / BM;
     if (i == 0) P.tiles_m0 = tm;
     tiles_m_total += tm;
   }
   P.tiles_m_total = tiles_m_total;
   P.total_tiles = tiles_m_total * P.tiles_n;
   cudaStream_t st = (cudaStream_t)stream;
+  if (two_cta) return bn == 128 ? dispatch2<128>(P, trans_b, epilogue, st) : dispatch2<256>(P, trans_b, epilogue, st);
   switch (bn) {
     case 64: return dispatch<64>(P, trans_b, epilogue, st);
     case 128: return dispatch<128>(P, trans_b, epilogue, st);

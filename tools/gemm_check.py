@@ -128,6 +128,19 @@ CASES = {}
 for bn in (64, 128, 192, 256):
     CASES[f"basic_nt_bn{bn}"] = (lambda bn=bn: basic(False, bn))
     CASES[f"basic_nn_bn{bn}"] = (lambda bn=bn: basic(True, bn))
+for bn in (1128, 1256):
+    CASES[f"cta2_basic_nt_bn{bn}"] = (lambda bn=bn: basic(False, bn, M=700, N=768, K=512))
+    CASES[f"cta2_basic_nn_bn{bn}"] = (lambda bn=bn: basic(True, bn, M=700, N=768, K=512))
+    CASES[f"cta2_lora_nt_bn{bn}"] = (lambda bn=bn: lora(False, bn, N=768, groups=3))
+    CASES[f"cta2_lora_nn_bn{bn}"] = (lambda bn=bn: lora(True, bn, kb2=3))
+CASES["cta2_epilogues"] = lambda: epilogues(1256)
+CASES["cta2_grouped_nt"] = lambda: grouped(False, 1256)
+CASES["cta2_grouped_nn"] = lambda: grouped(True, 1128)
+CASES["cta2_perf_nt"] = lambda: perf(False, 1256)
+CASES["cta2_perf_nn"] = lambda: perf(True, 1256)
+CASES["cta2_perf_nt_mlp_up"] = lambda: perf(False, 1256, N=12288, K=3072)
+CASES["cta2_perf_nt_mlp_down"] = lambda: perf(False, 1256, N=3072, K=12288)
+CASES["cta2_perf_nn_mlp_down"] = lambda: perf(True, 1256, N=12288, K=3072)
 CASES["basic_nt_alpha_nobias"] = lambda: basic(False, 0, M=128, N=64, K=64, bias=False, alpha=0.5)
 CASES["basic_nt_big"] = lambda: basic(False, 0, M=2400, N=3072, K=3072)
 CASES["basic_nn_big"] = lambda: basic(True, 0, M=2400, N=3072, K=12288)
