@@ -70,16 +70,19 @@ int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, int K, int tr
 /* ------------------------------------------------------------------------------------------------------------------
  * Joint text+image attention (head_dim 128), tcgen05.  Q/K/V/dO/dK/dV: [B, H, S, 128] bf16 head-major, text positions
  * first.  Replaces dispatch_attention_fn -> F.scaled_dot_product_attention on the concatenated sequence and its autograd
- * backward (transformer_qwenimage.py:322-345; transformer_flux.py:149-156).  kv_len (int32 [B], may be NULL) masks keys
- * >= kv_len[b] (pad-to-max multi-resolution batches: transformer_qwen_custom.py:444-553).
+ * backward (transformer_qwenimage.py:322-345; transformer_flux.py:149-156).  Pad-to-max multi-resolution batches
+ * (transformer_qwen_custom.py:444-553, transformer_flux_custom.py:607-616): kv_len (int32 [B], may be NULL) masks keys
+ * >= kv_len[b]; txt_len (int32 [B], may be NULL) additionally masks the text padding, keys in [txt_len[b], split).
  * Forward writes O token-major into two row groups: rows with joint position s < split of sample b go to
  * out0[(b*rows0 + s)*ld0 + h*128 ..], the others to out1[(b*rows1 + s - split)*ld1 + h*128 ..]; lse is the log2-domain
  * log-sum-exp [B,H,S].  Backward: dQ_accum is fp32 [B,H,S,128], zeroed by the caller (target of TMA reduce-adds);
  * delta = rowsum(dO * O) [B,H,S]. */
 int qfx_attn_fwd(const void* Q, const void* K, const void* V, void* out0, int64_t ld0, int rows0, void* out1, int64_t ld1,
-                 int rows1, int split, float* lse, const int* kv_len, int B, int H, int S, float softmax_scale, void* stream);
+                 int rows1, int split, float* lse, const int* kv_len, const int* txt_len, int B, int H, int S,
+                 float softmax_scale, void* stream);
 int qfx_attn_bwd(const void* Q, const void* K, const void* V, const void* dO, const float* lse, const float* delta,
-                 float* dQ_accum, void* dK, void* dV, const int* kv_len, int B, int H, int S, float softmax_scale, void* stream);
+                 float* dQ_accum, void* dK, void* dV, const int* kv_len, const int* txt_len, int split, int B, int H, int S,
+                 float softmax_scale, void* stream);
 /* delta[b,h,s] = sum_d O*dO from token-major rows (tokens_per_sample rows per sample at joint offset s_offset);
  * optionally scatters dO into the head-major layout the backward kernel loads with TMA. */
 int qfx_attn_delta(const void* O, int64_t ldo, const void* dO, int64_t lddo, float* delta, void* dO_joint, int tokens,

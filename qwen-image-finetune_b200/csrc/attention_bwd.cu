@@ -31,7 +31,9 @@ struct AttnBwdParams {
   bf16* dV;             // [B*H, S, 128]
   const float* lse;     // [B*H, S] log2 domain
   const float* delta;   // [B*H, S]
-  const int* kv_len;    // [B] or NULL
+  const int* kv_len;    // [B] or NULL: keys >= kv_len[b] masked
+  const int* txt_len;   // [B] or NULL: keys in [txt_len[b], split) masked (text padding)
+  int split;
   int S, H;
   float scale, scale_log2;
 };
@@ -61,7 +63,9 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
   const int b = bh / P.H;
   const int kv_len = P.kv_len ? P.kv_len[b] : P.S;
   const int n_q = (P.S + 127) / 128;
-  const bool active = kv0 < kv_len;  // a fully masked key tile contributes nothing: write zeros and leave
+  const int txt_len = P.txt_len ? P.txt_len[b] : P.split;
+  // a fully masked key tile (beyond kv_len, or entirely inside the text padding) contributes nothing: write zeros and leave
+  const bool active = kv0 < kv_len && !(kv0 >= txt_len && kv0 + 128 <= P.split);
 
   if (warp == 1 && lane == 0) {
     mbar_init(kv_full, 1);
@@ -140,6 +144,8 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
     const int tid = threadIdx.x - 64;  // 0..255
     if (active) {
       const int valid = kv_len - kv0;  // key columns >= valid are masked
+      const int gap0 = txt_len - kv0, gap1 = P.split - kv0;  // tile-local text-padding columns [gap0, gap1)
+      const bool full_tile = valid >= 128 && (gap0 >= gap1 || gap0 >= 128 || gap1 <= 0);
       for (int i = 0; i < n_q; ++i) {
         const int q = i * 128 + row;
         const bool q_ok = q < P.S;
@@ -155,7 +161,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
           tmem_ld_wait();
           uint32_t pk[16], dk[16];
           const float dls = dl * P.scale;
-          if (valid >= 128) {  // warp-uniform fast path: no key masking
+          if (full_tile) {  // warp-uniform fast path: no key masking
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               const float p0 = exp2f(__uint_as_float(rs[2 * e]) * P.scale_log2 - L);
@@ -166,8 +172,9 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
           } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-              const float p0 = (c + 2 * e < valid) ? exp2f(__uint_as_float(rs[2 * e]) * P.scale_log2 - L) : 0.f;
-              const float p1 = (c + 2 * e + 1 < valid) ? exp2f(__uint_as_float(rs[2 * e + 1]) * P.scale_log2 - L) : 0.f;
+              const int k0 = c + 2 * e, k1 = k0 + 1;
+              const float p0 = (k0 < valid && !(k0 >= gap0 && k0 < gap1)) ? exp2f(__uint_as_float(rs[2 * e]) * P.scale_log2 - L) : 0.f;
+              const float p1 = (k1 < valid && !(k1 >= gap0 && k1 < gap1)) ? exp2f(__uint_as_float(rs[2 * e + 1]) * P.scale_log2 - L) : 0.f;
               pk[e] = pack_bf16(p0, p1);
               dk[e] = pack_bf16(p0 * (__uint_as_float(rp[2 * e]) * P.scale - dls), p1 * (__uint_as_float(rp[2 * e + 1]) * P.scale - dls));
             }
@@ -267,8 +274,8 @@ using namespace qfx;
 /* All of Q, K, V, dO, dK, dV: [B, H, S, 128] bf16; dQ_accum: [B, H, S, 128] fp32, MUST be zeroed by the caller (it is the
  * target of TMA reduce-adds from every key tile).  lse: log2-domain logsumexp from qfx_attn_fwd; delta = rowsum(dO*O). */
 extern "C" int qfx_attn_bwd(const void* Q, const void* K, const void* V, const void* dO, const float* lse, const float* delta,
-                            float* dQ_accum, void* dK, void* dV, const int* kv_len, int B, int H, int S, float softmax_scale,
-                            void* stream) {
+                            float* dQ_accum, void* dK, void* dV, const int* kv_len, const int* txt_len, int split, int B, int H,
+                            int S, float softmax_scale, void* stream) {
   QFX_CHECK_ARG(B > 0 && H > 0 && S > 0 && dQ_accum && dK && dV && lse && delta, "qfx_attn_bwd: bad arguments");
   AttnBwdParams P;
   memset(&P, 0, sizeof(P));
@@ -283,7 +290,7 @@ extern "C" int qfx_attn_bwd(const void* Q, const void* K, const void* V, const v
     uint32_t box[3] = {32, 128, 1};
     if ((rc = make_tmap_f32(&P.tmdQ, dQ_accum, 3, dims, strides, box))) return rc;
   }
-  P.dK = (bf16*)dK; P.dV = (bf16*)dV; P.lse = lse; P.delta = delta; P.kv_len = kv_len; P.S = S; P.H = H;
+  P.dK = (bf16*)dK; P.dV = (bf16*)dV; P.lse = lse; P.delta = delta; P.kv_len = kv_len; P.txt_len = txt_len; P.split = txt_len ? split : 0; P.S = S; P.H = H;
   P.scale = softmax_scale;
   P.scale_log2 = softmax_scale * 1.4426950408889634f;
   static bool attr_done = false;

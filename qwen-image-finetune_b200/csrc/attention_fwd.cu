@@ -32,7 +32,8 @@ struct AttnFwdParams {
   int64_t ld0, ld1;
   int rows0, rows1, split;
   float* lse;          // [B*H, S] log2-domain logsumexp:  m + log2(l)
-  const int* kv_len;   // [B] valid joint length per sample (NULL: S)
+  const int* kv_len;   // [B] end of the valid joint sequence per sample (NULL: S): keys >= kv_len[b] are masked
+  const int* txt_len;  // [B] valid text tokens per sample (NULL: split): keys in [txt_len[b], split) are masked too
   int S, H;
   float scale_log2;    // (1/sqrt(d)) * log2(e)
 };
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
   const int bh = blockIdx.y;
   const int b = bh / P.H, h = bh - b * P.H;
   const int kv_len = P.kv_len ? P.kv_len[b] : P.S;
+  const int txt_len = P.txt_len ? P.txt_len[b] : P.split;  // >= 1; keys [txt_len, split) are text padding
   const int n_tiles = (kv_len + ATT_BK - 1) / ATT_BK;
 
   if (warp == 1 && lane == 0) {
@@ -154,11 +156,13 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
     for (int j = 0; j < n_tiles; ++j) {
       const int s = j & 1;
       const int valid = kv_len - j * ATT_BK;  // columns >= valid are masked
+      const int gap0 = txt_len - j * ATT_BK, gap1 = P.split - j * ATT_BK;  // tile-local text-padding range [gap0, gap1)
       mbar_wait(s_full(s), (j >> 1) & 1);
       tc_fence_after();
       const uint32_t tS = tS0 + s * 128 + lane_off + c0;
       float mx = -INFINITY;
-      const bool full_tile = valid >= ATT_BK;  // warp-uniform: no key masking needed (all tiles but the last)
+      // warp-uniform: no key masking needed (all tiles but the last, unless the tile touches text padding)
+      const bool full_tile = valid >= ATT_BK && (gap0 >= gap1 || gap0 >= ATT_BK || gap1 <= 0);
 #pragma unroll 1
       for (int c = 0; c < 64; c += 32) {
         uint32_t r[32];
@@ -170,12 +174,13 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c0 + c + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+            if (c0 + c + i < valid && !(c0 + c + i >= gap0 && c0 + c + i < gap1)) mx = fmaxf(mx, __uint_as_float(r[i]));
         }
       }
       red[(s * 2 + half) * 128 + row] = mx;
       pair_sync();
       mx = fmaxf(mx, red[(s * 2 + (half ^ 1)) * 128 + row]);
+      // (a tile that is entirely text padding leaves mx = -inf: m_new = m_used, all p = 0 — tile 0 always has a valid key)
       const float m_new = fmaxf(m_used, mx * P.scale_log2);
       // warp-uniform lazy rescale of the TMEM accumulator (both warps of a pair see the same rows -> same decision)
       const bool need = (j == 0) || (m_new > m_used + 8.f);
@@ -218,8 +223,9 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = (c0 + c + 2 * i < valid) ? exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used) : 0.f;
-            const float p1 = (c0 + c + 2 * i + 1 < valid) ? exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used) : 0.f;
+            const int k0 = c0 + c + 2 * i, k1 = k0 + 1;
+            const float p0 = (k0 < valid && !(k0 >= gap0 && k0 < gap1)) ? exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used) : 0.f;
+            const float p1 = (k1 < valid && !(k1 >= gap0 && k1 < gap1)) ? exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used) : 0.f;
             pk[i] = pack_bf16(p0, p1);
             lsum += p0 + p1;
           }
@@ -292,8 +298,8 @@ using namespace qfx;
 /* Q,K,V: [B, H, S, 128] bf16 (head-major joint sequence, text tokens first).  Output is written token-major into two
  * row groups (text rows -> out0, image rows -> out1) so the output projections consume it without a split/copy. */
 extern "C" int qfx_attn_fwd(const void* Q, const void* K, const void* V, void* out0, int64_t ld0, int rows0, void* out1,
-                            int64_t ld1, int rows1, int split, float* lse, const int* kv_len, int B, int H, int S,
-                            float softmax_scale, void* stream) {
+                            int64_t ld1, int rows1, int split, float* lse, const int* kv_len, const int* txt_len, int B, int H,
+                            int S, float softmax_scale, void* stream) {
   QFX_CHECK_ARG(B > 0 && H > 0 && S > 0 && out0 && (split >= S || out1), "qfx_attn_fwd: bad arguments");
   AttnFwdParams P;
   memset(&P, 0, sizeof(P));
@@ -303,7 +309,7 @@ extern "C" int qfx_attn_fwd(const void* Q, const void* K, const void* V, void* o
   if ((rc = make_qkv_tmap(&P.tmV, V, B * H, S))) return rc;
   P.out0 = (bf16*)out0; P.out1 = (bf16*)out1;
   P.ld0 = ld0; P.ld1 = ld1; P.rows0 = rows0; P.rows1 = rows1; P.split = split;
-  P.lse = lse; P.kv_len = kv_len; P.S = S; P.H = H;
+  P.lse = lse; P.kv_len = kv_len; P.txt_len = txt_len; P.S = S; P.H = H;
   P.scale_log2 = softmax_scale * 1.4426950408889634f;
   static bool attr_done = false;
   if (!attr_done) {

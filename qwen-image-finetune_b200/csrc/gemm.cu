@@ -338,7 +338,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm2_kernel
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(full_bar(s), 2);   // leader: own arrive.expect_tx + the peer's remote arrive
+      mbar_init(full_bar(s), 1);   // leader's arrive.expect_tx covers the bytes of BOTH CTAs (the peer only adds complete_tx)
       mbar_init(empty_bar(s), 1);  // multicast tcgen05.commit
     }
     for (int s = 0; s < 2; ++s) {
@@ -380,7 +380,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm2_kernel
           const uint32_t b_dst = a_dst + C::A_BYTES;
           const uint32_t fb = full_bar(stage);
           if (leader) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);
-          else mbar_arrive_remote(fb, 0);
           if (kb < nkb) {
             tma_load_2d_2sm(a_dst, &q.tmA, fb, kb * BK, m0);
             if (!TRANS_B) {

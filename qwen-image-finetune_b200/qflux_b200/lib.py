@@ -121,9 +121,9 @@ _noisy = _sig("qfx_flow_noisy_input", _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _
 _floss = _sig("qfx_flow_loss", _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _i, _i, _i, _i, _vp)
 _wgrad = _sig("qfx_lora_wgrad", _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp)
 _delta = _sig("qfx_attn_delta", _vp, _i64, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp)
-_attn_bwd = _sig("qfx_attn_bwd", _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp)
+_attn_bwd = _sig("qfx_attn_bwd", _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp)
 _gfin = _sig("qfx_grad_finalize", _vp, _i64, _f, _f, _vp, _vp, _vp)
-_attn_fwd = _sig("qfx_attn_fwd", _vp, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _vp, _vp, _i, _i, _i, _f, _vp)
+_attn_fwd = _sig("qfx_attn_fwd", _vp, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp)
 
 
 def ln_modulate_fwd(x, y, shift, scale, rows_per_batch, mean=None, rstd=None, eps=1e-6):
@@ -234,14 +234,14 @@ def attn_delta(O, dO, delta, tokens_per_sample, s_offset, dO_joint=None):
                  s_offset, S, H, cur_stream()), "qfx_attn_delta")
 
 
-def attn_bwd(Q, K, V, dO, lse, delta, dQ_accum, dK, dV, kv_len=None, scale=None):
+def attn_bwd(Q, K, V, dO, lse, delta, dQ_accum, dK, dV, kv_len=None, scale=None, txt_len=None, split=0):
     """All [B,H,S,128]; dQ_accum fp32 and zeroed by the caller; lse/delta [B,H,S] fp32."""
-    require_cuda(Q, K, V, dO, lse, delta, dQ_accum, dK, dV, kv_len)
+    require_cuda(Q, K, V, dO, lse, delta, dQ_accum, dK, dV, kv_len, txt_len)
     B, H, S, d = Q.shape
     assert d == 128 and dQ_accum.dtype == torch.float32
     scale = scale if scale is not None else d ** -0.5
-    check(_attn_bwd(ptr(Q), ptr(K), ptr(V), ptr(dO), ptr(lse), ptr(delta), ptr(dQ_accum), ptr(dK), ptr(dV), ptr(kv_len), B, H,
-                    S, scale, cur_stream()), "qfx_attn_bwd")
+    check(_attn_bwd(ptr(Q), ptr(K), ptr(V), ptr(dO), ptr(lse), ptr(delta), ptr(dQ_accum), ptr(dK), ptr(dV), ptr(kv_len),
+                    ptr(txt_len), split, B, H, S, scale, cur_stream()), "qfx_attn_bwd")
 
 
 def grad_finalize(g_f32, pre_scale, max_norm, sumsq, out_bf16):
@@ -249,11 +249,11 @@ def grad_finalize(g_f32, pre_scale, max_norm, sumsq, out_bf16):
     check(_gfin(ptr(g_f32), g_f32.numel(), pre_scale, max_norm, ptr(sumsq), ptr(out_bf16), cur_stream()), "qfx_grad_finalize")
 
 
-def attn_fwd(Q, K, V, out_txt, out_img, split, lse=None, kv_len=None, scale=None):
+def attn_fwd(Q, K, V, out_txt, out_img, split, lse=None, kv_len=None, scale=None, txt_len=None):
     """Q/K/V [B,H,S,128]; rows s<split of sample b -> out_txt[b*split + s], others -> out_img[b*(S-split) + s-split]."""
-    require_cuda(Q, K, V, out_txt, out_img, lse, kv_len)
+    require_cuda(Q, K, V, out_txt, out_img, lse, kv_len, txt_len)
     B, H, S, d = Q.shape
     assert d == 128 and Q.is_contiguous() and K.is_contiguous() and V.is_contiguous()
     scale = scale if scale is not None else d ** -0.5
     check(_attn_fwd(ptr(Q), ptr(K), ptr(V), ptr(out_txt), _ld(out_txt), split, ptr(out_img), _ld(out_img), S - split, split,
-                    ptr(lse), ptr(kv_len), B, H, S, scale, cur_stream()), "qfx_attn_fwd")
+                    ptr(lse), ptr(kv_len), ptr(txt_len), B, H, S, scale, cur_stream()), "qfx_attn_fwd")

@@ -210,19 +210,22 @@ def attn_delta(O, dO, delta, tokens_per_sample, s_offset, dO_joint=None):
         dO_joint[:, :, s_offset:s_offset + n] = dO.view(B, n, H, 128).permute(0, 2, 1, 3)
 
 
-def _scores(Q, K, kv_len, scale):
+def _scores(Q, K, kv_len, scale, txt_len=None, split=0):
     B, H, S, d = Q.shape
     sc = Q.float() @ K.float().transpose(-1, -2) * scale
+    pos = torch.arange(S)[None, :]
+    mask = torch.ones(B, S, dtype=torch.bool)
     if kv_len is not None:
-        mask = (torch.arange(S)[None, :] < kv_len[:, None].cpu())[:, None, None, :]
-        sc = sc.masked_fill(~mask, float("-inf"))
-    return sc
+        mask &= pos < kv_len[:, None].cpu()
+    if txt_len is not None:
+        mask &= ~((pos >= txt_len[:, None].cpu()) & (pos < split))
+    return sc.masked_fill(~mask[:, None, None, :], float("-inf"))
 
 
-def attn_fwd(Q, K, V, out_txt, out_img, split, lse=None, kv_len=None, scale=None):
+def attn_fwd(Q, K, V, out_txt, out_img, split, lse=None, kv_len=None, scale=None, txt_len=None):
     B, H, S, d = Q.shape
     scale = scale if scale is not None else d ** -0.5
-    sc = _scores(Q, K, kv_len, scale)
+    sc = _scores(Q, K, kv_len, scale, txt_len, split)
     o = (torch.softmax(sc, -1) @ V.float()).permute(0, 2, 1, 3).reshape(B, S, H * d)
     if split > 0:
         out_txt.copy_(o[:, :split].reshape(B * split, H * d).to(BF))
@@ -231,10 +234,10 @@ def attn_fwd(Q, K, V, out_txt, out_img, split, lse=None, kv_len=None, scale=None
         lse.copy_(torch.logsumexp(sc, -1) * 1.4426950408889634)
 
 
-def attn_bwd(Q, K, V, dO, lse, delta, dQ_accum, dK, dV, kv_len=None, scale=None):
+def attn_bwd(Q, K, V, dO, lse, delta, dQ_accum, dK, dV, kv_len=None, scale=None, txt_len=None, split=0):
     B, H, S, d = Q.shape
     scale = scale if scale is not None else d ** -0.5
-    sc = _scores(Q, K, kv_len, scale)
+    sc = _scores(Q, K, kv_len, scale, txt_len, split)
     P = torch.exp2(sc * 1.4426950408889634 - lse[..., None])
     dP = dO.float() @ V.float().transpose(-1, -2)
     dS = P * (dP - delta[..., None]) * scale

@@ -198,3 +198,29 @@ def test_flux_rope_table_matches_oracle():
     cos, sin = mo.flux_rope(ids, (16, 56, 56))
     tab = flux_rope_table(ids)
     assert torch.equal(tab[..., 0], cos[:, 0::2]) and torch.equal(tab[..., 1], sin[:, 0::2])
+
+
+def test_qwen_edit_plus_three_images_cumulative_rope(emu):
+    """BASELINE config 4 semantics (Qwen-Image-Edit-2509 'Plus'): target + 2 control images, frame-axis RoPE offsets 0,1,2
+    (transformer_qwenimage.py:213-224).  The trainer's `_compute_loss` is inherited unchanged (qwen_image_edit_plus_trainer.py)."""
+    from qflux_b200.train_step import QwenImageEditStep
+    orc, m = _pair(2, 2, 128, 4, ("to_q", "to_k", "to_v", "to_out.0"))
+    g = torch.Generator().manual_seed(5)
+    rn = lambda *s: torch.randn(*s, generator=g).bfloat16()
+    B, T = 1, 16
+    shapes = [[(1, 4, 4), (1, 4, 6), (1, 2, 4)]] * B  # target 16 tokens, controls 24 + 8 tokens of different sizes
+    x = dict(image_latents=rn(B, 16, 64), control_latents=rn(B, 32, 64), prompt_embeds=rn(B, T, 128) * 3,
+             prompt_embeds_mask=torch.ones(B, T, dtype=torch.int64), img_shapes=shapes, noise=rn(B, 16, 64), u=torch.tensor([0.25]))
+    xf = {k: (v.float() if torch.is_tensor(v) and v.is_floating_point() and k != "u" else v) for k, v in x.items()}
+    loss_o, pred_o = mo.qwen_compute_loss(orc, **xf)
+    loss_o.backward()
+    step = QwenImageEditStep(m)
+    emb = {k: x[k] for k in ("image_latents", "control_latents", "prompt_embeds", "img_shapes")}
+    loss_b = step.compute_loss(emb, noise=x["noise"], u=x["u"])
+    pred_b = m._ws["pred"].view(B, -1, 64)[:, :16].float().clone()
+    loss_b.backward()
+    assert ((pred_b - pred_o).norm() / pred_o.norm()).item() < 1e-2
+    go = {n: p.grad for n, p in orc.named_parameters() if p.requires_grad}
+    num = sum(((p.grad.float() - go[n]) ** 2).sum() for n, p in m.named_parameters())
+    den = sum((v ** 2).sum() for v in go.values())
+    assert float((num / den).sqrt()) < 2e-2

@@ -206,7 +206,7 @@ def wgrad_tc(perf=False):
     return res
 
 
-def attn(Bsz=2, H=3, S=300, split=44, ragged=False, perf=False):
+def attn(Bsz=2, H=3, S=300, split=44, ragged=False, perf=False, txt_gap=False):
     from qflux_b200 import lib
     Q, K, V = (_mk(Bsz, H, S, 128, seed=i, scale=1.0) for i in (1, 2, 3))
     Q = Q * 2.0  # sharper softmax so the running-max logic is exercised
@@ -217,11 +217,20 @@ def attn(Bsz=2, H=3, S=300, split=44, ragged=False, perf=False):
     kv_len = None
     if ragged:
         kv_len = torch.tensor([S - 37 * i for i in range(Bsz)], device="cuda", dtype=torch.int32)
-    lib.attn_fwd(Q, K, V, ot, oi, split, lse, kv_len)
+    txt_len = None
+    if txt_gap:  # text padding inside the joint sequence: keys [txt_len[b], split) are masked
+        txt_len = torch.tensor([max(1, split - 5 - 60 * i) for i in range(Bsz)], device="cuda", dtype=torch.int32)
+    lib.attn_fwd(Q, K, V, ot, oi, split, lse, kv_len, txt_len=txt_len)
     torch.cuda.synchronize()
     mask = None
-    if ragged:
-        mask = (torch.arange(S, device="cuda")[None, :] < kv_len[:, None])[:, None, None, :]
+    if ragged or txt_gap:
+        pos = torch.arange(S, device="cuda")[None, :]
+        m2 = torch.ones(Bsz, S, dtype=torch.bool, device="cuda")
+        if ragged:
+            m2 &= pos < kv_len[:, None]
+        if txt_gap:
+            m2 &= ~((pos >= txt_len[:, None]) & (pos < split))
+        mask = m2[:, None, None, :]
     ref = F.scaled_dot_product_attention(Q.float(), K.float(), V.float(), attn_mask=mask)  # [B,H,S,d]
     out = torch.cat([ot.view(Bsz, T, H, 128), oi.view(Bsz, L, H, 128)], 1).permute(0, 2, 1, 3).float()
     sc = Q.float() @ K.float().transpose(-1, -2) / math.sqrt(128)
@@ -238,7 +247,7 @@ def attn(Bsz=2, H=3, S=300, split=44, ragged=False, perf=False):
     return res
 
 
-def attn_bwd(Bsz=2, H=3, S=300, split=44, ragged=False, perf=False):
+def attn_bwd(Bsz=2, H=3, S=300, split=44, ragged=False, perf=False, txt_gap=False):
     from qflux_b200 import lib
     Q, K, V = (_mk(Bsz, H, S, 128, seed=i) for i in (1, 2, 3))
     Q = Q * 2.0
@@ -247,8 +256,12 @@ def attn_bwd(Bsz=2, H=3, S=300, split=44, ragged=False, perf=False):
     oi = torch.zeros(Bsz * L, H * 128, device="cuda", dtype=BF)
     lse = torch.zeros(Bsz, H, S, device="cuda")
     kv_len = torch.tensor([S - 37 * i for i in range(Bsz)], device="cuda", dtype=torch.int32) if ragged else None
-    lib.attn_fwd(Q, K, V, ot, oi, split, lse, kv_len)
+    txt_len = torch.tensor([max(1, split - 5 - 60 * i) for i in range(Bsz)], device="cuda", dtype=torch.int32) if txt_gap else None
+    lib.attn_fwd(Q, K, V, ot, oi, split, lse, kv_len, txt_len=txt_len)
     dot, doi = _mk(Bsz * T, H * 128, seed=7), _mk(Bsz * L, H * 128, seed=8)
+    if txt_gap:
+        for b in range(Bsz):
+            dot.view(Bsz, T, -1)[b, int(txt_len[b]):] = 0
     if ragged:  # padded query rows carry no gradient
         for b in range(Bsz):
             doi.view(Bsz, L, -1)[b, int(kv_len[b]) - T:] = 0
@@ -258,18 +271,24 @@ def attn_bwd(Bsz=2, H=3, S=300, split=44, ragged=False, perf=False):
     lib.attn_delta(oi, doi, delta, L, T, dOj)
     dQ = torch.zeros(Bsz, H, S, 128, device="cuda")
     dK, dV = torch.empty_like(K), torch.empty_like(V)
-    lib.attn_bwd(Q, K, V, dOj, lse, delta, dQ, dK, dV, kv_len)
+    lib.attn_bwd(Q, K, V, dOj, lse, delta, dQ, dK, dV, kv_len, txt_len=txt_len, split=split)
     torch.cuda.synchronize()
     qf, kf, vf = (t.float().requires_grad_(True) for t in (Q, K, V))
     mask = None
-    if ragged:
-        mask = (torch.arange(S, device="cuda")[None, :] < kv_len[:, None])[:, None, None, :]
+    if ragged or txt_gap:
+        pos = torch.arange(S, device="cuda")[None, :]
+        m2 = torch.ones(Bsz, S, dtype=torch.bool, device="cuda")
+        if ragged:
+            m2 &= pos < kv_len[:, None]
+        if txt_gap:
+            m2 &= ~((pos >= txt_len[:, None]) & (pos < split))
+        mask = m2[:, None, None, :]
     ref = F.scaled_dot_product_attention(qf, kf, vf, attn_mask=mask)
     dO_ref = torch.cat([dot.view(Bsz, T, H, 128), doi.view(Bsz, L, H, 128)], 1).permute(0, 2, 1, 3).float()
     ref.backward(dO_ref)
     res = dict(dOj=rel_l2(dOj.float(), dO_ref), delta=rel_l2(delta, (ref.detach() * dO_ref).sum(-1)),
                dQ=rel_l2(dQ, qf.grad), dK=rel_l2(dK.float(), kf.grad), dV=rel_l2(dV.float(), vf.grad))
-    if ragged:
+    if ragged or txt_gap:
         res.pop("delta")  # padded rows differ by construction
     res["err"] = max(res.values())
     if perf:
@@ -299,6 +318,8 @@ CASES = {
     "attn_300": lambda: attn(2, 3, 300, 44),
     "attn_1tile_tail": lambda: attn(1, 1, 70, 10),
     "attn_ragged": lambda: attn(3, 2, 700, 100, ragged=True),
+    "attn_txtgap": lambda: attn(3, 2, 700, 300, ragged=True, txt_gap=True),
+    "attn_bwd_txtgap": lambda: attn_bwd(3, 2, 700, 300, ragged=True, txt_gap=True),
     "attn_qwen_perf": lambda: attn(4, 24, 2400, 352, perf=True),
     "attn_bwd_small": lambda: attn_bwd(1, 2, 128, 32),
     "attn_bwd_300": lambda: attn_bwd(2, 3, 300, 44),
