@@ -122,6 +122,10 @@ int qfx_timestep_sinusoid(const float* t, float scale, void* out, int B, int dim
 /* packed[b] = [ (1-sigma_b) x0 + sigma_b noise | control ]   (qwen_image_edit_trainer.py:811-812) */
 int qfx_flow_noisy_input(const void* x0, const void* noise, const void* control, const float* sigma, void* packed, int B, int L,
                          int Lc, int C, void* stream);
+/* multi-resolution variant: sample b = [ noisy target (Lt[b] tokens) | control (Lc[b] tokens) | zero padding ], Ltot tokens
+ * (per-sample concatenation of flux_kontext_trainer.py:660-700 / tools.py:319-396 pad_latents_for_multi_res) */
+int qfx_flow_noisy_input_var(const void* x0, const void* noise, const void* control, const float* sigma, const int* Lt,
+                             const int* Lc, void* packed, int B, int Ltmax, int Lcmax, int Ltot, int C, void* stream);
 /* loss = norm * sum_{b,t<L,c} w[b,t] (pred - (noise - x0))^2 ; dpred = d loss / d pred * grad_scale (zeros for t >= L)
  * — covers MseLoss / MaskEditLoss / AttentionMaskMseLoss (losses/*.py) through (w, norm). */
 int qfx_flow_loss(const void* pred, const void* x0, const void* noise, const float* w, float norm, float grad_scale, float* loss,

@@ -376,6 +376,31 @@ __global__ void flow_noisy_input_kernel(const bf16* __restrict__ x0, const bf16*
   }
 }
 
+// multi-resolution variant: per-sample target / control lengths; sample b's sequence is [noisy target (Lt[b]) | control (Lc[b]) | 0-pad]
+// (flux_kontext_trainer.py:660-700 builds the same per-sample concatenation before padding to the batch maximum)
+__global__ void flow_noisy_input_var_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ noise,
+                                            const bf16* __restrict__ control, const float* __restrict__ sigma,
+                                            const int* __restrict__ Lt, const int* __restrict__ Lc, bf16* __restrict__ packed, int B,
+                                            int Ltmax, int Lcmax, int Ltot, int Cc) {
+  const int64_t per = (int64_t)Ltot * Cc;
+  const int64_t total = (int64_t)B * per;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per);
+    const int64_t r = i - (int64_t)b * per;
+    const int t = (int)(r / Cc), c = (int)(r - (int64_t)t * Cc);
+    const int lt = Lt[b], lc = Lc[b];
+    float v = 0.f;
+    if (t < lt) {
+      const int64_t j = ((int64_t)b * Ltmax + t) * Cc + c;
+      const float sg = round_bf16(sigma[b]);
+      v = round_bf16(round_bf16(1.f - sg) * __bfloat162float(x0[j])) + round_bf16(sg * __bfloat162float(noise[j]));
+    } else if (t < lt + lc) {
+      v = __bfloat162float(control[((int64_t)b * Lcmax + (t - lt)) * Cc + c]);
+    }
+    packed[i] = __float2bfloat16_rn(v);
+  }
+}
+
 // loss += norm * sum w[b,t] * (pred - (noise - x0))^2 ;  dpred = 2 * norm * w * (pred - target) * loss_scale  (bf16),
 // zero for the control tokens.  pred is [B, Ltot, C]; only the first L tokens carry loss (trainer :839).
 __global__ void __launch_bounds__(256) flow_loss_kernel(const bf16* __restrict__ pred, const bf16* __restrict__ x0,
@@ -624,6 +649,13 @@ extern "C" int qfx_flow_noisy_input(const void* x0, const void* noise, const voi
                                     int B, int L, int Lc, int C, void* stream) {
   flow_noisy_input_kernel<<<296, 256, 0, (cudaStream_t)stream>>>((const bf16*)x0, (const bf16*)noise, (const bf16*)control, sigma,
                                                                  (bf16*)packed, B, L, Lc, C);
+  LAUNCH_OK();
+}
+
+extern "C" int qfx_flow_noisy_input_var(const void* x0, const void* noise, const void* control, const float* sigma, const int* Lt,
+                                        const int* Lc, void* packed, int B, int Ltmax, int Lcmax, int Ltot, int C, void* stream) {
+  flow_noisy_input_var_kernel<<<296, 256, 0, (cudaStream_t)stream>>>((const bf16*)x0, (const bf16*)noise, (const bf16*)control, sigma,
+                                                                     Lt, Lc, (bf16*)packed, B, Ltmax, Lcmax, Ltot, C);
   LAUNCH_OK();
 }
 

@@ -187,7 +187,7 @@ class FluxB200(FusedMMDiTBase):
         for s in (0, 1):
             lib.qk_norm_rope_fwd(self._rows(ws, qkv, s), w["s_qknorm_w"][l, 0], w["s_qknorm_w"][l, 1], ws["rope"], ws["Q"], ws["K"],
                                  ws["V"], self._rpb(ws, s), T if s == 0 else 0, round_mid=False)
-        lib.attn_fwd(ws["Q"], ws["K"], ws["V"], O[:Mt], O[Mt:], T, save["lse"])
+        lib.attn_fwd(ws["Q"], ws["K"], ws["V"], O[:Mt], O[Mt:], T, save["lse"], kv_len=ws.get("kv_len"), txt_len=ws.get("txt_len"))
         # x = x + gate * proj_out(cat[attn, gelu(mlp)]):  K loop over the attention output, then over the MLP activations
         Wo, bo = w["s_out_w"][l], w["s_out_b"][l]
         probs = [lib.gemm_problem(self._rows(ws, O, s), Wo[:, :D], self._rows(ws, Xout, s), A2=self._rows(ws, ws["h"], s),

@@ -199,6 +199,17 @@ def flow_noisy_input(x0, noise, control, sigma_f32, packed):
           "qfx_flow_noisy_input")
 
 
+_noisy_var = _sig("qfx_flow_noisy_input_var", _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp)
+
+
+def flow_noisy_input_var(x0, noise, control, sigma_f32, Lt, Lc, packed):
+    """per-sample lengths Lt/Lc (int32 [B]): packed[b] = [noisy target | control | 0]."""
+    require_cuda(x0, noise, control, sigma_f32, Lt, Lc, packed)
+    B, Ltmax, Cc = x0.shape
+    check(_noisy_var(ptr(x0), ptr(noise), ptr(control), ptr(sigma_f32), ptr(Lt), ptr(Lc), ptr(packed), B, Ltmax, control.shape[1],
+                     packed.shape[1], Cc, cur_stream()), "qfx_flow_noisy_input_var")
+
+
 def flow_loss(pred, x0, noise, w, norm, loss, dpred=None, grad_scale=1.0):
     require_cuda(pred, x0, noise, w, loss, dpred)
     B, L, Cc = x0.shape

@@ -314,7 +314,7 @@ class FusedMMDiTBase(nn.Module):
         for s in (0, 1):
             lib.qk_norm_rope_fwd(self._rows(ws, qkv, s), w["qknorm_w"][l, 2 * s], w["qknorm_w"][l, 2 * s + 1], ws["rope"], ws["Q"],
                                  ws["K"], ws["V"], self._rpb(ws, s), T if s == 0 else 0, round_mid=self.round_mid)
-        lib.attn_fwd(ws["Q"], ws["K"], ws["V"], O[:Mt], O[Mt:], T, save["lse"])
+        lib.attn_fwd(ws["Q"], ws["K"], ws["V"], O[:Mt], O[Mt:], T, save["lse"], kv_len=ws.get("kv_len"), txt_len=ws.get("txt_len"))
         self._grouped(ws, l, "out", O, xmid, D, D, lib.EPI_RESID_GATE, resid=Xin, gate=mods(2))
         for s in (0, 1):
             lib.ln_modulate_fwd(self._rows(ws, xmid, s), self._rows(ws, ws["xm"], s), mods(3)[s], mods(4)[s], self._rpb(ws, s),
@@ -332,7 +332,8 @@ class FusedMMDiTBase(nn.Module):
             lib.qk_norm_rope_fwd(self._rows(ws, qkv, s), wq, wk, ws["rope"], ws["Q"], ws["K"], ws["V"], self._rpb(ws, s),
                                  T if s == 0 else 0, round_mid=self.round_mid)
         ws["dQ"].zero_()
-        lib.attn_bwd(ws["Q"], ws["K"], ws["V"], ws["dOj"], lse, ws["delta"], ws["dQ"], ws["dK"], ws["dV"])
+        lib.attn_bwd(ws["Q"], ws["K"], ws["V"], ws["dOj"], lse, ws["delta"], ws["dQ"], ws["dK"], ws["dV"], kv_len=ws.get("kv_len"),
+                     txt_len=ws.get("txt_len"), split=T)
         for s in (0, 1):
             wq, wk = wq_wk(s)
             lib.qk_norm_rope_bwd(ws["dQ"], ws["dK"], ws["dV"], self._rows(ws, qkv, s), wq, wk, ws["rope"],

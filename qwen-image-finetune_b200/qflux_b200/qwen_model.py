@@ -143,17 +143,42 @@ class QwenImageB200(FusedMMDiTBase):
         return f
 
     # ------------------------------------------------------------------------------------------------ forward
-    def _forward_impl(self, hidden_states, encoder_hidden_states, timestep, img_shapes, train: bool):
-        lib.require_cuda(hidden_states, encoder_hidden_states, timestep)
+    def _rope_multi(self, img_shapes, T, Limg):
+        """Per-sample tables [B, T+Limg, 64, 2] for a pad-to-max multi-resolution batch; padded rows get the identity rotation
+        (cos 1, sin 0 — transformer_flux_custom.py:148-154), their keys are masked anyway.  Returns (table, kv_len int32 [B])."""
+        key = ("multi", tuple(tuple(tuple(s) for s in sh) for sh in img_shapes), T, Limg)
+        if key not in self._rope_cache:
+            tabs, lens = [], []
+            for sh in img_shapes:
+                t = qwen_rope_table(sh, T, self.config.axes_dims_rope)
+                pad = torch.zeros(T + Limg - t.shape[0], t.shape[1], 2)
+                pad[..., 0] = 1.0
+                tabs.append(torch.cat([t, pad], 0))
+                lens.append(t.shape[0])
+            self._rope_cache[key] = (torch.stack(tabs).contiguous().to(self.dev),
+                                     torch.tensor(lens, dtype=torch.int32).to(self.dev))
+        return self._rope_cache[key]
+
+    def _forward_impl(self, hidden_states, encoder_hidden_states, timestep, img_shapes, txt_len=None, train: bool = False):
+        """img_shapes: one list of (frame, h, w) per sample.  When the samples differ (multi-resolution, pad-to-max) every
+        sample gets its own RoPE table and key mask (transformer_qwen_custom.py:444-553); `txt_len` (int32 [B] on the device)
+        additionally masks text padding."""
+        lib.require_cuda(hidden_states, encoder_hidden_states, timestep, txt_len)
         B, Limg, _ = hidden_states.shape
         T = encoder_hidden_states.shape[1]
         D, L, w = self.D, self.L, self.w
         ws = self._workspace(B, T, Limg, train)
         Mt = ws["Mt"]
-        shapes0 = img_shapes[0] if isinstance(img_shapes[0], (list, tuple)) and isinstance(img_shapes[0][0], (list, tuple)) else img_shapes
-        rope = self._rope(shapes0, T)
-        assert rope.shape[0] == ws["S"], f"img_shapes {shapes0} do not add up to {Limg} image tokens"
-        ws["rope"] = rope
+        nested = isinstance(img_shapes[0], (list, tuple)) and isinstance(img_shapes[0][0], (list, tuple))
+        per_sample = [list(map(tuple, sh)) for sh in img_shapes] if nested else [list(map(tuple, img_shapes))] * B
+        if any(sh != per_sample[0] for sh in per_sample):
+            assert len(per_sample) == B
+            ws["rope"], ws["kv_len"] = self._rope_multi(per_sample, T, Limg)
+        else:
+            rope = self._rope(per_sample[0], T)
+            assert rope.shape[0] == ws["S"], f"img_shapes {per_sample[0]} do not add up to {Limg} image tokens"
+            ws["rope"], ws["kv_len"] = rope, None
+        ws["txt_len"] = txt_len
         X0 = ws["X"][0]
         # --- conditioning: sigma (bf16-rounded, transformer_qwenimage.py:624) -> sinusoid -> MLP -> all modulation vectors
         t32 = timestep.to(BF).float().contiguous()
@@ -203,9 +228,21 @@ class QwenImageB200(FusedMMDiTBase):
                 img_shapes=None, txt_seq_lens=None, guidance=None, attention_kwargs=None, return_dict=False):
         """Same signature as the reference model.  With grad enabled and an adapter attached the result carries
         autograd history to the LoRA parameters (custom Function around the fused backward)."""
+        nested = isinstance(img_shapes[0], (list, tuple)) and isinstance(img_shapes[0][0], (list, tuple))
+        multi = nested and any(list(map(tuple, sh)) != list(map(tuple, img_shapes[0])) for sh in img_shapes)
+        txt_len = None
+        if multi and encoder_hidden_states_mask is not None:  # the mask is only honoured in multi-resolution mode (like the reference)
+            txt_len = encoder_hidden_states_mask.to(self.dev).sum(dim=1).to(torch.int32)
         args = (hidden_states, encoder_hidden_states, timestep, img_shapes)
+        if multi:
+            args = args + (txt_len,)
         if torch.is_grad_enabled() and self._lora_params:
             out = ModelFn.apply(self, args, *self._lora_params.values())
         else:
             out = self._forward_impl(*args, train=False).clone()
+        kv = self._ws.get("kv_len")
+        if kv is not None:  # padded image rows of a multi-resolution batch are returned as exact zeros (test_qwen_custom.py:672-692)
+            T = encoder_hidden_states.shape[1]
+            valid = torch.arange(out.shape[1], device=out.device)[None, :] < (kv[:, None] - T)
+            out = out * valid[..., None].to(out.dtype)
         return (out,)

@@ -75,12 +75,18 @@ class QwenImageEditStep:
         timesteps = (self.num_train_timesteps - idx).float()  # scheduler.timesteps = linspace(1, 1000, 1000)[::-1]
         return (timesteps / self.num_train_timesteps)
 
-    def _run(self, image_latents, control_latents, prompt_embeds, img_shapes, noise, sigma, w, norm):
+    def _run(self, image_latents, control_latents, prompt_embeds, img_shapes, noise, sigma, w, norm, var=None):
         m = self.dit
         B, L, C = image_latents.shape
-        packed = torch.empty(B, L + control_latents.shape[1], C, device=m.dev, dtype=BF)
-        lib.flow_noisy_input(image_latents, noise, control_latents, sigma, packed)
-        pred = m._forward_impl(packed, prompt_embeds, sigma, img_shapes, train=True)
+        if var is None:
+            packed = torch.empty(B, L + control_latents.shape[1], C, device=m.dev, dtype=BF)
+            lib.flow_noisy_input(image_latents, noise, control_latents, sigma, packed)
+            pred = m._forward_impl(packed, prompt_embeds, sigma, img_shapes, train=True)
+        else:  # multi-resolution pad-to-max batch: per-sample [target | control] concatenation, masks and RoPE
+            Lt, Lc, Ltot, txt_len = var
+            packed = torch.empty(B, Ltot, C, device=m.dev, dtype=BF)
+            lib.flow_noisy_input_var(image_latents, noise, control_latents, sigma, Lt, Lc, packed)
+            pred = m._forward_impl(packed, prompt_embeds, sigma, img_shapes, txt_len, train=True)
         ws = m._ws
         lib.flow_loss(pred, image_latents, noise, w, norm, ws["loss"], ws["dpred"])
         m.G32.zero_()
@@ -98,6 +104,22 @@ class QwenImageEditStep:
             noise = torch.randn(x0.shape, device=dev, dtype=BF)
         sigma = self._sigmas(B, u).to(dev, non_blocking=True)
         edit_mask = embeddings.get("edit_mask")
+        shapes = embeddings["img_shapes"]
+        multi = isinstance(shapes[0][0], (list, tuple)) and any(list(map(tuple, sh)) != list(map(tuple, shapes[0])) for sh in shapes)
+        if multi:
+            # pad-to-max multi-resolution batch: token counts come from the latent-space shapes (host
+            # metadata), the loss is AttentionMaskMseLoss over the valid target tokens (attention_mask_loss.py:146-226)
+            lt = [sh[0][0] * sh[0][1] * sh[0][2] for sh in shapes]
+            lc = [sum(f * h * w_ for (f, h, w_) in sh[1:]) for sh in shapes]
+            Ltot = max(a + b for a, b in zip(lt, lc))
+            Lt = torch.tensor(lt, dtype=torch.int32).to(dev, non_blocking=True)
+            Lc = torch.tensor(lc, dtype=torch.int32).to(dev, non_blocking=True)
+            mask = embeddings.get("prompt_embeds_mask")
+            txt_len = None if mask is None else mask.to(dev).sum(dim=1).to(torch.int32)
+            amask = (torch.arange(L)[None, :] < torch.tensor(lt)[:, None]).float()
+            w = amask if edit_mask is None else amask * (edit_mask.float().cpu() * self.fg + (1 - edit_mask.float().cpu()) * self.bg)
+            norm = 1.0 / (C * (float(sum(lt)) + 1e-12))
+            return (x0, ctrl, pe, shapes, noise.to(dev, BF), sigma, w.to(dev).contiguous(), norm, (Lt, Lc, Ltot, txt_len))
         if self.loss_kind == "mse" and edit_mask is None:
             key = (B, L)
             if key not in self._ones:
@@ -107,7 +129,7 @@ class QwenImageEditStep:
             w, norm = token_weights_and_norm(self.loss_kind, B, L, C, None, None,
                                              None if edit_mask is None else edit_mask.to(dev), self.fg, self.bg)
             w = w.to(dev).contiguous()
-        return (x0, ctrl, pe, embeddings["img_shapes"], noise.to(dev, BF), sigma, w, norm)
+        return (x0, ctrl, pe, shapes, noise.to(dev, BF), sigma, w, norm)
 
     # --------------------------------------------------------------------------------------------- public
     def compute_loss(self, embeddings: dict, noise=None, u=None) -> torch.Tensor:

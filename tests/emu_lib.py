@@ -170,6 +170,16 @@ def flow_noisy_input(x0, noise, control, sigma_f32, packed):
     packed[:, L:] = control
 
 
+def flow_noisy_input_var(x0, noise, control, sigma_f32, Lt, Lc, packed):
+    B = x0.shape[0]
+    packed.zero_()
+    sg = sigma_f32.to(BF)
+    for b in range(B):
+        lt, lc = int(Lt[b]), int(Lc[b])
+        packed[b, :lt] = (1.0 - sg[b]) * x0[b, :lt] + sg[b] * noise[b, :lt]
+        packed[b, lt:lt + lc] = control[b, :lc]
+
+
 def flow_loss(pred, x0, noise, w, norm, loss, dpred=None, grad_scale=1.0):
     B, L, C = x0.shape
     p = pred.float().view(B, -1, C)
@@ -260,7 +270,7 @@ def require_cuda(*tensors):
 
 
 _NAMES = ["gemm_problem", "gemm", "ln_modulate_fwd", "ln_modulate_bwd", "gate_mul", "add_bf16", "rmsnorm_rows", "qk_norm_rope_fwd",
-          "qk_norm_rope_bwd", "gemv_act", "timestep_sinusoid", "flow_noisy_input", "flow_loss", "lora_wgrad", "lora_wgrad_tc", "attn_delta",
+          "qk_norm_rope_bwd", "gemv_act", "timestep_sinusoid", "flow_noisy_input", "flow_noisy_input_var", "flow_loss", "lora_wgrad", "lora_wgrad_tc", "attn_delta",
           "attn_fwd", "attn_bwd", "grad_finalize", "require_cuda"]
 
 
