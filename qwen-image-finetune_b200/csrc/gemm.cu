@@ -12,6 +12,7 @@
 #include "../../include/qfx.h"
 #include "host_common.h"
 #include "sm100.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace qfx {
@@ -554,7 +555,12 @@ extern "C" int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, in
                              int lora_group_n, int block_n, void* stream) {
   QFX_CHECK_ARG(nprob >= 1 && nprob <= QFX_MAX_PROBLEMS, "qfx_gemm_bf16: nprob=%d", nprob);
   QFX_CHECK_ARG(K > 0 && K % BK == 0, "qfx_gemm_bf16: K=%d must be a positive multiple of 64", K);
-  const bool two_cta = block_n >= 1000;  // block_n = 1000 + {128, 256}: CTA-pair (cta_group::2) kernel, 256-row tiles
+  // block_n = 1000 + {128, 256}: CTA-pair (cta_group::2) kernel with 256-row tiles.  Auto (block_n = 0): the pair kernel whenever
+  // N is a multiple of 256 (1.37-1.56 PFLOP/s vs 1.17-1.32 for the single-CTA kernel on the block projections; QFX_GEMM_1CTA=1
+  // forces the single-CTA kernel for A/B comparisons).
+  static const bool force_1cta = getenv("QFX_GEMM_1CTA") != nullptr;
+  if (block_n == 0 && N % 256 == 0 && !force_1cta) block_n = 1256;
+  const bool two_cta = block_n >= 1000;
   if (two_cta) block_n -= 1000;
   int bn = block_n;
   if (bn == 0) bn = N % 256 == 0 ? 256 : N % 192 == 0 ? 192 : N % 128 == 0 ? 128 : 64;
