@@ -38,7 +38,7 @@ struct AttnBwdParams {
   float scale, scale_log2;
 };
 
-constexpr int BW_SMEM = 6 * BW_TILE + 1024 + 256;  // K, V, Q, dO, P, dS
+constexpr int BW_SMEM = 7 * BW_TILE + 256;  // K, V, Q x2, dO, P, dS (+ barriers); 1024-aligned base, no slack
 
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(m), "r"(src),
@@ -46,16 +46,29 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t
                : "memory");
 }
 
+// Pipeline per query tile i (key tile fixed per CTA):
+//   MMA     : S = Q_i K^T, dP = dO_i V^T                 -> s_full
+//   compute : P = exp2(S c - L)  -> smem                    -> p_full      (thread = query row x 64 key columns)
+//   MMA     : dV += P^T dO_i                                -> do_empty    (dO_{i+1} starts loading)
+//   compute : dS = P (dP - delta) scale -> smem             -> ds_full
+//   MMA     : dK += dS^T Q_i  -> q_empty[i&1] ;  dQ_i = dS K (into the S columns)  -> dq_full
+//   compute : dQ_i TMEM -> fp32 slabs in the idle P|dS smem -> dq_empty (S_{i+1}/dP_{i+1} may issue) -> TMA reduce-add -> stage_free
+// Q is double-buffered and dO is released right after dV, so the loads of tile i+1 hide behind the math of tile i.
 __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams P) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sK = smem_base, sV = smem_base + BW_TILE, sQ = smem_base + 2 * BW_TILE, sdO = smem_base + 3 * BW_TILE;
-  const uint32_t sP = smem_base + 4 * BW_TILE, sdS = smem_base + 5 * BW_TILE;
-  const uint32_t bar_base = smem_base + 6 * BW_TILE;
-  const uint32_t kv_full = bar_base, qdo_full = bar_base + 8, qdo_empty = bar_base + 16, s_full = bar_base + 24;
-  const uint32_t pds_full = bar_base + 32, dq_full = bar_base + 40, dq_empty = bar_base + 48, acc_full = bar_base + 56;
-  const uint32_t tmem_slot = bar_base + 64;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  const uint32_t sK = smem_base, sV = smem_base + BW_TILE, sdO = smem_base + 4 * BW_TILE;
+  auto sQ = [&](int st) { return smem_base + (2 + st) * BW_TILE; };
+  const uint32_t sP = smem_base + 5 * BW_TILE, sdS = smem_base + 6 * BW_TILE;
+  const uint32_t bar_base = smem_base + 7 * BW_TILE;
+  const uint32_t kv_full = bar_base, do_full = bar_base + 8, do_empty = bar_base + 16, s_full = bar_base + 24;
+  const uint32_t p_full = bar_base + 32, ds_full = bar_base + 40, dq_full = bar_base + 48, dq_empty = bar_base + 56;
+  const uint32_t stage_free = bar_base + 64, acc_full = bar_base + 72;
+  auto q_full = [&](int st) { return bar_base + 80 + 8u * st; };
+  auto q_empty = [&](int st) { return bar_base + 96 + 8u * st; };
+  const uint32_t tmem_slot = bar_base + 112;
+  uint8_t* smem_gen = smem_raw;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv0 = blockIdx.x * 128;
@@ -69,13 +82,19 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
 
   if (warp == 1 && lane == 0) {
     mbar_init(kv_full, 1);
-    mbar_init(qdo_full, 1);
-    mbar_init(qdo_empty, 1);
+    mbar_init(do_full, 1);
+    mbar_init(do_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(pds_full, 8);
+    mbar_init(p_full, 8);
+    mbar_init(ds_full, 8);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 1);
+    mbar_init(dq_empty, 8);
+    mbar_init(stage_free, 1);
     mbar_init(acc_full, 1);
+    for (int st = 0; st < 2; ++st) {
+      mbar_init(q_full(st), 1);
+      mbar_init(q_empty(st), 1);
+    }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -86,7 +105,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 384;
 
   if (warp == 0) {
-    // ================================================================= TMA producer
+    // ================================================================= TMA producers: lane 0 = K, V, Q tiles; lane 1 = dO tiles
     if (lane == 0 && active) {
       mbar_expect_tx(kv_full, 2 * BW_TILE);
       tma_load_3d(sK, &P.tmK, kv_full, 0, kv0, bh);
@@ -94,12 +113,18 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
       tma_load_3d(sV, &P.tmV, kv_full, 0, kv0, bh);
       tma_load_3d(sV + BW_ATOM, &P.tmV, kv_full, 64, kv0, bh);
       for (int i = 0; i < n_q; ++i) {
-        if (i > 0) mbar_wait(qdo_empty, (i - 1) & 1);
-        mbar_expect_tx(qdo_full, 2 * BW_TILE);
-        tma_load_3d(sQ, &P.tmQ, qdo_full, 0, i * 128, bh);
-        tma_load_3d(sQ + BW_ATOM, &P.tmQ, qdo_full, 64, i * 128, bh);
-        tma_load_3d(sdO, &P.tmdO, qdo_full, 0, i * 128, bh);
-        tma_load_3d(sdO + BW_ATOM, &P.tmdO, qdo_full, 64, i * 128, bh);
+        const int st = i & 1;
+        if (i >= 2) mbar_wait(q_empty(st), ((i - 2) >> 1) & 1);
+        mbar_expect_tx(q_full(st), BW_TILE);
+        tma_load_3d(sQ(st), &P.tmQ, q_full(st), 0, i * 128, bh);
+        tma_load_3d(sQ(st) + BW_ATOM, &P.tmQ, q_full(st), 64, i * 128, bh);
+      }
+    } else if (lane == 1 && active) {
+      for (int i = 0; i < n_q; ++i) {
+        if (i >= 1) mbar_wait(do_empty, (i - 1) & 1);
+        mbar_expect_tx(do_full, BW_TILE);
+        tma_load_3d(sdO, &P.tmdO, do_full, 0, i * 128, bh);
+        tma_load_3d(sdO + BW_ATOM, &P.tmdO, do_full, 64, i * 128, bh);
       }
     }
   } else if (warp == 1) {
@@ -112,21 +137,27 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
       auto mnmaj = [](uint32_t base, int k) { return sdesc_sw128(base + k * 2048, BW_ATOM, 1024); };
       mbar_wait(kv_full, 0);
       for (int i = 0; i < n_q; ++i) {
-        mbar_wait(qdo_full, i & 1);
-        if (i > 0) mbar_wait(dq_empty, (i - 1) & 1);  // S columns (shared with dQ) drained, P/dS smem free
+        const int st = i & 1;
+        const uint32_t q = sQ(st);
+        mbar_wait(q_full(st), (i >> 1) & 1);
+        mbar_wait(do_full, i & 1);
+        if (i > 0) mbar_wait(dq_empty, (i - 1) & 1);  // S columns (shared with dQ) drained
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_bf16(tS, kmaj(sQ, k), kmaj(sK, k), id_kk, k != 0);
+        for (int k = 0; k < 8; ++k) umma_bf16(tS, kmaj(q, k), kmaj(sK, k), id_kk, k != 0);
 #pragma unroll
         for (int k = 0; k < 8; ++k) umma_bf16(tdP, kmaj(sdO, k), kmaj(sV, k), id_kk, k != 0);
         umma_commit(s_full);
-        mbar_wait(pds_full, i & 1);
+        mbar_wait(p_full, i & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k) umma_bf16(tdV, mnmaj(sP, k), mnmaj(sdO, k), id_mm, (i | k) != 0);
+        umma_commit(do_empty);  // dO_i no longer needed
+        mbar_wait(ds_full, i & 1);
+        tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_bf16(tdK, mnmaj(sdS, k), mnmaj(sQ, k), id_mm, (i | k) != 0);
-        umma_commit(qdo_empty);  // Q_i / dO_i no longer needed: the next tile may load while dQ is computed and drained
+        for (int k = 0; k < 8; ++k) umma_bf16(tdK, mnmaj(sdS, k), mnmaj(q, k), id_mm, (i | k) != 0);
+        umma_commit(q_empty(st));  // Q_i no longer needed
 #pragma unroll
         for (int k = 0; k < 8; ++k) umma_bf16(tS, kmaj(sdS, k), mnmaj(sK, k), id_km, k != 0);
         umma_commit(dq_full);
@@ -146,47 +177,61 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
       const int valid = kv_len - kv0;  // key columns >= valid are masked
       const int gap0 = txt_len - kv0, gap1 = P.split - kv0;  // tile-local text-padding columns [gap0, gap1)
       const bool full_tile = valid >= 128 && (gap0 >= gap1 || gap0 >= 128 || gap1 <= 0);
+      const uint32_t off_row = (uint32_t)row * 128 + half * BW_ATOM;  // this thread's 64 columns = one swizzle-atom row
       for (int i = 0; i < n_q; ++i) {
         const int q = i * 128 + row;
         const bool q_ok = q < P.S;
         const float L = q_ok ? P.lse[(int64_t)bh * P.S + q] : INFINITY;
-        const float dl = q_ok ? P.delta[(int64_t)bh * P.S + q] : 0.f;
+        const float dls = (q_ok ? P.delta[(int64_t)bh * P.S + q] : 0.f) * P.scale;
         mbar_wait(s_full, i & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int c = c0; c < c0 + 64; c += 32) {
-          uint32_t rs[32], rp[32];
-          tmem_ld32(tS + lane_off + c, rs);
-          tmem_ld32(tdP + lane_off + c, rp);
-          tmem_ld_wait();
-          uint32_t pk[16], dk[16];
-          const float dls = dl * P.scale;
-          if (full_tile) {  // warp-uniform fast path: no key masking
+        if (i > 0) mbar_wait(stage_free, (i - 1) & 1);  // the dQ_{i-1} reduce has finished reading the P|dS buffers
+        float p[64];
+        // ---- pass 1: P
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float p0 = exp2f(__uint_as_float(rs[2 * e]) * P.scale_log2 - L);
-              const float p1 = exp2f(__uint_as_float(rs[2 * e + 1]) * P.scale_log2 - L);
-              pk[e] = pack_bf16(p0, p1);
-              dk[e] = pack_bf16(p0 * (__uint_as_float(rp[2 * e]) * P.scale - dls), p1 * (__uint_as_float(rp[2 * e + 1]) * P.scale - dls));
-            }
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t rs[32];
+          tmem_ld32(tS + lane_off + c0 + cc * 32, rs);
+          tmem_ld_wait();
+          uint32_t pk[16];
+          if (full_tile) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) p[cc * 32 + e] = exp2f(__uint_as_float(rs[e]) * P.scale_log2 - L);
           } else {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int k0 = c + 2 * e, k1 = k0 + 1;
-              const float p0 = (k0 < valid && !(k0 >= gap0 && k0 < gap1)) ? exp2f(__uint_as_float(rs[2 * e]) * P.scale_log2 - L) : 0.f;
-              const float p1 = (k1 < valid && !(k1 >= gap0 && k1 < gap1)) ? exp2f(__uint_as_float(rs[2 * e + 1]) * P.scale_log2 - L) : 0.f;
-              pk[e] = pack_bf16(p0, p1);
-              dk[e] = pack_bf16(p0 * (__uint_as_float(rp[2 * e]) * P.scale - dls), p1 * (__uint_as_float(rp[2 * e + 1]) * P.scale - dls));
+            for (int e = 0; e < 32; ++e) {
+              const int kk = c0 + cc * 32 + e;
+              p[cc * 32 + e] = (kk < valid && !(kk >= gap0 && kk < gap1)) ? exp2f(__uint_as_float(rs[e]) * P.scale_log2 - L) : 0.f;
             }
           }
-          const uint32_t off = (uint32_t)row * 128 + (c >> 6) * BW_ATOM;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pk[e] = pack_bf16(p[cc * 32 + 2 * e], p[cc * 32 + 2 * e + 1]);
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
-            const uint32_t chunk = (uint32_t)(((c & 63) >> 3) + v) ^ (uint32_t)(row & 7);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off + chunk * 16), "r"(pk[4 * v]),
+            const uint32_t chunk = (uint32_t)(cc * 4 + v) ^ (uint32_t)(row & 7);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off_row + chunk * 16), "r"(pk[4 * v]),
                          "r"(pk[4 * v + 1]), "r"(pk[4 * v + 2]), "r"(pk[4 * v + 3])
                          : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS + off + chunk * 16), "r"(dk[4 * v]),
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        // ---- pass 2: dS = P * (dP * scale - delta * scale)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t rp[32];
+          tmem_ld32(tdP + lane_off + c0 + cc * 32, rp);
+          tmem_ld_wait();
+          uint32_t dk[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            dk[e] = pack_bf16(p[cc * 32 + 2 * e] * (__uint_as_float(rp[2 * e]) * P.scale - dls),
+                              p[cc * 32 + 2 * e + 1] * (__uint_as_float(rp[2 * e + 1]) * P.scale - dls));
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const uint32_t chunk = (uint32_t)(cc * 4 + v) ^ (uint32_t)(row & 7);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS + off_row + chunk * 16), "r"(dk[4 * v]),
                          "r"(dk[4 * v + 1]), "r"(dk[4 * v + 2]), "r"(dk[4 * v + 3])
                          : "memory");
           }
@@ -194,14 +239,15 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(pds_full);
+        if (lane == 0) mbar_arrive(ds_full);
 
         // ---- drain dQ_i: TMEM -> fp32 swizzled slabs in the (now idle) P|dS buffers -> TMA reduce-add to global
         mbar_wait(dq_full, i & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int c = c0; c < c0 + 64; c += 32) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
           uint32_t r[32];
+          const int c = c0 + cc * 32;
           tmem_ld32(tS + lane_off + c, r);
           tmem_ld_wait();
           const uint32_t slab = sP + (c >> 5) * BW_ATOM + (uint32_t)row * 128;  // [128 rows x 32 fp32], 128 B rows
@@ -213,15 +259,17 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
                          : "memory");
           }
         }
-        fence_proxy_async_smem();
         tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_empty);  // the S columns are free: S_{i+1} / dP_{i+1} may issue while the reduce drains
+        fence_proxy_async_smem();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (tid == 0) {
 #pragma unroll
           for (int sl = 0; sl < 4; ++sl) tma_reduce_add_3d(&P.tmdQ, sP + sl * BW_ATOM, sl * 32, i * 128, bh);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          mbar_arrive(dq_empty);
+          mbar_arrive(stage_free);
         }
       }
       mbar_wait(acc_full, 0);

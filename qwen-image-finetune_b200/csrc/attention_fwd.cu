@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
   auto p_full = [&](int s) { return bar_base + 8u * (7 + s); };
   auto pv_done = [&](int s) { return bar_base + 8u * (9 + s); };
   const uint32_t o_full = bar_base + 8u * 11;
-  const uint32_t tmem_slot = bar_base + 8u * 12;
+  auto k_empty = [&](int s) { return bar_base + 8u * (12 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * 14;
   const uint32_t red_base = bar_base + 256;  // float red[2 (tile parity)][2 (half)][128 rows]
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
       mbar_init(s_full(s), 1);
       mbar_init(p_full(s), 8);
       mbar_init(pv_done(s), 1);
+      mbar_init(k_empty(s), 1);
     }
     mbar_init(o_full, 1);
     fence_barrier_init();
@@ -88,20 +90,28 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
   const uint32_t tS0 = tmem_base, tO = tmem_base + 256;
 
   if (warp == 0) {
-    // ================================================================= TMA producer
+    // ================================================================= TMA producers: lane 0 streams Q + K tiles, lane 1 streams V
+    // tiles (independent threads so a wait on a V stage never delays the next K load)
     if (lane == 0) {
       tma_prefetch_desc(&P.tmQ);
       tma_prefetch_desc(&P.tmK);
-      tma_prefetch_desc(&P.tmV);
       mbar_expect_tx(q_full, TILE_BYTES);
       tma_load_3d(sQ, &P.tmQ, q_full, 0, q0, bh);
       tma_load_3d(sQ + ATOM_BYTES, &P.tmQ, q_full, 64, q0, bh);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j & 1;
-        if (j >= 2) mbar_wait(pv_done(s), ((j - 2) >> 1) & 1);  // P V of tile j-2 finished reading K/V stage s
+        // K stage s is free as soon as Q K^T of tile j-2 has completed (long before its P V): the K load of tile j then overlaps
+        // the softmax of tile j-2, so the next Q K^T never waits on HBM/L2 latency
+        if (j >= 2) mbar_wait(k_empty(s), ((j - 2) >> 1) & 1);
         mbar_expect_tx(k_full(s), TILE_BYTES);
         tma_load_3d(sK(s), &P.tmK, k_full(s), 0, j * ATT_BK, bh);
         tma_load_3d(sK(s) + ATOM_BYTES, &P.tmK, k_full(s), 64, j * ATT_BK, bh);
+      }
+    } else if (lane == 1) {
+      tma_prefetch_desc(&P.tmV);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        if (j >= 2) mbar_wait(pv_done(s), ((j - 2) >> 1) & 1);  // P V of tile j-2 finished reading V stage s
         mbar_expect_tx(v_full(s), TILE_BYTES);
         tma_load_3d(sV(s), &P.tmV, v_full(s), 0, j * ATT_BK, bh);
         tma_load_3d(sV(s) + ATOM_BYTES, &P.tmV, v_full(s), 64, j * ATT_BK, bh);
@@ -138,6 +148,7 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
           umma_bf16(tS0 + s * 128, ad, bd, idesc_qk, k != 0);
         }
         umma_commit(s_full(s));
+        umma_commit(k_empty(s));
         if (j > 0) issue_pv(j - 1);
       }
       issue_pv(n_tiles - 1);
