@@ -38,6 +38,7 @@ class LoraSite:
 class FusedMMDiTBase(nn.Module):
     # subclasses fill these -------------------------------------------------------------------------------------------
     round_mid = True  # diffusers RMSNorm (Qwen) rounds before the weight multiply; torch.nn.RMSNorm (FLUX) does not
+    keep_qkv = True   # keep normalised/rotated Q,K,V and the LN1 output of double blocks for the backward (HBM for time)
 
     def _weight_views(self) -> dict:
         raise NotImplementedError
@@ -307,14 +308,16 @@ class FusedMMDiTBase(nn.Module):
         T, Limg, Mt = ws["T"], ws["Limg"], ws["Mt"]
         st, qkv, O, xmid, u = save["stats"], save["qkv"], save["O"], save["xmid"], save["u"]
         w = self.w
+        xm1 = save.get("xm1", ws["xm"])  # kept per block in training: it is the LoRA input of the q|k|v sites in the backward
+        Qs, Ks, Vs = save.get("Q", ws["Q"]), save.get("K", ws["K"]), save.get("V", ws["V"])
         for s in (0, 1):
-            lib.ln_modulate_fwd(self._rows(ws, Xin, s), self._rows(ws, ws["xm"], s), mods(0)[s], mods(1)[s], self._rpb(ws, s),
+            lib.ln_modulate_fwd(self._rows(ws, Xin, s), self._rows(ws, xm1, s), mods(0)[s], mods(1)[s], self._rpb(ws, s),
                                 self._rows(ws, st[0], s), self._rows(ws, st[1], s))
-        self._grouped(ws, l, "qkv", ws["xm"], qkv, 3 * D, D, lib.EPI_BIAS)
+        self._grouped(ws, l, "qkv", xm1, qkv, 3 * D, D, lib.EPI_BIAS)
         for s in (0, 1):
-            lib.qk_norm_rope_fwd(self._rows(ws, qkv, s), w["qknorm_w"][l, 2 * s], w["qknorm_w"][l, 2 * s + 1], ws["rope"], ws["Q"],
-                                 ws["K"], ws["V"], self._rpb(ws, s), T if s == 0 else 0, round_mid=self.round_mid)
-        lib.attn_fwd(ws["Q"], ws["K"], ws["V"], O[:Mt], O[Mt:], T, save["lse"], kv_len=ws.get("kv_len"), txt_len=ws.get("txt_len"))
+            lib.qk_norm_rope_fwd(self._rows(ws, qkv, s), w["qknorm_w"][l, 2 * s], w["qknorm_w"][l, 2 * s + 1], ws["rope"], Qs, Ks, Vs,
+                                 self._rpb(ws, s), T if s == 0 else 0, round_mid=self.round_mid)
+        lib.attn_fwd(Qs, Ks, Vs, O[:Mt], O[Mt:], T, save["lse"], kv_len=ws.get("kv_len"), txt_len=ws.get("txt_len"))
         self._grouped(ws, l, "out", O, xmid, D, D, lib.EPI_RESID_GATE, resid=Xin, gate=mods(2))
         for s in (0, 1):
             lib.ln_modulate_fwd(self._rows(ws, xmid, s), self._rows(ws, ws["xm"], s), mods(3)[s], mods(4)[s], self._rpb(ws, s),
@@ -322,17 +325,21 @@ class FusedMMDiTBase(nn.Module):
         self._grouped(ws, l, "up", ws["xm"], ws["h"], 4 * D, D, lib.EPI_GELU, out2=u)
         self._grouped(ws, l, "down", ws["h"], Xout, D, 4 * D, lib.EPI_RESID_GATE, resid=xmid, gate=mods(5))
 
-    def _attn_bwd_core(self, ws, qkv, O, lse, wq_wk):
-        """dO (token-major, ws['dO']) -> dqkv (ws['dqkv']); wq_wk(s) -> (wq, wk) norm weights of stream s."""
+    def _attn_bwd_core(self, ws, qkv, O, lse, wq_wk, save=None):
+        """dO (token-major, ws['dO']) -> dqkv (ws['dqkv']); wq_wk(s) -> (wq, wk) norm weights of stream s.
+        The normalised / rotated Q, K, V come from the block's saved tensors when present, else they are regenerated."""
         T = ws["T"]
+        have = save is not None and "Q" in save
+        Qs, Ks, Vs = (save["Q"], save["K"], save["V"]) if have else (ws["Q"], ws["K"], ws["V"])
         for s in (0, 1):
             wq, wk = wq_wk(s)
             lib.attn_delta(self._rows(ws, O, s), self._rows(ws, ws["dO"], s), ws["delta"], self._rpb(ws, s), T if s == 0 else 0,
                            ws["dOj"])
-            lib.qk_norm_rope_fwd(self._rows(ws, qkv, s), wq, wk, ws["rope"], ws["Q"], ws["K"], ws["V"], self._rpb(ws, s),
-                                 T if s == 0 else 0, round_mid=self.round_mid)
+            if not have:
+                lib.qk_norm_rope_fwd(self._rows(ws, qkv, s), wq, wk, ws["rope"], Qs, Ks, Vs, self._rpb(ws, s),
+                                     T if s == 0 else 0, round_mid=self.round_mid)
         ws["dQ"].zero_()
-        lib.attn_bwd(ws["Q"], ws["K"], ws["V"], ws["dOj"], lse, ws["delta"], ws["dQ"], ws["dK"], ws["dV"], kv_len=ws.get("kv_len"),
+        lib.attn_bwd(Qs, Ks, Vs, ws["dOj"], lse, ws["delta"], ws["dQ"], ws["dK"], ws["dV"], kv_len=ws.get("kv_len"),
                      txt_len=ws.get("txt_len"), split=T)
         for s in (0, 1):
             wq, wk = wq_wk(s)
@@ -358,11 +365,14 @@ class FusedMMDiTBase(nn.Module):
                                 dres=self._rows(ws, dX, s), gate=mods(2)[s], dx_gated=self._rows(ws, ws["dY"], s))
         # ---- attention output projection (LoRA input = O), attention, q|k|v projection (LoRA input = xm1, recomputed)
         self._dgrad_grouped(ws, l, "out", ws["dY"], ws["dO"], D, D, D, O)
-        self._attn_bwd_core(ws, qkv, O, save["lse"], lambda s: (w["qknorm_w"][l, 2 * s], w["qknorm_w"][l, 2 * s + 1]))
-        if self._site(l, "qkv", 0) or self._site(l, "qkv", 1):
-            for s in (0, 1):
-                lib.ln_modulate_fwd(self._rows(ws, Xin, s), self._rows(ws, ws["xm"], s), mods(0)[s], mods(1)[s], self._rpb(ws, s))
-        self._dgrad_grouped(ws, l, "qkv", ws["dqkv"], ws["dxm"], D, 3 * D, D, ws["xm"])
+        self._attn_bwd_core(ws, qkv, O, save["lse"], lambda s: (w["qknorm_w"][l, 2 * s], w["qknorm_w"][l, 2 * s + 1]), save)
+        xm1 = save.get("xm1")
+        if xm1 is None:
+            xm1 = ws["xm"]
+            if self._site(l, "qkv", 0) or self._site(l, "qkv", 1):
+                for s in (0, 1):
+                    lib.ln_modulate_fwd(self._rows(ws, Xin, s), self._rows(ws, xm1, s), mods(0)[s], mods(1)[s], self._rpb(ws, s))
+        self._dgrad_grouped(ws, l, "qkv", ws["dqkv"], ws["dxm"], D, 3 * D, D, xm1)
         # ---- norm1 backward: dXin = dXmid + LN_bwd ; emit dXin * (gate of the block before)
         for s in (0, 1):
             lib.ln_modulate_bwd(self._rows(ws, ws["dxm"], s), self._rows(ws, Xin, s), self._rows(ws, st[0], s),
@@ -385,6 +395,9 @@ class FusedMMDiTBase(nn.Module):
         ns = n_single if train else min(1, n_single)
         ws["dbl"] = [dict(stats=e(4, M, dt=torch.float32), qkv=e(M, 3 * D), O=e(M, D), lse=e(B, H, S, dt=torch.float32),
                           xmid=e(M, D), u=e(M, 4 * D)) for _ in range(nd)]
+        if train and self.keep_qkv:  # +4 x [M, D] per block in HBM instead of regenerating them in the backward
+            for blk in ws["dbl"]:
+                blk.update(Q=e(B, H, S, 128), K=e(B, H, S, 128), V=e(B, H, S, 128), xm1=e(M, D))
         ws["sgl"] = [dict(stats=e(2, M, dt=torch.float32), qkv=e(M, 3 * D), O=e(M, D), lse=e(B, H, S, dt=torch.float32),
                           u=e(M, 4 * D)) for _ in range(ns)]
         ws["hn"], ws["pred"] = e(Mi, D), e(Mi, self.C_out)
