@@ -34,6 +34,7 @@ struct AttnBwdParams {
   const int* kv_len;    // [B] or NULL: keys >= kv_len[b] masked
   const int* txt_len;   // [B] or NULL: keys in [txt_len[b], split) masked (text padding)
   int split;
+  long long* dbg;       // optional: clock64 stamps of CTA (1, 0) — [iteration][16] (tools/attn_timeline.py)
   int S, H;
   float scale, scale_log2;
 };
@@ -79,6 +80,8 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
   const int txt_len = P.txt_len ? P.txt_len[b] : P.split;
   // a fully masked key tile (beyond kv_len, or entirely inside the text padding) contributes nothing: write zeros and leave
   const bool active = kv0 < kv_len && !(kv0 >= txt_len && kv0 + 128 <= P.split);
+  const bool dbg_on = P.dbg != nullptr && blockIdx.x == 1 && blockIdx.y == 0;
+#define DBG(i, e) do { if (dbg_on) P.dbg[(i) * 16 + (e)] = clock64(); } while (0)
 
   if (warp == 1 && lane == 0) {
     mbar_init(kv_full, 1);
@@ -141,8 +144,10 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
         const uint32_t q = sQ(st);
         mbar_wait(q_full(st), (i >> 1) & 1);
         mbar_wait(do_full, i & 1);
+        DBG(i, 0);
         if (i > 0) mbar_wait(dq_empty, (i - 1) & 1);  // S columns (shared with dQ) drained
         tc_fence_after();
+        DBG(i, 1);
 #pragma unroll
         for (int k = 0; k < 8; ++k) umma_bf16(tS, kmaj(q, k), kmaj(sK, k), id_kk, k != 0);
 #pragma unroll
@@ -150,11 +155,13 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
         umma_commit(s_full);
         mbar_wait(p_full, i & 1);
         tc_fence_after();
+        DBG(i, 2);
 #pragma unroll
         for (int k = 0; k < 8; ++k) umma_bf16(tdV, mnmaj(sP, k), mnmaj(sdO, k), id_mm, (i | k) != 0);
         umma_commit(do_empty);  // dO_i no longer needed
         mbar_wait(ds_full, i & 1);
         tc_fence_after();
+        DBG(i, 3);
 #pragma unroll
         for (int k = 0; k < 8; ++k) umma_bf16(tdK, mnmaj(sdS, k), mnmaj(q, k), id_mm, (i | k) != 0);
         umma_commit(q_empty(st));  // Q_i no longer needed
@@ -183,9 +190,12 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
         const bool q_ok = q < P.S;
         const float L = q_ok ? P.lse[(int64_t)bh * P.S + q] : INFINITY;
         const float dls = (q_ok ? P.delta[(int64_t)bh * P.S + q] : 0.f) * P.scale;
+        if (tid == 0) DBG(i, 8);
         mbar_wait(s_full, i & 1);
         tc_fence_after();
+        if (tid == 0) DBG(i, 9);
         if (i > 0) mbar_wait(stage_free, (i - 1) & 1);  // the dQ_{i-1} reduce has finished reading the P|dS buffers
+        if (tid == 0) DBG(i, 10);
         float p[64];
         // ---- pass 1: P
 #pragma unroll
@@ -217,6 +227,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
+        if (tid == 0) DBG(i, 11);
         // ---- pass 2: dS = P * (dP * scale - delta * scale)
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
@@ -240,10 +251,12 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(ds_full);
+        if (tid == 0) DBG(i, 12);
 
         // ---- drain dQ_i: TMEM -> fp32 swizzled slabs in the (now idle) P|dS buffers -> TMA reduce-add to global
         mbar_wait(dq_full, i & 1);
         tc_fence_after();
+        if (tid == 0) DBG(i, 13);
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           uint32_t r[32];
@@ -268,8 +281,10 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
 #pragma unroll
           for (int sl = 0; sl < 4; ++sl) tma_reduce_add_3d(&P.tmdQ, sP + sl * BW_ATOM, sl * 32, i * 128, bh);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          DBG(i, 14);
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           mbar_arrive(stage_free);
+          DBG(i, 15);
         }
       }
       mbar_wait(acc_full, 0);
@@ -319,11 +334,16 @@ int make_qkv_tmap(CUtensorMap* m, const void* base, int BH, int S);
 
 using namespace qfx;
 
+long long* g_qfx_attn_bwd_dbg = nullptr;
+/* debugging aid: device buffer of >= 16 * n_query_tiles int64 that receives clock64 stamps of CTA (1,0) (NULL disables) */
+extern "C" void qfx_attn_bwd_set_debug(long long* buf) { g_qfx_attn_bwd_dbg = buf; }
+
 /* All of Q, K, V, dO, dK, dV: [B, H, S, 128] bf16; dQ_accum: [B, H, S, 128] fp32, MUST be zeroed by the caller (it is the
  * target of TMA reduce-adds from every key tile).  lse: log2-domain logsumexp from qfx_attn_fwd; delta = rowsum(dO*O). */
 extern "C" int qfx_attn_bwd(const void* Q, const void* K, const void* V, const void* dO, const float* lse, const float* delta,
                             float* dQ_accum, void* dK, void* dV, const int* kv_len, const int* txt_len, int split, int B, int H,
                             int S, float softmax_scale, void* stream) {
+  extern long long* g_qfx_attn_bwd_dbg;
   QFX_CHECK_ARG(B > 0 && H > 0 && S > 0 && dQ_accum && dK && dV && lse && delta, "qfx_attn_bwd: bad arguments");
   AttnBwdParams P;
   memset(&P, 0, sizeof(P));
@@ -339,6 +359,7 @@ extern "C" int qfx_attn_bwd(const void* Q, const void* K, const void* V, const v
     if ((rc = make_tmap_f32(&P.tmdQ, dQ_accum, 3, dims, strides, box))) return rc;
   }
   P.dK = (bf16*)dK; P.dV = (bf16*)dV; P.lse = lse; P.delta = delta; P.kv_len = kv_len; P.txt_len = txt_len; P.split = txt_len ? split : 0; P.S = S; P.H = H;
+  P.dbg = g_qfx_attn_bwd_dbg;
   P.scale = softmax_scale;
   P.scale_log2 = softmax_scale * 1.4426950408889634f;
   static bool attr_done = false;
