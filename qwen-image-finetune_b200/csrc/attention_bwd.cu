@@ -53,7 +53,8 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t
 //   MMA     : dV += P^T dO_i                                -> do_empty    (dO_{i+1} starts loading)
 //   compute : dS = P (dP - delta) scale -> smem             -> ds_full
 //   MMA     : dK += dS^T Q_i  -> q_empty[i&1] ;  dQ_i = dS K (into the S columns)  -> dq_full
-//   compute : dQ_i TMEM -> fp32 slabs in the idle P|dS smem -> dq_empty (S_{i+1}/dP_{i+1} may issue) -> TMA reduce-add -> stage_free
+//   compute : dQ_i TMEM -> fp32 slabs parked in the consumed Q_i slot + the dS buffer -> dq_empty (S_{i+1}/dP_{i+1} may issue)
+//             -> TMA reduce-add -> stage_free / qstage_free   (P is not aliased: the next P pass overlaps the reduce)
 // Q is double-buffered and dO is released right after dV, so the loads of tile i+1 hide behind the math of tile i.
 __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -68,7 +69,8 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
   const uint32_t stage_free = bar_base + 64, acc_full = bar_base + 72;
   auto q_full = [&](int st) { return bar_base + 80 + 8u * st; };
   auto q_empty = [&](int st) { return bar_base + 96 + 8u * st; };
-  const uint32_t tmem_slot = bar_base + 112;
+  auto qstage_free = [&](int st) { return bar_base + 112 + 8u * st; };  // dQ reduce finished reading the slabs parked in Q slot st
+  const uint32_t tmem_slot = bar_base + 128;
   uint8_t* smem_gen = smem_raw;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
     for (int st = 0; st < 2; ++st) {
       mbar_init(q_full(st), 1);
       mbar_init(q_empty(st), 1);
+      mbar_init(qstage_free(st), 1);
     }
     fence_barrier_init();
   }
@@ -117,7 +120,10 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
       tma_load_3d(sV + BW_ATOM, &P.tmV, kv_full, 64, kv0, bh);
       for (int i = 0; i < n_q; ++i) {
         const int st = i & 1;
-        if (i >= 2) mbar_wait(q_empty(st), ((i - 2) >> 1) & 1);
+        if (i >= 2) {
+          mbar_wait(q_empty(st), ((i - 2) >> 1) & 1);      // dK_{i-2} has consumed Q_{i-2}
+          mbar_wait(qstage_free(st), ((i - 2) >> 1) & 1);  // ... and the dQ_{i-2} slabs parked in this slot have been reduced out
+        }
         mbar_expect_tx(q_full(st), BW_TILE);
         tma_load_3d(sQ(st), &P.tmQ, q_full(st), 0, i * 128, bh);
         tma_load_3d(sQ(st) + BW_ATOM, &P.tmQ, q_full(st), 64, i * 128, bh);
@@ -194,8 +200,6 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
         mbar_wait(s_full, i & 1);
         tc_fence_after();
         if (tid == 0) DBG(i, 9);
-        if (i > 0) mbar_wait(stage_free, (i - 1) & 1);  // the dQ_{i-1} reduce has finished reading the P|dS buffers
-        if (tid == 0) DBG(i, 10);
         float p[64];
         // ---- pass 1: P
 #pragma unroll
@@ -228,7 +232,9 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
         if (tid == 0) DBG(i, 11);
-        // ---- pass 2: dS = P * (dP * scale - delta * scale)
+        // ---- pass 2: dS = P * (dP * scale - delta * scale).  The dS buffer doubles as staging for half of dQ_{i-1}: wait for its reduce.
+        if (i > 0) mbar_wait(stage_free, (i - 1) & 1);
+        if (tid == 0) DBG(i, 10);
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           uint32_t rp[32];
@@ -263,7 +269,9 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
           const int c = c0 + cc * 32;
           tmem_ld32(tS + lane_off + c, r);
           tmem_ld_wait();
-          const uint32_t slab = sP + (c >> 5) * BW_ATOM + (uint32_t)row * 128;  // [128 rows x 32 fp32], 128 B rows
+          // [128 rows x 32 fp32] slabs, 128 B rows: head-dim columns 0..63 are parked in the (consumed) Q_i slot, 64..127 in the dS
+          // buffer — P is NOT aliased, so the next tile's P pass never waits for this reduce
+          const uint32_t slab = (c < 64 ? sQ(i & 1) + (c >> 5) * BW_ATOM : sdS + ((c - 64) >> 5) * BW_ATOM) + (uint32_t)row * 128;
 #pragma unroll
           for (int v = 0; v < 8; ++v) {
             const uint32_t chunk = (uint32_t)v ^ (uint32_t)(row & 7);
@@ -279,11 +287,13 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (tid == 0) {
 #pragma unroll
-          for (int sl = 0; sl < 4; ++sl) tma_reduce_add_3d(&P.tmdQ, sP + sl * BW_ATOM, sl * 32, i * 128, bh);
+          for (int sl = 0; sl < 4; ++sl)
+            tma_reduce_add_3d(&P.tmdQ, sl < 2 ? sQ(i & 1) + sl * BW_ATOM : sdS + (sl - 2) * BW_ATOM, sl * 32, i * 128, bh);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           DBG(i, 14);
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           mbar_arrive(stage_free);
+          mbar_arrive(qstage_free(i & 1));
           DBG(i, 15);
         }
       }
