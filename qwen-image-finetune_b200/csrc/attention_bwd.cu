@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
   auto q_full = [&](int st) { return bar_base + 80 + 8u * st; };
   auto q_empty = [&](int st) { return bar_base + 96 + 8u * st; };
   auto qstage_free = [&](int st) { return bar_base + 112 + 8u * st; };  // dQ reduce finished reading the slabs parked in Q slot st
-  const uint32_t tmem_slot = bar_base + 128;
+  const uint32_t dq_staged = bar_base + 128;  // all 8 compute warps have parked their dQ slabs in shared memory
+  const uint32_t tmem_slot = bar_base + 136;
   uint8_t* smem_gen = smem_raw;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 8);
     mbar_init(stage_free, 1);
+    mbar_init(dq_staged, 8);
     mbar_init(acc_full, 1);
     for (int st = 0; st < 2; ++st) {
       mbar_init(q_full(st), 1);
@@ -135,6 +137,21 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
         tma_load_3d(sdO, &P.tmdO, do_full, 0, i * 128, bh);
         tma_load_3d(sdO + BW_ATOM, &P.tmdO, do_full, 64, i * 128, bh);
       }
+    } else if (lane == 2 && active) {
+      // dQ reducer: a thread of its own, so that waiting for the TMA reduce-add to drain shared memory never stalls a compute warp
+      for (int i = 0; i < n_q; ++i) {
+        mbar_wait(dq_staged, i & 1);
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl)
+          tma_reduce_add_3d(&P.tmdQ, sl < 2 ? sQ(i & 1) + sl * BW_ATOM : sdS + (sl - 2) * BW_ATOM, sl * 32, i * 128, bh);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        DBG(i, 14);
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(stage_free);
+        mbar_arrive(qstage_free(i & 1));
+        DBG(i, 15);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all reduce-adds have been performed before the CTA exits
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer
@@ -283,19 +300,10 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dq_empty);  // the S columns are free: S_{i+1} / dP_{i+1} may issue while the reduce drains
+        if (tid == 0) DBG(i, 7);
         fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (tid == 0) {
-#pragma unroll
-          for (int sl = 0; sl < 4; ++sl)
-            tma_reduce_add_3d(&P.tmdQ, sl < 2 ? sQ(i & 1) + sl * BW_ATOM : sdS + (sl - 2) * BW_ATOM, sl * 32, i * 128, bh);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          DBG(i, 14);
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          mbar_arrive(stage_free);
-          mbar_arrive(qstage_free(i & 1));
-          DBG(i, 15);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_staged);  // the reducer thread (warp 0, lane 2) takes it from here
       }
       mbar_wait(acc_full, 0);
       tc_fence_after();

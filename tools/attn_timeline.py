@@ -28,7 +28,7 @@ torch.cuda.synchronize()
 lib._lib.qfx_attn_bwd_set_debug(C.c_void_p(0))
 d = dbg.view(19, 16).cpu()
 t0 = int(d[0, 0])
-names = {0: "mma:loads_ready", 1: "mma:Scols_free", 2: "mma:P_ready", 3: "mma:dS_ready", 8: "cmp:iter_start", 9: "cmp:S_ready", 10: "cmp:stage_free",
+names = {7: "cmp:dQ_drained", 0: "mma:loads_ready", 1: "mma:Scols_free", 2: "mma:P_ready", 3: "mma:dS_ready", 8: "cmp:iter_start", 9: "cmp:S_ready", 10: "cmp:stage_free",
          11: "cmp:P_written", 12: "cmp:dS_written", 13: "cmp:dQ_ready", 14: "cmp:reduce_issued", 15: "cmp:reduce_read_done"}
 print("iter " + " ".join(f"{names[k]:>20s}" for k in sorted(names)))
 for i in range(19):
