@@ -318,12 +318,31 @@ __global__ void __launch_bounds__(256) gemv_act_kernel(const bf16* __restrict__ 
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  const int nvec = K / 8;
   for (int n = blockIdx.x * 8 + (threadIdx.x >> 5); n < N; n += gridDim.x * 8) {
     const uint4* wr = reinterpret_cast<const uint4*>(W + (int64_t)n * ldw);
     float acc[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) acc[b] = 0.f;
-    for (int i = lane; i < K / 8; i += 32) {
+    // 4 independent 16-byte loads in flight per lane (the kernel streams 13.6 GB of modulation weights once per step)
+    int i = lane;
+    for (; i + 96 < nvec; i += 128) {
+      uint4 wv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wv[u] = __ldg(wr + i + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float fw[8];
+        unpack8(wv[u], fw);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const float* xb = xs + b * K + (i + 32 * u) * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[b] += fw[e] * xb[e];
+        }
+      }
+    }
+    for (; i < nvec; i += 32) {
       float fw[8];
       unpack8(__ldg(wr + i), fw);
 #pragma unroll

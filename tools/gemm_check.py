@@ -141,6 +141,10 @@ CASES["cta2_perf_nn"] = lambda: perf(True, 1256)
 CASES["cta2_perf_nt_mlp_up"] = lambda: perf(False, 1256, N=12288, K=3072)
 CASES["cta2_perf_nt_mlp_down"] = lambda: perf(False, 1256, N=3072, K=12288)
 CASES["cta2_perf_nn_mlp_down"] = lambda: perf(True, 1256, N=12288, K=3072)
+CASES["cta2_perf_nt_bn128"] = lambda: perf(False, 1128)
+CASES["cta2_perf_nn_bn128_k9216"] = lambda: perf(True, 1128, N=3072, K=9216)
+CASES["cta2_perf_nn_bn256_k9216"] = lambda: perf(True, 1256, N=3072, K=9216)
+CASES["cta2_perf_nt_bn128_down"] = lambda: perf(False, 1128, N=3072, K=12288)
 CASES["basic_nt_alpha_nobias"] = lambda: basic(False, 0, M=128, N=64, K=64, bias=False, alpha=0.5)
 CASES["basic_nt_big"] = lambda: basic(False, 0, M=2400, N=3072, K=3072)
 CASES["basic_nn_big"] = lambda: basic(True, 0, M=2400, N=3072, K=12288)
