@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
           uint32_t pk[16];
           if (full_tile) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) p[cc * 32 + e] = exp2f(__uint_as_float(rs[e]) * P.scale_log2 - L);
+            for (int e = 0; e < 32; e += 2) {  // even elements on the MUFU unit, odd ones on the FMA pipe
+              p[cc * 32 + e] = exp2f(__uint_as_float(rs[e]) * P.scale_log2 - L);
+              p[cc * 32 + e + 1] = exp2_fma(__uint_as_float(rs[e + 1]) * P.scale_log2 - L);
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < 32; ++e) {

@@ -195,8 +195,8 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
         if (full_tile) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float p0 = exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used);
-            const float p1 = exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used);
+            const float p0 = exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used);         // MUFU
+            const float p1 = exp2_fma(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used);  // FMA pipe
             pk[i] = pack_bf16(p0, p1);
             lsum += p0 + p1;
           }
