@@ -51,7 +51,7 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t
 //   MMA     : S = Q_i K^T, dP = dO_i V^T                 -> s_full
 //   compute : P = exp2(S c - L)  -> smem                    -> p_full      (thread = query row x 64 key columns)
 //   MMA     : dV += P^T dO_i                                -> do_empty    (dO_{i+1} starts loading)
-//   compute : dS = P (dP - delta) scale -> smem             -> ds_full
+//   compute : dS = P (dP - delta) scale -> smem (over P, after dv_done)  -> ds_full
 //   MMA     : dK += dS^T Q_i  -> q_empty[i&1] ;  dQ_i = dS K (into the S columns)  -> dq_full
 //   compute : dQ_i TMEM -> fp32 slabs parked in the consumed Q_i slot + the dS buffer -> dq_empty (S_{i+1}/dP_{i+1} may issue)
 //             -> TMA reduce-add -> stage_free / qstage_free   (P is not aliased: the next P pass overlaps the reduce)
@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
   auto q_empty = [&](int st) { return bar_base + 96 + 8u * st; };
   auto qstage_free = [&](int st) { return bar_base + 112 + 8u * st; };  // dQ reduce finished reading the slabs parked in Q slot st
   const uint32_t dq_staged = bar_base + 128;  // all 8 compute warps have parked their dQ slabs in shared memory
-  const uint32_t tmem_slot = bar_base + 136;
+  const uint32_t dv_done = bar_base + 136;    // dV_i has consumed P: the P buffer may be overwritten with dS
+  const uint32_t tmem_slot = bar_base + 144;
   uint8_t* smem_gen = smem_raw;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
     mbar_init(dq_empty, 8);
     mbar_init(stage_free, 1);
     mbar_init(dq_staged, 8);
+    mbar_init(dv_done, 1);
     mbar_init(acc_full, 1);
     for (int st = 0; st < 2; ++st) {
       mbar_init(q_full(st), 1);
@@ -182,14 +184,15 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
 #pragma unroll
         for (int k = 0; k < 8; ++k) umma_bf16(tdV, mnmaj(sP, k), mnmaj(sdO, k), id_mm, (i | k) != 0);
         umma_commit(do_empty);  // dO_i no longer needed
+        umma_commit(dv_done);   // ... and neither is P: dS is written over it (the old dS buffer only stages dQ now)
         mbar_wait(ds_full, i & 1);
         tc_fence_after();
         DBG(i, 3);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_bf16(tdK, mnmaj(sdS, k), mnmaj(q, k), id_mm, (i | k) != 0);
+        for (int k = 0; k < 8; ++k) umma_bf16(tdK, mnmaj(sP, k), mnmaj(q, k), id_mm, (i | k) != 0);
         umma_commit(q_empty(st));  // Q_i no longer needed
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_bf16(tS, kmaj(sdS, k), mnmaj(sK, k), id_km, k != 0);
+        for (int k = 0; k < 8; ++k) umma_bf16(tS, kmaj(sP, k), mnmaj(sK, k), id_km, k != 0);
         umma_commit(dq_full);
       }
       umma_commit(acc_full);
@@ -227,10 +230,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
           uint32_t pk[16];
           if (full_tile) {
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {  // even elements on the MUFU unit, odd ones on the FMA pipe
-              p[cc * 32 + e] = exp2f(__uint_as_float(rs[e]) * P.scale_log2 - L);
-              p[cc * 32 + e + 1] = exp2_fma(__uint_as_float(rs[e + 1]) * P.scale_log2 - L);
-            }
+            for (int e = 0; e < 32; ++e) p[cc * 32 + e] = exp2f(__uint_as_float(rs[e]) * P.scale_log2 - L);
           } else {
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
@@ -252,8 +252,7 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
         if (tid == 0) DBG(i, 11);
-        // ---- pass 2: dS = P * (dP * scale - delta * scale).  The dS buffer doubles as staging for half of dQ_{i-1}: wait for its reduce.
-        if (i > 0) mbar_wait(stage_free, (i - 1) & 1);
+        // ---- pass 2: dS = P * (dP * scale - delta * scale), written over P once dV_i has consumed it
         if (tid == 0) DBG(i, 10);
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
@@ -265,10 +264,11 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
           for (int e = 0; e < 16; ++e)
             dk[e] = pack_bf16(p[cc * 32 + 2 * e] * (__uint_as_float(rp[2 * e]) * P.scale - dls),
                               p[cc * 32 + 2 * e + 1] * (__uint_as_float(rp[2 * e + 1]) * P.scale - dls));
+          if (cc == 0) mbar_wait(dv_done, i & 1);
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             const uint32_t chunk = (uint32_t)(cc * 4 + v) ^ (uint32_t)(row & 7);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS + off_row + chunk * 16), "r"(dk[4 * v]),
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off_row + chunk * 16), "r"(dk[4 * v]),
                          "r"(dk[4 * v + 1]), "r"(dk[4 * v + 2]), "r"(dk[4 * v + 3])
                          : "memory");
           }
@@ -283,14 +283,15 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
         mbar_wait(dq_full, i & 1);
         tc_fence_after();
         if (tid == 0) DBG(i, 13);
+        if (i > 0) mbar_wait(stage_free, (i - 1) & 1);  // the staging buffer of dQ_{i-1} has been reduced out (long ago)
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           uint32_t r[32];
           const int c = c0 + cc * 32;
           tmem_ld32(tS + lane_off + c, r);
           tmem_ld_wait();
-          // [128 rows x 32 fp32] slabs, 128 B rows: head-dim columns 0..63 are parked in the (consumed) Q_i slot, 64..127 in the dS
-          // buffer — P is NOT aliased, so the next tile's P pass never waits for this reduce
+          // [128 rows x 32 fp32] slabs, 128 B rows: head-dim columns 0..63 are parked in the (consumed) Q_i slot, 64..127 in a staging
+          // buffer of their own — nothing the next tile writes is aliased, so its P / dS passes never wait for this reduce
           const uint32_t slab = (c < 64 ? sQ(i & 1) + (c >> 5) * BW_ATOM : sdS + ((c - 64) >> 5) * BW_ATOM) + (uint32_t)row * 128;
 #pragma unroll
           for (int v = 0; v < 8; ++v) {

@@ -171,85 +171,83 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
       mbar_wait(s_full(s), (j >> 1) & 1);
       tc_fence_after();
       const uint32_t tS = tS0 + s * 128 + lane_off + c0;
+      float mx = -INFINITY;
       // warp-uniform: no key masking needed (all tiles but the last, unless the tile touches text padding)
       const bool full_tile = valid >= ATT_BK && (gap0 >= gap1 || gap0 >= ATT_BK || gap1 <= 0);
-      // one TMEM round trip per tile: this thread's 64 scores stay in registers for the max AND the exponentials
-      uint32_t r[64];
-      tmem_ld32(tS, r);
-      tmem_ld32(tS + 32, r + 32);
-      tmem_ld_wait();
-      float mx = -INFINITY;
-      if (full_tile) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (c0 + i < valid && !(c0 + i >= gap0 && c0 + i < gap1)) mx = fmaxf(mx, __uint_as_float(r[i]));
-      }
-      red[(s * 2 + half) * 128 + row] = mx;
-      uint32_t pk[32];
-      float lsum;
-      auto compute_p = [&]() {  // P = exp2(S*c - m_used) (bf16 pairs) and its row sum
-        lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tS + c, r);
+        tmem_ld_wait();
         if (full_tile) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float p0 = exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used);         // MUFU
-            const float p1 = exp2_fma(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used);  // FMA pipe
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + c + i < valid && !(c0 + c + i >= gap0 && c0 + c + i < gap1)) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+      }
+      red[(s * 2 + half) * 128 + row] = mx;
+      pair_sync();
+      mx = fmaxf(mx, red[(s * 2 + (half ^ 1)) * 128 + row]);
+      // (a tile that is entirely text padding leaves mx = -inf: m_new = m_used, all p = 0 — tile 0 always has a valid key)
+      const float m_new = fmaxf(m_used, mx * P.scale_log2);
+      // warp-uniform lazy rescale of the TMEM accumulator (both warps of a pair see the same rows -> same decision)
+      const bool need = (j == 0) || (m_new > m_used + 8.f);
+      if (__any_sync(0xffffffffu, need)) {
+        if (j > 0) {
+          mbar_wait(pv_done((j - 1) & 1), ((j - 1) >> 1) & 1);  // all earlier P V MMAs have landed in O
+          tc_fence_after();
+          const float alpha = exp2f(m_used - m_new);
+#pragma unroll 1
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(tO + lane_off + c0 + c, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st32(tO + lane_off + c0 + c, r);
+          }
+          tmem_st_wait();
+          l *= alpha;
+        }
+        m_used = m_new;
+      }
+      if (j >= 2) mbar_wait(pv_done(s), ((j - 2) >> 1) & 1);  // P buffer s no longer read by the tensor core
+      const uint32_t p_row = sP(s) + half * ATOM_BYTES + row * 128;  // this thread's 64 columns = one swizzle atom row
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tS + c, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+        if (full_tile) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used);
+            const float p1 = exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used);
             pk[i] = pack_bf16(p0, p1);
             lsum += p0 + p1;
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int k0 = c0 + 2 * i, k1 = k0 + 1;
+          for (int i = 0; i < 16; ++i) {
+            const int k0 = c0 + c + 2 * i, k1 = k0 + 1;
             const float p0 = (k0 < valid && !(k0 >= gap0 && k0 < gap1)) ? exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used) : 0.f;
             const float p1 = (k1 < valid && !(k1 >= gap0 && k1 < gap1)) ? exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used) : 0.f;
             pk[i] = pack_bf16(p0, p1);
             lsum += p0 + p1;
           }
         }
-      };
-      if (j == 0) {
-        pair_sync();
-        m_used = fmaxf(mx, red[(s * 2 + (half ^ 1)) * 128 + row]) * P.scale_log2;  // tile 0 always holds a valid key
-        compute_p();
-      } else {
-        // speculate with the running max (exact unless it grew by more than 2^8 — checked right after, off the MUFU path)
-        compute_p();
-        pair_sync();
-        mx = fmaxf(mx, red[(s * 2 + (half ^ 1)) * 128 + row]);
-        // (a tile that is entirely text padding leaves mx = -inf: m_new = m_used, all p = 0)
-        const float m_new = fmaxf(m_used, mx * P.scale_log2);
-        // warp-uniform lazy rescale of the TMEM accumulator (both warps of a pair see the same rows -> same decision)
-        if (__any_sync(0xffffffffu, m_new > m_used + 8.f)) {
-          mbar_wait(pv_done((j - 1) & 1), ((j - 1) >> 1) & 1);  // all earlier P V MMAs have landed in O
-          tc_fence_after();
-          const float alpha = exp2f(m_used - m_new);
-#pragma unroll 1
-          for (int c = 0; c < 64; c += 32) {
-            uint32_t o[32];
-            tmem_ld32(tO + lane_off + c0 + c, o);
-            tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tO + lane_off + c0 + c, o);
-          }
-          tmem_st_wait();
-          l *= alpha;
-          m_used = m_new;
-          compute_p();
+        for (int v = 0; v < 4; ++v) {
+          const uint32_t chunk = (uint32_t)((c >> 3) + v) ^ (uint32_t)(row & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16), "r"(pk[4 * v]), "r"(pk[4 * v + 1]),
+                       "r"(pk[4 * v + 2]), "r"(pk[4 * v + 3])
+                       : "memory");
         }
-      }
-      if (j >= 2) mbar_wait(pv_done(s), ((j - 2) >> 1) & 1);  // P buffer s no longer read by the tensor core
-      const uint32_t p_row = sP(s) + half * ATOM_BYTES + row * 128;  // this thread's 64 columns = one swizzle atom row
-#pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        const uint32_t chunk = (uint32_t)v ^ (uint32_t)(row & 7);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16), "r"(pk[4 * v]), "r"(pk[4 * v + 1]),
-                     "r"(pk[4 * v + 2]), "r"(pk[4 * v + 3])
-                     : "memory");
       }
       l += lsum;
       fence_proxy_async_smem();

@@ -220,8 +220,9 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // exp2 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic minimax for 2^f, exponent
-// patched in with an integer add.  Relative error < 8e-5 (bf16 probabilities carry 3.9e-3).  The attention kernels send every
-// other element through this path so the 16-op/clk MUFU unit and the FMA pipe share the softmax exponentials.
+// patched in with an integer add.  Relative error < 8e-5 (bf16 probabilities carry 3.9e-3).  MEASURED (round 1): sending every
+// other softmax exponential through this path made attention forward 18 % SLOWER (0.50 vs 0.43 ms) — the softmax warps are
+// instruction-issue bound, not MUFU bound, with one query tile per CTA — so the kernels do not use it yet.
 __device__ __forceinline__ float exp2_fma(float x) {
   x = fmaxf(x, -125.f);
   const float magic = 12582912.f;                 // 1.5 * 2^23: adding it rounds x to the nearest integer in the low mantissa bits
