@@ -47,6 +47,14 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t
                : "memory");
 }
 
+__device__ __forceinline__ void mask_scores_bwd(uint32_t* r, int col0, int valid, int gap0, int gap1) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int k = col0 + i;
+    if (!(k < valid) || (k >= gap0 && k < gap1)) r[i] = 0xff800000u;  // -inf
+  }
+}
+
 // Pipeline per query tile i (key tile fixed per CTA):
 //   MMA     : S = Q_i K^T, dP = dO_i V^T                 -> s_full
 //   compute : P = exp2(S c - L)  -> smem                    -> p_full      (thread = query row x 64 key columns)
@@ -228,16 +236,9 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_kernel(const __grid_constant_
           tmem_ld32(tS + lane_off + c0 + cc * 32, rs);
           tmem_ld_wait();
           uint32_t pk[16];
-          if (full_tile) {
+          if (!full_tile) mask_scores_bwd(rs, c0 + cc * 32, valid, gap0, gap1);  // rare: masked keys -> -inf -> P = 0
 #pragma unroll
-            for (int e = 0; e < 32; ++e) p[cc * 32 + e] = exp2f(__uint_as_float(rs[e]) * P.scale_log2 - L);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int kk = c0 + cc * 32 + e;
-              p[cc * 32 + e] = (kk < valid && !(kk >= gap0 && kk < gap1)) ? exp2f(__uint_as_float(rs[e]) * P.scale_log2 - L) : 0.f;
-            }
-          }
+          for (int e = 0; e < 32; ++e) p[cc * 32 + e] = exp2f(__uint_as_float(rs[e]) * P.scale_log2 - L);
 #pragma unroll
           for (int e = 0; e < 16; ++e) pk[e] = pack_bf16(p[cc * 32 + 2 * e], p[cc * 32 + 2 * e + 1]);
 #pragma unroll

@@ -11,6 +11,7 @@
 // QK^T of tile j+1 is issued before P V of tile j so the tensor pipe works while the softmax warps run.
 // O is rescaled in TMEM only when the running max grows by more than 2^8 (warp-uniform decision), as the final
 // normalisation by the running sum makes a stale max exact.
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/qfx.h"
@@ -27,6 +28,7 @@ constexpr int ATOM_BYTES = 128 * 128;      // 16 KB
 
 struct AttnFwdParams {
   CUtensorMap tmQ, tmK, tmV;  // [B*H, S, 128] bf16, box {64, 128, 1}
+  CUtensorMap tmK64, tmV64;   // same tensors, box {64, 64, 1} (64-key tiles of the two-CTAs-per-SM kernel)
   bf16* out0;                 // rows with joint position s < split  -> out0[(b*rows0 + s) * ld0 + h*128 ..]
   bf16* out1;                 // rows with s >= split               -> out1[(b*rows1 + s - split) * ld1 + h*128 ..]
   int64_t ld0, ld1;
@@ -39,6 +41,16 @@ struct AttnFwdParams {
 };
 
 constexpr int ATT_SMEM = 7 * TILE_BYTES + 256 + 2 * 2 * 128 * 4;  // Q, K x2, V x2, P x2, barriers, row-max exchange
+
+// Key masking happens OUTSIDE the hot loops: in the (rare) partially valid tile the masked scores are overwritten with -inf, so
+// the max / exp2 loops carry no predicates (the if-converted per-element compares doubled the softmax instruction count).
+__device__ __forceinline__ void mask_scores(uint32_t* r, int col0, int valid, int gap0, int gap1) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int k = col0 + i;
+    if (!(k < valid) || (k >= gap0 && k < gap1)) r[i] = 0xff800000u;  // -inf
+  }
+}
 
 __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // 128B-swizzle atoms need 1024 B alignment (no slack left to round up)
@@ -179,14 +191,9 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
         uint32_t r[32];
         tmem_ld32(tS + c, r);
         tmem_ld_wait();
-        if (full_tile) {
+        if (!full_tile) mask_scores(r, c0 + c, valid, gap0, gap1);  // rare (last tile / text padding): masked keys -> -inf
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + c + i < valid && !(c0 + c + i >= gap0 && c0 + c + i < gap1)) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
       }
       red[(s * 2 + half) * 128 + row] = mx;
       pair_sync();
@@ -223,23 +230,13 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
         tmem_ld32(tS + c, r);
         tmem_ld_wait();
         uint32_t pk[16];
-        if (full_tile) {
+        if (!full_tile) mask_scores(r, c0 + c, valid, gap0, gap1);  // exp2(-inf) = 0 for masked keys
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used);
-            const float p1 = exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used);
-            pk[i] = pack_bf16(p0, p1);
-            lsum += p0 + p1;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int k0 = c0 + c + 2 * i, k1 = k0 + 1;
-            const float p0 = (k0 < valid && !(k0 >= gap0 && k0 < gap1)) ? exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used) : 0.f;
-            const float p1 = (k1 < valid && !(k1 >= gap0 && k1 < gap1)) ? exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used) : 0.f;
-            pk[i] = pack_bf16(p0, p1);
-            lsum += p0 + p1;
-          }
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used);
+          const float p1 = exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used);
+          pk[i] = pack_bf16(p0, p1);
+          lsum += p0 + p1;
         }
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
@@ -295,6 +292,223 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
   }
 }
 
+// =====================================================================================================================
+// 64-key-tile variant, TWO CTAs resident per SM.  The 128-key kernel above is latency bound: every tile walks the chain
+// S ready -> tcgen05.ld -> max -> exp2 (MUFU) -> st.shared -> fence -> P V, and its 224 KB of shared memory leave the SM to a
+// single CTA.  Here a CTA needs 112 KB of shared memory and 256 TMEM columns (S 2 x 64, O 128), so two CTAs share an SM and the
+// tensor pipe of one runs under the softmax of the other.  4 softmax warps, thread = query row x all 64 keys of the tile (one TMEM
+// round trip per tile, no cross-warp exchange).  K is released right after Q K^T, V after P V; P is single-buffered.
+constexpr int F64_KT = 64 * 128 * 2;                                 // one K or V tile: 64 keys x 128 dims = 16 KB (two 8 KB atoms)
+constexpr int F64_SMEM = TILE_BYTES + 4 * F64_KT + 128 * 128 + 256;  // Q + K x2 + V x2 + P[128 x 64] + barriers = 112.25 KB
+
+__global__ void __launch_bounds__(192, 2) attn_fwd64_kernel(const __grid_constant__ AttnFwdParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  const uint32_t sQ = smem_base;
+  auto sK = [&](int s) { return smem_base + TILE_BYTES + F64_KT * s; };
+  auto sV = [&](int s) { return smem_base + TILE_BYTES + F64_KT * (2 + s); };
+  const uint32_t sP = smem_base + TILE_BYTES + 4 * F64_KT;
+  const uint32_t bar_base = sP + 128 * 128;
+  const uint32_t q_full = bar_base;
+  auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto v_full = [&](int s) { return bar_base + 8u * (3 + s); };
+  auto s_full = [&](int s) { return bar_base + 8u * (5 + s); };
+  const uint32_t p_full = bar_base + 8u * 7;
+  auto pv_done = [&](int s) { return bar_base + 8u * (8 + s); };
+  const uint32_t o_full = bar_base + 8u * 10;
+  auto k_empty = [&](int s) { return bar_base + 8u * (11 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * 13;
+  uint8_t* smem_gen = smem_raw;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BQ;
+  const int bh = blockIdx.y;
+  const int b = bh / P.H, h = bh - b * P.H;
+  const int kv_len = P.kv_len ? P.kv_len[b] : P.S;
+  const int txt_len = P.txt_len ? P.txt_len[b] : P.split;
+  const int n_tiles = (kv_len + 63) / 64;
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full(s), 1);
+      mbar_init(v_full(s), 1);
+      mbar_init(s_full(s), 1);
+      mbar_init(pv_done(s), 1);
+      mbar_init(k_empty(s), 1);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  const uint32_t tS0 = tmem_base, tO = tmem_base + 128;
+
+  if (warp == 0) {
+    // ================================================================= TMA producers: lane 0 = Q + K tiles, lane 1 = V tiles
+    if (lane == 0) {
+      tma_prefetch_desc(&P.tmQ);
+      tma_prefetch_desc(&P.tmK64);
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(sQ, &P.tmQ, q_full, 0, q0, bh);
+      tma_load_3d(sQ + ATOM_BYTES, &P.tmQ, q_full, 64, q0, bh);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        if (j >= 2) mbar_wait(k_empty(s), ((j - 2) >> 1) & 1);
+        mbar_expect_tx(k_full(s), F64_KT);
+        tma_load_3d(sK(s), &P.tmK64, k_full(s), 0, j * 64, bh);
+        tma_load_3d(sK(s) + 8192, &P.tmK64, k_full(s), 64, j * 64, bh);
+      }
+    } else if (lane == 1) {
+      tma_prefetch_desc(&P.tmV64);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        if (j >= 2) mbar_wait(pv_done(s), ((j - 2) >> 1) & 1);
+        mbar_expect_tx(v_full(s), F64_KT);
+        tma_load_3d(sV(s), &P.tmV64, v_full(s), 0, j * 64, bh);
+        tma_load_3d(sV(s) + 8192, &P.tmV64, v_full(s), 64, j * 64, bh);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_pv = idesc_bf16(128, 128, 0, 1);
+      mbar_wait(q_full, 0);
+      auto issue_pv = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(p_full, j & 1);
+        mbar_wait(v_full(s), (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // K = 64 keys: P is one 128B-swizzle atom column, V is MN-major (two 64-wide d atoms, 8 KB apart)
+          umma_bf16(tO, sdesc_sw128(sP + k * 32, 16, 1024), sdesc_sw128(sV(s) + k * 2048, 8192, 1024), idesc_pv, (j | k) != 0);
+        umma_commit(pv_done(s));
+      };
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        mbar_wait(k_full(s), (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tS0 + s * 64, sdesc_sw128(sQ + (k >> 2) * ATOM_BYTES + (k & 3) * 32, 16, 1024),
+                    sdesc_sw128(sK(s) + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024), idesc_qk, k != 0);
+        umma_commit(s_full(s));
+        umma_commit(k_empty(s));
+        if (j > 0) issue_pv(j - 1);
+      }
+      issue_pv(n_tiles - 1);
+      umma_commit(o_full);
+    }
+  } else {
+    // ================================================================= softmax warps (thread = query row)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j & 1;
+      const int valid = kv_len - j * 64;
+      const int gap0 = txt_len - j * 64, gap1 = P.split - j * 64;
+      const bool full_tile = valid >= 64 && (gap0 >= gap1 || gap0 >= 64 || gap1 <= 0);
+      mbar_wait(s_full(s), (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[64];
+      tmem_ld32(tS0 + s * 64 + lane_off, r);
+      tmem_ld32(tS0 + s * 64 + lane_off + 32, r + 32);
+      tmem_ld_wait();
+      if (!full_tile) {
+        mask_scores(r, 0, valid, gap0, gap1);
+        mask_scores(r + 32, 32, valid, gap0, gap1);
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+      const float m_new = fmaxf(m_used, mx * P.scale_log2);  // a fully padded tile: mx = -inf, m_new = m_used (tile 0 has a valid key)
+      if (__any_sync(0xffffffffu, (j == 0) || (m_new > m_used + 8.f))) {  // warp-uniform lazy rescale
+        if (j > 0) {
+          mbar_wait(pv_done((j - 1) & 1), ((j - 1) >> 1) & 1);
+          tc_fence_after();
+          const float alpha = exp2f(m_used - m_new);
+#pragma unroll 1
+          for (int c = 0; c < 128; c += 32) {
+            uint32_t o[32];
+            tmem_ld32(tO + lane_off + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tO + lane_off + c, o);
+          }
+          tmem_st_wait();
+          l *= alpha;
+        }
+        m_used = m_new;
+      }
+      uint32_t pk[32];
+      float lsum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float p0 = exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used);
+        const float p1 = exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used);
+        pk[i] = pack_bf16(p0, p1);
+        lsum += p0 + p1;
+      }
+      l += lsum;
+      if (j >= 1) mbar_wait(pv_done((j - 1) & 1), ((j - 1) >> 1) & 1);  // the single P buffer has been consumed by P V of tile j-1
+      const uint32_t p_row = sP + row * 128;
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const uint32_t chunk = (uint32_t)v ^ (uint32_t)(row & 7);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16), "r"(pk[4 * v]), "r"(pk[4 * v + 1]),
+                     "r"(pk[4 * v + 2]), "r"(pk[4 * v + 3])
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ----------------------------------------------------------------- epilogue
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int sq = q0 + row;
+    const bool ok = sq < P.S;
+    const float inv = 1.f / l;
+    bf16* dst = nullptr;
+    if (ok) {
+      dst = sq < P.split ? P.out0 + ((int64_t)b * P.rows0 + sq) * P.ld0 + h * ATT_D
+                         : P.out1 + ((int64_t)b * P.rows1 + (sq - P.split)) * P.ld1 + h * ATT_D;
+      if (P.lse) P.lse[(int64_t)bh * P.S + sq] = m_used + log2f(l);
+    }
+#pragma unroll 1
+    for (int c = 0; c < 128; c += 32) {
+      uint32_t o[32];
+      tmem_ld32(tO + lane_off + c, o);
+      tmem_ld_wait();
+      if (ok) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c);
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          d4[v] = make_uint4(pack_bf16(__uint_as_float(o[8 * v]) * inv, __uint_as_float(o[8 * v + 1]) * inv),
+                             pack_bf16(__uint_as_float(o[8 * v + 2]) * inv, __uint_as_float(o[8 * v + 3]) * inv),
+                             pack_bf16(__uint_as_float(o[8 * v + 4]) * inv, __uint_as_float(o[8 * v + 5]) * inv),
+                             pack_bf16(__uint_as_float(o[8 * v + 6]) * inv, __uint_as_float(o[8 * v + 7]) * inv));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 int make_qkv_tmap(CUtensorMap* m, const void* base, int BH, int S) {
   uint64_t dims[3] = {128, (uint64_t)S, (uint64_t)BH};
   uint64_t strides[2] = {128 * 2, (uint64_t)S * 128 * 2};
@@ -322,12 +536,28 @@ extern "C" int qfx_attn_fwd(const void* Q, const void* K, const void* V, void* o
   P.ld0 = ld0; P.ld1 = ld1; P.rows0 = rows0; P.rows1 = rows1; P.split = split;
   P.lse = lse; P.kv_len = kv_len; P.txt_len = txt_len; P.S = S; P.H = H;
   P.scale_log2 = softmax_scale * 1.4426950408889634f;
+  static const bool use128 = getenv("QFX_ATTN_FWD128") != nullptr;  // A/B switch: the single-CTA-per-SM 128-key-tile kernel
+  dim3 grid((S + ATT_BQ - 1) / ATT_BQ, B * H);
+  if (!use128) {
+    uint64_t dims[3] = {128, (uint64_t)S, (uint64_t)(B * H)};
+    uint64_t strides[2] = {128 * 2, (uint64_t)S * 128 * 2};
+    uint32_t box[3] = {64, 64, 1};
+    if ((rc = make_tmap_bf16(&P.tmK64, K, 3, dims, strides, box))) return rc;
+    if ((rc = make_tmap_bf16(&P.tmV64, V, 3, dims, strides, box))) return rc;
+    static bool attr64 = false;
+    if (!attr64) {
+      QFX_CUDA(cudaFuncSetAttribute(attn_fwd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F64_SMEM));
+      attr64 = true;
+    }
+    attn_fwd64_kernel<<<grid, 192, F64_SMEM, (cudaStream_t)stream>>>(P);
+    QFX_CUDA(cudaGetLastError());
+    return 0;
+  }
   static bool attr_done = false;
   if (!attr_done) {
     QFX_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_done = true;
   }
-  dim3 grid((S + ATT_BQ - 1) / ATT_BQ, B * H);
   attn_fwd_kernel<<<grid, 320, ATT_SMEM, (cudaStream_t)stream>>>(P);
   QFX_CUDA(cudaGetLastError());
   return 0;
