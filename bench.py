@@ -226,6 +226,12 @@ def run_b200(args):
     ms_step = ms.item() / args.steps
     clk = clocks.stop() if rank == 0 else None
     loss_val = float(loss.item())
+    # host-side issue time of one step (no synchronisation inside): must stay below the device time, else the GPU starves
+    torch.cuda.synchronize()
+    th0 = time.perf_counter()
+    step.train_step(devd, opt)
+    host_issue_ms = (time.perf_counter() - th0) * 1e3
+    torch.cuda.synchronize()
     # ---------------- end-to-end arm: pinned host inputs, loss read back every step
     step.train_step(host, opt)
     sync()
@@ -260,7 +266,7 @@ def run_b200(args):
                                    f"S=352 txt + 2x1024 img tokens", "global_batch": B * world, "batch_per_gpu": B,
                        "parallelism": f"dp{world}", "l2": "inputs > L2: 41 GB weights + 35 GB activations stream through 126 MB L2",
                        "optimizer": "torch AdamW(foreach) on LoRA params", "loss": loss_val},
-            "clocks": clk, "gpu_launches": launches,
+            "clocks": clk, "gpu_launches": launches, "host_issue_ms_per_step": host_issue_ms,
             "e2e": {"value": e2e_ips, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel<256,false,GELU> grouped img+txt MLP-up [8192+1408,3072]x[12288,3072]",
                          "achieved": g_tf, "peak": burst, "unit": "TFLOP/s", "frac": g_tf / burst, "traffic": 1.363e9,

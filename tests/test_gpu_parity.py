@@ -60,6 +60,11 @@ def test_fused_step_vs_oracle(name):
     assert r["fast_vs_autograd"] < 5e-3
 
 
+def test_qwen_multi_resolution_vs_unpadded_oracle():
+    r = _cases("model_check")["qwen_multires"]()
+    assert r["pred_vs_fp32"] < 2e-2 and r["grad_vs_fp32"] < 3e-2 and r["loss_rel"] < 1e-2
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

@@ -181,12 +181,59 @@ def flux_step_parity(H=2, L=2, Ls=2, J=64, Pp=64, B=2, hw=4, T=8, r=4,
     return res
 
 
+def qwen_multires(H=2, L=2, J=128):
+    """pad-to-max multi-resolution batch (per-sample RoPE, text + image key masks, AttentionMask loss) vs un-padded oracle runs."""
+    from oracle import mmdit_oracle as mo
+    from qflux_b200.train_step import QwenImageEditStep
+    orc, m = build_pair(H, L, J, 4, ("to_q", "to_k", "to_v", "to_out.0"))
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()
+    shapes = [[(1, 16, 12), (1, 16, 12)], [(1, 8, 10), (1, 8, 10)], [(1, 12, 12), (1, 12, 12)]]
+    lt = [sh[0][1] * sh[0][2] for sh in shapes]
+    lc = lt
+    B, T, txt = 3, 40, [40, 23, 31]
+    Lt = max(lt)
+    x0, ctrl, pe, noise = rn(B, Lt, 64), rn(B, Lt, 64), rn(B, T, J) * 3, rn(B, Lt, 64)
+    mask = torch.zeros(B, T, dtype=torch.int64, device="cuda")
+    for b in range(B):
+        x0[b, lt[b]:] = 0; ctrl[b, lc[b]:] = 0; noise[b, lt[b]:] = 0; pe[b, txt[b]:] = 0; mask[b, :txt[b]] = 1
+    u = torch.tensor([0.5, 0.25, 0.75])
+    sig = ((1000 - (u * 1000).long()).float() / 1000).cuda()
+    preds, total = [], 0.0
+    for b in range(B):
+        s = sig[b]
+        noisy = (1 - s) * x0[b, :lt[b]].float() + s * noise[b, :lt[b]].float()
+        packed = torch.cat([noisy, ctrl[b, :lc[b]].float()], 0)[None]
+        p = orc(hidden_states=packed, timestep=sig[b:b + 1], encoder_hidden_states=pe[b:b + 1, :txt[b]].float(),
+                encoder_hidden_states_mask=mask[b:b + 1, :txt[b]], img_shapes=[shapes[b]], txt_seq_lens=[txt[b]])[0][0, :lt[b]]
+        preds.append(p)
+        total = total + ((p - (noise[b, :lt[b]].float() - x0[b, :lt[b]].float())) ** 2).mean(-1).sum()
+    loss_o = total / (sum(lt) + 1e-12)
+    loss_o.backward()
+    step = QwenImageEditStep(m, "attention_mask")
+    emb = dict(image_latents=x0, control_latents=ctrl, prompt_embeds=pe, prompt_embeds_mask=mask, img_shapes=shapes)
+    loss_b = step.compute_loss(emb, noise=noise, u=u)
+    pred_b = m._ws["pred"].view(B, -1, 64).float().clone()
+    loss_b.backward()
+    torch.cuda.synchronize()
+    res = dict(pred_vs_fp32=max(rel_l2(pred_b[b, :lt[b]], preds[b]) for b in range(B)), loss=loss_o.item(),
+               loss_abs=abs(loss_b.item() - loss_o.item()))
+    res["loss_rel"] = res["loss_abs"] / max(1.0, abs(loss_o.item()))
+    go = {n: p.grad for n, p in orc.named_parameters() if p.requires_grad}
+    num = sum(((p.grad.float() - go[n]).double() ** 2).sum() for n, p in m.named_parameters())
+    den = sum((v.double() ** 2).sum() for v in go.values())
+    res["grad_vs_fp32"] = float((num / den).sqrt())
+    res["err"] = max(res["pred_vs_fp32"], res["grad_vs_fp32"])
+    return res
+
+
 CASES = {
     "inference_tiny": inference_parity,
     "step_tiny": lambda: step_parity(),
     "step_tiny_nolora_targets_all_attn": lambda: step_parity(targets=("to_q", "to_k", "to_v", "to_out.0", "add_q_proj", "add_k_proj", "add_v_proj", "to_add_out", "net.0.proj"), r=8),
     "step_mid": lambda: step_parity(H=4, L=3, J=256, B=2, hw=16, T=40, r=16),
     "step_full_width_1blk": full_width_block,
+    "qwen_multires": qwen_multires,
     "flux_tiny": lambda: flux_step_parity(),
     "flux_tiny_regex_noguidance": lambda: flux_step_parity(guidance=False, r=8,
                                                            targets=r".*(attn\.(to_[qkv]|add_[qkv]_proj|to_add_out)|proj_mlp|ff\.net\.0\.proj)"),
