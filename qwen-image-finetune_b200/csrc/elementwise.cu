@@ -36,37 +36,65 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 
 // ============================================================================================ LayerNorm + modulate
-// y = bf16( bf16( bf16(LN(x)) * bf16(1 + scale[b]) ) + shift[b] ),   b = row / rows_per_batch.   NV = D / 256.
-template <int NV>
+// Row kernels are HBM-bound, so they are organised for bytes in flight: a row of D = W*32*VPT*8 elements is owned by W warps
+// (VPT 16-byte vectors per thread, 24-48 live floats instead of a whole row per warp), 256-thread CTAs hold 8/W rows and the
+// row's warps meet on a named barrier.  (Round-1 first version: one warp per row kept 96-192 floats per lane -> 8-16 warps
+// per SM -> 2.6 TB/s forward, 1.9 TB/s backward.)
+template <int W>
+__device__ __forceinline__ void row_sum2(float& a, float& b, float* red) {  // red: [2 * W] floats private to this row and use
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (W > 1) {
+    const int w = (threadIdx.x >> 5) % W;
+    if ((threadIdx.x & 31) == 0) {
+      red[w] = a;
+      red[W + w] = b;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / W), "r"(W * 32) : "memory");
+    a = 0.f;
+    b = 0.f;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      a += red[i];
+      b += red[W + i];
+    }
+  }
+}
+
+// y = bf16( bf16( bf16(LN(x)) * bf16(1 + scale[b]) ) + shift[b] ),   b = row / rows_per_batch.
+template <int W, int VPT>
 __global__ void __launch_bounds__(256) ln_modulate_fwd_kernel(const bf16* __restrict__ x, int64_t ldx, bf16* __restrict__ y,
                                                               int64_t ldy, const bf16* __restrict__ shift,
                                                               const bf16* __restrict__ scale, int64_t ldmod,
                                                               int rows_per_batch, float* __restrict__ mean_out,
                                                               float* __restrict__ rstd_out, int M, float eps) {
-  constexpr int D = NV * 256;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  float v[NV][8];
+  constexpr int T = W * 32, D = T * VPT * 8, RPC = 8 / W;
+  __shared__ float red[RPC][4 * W];
+  const int rl = (threadIdx.x >> 5) / W;
+  const int row = min(blockIdx.x * RPC + rl, M - 1);  // surplus rows of the last CTA redo row M-1 (keeps the barrier uniform)
+  const int t = threadIdx.x % T;
+  float v[VPT][8];
   const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * ldx);
-  float s = 0.f;
+  float s = 0.f, unused = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    unpack8(xr[i * 32 + lane], v[i]);
+  for (int i = 0; i < VPT; ++i) {
+    unpack8(xr[i * T + t], v[i]);
 #pragma unroll
     for (int e = 0; e < 8; ++e) s += v[i][e];
   }
-  const float mean = warp_sum(s) * (1.f / D);
+  row_sum2<W>(s, unused, red[rl]);
+  const float mean = s * (1.f / D);
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
+  for (int i = 0; i < VPT; ++i)
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float d = v[i][e] - mean;
       ss += d * d;
     }
-  const float rstd = rsqrtf(warp_sum(ss) * (1.f / D) + eps);
-  if (lane == 0 && mean_out) {
+  row_sum2<W>(ss, unused, red[rl] + 2 * W);
+  const float rstd = rsqrtf(ss * (1.f / D) + eps);
+  if (t == 0 && mean_out) {
     mean_out[row] = mean;
     rstd_out[row] = rstd;
   }
@@ -75,22 +103,22 @@ __global__ void __launch_bounds__(256) ln_modulate_fwd_kernel(const bf16* __rest
   const uint4* sc = reinterpret_cast<const uint4*>(scale + (int64_t)b * ldmod);
   uint4* yr = reinterpret_cast<uint4*>(y + (int64_t)row * ldy);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
+  for (int i = 0; i < VPT; ++i) {
     float fs[8], fc[8], o[8];
-    unpack8(__ldg(sh + i * 32 + lane), fs);
-    unpack8(__ldg(sc + i * 32 + lane), fc);
+    unpack8(__ldg(sh + i * T + t), fs);
+    unpack8(__ldg(sc + i * T + t), fc);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float n = round_bf16((v[i][e] - mean) * rstd);
       float m = round_bf16(n * round_bf16(1.f + fc[e]));
       o[e] = m + fs[e];
     }
-    yr[i * 32 + lane] = pack8(o);
+    yr[i * T + t] = pack8(o);
   }
 }
 
 // dx = dres + LN_bwd( dy * (1 + scale[b]) );  optional second output dx_gated = dx * gate[b]  (feeds the next dgrad GEMM)
-template <int NV>
+template <int W, int VPT>
 __global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const bf16* __restrict__ dy, int64_t lddy,
                                                               const bf16* __restrict__ x, int64_t ldx,
                                                               const float* __restrict__ mean_in,
@@ -100,23 +128,30 @@ __global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const bf16* __rest
                                                               int64_t lddres, bf16* __restrict__ dx, int64_t lddx,
                                                               const bf16* __restrict__ gate, int64_t ldgate,
                                                               bf16* __restrict__ dx_gated, int64_t lddxg, int M) {
-  constexpr int D = NV * 256;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= M) return;
+  constexpr int T = W * 32, D = T * VPT * 8, RPC = 8 / W;
+  __shared__ float red[RPC][2 * W];
+  const int rl = (threadIdx.x >> 5) / W;
+  const int row = min(blockIdx.x * RPC + rl, M - 1);
+  const int t = threadIdx.x % T;
   const int b = row / rows_per_batch;
   const float mean = mean_in[row], rstd = rstd_in[row];
   const uint4* dyr = reinterpret_cast<const uint4*>(dy + (int64_t)row * lddy);
   const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * ldx);
   const uint4* sc = reinterpret_cast<const uint4*>(scale + (int64_t)b * ldmod);
-  float g[NV][8], xh[NV][8];
+  const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + (int64_t)row * lddres) : nullptr;
+  uint4 rv[VPT];
+  if (rr) {  // issued up front: these loads do not depend on the row statistics
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) rv[i] = rr[i * T + t];
+  }
+  float g[VPT][8], xh[VPT][8];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
+  for (int i = 0; i < VPT; ++i) {
     float fd[8], fx[8], fc[8];
-    unpack8(dyr[i * 32 + lane], fd);
-    unpack8(xr[i * 32 + lane], fx);
-    unpack8(__ldg(sc + i * 32 + lane), fc);
+    unpack8(dyr[i * T + t], fd);
+    unpack8(xr[i * T + t], fx);
+    unpack8(__ldg(sc + i * T + t), fc);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       g[i][e] = round_bf16(fd[e] * round_bf16(1.f + fc[e]));  // autograd: grad wrt LN output, bf16
@@ -125,28 +160,28 @@ __global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const bf16* __rest
       s2 += g[i][e] * xh[i][e];
     }
   }
-  s1 = warp_sum(s1) * (1.f / D);
-  s2 = warp_sum(s2) * (1.f / D);
-  const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + (int64_t)row * lddres) : nullptr;
+  row_sum2<W>(s1, s2, red[rl]);
+  s1 *= (1.f / D);
+  s2 *= (1.f / D);
   uint4* dxr = reinterpret_cast<uint4*>(dx + (int64_t)row * lddx);
   const uint4* gt = dx_gated ? reinterpret_cast<const uint4*>(gate + (int64_t)b * ldgate) : nullptr;
   uint4* dxg = dx_gated ? reinterpret_cast<uint4*>(dx_gated + (int64_t)row * lddxg) : nullptr;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
+  for (int i = 0; i < VPT; ++i) {
     float o[8], fr[8];
-    if (rr) unpack8(rr[i * 32 + lane], fr);
+    if (rr) unpack8(rv[i], fr);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float d = round_bf16(rstd * (g[i][e] - s1 - xh[i][e] * s2));
       o[e] = rr ? round_bf16(fr[e] + d) : d;
     }
-    dxr[i * 32 + lane] = pack8(o);
+    dxr[i * T + t] = pack8(o);
     if (dxg) {
       float fg[8], og[8];
-      unpack8(__ldg(gt + i * 32 + lane), fg);
+      unpack8(__ldg(gt + i * T + t), fg);
 #pragma unroll
       for (int e = 0; e < 8; ++e) og[e] = o[e] * fg[e];
-      dxg[i * 32 + lane] = pack8(og);
+      dxg[i * T + t] = pack8(og);
     }
   }
 }
@@ -304,58 +339,73 @@ __global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(const float* __re
 
 // ============================================================================================ conditioning GEMV
 // y[b, n] = bf16( sum_k act(x[b,k]) * W[n,k] + bias[n] ),  b < 8.  act: 0 none, 1 SiLU (rounded to bf16 like eager).
-// One warp per output row n; W streamed once (13.6 GB for all 60 Qwen blocks' modulation linears).
+// HBM-bound: W is streamed exactly once (13.6 GB for the modulation linears of all 60 Qwen blocks in ONE launch), so the kernel is
+// built around bytes in flight: persistent CTAs of 16 warps, each warp owns GEMV_ROWS output rows at a time and keeps GEMV_ROWS
+// (x2 unrolled) independent 16-byte weight loads per lane in flight; act(x) is staged once per CTA in shared memory as fp32, laid
+// out [batch][half][k/8][4] so that the lanes' 16-byte reads are contiguous (conflict-free) and every x read is shared by the
+// GEMV_ROWS rows.  (The first version — one row per warp, 8 rows per CTA, scalar prologue per 8 rows — reached 0.76 TB/s.)
+constexpr int GEMV_ROWS = 4;
 template <int NB>
-__global__ void __launch_bounds__(256) gemv_act_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* __restrict__ W,
+__global__ void __launch_bounds__(512) gemv_act_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* __restrict__ W,
                                                        int64_t ldw, const bf16* __restrict__ bias, bf16* __restrict__ y,
                                                        int64_t ldy, int N, int K, int act) {
-  extern __shared__ float xs[];  // [NB][K]
-  for (int i = threadIdx.x; i < NB * K; i += blockDim.x) {
-    int b = i / K, k = i - b * K;
-    float v = __bfloat162float(x[(int64_t)b * ldx + k]);
-    if (act == 1) v = round_bf16(v / (1.f + __expf(-v)));
-    xs[i] = v;
+  extern __shared__ __align__(16) float xs[];  // [NB][2][K/8][4]
+  const int nvec = K / 8;
+  for (int v = threadIdx.x; v < NB * nvec; v += blockDim.x) {
+    const int b = v / nvec, i = v - b * nvec;
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + (int64_t)b * ldx) + i), f);
+    if (act == 1) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = round_bf16(f[e] / (1.f + __expf(-f[e])));
+    }
+    float4* dst = reinterpret_cast<float4*>(xs) + (int64_t)b * 2 * nvec + i;
+    dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+    dst[nvec] = make_float4(f[4], f[5], f[6], f[7]);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int nvec = K / 8;
-  for (int n = blockIdx.x * 8 + (threadIdx.x >> 5); n < N; n += gridDim.x * 8) {
-    const uint4* wr = reinterpret_cast<const uint4*>(W + (int64_t)n * ldw);
-    float acc[NB];
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int n_groups = (N + GEMV_ROWS - 1) / GEMV_ROWS;
+  const float4* xs4 = reinterpret_cast<const float4*>(xs);
+  for (int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < n_groups; g += warps_total) {
+    const int n0 = g * GEMV_ROWS;
+    const uint4* wr[GEMV_ROWS];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) acc[b] = 0.f;
-    // 4 independent 16-byte loads in flight per lane (the kernel streams 13.6 GB of modulation weights once per step)
-    int i = lane;
-    for (; i + 96 < nvec; i += 128) {
-      uint4 wv[4];
+    for (int r = 0; r < GEMV_ROWS; ++r) wr[r] = reinterpret_cast<const uint4*>(W + (int64_t)min(n0 + r, N - 1) * ldw);
+    float acc[GEMV_ROWS][NB];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) wv[u] = __ldg(wr + i + 32 * u);
+    for (int r = 0; r < GEMV_ROWS; ++r)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float fw[8];
-        unpack8(wv[u], fw);
+      for (int b = 0; b < NB; ++b) acc[r][b] = 0.f;
+#pragma unroll 2
+    for (int i = lane; i < nvec; i += 32) {
+      uint4 wv[GEMV_ROWS];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          const float* xb = xs + b * K + (i + 32 * u) * 8;
+      for (int r = 0; r < GEMV_ROWS; ++r) wv[r] = __ldg(wr[r] + i);
+      float fw[GEMV_ROWS][8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[b] += fw[e] * xb[e];
-        }
-      }
-    }
-    for (; i < nvec; i += 32) {
-      float fw[8];
-      unpack8(__ldg(wr + i), fw);
+      for (int r = 0; r < GEMV_ROWS; ++r) unpack8(wv[r], fw[r]);
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
-        const float* xb = xs + b * K + i * 8;
+        const float4 x0 = xs4[(b * 2) * nvec + i], x1 = xs4[(b * 2 + 1) * nvec + i];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[b] += fw[e] * xb[e];
+        for (int r = 0; r < GEMV_ROWS; ++r)
+          acc[r][b] += fw[r][0] * x0.x + fw[r][1] * x0.y + fw[r][2] * x0.z + fw[r][3] * x0.w + fw[r][4] * x1.x + fw[r][5] * x1.y +
+                       fw[r][6] * x1.z + fw[r][7] * x1.w;
       }
     }
+    float mine = 0.f;  // lane r * NB + b keeps (row r, batch b)
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      float v = warp_sum(acc[b]);
-      if (lane == 0) y[(int64_t)b * ldy + n] = __float2bfloat16_rn(v + (bias ? __bfloat162float(bias[n]) : 0.f));
+    for (int r = 0; r < GEMV_ROWS; ++r)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float v = warp_sum(acc[r][b]);
+        if (lane == r * NB + b) mine = v;
+      }
+    if (lane < GEMV_ROWS * NB) {
+      const int r = lane / NB, b = lane - r * NB, n = n0 + r;
+      if (n < N) y[(int64_t)b * ldy + n] = __float2bfloat16_rn(mine + (bias ? __bfloat162float(bias[n]) : 0.f));
     }
   }
 }
@@ -546,15 +596,16 @@ using namespace qfx;
   QFX_CUDA(cudaGetLastError()); \
   return 0
 
+// D = 256 * nv  ->  (warps per row, 16-byte vectors per thread)
 template <typename F>
 static int dispatch_nv(int D, F&& f) {
   switch (D / 256) {
-    case 1: return f(std::integral_constant<int, 1>());
-    case 2: return f(std::integral_constant<int, 2>());
-    case 4: return f(std::integral_constant<int, 4>());
-    case 8: return f(std::integral_constant<int, 8>());
-    case 12: return f(std::integral_constant<int, 12>());
-    case 16: return f(std::integral_constant<int, 16>());
+    case 1: return f(std::integral_constant<int, 1>(), std::integral_constant<int, 1>());
+    case 2: return f(std::integral_constant<int, 2>(), std::integral_constant<int, 1>());
+    case 4: return f(std::integral_constant<int, 4>(), std::integral_constant<int, 1>());
+    case 8: return f(std::integral_constant<int, 4>(), std::integral_constant<int, 2>());
+    case 12: return f(std::integral_constant<int, 4>(), std::integral_constant<int, 3>());
+    case 16: return f(std::integral_constant<int, 4>(), std::integral_constant<int, 4>());
   }
   set_error("hidden size %d unsupported (need 256*{1,2,4,8,12,16})", D);
   return -1;
@@ -564,8 +615,9 @@ extern "C" int qfx_ln_modulate_fwd(const void* x, int64_t ldx, void* y, int64_t 
                                    int64_t ldmod, int rows_per_batch, float* mean, float* rstd, int M, int D, float eps,
                                    void* stream) {
   QFX_CHECK_ARG(D % 256 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldmod % 8 == 0, "qfx_ln_modulate_fwd: bad dims");
-  return dispatch_nv(D, [&](auto nv) {
-    ln_modulate_fwd_kernel<decltype(nv)::value><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+  return dispatch_nv(D, [&](auto w, auto vpt) {
+    constexpr int W = decltype(w)::value, RPC = 8 / W;
+    ln_modulate_fwd_kernel<W, decltype(vpt)::value><<<(M + RPC - 1) / RPC, 256, 0, (cudaStream_t)stream>>>(
         (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)shift, (const bf16*)scale, ldmod, rows_per_batch, mean, rstd, M, eps);
     LAUNCH_OK();
   });
@@ -576,8 +628,9 @@ extern "C" int qfx_ln_modulate_bwd(const void* dy, int64_t lddy, const void* x, 
                                    int64_t lddres, void* dx, int64_t lddx, const void* gate, int64_t ldgate, void* dx_gated,
                                    int64_t lddxg, int M, int D, void* stream) {
   QFX_CHECK_ARG(D % 256 == 0, "qfx_ln_modulate_bwd: bad dims");
-  return dispatch_nv(D, [&](auto nv) {
-    ln_modulate_bwd_kernel<decltype(nv)::value><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+  return dispatch_nv(D, [&](auto w, auto vpt) {
+    constexpr int W = decltype(w)::value, RPC = 8 / W;
+    ln_modulate_bwd_kernel<W, decltype(vpt)::value><<<(M + RPC - 1) / RPC, 256, 0, (cudaStream_t)stream>>>(
         (const bf16*)dy, lddy, (const bf16*)x, ldx, mean, rstd, (const bf16*)scale, ldmod, rows_per_batch, (const bf16*)dres,
         lddres, (bf16*)dx, lddx, (const bf16*)gate, ldgate, (bf16*)dx_gated, lddxg, M);
     LAUNCH_OK();
@@ -638,8 +691,9 @@ extern "C" int qfx_qk_norm_rope_bwd(const void* dQ, const void* dK, const void* 
 extern "C" int qfx_gemv_act(const void* x, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* y, int64_t ldy,
                             int B, int N, int K, int act, void* stream) {
   QFX_CHECK_ARG(B >= 1 && B <= 8 && K % 8 == 0 && ldw % 8 == 0, "qfx_gemv_act: B=%d K=%d", B, K);
-  int grid = (N + 7) / 8;
-  if (grid > 148 * 8) grid = 148 * 8;
+  QFX_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)W % 16) == 0 && ldx % 8 == 0, "qfx_gemv_act: x / W must be 16-byte aligned");
+  int grid = (N + GEMV_ROWS * 16 - 1) / (GEMV_ROWS * 16);  // 16 warps x GEMV_ROWS rows per CTA pass; persistent beyond one CTA per SM
+  if (grid > num_sms()) grid = num_sms();
   size_t sm = (size_t)B * K * sizeof(float);
   QFX_CHECK_ARG(sm <= 200 * 1024, "qfx_gemv_act: K too large");
 #define GEMV(NB)                                                                                                             \
@@ -649,7 +703,7 @@ extern "C" int qfx_gemv_act(const void* x, int64_t ldx, const void* W, int64_t l
       QFX_CUDA(cudaFuncSetAttribute(gemv_act_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));          \
       done = true;                                                                                                           \
     }                                                                                                                        \
-    gemv_act_kernel<NB><<<grid, 256, sm, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)W, ldw, (const bf16*)bias, \
+    gemv_act_kernel<NB><<<grid, 512, sm, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)W, ldw, (const bf16*)bias, \
                                                                  (bf16*)y, ldy, N, K, act);                                 \
   } break;
   switch (B) {
