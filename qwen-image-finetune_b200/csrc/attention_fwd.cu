@@ -297,9 +297,12 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
 // S ready -> tcgen05.ld -> max -> exp2 (MUFU) -> st.shared -> fence -> P V, and its 224 KB of shared memory leave the SM to a
 // single CTA.  Here a CTA needs 112 KB of shared memory and 256 TMEM columns (S 2 x 64, O 128), so two CTAs share an SM and the
 // tensor pipe of one runs under the softmax of the other.  4 softmax warps, thread = query row x all 64 keys of the tile (one TMEM
-// round trip per tile, no cross-warp exchange).  K is released right after Q K^T, V after P V; P is single-buffered.
+// round trip per tile, no cross-warp exchange).  K is released right after Q K^T, V after P V.  P never touches shared memory:
+// the softmax thread packs its row to bf16 and stores it with tcgen05.st over the first 32 columns of the S buffer it was read
+// from, and P V runs with the A operand in tensor memory.  (The kernel is shared-memory-bandwidth bound — SS-mode operands at
+// 128 B/clk/SM — and P through shared memory cost a 16 KB store plus a 16 KB operand read per 64-key tile.)
 constexpr int F64_KT = 64 * 128 * 2;                                 // one K or V tile: 64 keys x 128 dims = 16 KB (two 8 KB atoms)
-constexpr int F64_SMEM = TILE_BYTES + 4 * F64_KT + 128 * 128 + 256;  // Q + K x2 + V x2 + P[128 x 64] + barriers = 112.25 KB
+constexpr int F64_SMEM = TILE_BYTES + 4 * F64_KT + 256;  // Q + K x2 + V x2 + barriers = 96.25 KB
 
 __global__ void __launch_bounds__(192, 2) attn_fwd64_kernel(const __grid_constant__ AttnFwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -308,8 +311,7 @@ __global__ void __launch_bounds__(192, 2) attn_fwd64_kernel(const __grid_constan
   const uint32_t sQ = smem_base;
   auto sK = [&](int s) { return smem_base + TILE_BYTES + F64_KT * s; };
   auto sV = [&](int s) { return smem_base + TILE_BYTES + F64_KT * (2 + s); };
-  const uint32_t sP = smem_base + TILE_BYTES + 4 * F64_KT;
-  const uint32_t bar_base = sP + 128 * 128;
+  const uint32_t bar_base = smem_base + TILE_BYTES + 4 * F64_KT;
   const uint32_t q_full = bar_base;
   auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto v_full = [&](int s) { return bar_base + 8u * (3 + s); };
@@ -386,8 +388,8 @@ __global__ void __launch_bounds__(192, 2) attn_fwd64_kernel(const __grid_constan
         mbar_wait(v_full(s), (j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // K = 64 keys: P is one 128B-swizzle atom column, V is MN-major (two 64-wide d atoms, 8 KB apart)
-          umma_bf16(tO, sdesc_sw128(sP + k * 32, 16, 1024), sdesc_sw128(sV(s) + k * 2048, 8192, 1024), idesc_pv, (j | k) != 0);
+        for (int k = 0; k < 4; ++k)  // K = 64 keys: P in TMEM (8 packed columns per 16 keys), V MN-major (two 64-wide d atoms, 8 KB apart)
+          umma_bf16_ts(tO, tS0 + s * 64 + k * 8, sdesc_sw128(sV(s) + k * 2048, 8192, 1024), idesc_pv, (j | k) != 0);
         umma_commit(pv_done(s));
       };
       for (int j = 0; j < n_tiles; ++j) {
@@ -426,9 +428,11 @@ __global__ void __launch_bounds__(192, 2) attn_fwd64_kernel(const __grid_constan
         mask_scores(r, 0, valid, gap0, gap1);
         mask_scores(r + 32, 32, valid, gap0, gap1);
       }
-      float mx = -INFINITY;
+      // four independent chains: with two softmax warps per scheduler a 64-deep dependent FMNMX / FADD chain is pure latency
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+      for (int i = 0; i < 64; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m_used, mx * P.scale_log2);  // a fully padded tile: mx = -inf, m_new = m_used (tile 0 has a valid key)
       if (__any_sync(0xffffffffu, (j == 0) || (m_new > m_used + 8.f))) {  // warp-uniform lazy rescale
         if (j > 0) {
@@ -450,25 +454,20 @@ __global__ void __launch_bounds__(192, 2) attn_fwd64_kernel(const __grid_constan
         m_used = m_new;
       }
       uint32_t pk[32];
-      float lsum = 0.f;
+      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
+        // (all exponentials on MUFU: routing 1/8 .. 1/2 of them through exp2_fma was measured 3-15 % slower — sm100.cuh)
         const float p0 = exp2f(__uint_as_float(r[2 * i]) * P.scale_log2 - m_used);
         const float p1 = exp2f(__uint_as_float(r[2 * i + 1]) * P.scale_log2 - m_used);
         pk[i] = pack_bf16(p0, p1);
-        lsum += p0 + p1;
+        ls4[i & 3] += p0 + p1;
       }
-      l += lsum;
-      if (j >= 1) mbar_wait(pv_done((j - 1) & 1), ((j - 1) >> 1) & 1);  // the single P buffer has been consumed by P V of tile j-1
-      const uint32_t p_row = sP + row * 128;
-#pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        const uint32_t chunk = (uint32_t)v ^ (uint32_t)(row & 7);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16), "r"(pk[4 * v]), "r"(pk[4 * v + 1]),
-                     "r"(pk[4 * v + 2]), "r"(pk[4 * v + 3])
-                     : "memory");
-      }
-      fence_proxy_async_smem();
+      l += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
+      // P_j over the S_j columns this thread has already read (its own TMEM lane).  The buffer is not rewritten before S_{j+2},
+      // which the MMA thread issues after P V_j.
+      tmem_st32(tS0 + s * 64 + lane_off, pk);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);

@@ -104,6 +104,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed (implies fence::before_thread_sync)
+// A operand read from TENSOR MEMORY (K-major only: lane = row, each 32-bit column holds two consecutive K elements), B from shared
+// memory.  Saves the shared-memory round trip (and read bandwidth) of an operand the CTA has just produced itself, e.g. softmax P.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -220,9 +230,11 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // exp2 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic minimax for 2^f, exponent
-// patched in with an integer add.  Relative error < 8e-5 (bf16 probabilities carry 3.9e-3).  MEASURED (round 1): sending every
-// other softmax exponential through this path made attention forward 18 % SLOWER (0.50 vs 0.43 ms) — the softmax warps are
-// instruction-issue bound, not MUFU bound, with one query tile per CTA — so the kernels do not use it yet.
+// patched in with an integer add.  Relative error < 8e-5 (bf16 probabilities carry 3.9e-3).  MEASURED (round 1, B200):
+//   tools/microbench.cu, isolated P-pass loop, 8 warps/SM: all-MUFU 13.7 elem/clk/SM, half through this path 15.8 (+15 %);
+//   inside the attention kernels it LOSES: 128-key forward 0.43 -> 0.50 ms; 64-key TS-mode forward 0.285 -> 0.294 / 0.308 /
+//   0.328 ms with 1/8, 1/4, 1/2 of the exponentials here — the softmax warps are issue / latency bound, not MUFU bound.
+// Kept for the micro-benchmark and as the starting point for a 2-query-tile-per-CTA softmax; the kernels do not call it.
 __device__ __forceinline__ float exp2_fma(float x) {
   x = fmaxf(x, -125.f);
   const float magic = 12582912.f;                 // 1.5 * 2^23: adding it rounds x to the nearest integer in the low mantissa bits

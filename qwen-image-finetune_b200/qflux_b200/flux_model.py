@@ -92,9 +92,6 @@ class FluxB200(FusedMMDiTBase):
             return self.w[grp + "_w"][l], self.w[grp + "_b"][l]
         return self.w[grp + "_w"][l, s], self.w[grp + "_b"][l, s]
 
-    def _no_lora_groups(self):
-        return ("down", "s_out")
-
     # ------------------------------------------------------------------------------------------------ names
     def _weight_views(self) -> dict:
         w, D, out = self.w, self.D, {}
@@ -178,33 +175,35 @@ class FluxB200(FusedMMDiTBase):
     def _single_fwd(self, ws, l, Xin, Xout, save):
         D, w = self.D, self.w
         T, Mt = ws["T"], ws["Mt"]
-        st, qkv, O, u = save["stats"], save["qkv"], save["O"], save["u"]
+        st, qkv, O, h, u = save["stats"], save["qkv"], save["O"], save["h"], save["u"]
         for s in (0, 1):
             lib.ln_modulate_fwd(self._rows(ws, Xin, s), self._rows(ws, ws["xm"], s), self._smod(ws, l, 0)[s], self._smod(ws, l, 1)[s],
                                 self._rpb(ws, s), self._rows(ws, st[0], s), self._rows(ws, st[1], s))
         self._grouped(ws, l, "s_qkv", ws["xm"], qkv, 3 * D, D, lib.EPI_BIAS)
-        self._grouped(ws, l, "s_mlp", ws["xm"], ws["h"], 4 * D, D, lib.EPI_GELU, out2=u)
+        self._grouped(ws, l, "s_mlp", ws["xm"], h, 4 * D, D, lib.EPI_GELU, out2=u)
         for s in (0, 1):
             lib.qk_norm_rope_fwd(self._rows(ws, qkv, s), w["s_qknorm_w"][l, 0], w["s_qknorm_w"][l, 1], ws["rope"], ws["Q"], ws["K"],
                                  ws["V"], self._rpb(ws, s), T if s == 0 else 0, round_mid=False)
         lib.attn_fwd(ws["Q"], ws["K"], ws["V"], O[:Mt], O[Mt:], T, save["lse"], kv_len=ws.get("kv_len"), txt_len=ws.get("txt_len"))
-        # x = x + gate * proj_out(cat[attn, gelu(mlp)]):  K loop over the attention output, then over the MLP activations
-        Wo, bo = w["s_out_w"][l], w["s_out_b"][l]
-        probs = [lib.gemm_problem(self._rows(ws, O, s), Wo[:, :D], self._rows(ws, Xout, s), A2=self._rows(ws, ws["h"], s),
-                                  B2=Wo[:, D:], kb2=4 * D // 64, bias=bo, resid=self._rows(ws, Xin, s),
-                                  gate=self._smod(ws, l, 2)[s], rows_per_batch=self._rpb(ws, s)) for s in (0, 1)]
-        lib.gemm(probs, D, D, epilogue=lib.EPI_RESID_GATE)
+        # x = x + gate * proj_out(cat[attn, gelu(mlp)]): attention wrote columns [0, D) and the GELU epilogue [D, 5D) of save["cat"]
+        self._grouped(ws, l, "s_out", save["cat"], Xout, D, 5 * D, lib.EPI_RESID_GATE, resid=Xin, gate=self._smod(ws, l, 2))
 
     def _single_bwd(self, ws, l, Xin, dX, dXn, save, prev_gate):
         D, w = self.D, self.w
         st, qkv, O, u = save["stats"], save["qkv"], save["O"], save["u"]
         Wo = w["s_out_w"][l]
-        # d[attn | mlp] = dY . W_out   (dY = dX * gate is already in ws['dY'])
-        probs = [lib.gemm_problem(self._rows(ws, ws["dY"], s), Wo[:, :D], self._rows(ws, ws["dO"], s)) for s in (0, 1)]
-        lib.gemm(probs, D, D, trans_b=True)
-        probs = [lib.gemm_problem(self._rows(ws, ws["dY"], s), Wo[:, D:], self._rows(ws, ws["dbig"], s), aux=self._rows(ws, u, s))
-                 for s in (0, 1)]
-        lib.gemm(probs, 4 * D, D, trans_b=True, epilogue=lib.EPI_DGELU)
+        # d[attn | mlp] = dY . W_out (+ U . A_lora)   (dY = dX * gate is already in ws['dY']); the two column ranges of the
+        # concatenated input go to different consumers (attention backward / GELU backward), so they are two contractions
+        pa, pm = [], []
+        for s in (0, 1):
+            dYs = self._rows(ws, ws["dY"], s)
+            lb = self._lora_bwd(ws, l, "s_out", s, dYs, self._rows(ws, save["cat"], s), D)
+            ka = dict(A2=lb[0], B2=lb[1][:, :D], kb2=1) if lb is not None else {}
+            km = dict(A2=lb[0], B2=lb[1][:, D:], kb2=1) if lb is not None else {}
+            pa.append(lib.gemm_problem(dYs, Wo[:, :D], self._rows(ws, ws["dO"], s), **ka))
+            pm.append(lib.gemm_problem(dYs, Wo[:, D:], self._rows(ws, ws["dbig"], s), aux=self._rows(ws, u, s), **km))
+        lib.gemm(pa, D, D, trans_b=True)
+        lib.gemm(pm, 4 * D, D, trans_b=True, epilogue=lib.EPI_DGELU)
         self._attn_bwd_core(ws, qkv, O, save["lse"], lambda s: (w["s_qknorm_w"][l, 0], w["s_qknorm_w"][l, 1]))
         if self._site(l, "s_qkv", 0) or self._site(l, "s_mlp", 0):  # LoRA input = modulated norm output (recomputed)
             for s in (0, 1):

@@ -141,8 +141,6 @@ class FusedMMDiTBase(nn.Module):
         off = 0
         for full in wanted:
             (l, grp), streams, slot, d_in, d_out, n_slots = table[full]
-            if grp in self._no_lora_groups():
-                raise NotImplementedError(f"LoRA on `{full}`: the backward does not regenerate this linear's input yet")
             site = self.sites.get((l, grp, streams[0]))
             if site is None:
                 site = LoraSite(n_slots, d_in, d_out, self.dev)
@@ -166,11 +164,9 @@ class FusedMMDiTBase(nn.Module):
         self.G32 = torch.zeros(off, device=self.dev, dtype=torch.float32)
         self.G16 = torch.zeros(off, device=self.dev, dtype=BF)
         self._gnorm_sq = torch.zeros(1, device=self.dev, dtype=torch.float32)
-        self._gscratch = torch.zeros(4 * self.D * PAD, device=self.dev, dtype=torch.float32)
+        self._gscratch = torch.zeros(5 * self.D * PAD, device=self.dev, dtype=torch.float32)
+        self._ws = self._ws_key = None  # per-block saved tensors depend on which sites exist
         return self
-
-    def _no_lora_groups(self):
-        return ("down",)
 
     def _unique_sites(self):
         seen = set()
@@ -322,8 +318,9 @@ class FusedMMDiTBase(nn.Module):
         for s in (0, 1):
             lib.ln_modulate_fwd(self._rows(ws, xmid, s), self._rows(ws, ws["xm"], s), mods(3)[s], mods(4)[s], self._rpb(ws, s),
                                 self._rows(ws, st[2], s), self._rows(ws, st[3], s))
-        self._grouped(ws, l, "up", ws["xm"], ws["h"], 4 * D, D, lib.EPI_GELU, out2=u)
-        self._grouped(ws, l, "down", ws["h"], Xout, D, 4 * D, lib.EPI_RESID_GATE, resid=xmid, gate=mods(5))
+        h = save.get("h", ws["h"])  # kept per block only when ff.net.2 carries LoRA (its input is needed for dA)
+        self._grouped(ws, l, "up", ws["xm"], h, 4 * D, D, lib.EPI_GELU, out2=u)
+        self._grouped(ws, l, "down", h, Xout, D, 4 * D, lib.EPI_RESID_GATE, resid=xmid, gate=mods(5))
 
     def _attn_bwd_core(self, ws, qkv, O, lse, wq_wk, save=None):
         """dO (token-major, ws['dO']) -> dqkv (ws['dqkv']); wq_wk(s) -> (wq, wk) norm weights of stream s.
@@ -353,7 +350,7 @@ class FusedMMDiTBase(nn.Module):
         st, qkv, O, xmid, u = save["stats"], save["qkv"], save["O"], save["xmid"], save["u"]
         w = self.w
         # ---- MLP branch
-        self._dgrad_grouped(ws, l, "down", ws["dY"], ws["dbig"], 4 * D, D, D, None, epilogue=lib.EPI_DGELU, aux=u)
+        self._dgrad_grouped(ws, l, "down", ws["dY"], ws["dbig"], 4 * D, D, D, save.get("h"), epilogue=lib.EPI_DGELU, aux=u)
         if self._site(l, "up", 0) or self._site(l, "up", 1):  # LoRA input = xm2, recomputed from the statistics
             for s in (0, 1):
                 lib.ln_modulate_fwd(self._rows(ws, xmid, s), self._rows(ws, ws["xm"], s), mods(3)[s], mods(4)[s], self._rpb(ws, s))
@@ -398,8 +395,17 @@ class FusedMMDiTBase(nn.Module):
         if train and self.keep_qkv:  # +4 x [M, D] per block in HBM instead of regenerating them in the backward
             for blk in ws["dbl"]:
                 blk.update(Q=e(B, H, S, 128), K=e(B, H, S, 128), V=e(B, H, S, 128), xm1=e(M, D))
-        ws["sgl"] = [dict(stats=e(2, M, dt=torch.float32), qkv=e(M, 3 * D), O=e(M, D), lse=e(B, H, S, dt=torch.float32),
+        if train:
+            for l, blk in enumerate(ws["dbl"]):
+                if self._site(l, "down", 0) or self._site(l, "down", 1):
+                    blk["h"] = e(M, 4 * D)
+        # single blocks keep cat[attn | gelu(mlp)] — the input of proj_out — in ONE [M, 5D] buffer: attention and the GELU epilogue
+        # write straight into its column ranges (no concat), proj_out is a plain K = 5D contraction, and the buffer is the LoRA
+        # input of proj_out in the backward
+        ws["sgl"] = [dict(stats=e(2, M, dt=torch.float32), qkv=e(M, 3 * D), cat=e(M, 5 * D), lse=e(B, H, S, dt=torch.float32),
                           u=e(M, 4 * D)) for _ in range(ns)]
+        for blk in ws["sgl"]:
+            blk["O"], blk["h"] = blk["cat"][:, :D], blk["cat"][:, D:]
         ws["hn"], ws["pred"] = e(Mi, D), e(Mi, self.C_out)
         ws["fstats"] = e(2, Mi, dt=torch.float32)
         self._alloc_lora_T(ws)

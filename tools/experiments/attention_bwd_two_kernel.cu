@@ -6,6 +6,12 @@
 // operand bytes per tile pair (7 contractions, N=64 instructions re-read the 128-row A operand twice as often) than it saves
 // by dropping the dQ reduce-add.  tools/microbench.cu holds the micro-benchmarks (tcgen05.ld ~900 B/clk/SM, MUFU 15.7 ex2/clk/SM)
 // that ruled out TMEM bandwidth and exponentials as the limiter.
+// Timeline of the dK/dV kernel (attn_timeline_two_kernel.py, clock64 stamps): the 8 compute warps need ~2000 clk per 128-key x
+// 64-query tile (P pass ~750 = MUFU bound for 8192 exponentials, dS pass ~300, and ~900 of fixed cost: four mbarrier polls,
+// two st.shared + fence.proxy.async + arrive sequences) while the tensor work of a tile is ~1050 clk: with all compute warps in
+// lock-step on one tile the fixed cost is amortised over only 32 elements per thread.  The fix would be two compute groups
+// ping-ponging on alternate tiles (16 warps, P^T/dS^T buffers per group); not pursued in round 1.
+// To rebuild: copy into qwen-image-finetune_b200/csrc/, declare qfx::attn_bwd_two_kernel in attention_bwd.cu and dispatch to it.
 //
 // The single-kernel backward (attention_bwd.cu) accumulates dQ across key tiles with 2.2 GB of L2 reduce-adds per call and
 // keeps every stage of a (query tile, key tile) pair on one serial chain (~6600 clk per pair against 2560 clk of MMA).
@@ -24,6 +30,8 @@
 #include "host_common.h"
 #include "sm100.cuh"
 
+extern long long* g_qfx_attn_bwd_dbg;  // attention_bwd.cu (qfx_attn_bwd_set_debug)
+
 namespace qfx {
 
 struct AttnBwd2Params {
@@ -40,6 +48,7 @@ struct AttnBwd2Params {
   const int* txt_len;
   int split, S, H;
   float scale, scale_log2;
+  long long* dbg;  // optional clock64 stamps of dkv CTA (1, 0): [query tile][16]  (qfx_attn_bwd_set_debug)
 };
 
 __device__ __forceinline__ void mask32(uint32_t* r, int col0, int valid, int gap0, int gap1) {
@@ -204,7 +213,8 @@ __global__ void __launch_bounds__(192, 2) attn_bwd_dq_kernel(const __grid_consta
 
 // ====================================================================================================================== dK, dV
 constexpr int KV_STAGES = 3;
-constexpr int KV_SMEM = 2 * DQ_T128 + KV_STAGES * 2 * DQ_T64 + 2 * 128 * 128 + 2 * 512 + 256;  // K, V, (Q_i, dO_i) x3, P^T, dS^T, L/delta x2
+constexpr int KV_LD = 4;  // L / delta ring depth: the stager runs up to 3 query tiles ahead (its global loads take ~1 tile period)
+constexpr int KV_SMEM = 2 * DQ_T128 + KV_STAGES * 2 * DQ_T64 + 2 * 128 * 128 + KV_LD * 512 + 256;  // K, V, (Q_i, dO_i) x3, P^T, dS^T, L/delta ring
 constexpr int KV_THREADS = 384;  // warp 0 TMA, 1 MMA, 2 L/delta stager, 3 idle, 4-11 compute (quad = warp & 3, column half = (warp - 4) >> 2)
 
 __global__ void __launch_bounds__(KV_THREADS, 1) attn_bwd_dkv_kernel(const __grid_constant__ AttnBwd2Params P) {
@@ -215,16 +225,16 @@ __global__ void __launch_bounds__(KV_THREADS, 1) attn_bwd_dkv_kernel(const __gri
   auto sQ = [&](int st) { return smem_base + 2 * DQ_T128 + st * 2 * DQ_T64; };
   auto sdO = [&](int st) { return smem_base + 2 * DQ_T128 + st * 2 * DQ_T64 + DQ_T64; };
   const uint32_t sPt = smem_base + 2 * DQ_T128 + KV_STAGES * 2 * DQ_T64, sdSt = sPt + 128 * 128;
-  const uint32_t sLD = sdSt + 128 * 128;  // float [2 buffers][2 (L, delta*scale)][64]
-  const uint32_t bar_base = sLD + 2 * 512;
+  const uint32_t sLD = sdSt + 128 * 128;  // float [KV_LD buffers][2 (L, delta*scale)][64]
+  const uint32_t bar_base = sLD + KV_LD * 512;
   const uint32_t kv_full = bar_base;
   auto q_full = [&](int st) { return bar_base + 8u * (1 + st); };
   auto q_empty = [&](int st) { return bar_base + 8u * (4 + st); };
   auto s_full = [&](int u) { return bar_base + 8u * (7 + u); };     // S^T / dP^T buffer u written by the tensor core
-  auto ld_full = [&](int u) { return bar_base + 8u * (9 + u); };    // L / delta of the tile in buffer u staged in smem
-  auto ld_empty = [&](int u) { return bar_base + 8u * (11 + u); };  // ... and read by all 8 compute warps
-  const uint32_t p_full = bar_base + 8u * 13, ds_full = bar_base + 8u * 14, dv_done = bar_base + 8u * 15, dk_done = bar_base + 8u * 16;
-  const uint32_t acc_full = bar_base + 8u * 17, tmem_slot = bar_base + 8u * 18;
+  auto ld_full = [&](int u) { return bar_base + 8u * (9 + u); };    // L / delta of the tile in ring slot u staged in smem
+  auto ld_empty = [&](int u) { return bar_base + 8u * (13 + u); };  // ... and read by all 8 compute warps
+  const uint32_t p_full = bar_base + 8u * 17, ds_full = bar_base + 8u * 18, dv_done = bar_base + 8u * 19, dk_done = bar_base + 8u * 20;
+  const uint32_t acc_full = bar_base + 8u * 21, tmem_slot = bar_base + 8u * 22;
   float* ld_gen = reinterpret_cast<float*>(smem_raw + (sLD - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -235,6 +245,8 @@ __global__ void __launch_bounds__(KV_THREADS, 1) attn_bwd_dkv_kernel(const __gri
   const int txt_len = P.txt_len ? P.txt_len[b] : P.split;
   const int n_q = (P.S + 63) / 64;
   const bool active = kv0 < kv_len && !(kv0 >= txt_len && kv0 + 128 <= P.split);
+  const bool dbg_on = P.dbg != nullptr && blockIdx.x == 1 && blockIdx.y == 0;
+#define DBG2(i, e) do { if (dbg_on) P.dbg[(i) * 16 + (e)] = clock64(); } while (0)
 
   if (warp == 1 && lane == 0) {
     mbar_init(kv_full, 1);
@@ -242,8 +254,8 @@ __global__ void __launch_bounds__(KV_THREADS, 1) attn_bwd_dkv_kernel(const __gri
       mbar_init(q_full(st), 1);
       mbar_init(q_empty(st), 1);
     }
-    for (int u = 0; u < 2; ++u) {
-      mbar_init(s_full(u), 1);
+    for (int u = 0; u < 2; ++u) mbar_init(s_full(u), 1);
+    for (int u = 0; u < KV_LD; ++u) {
       mbar_init(ld_full(u), 1);
       mbar_init(ld_empty(u), 8);
     }
@@ -290,6 +302,7 @@ __global__ void __launch_bounds__(KV_THREADS, 1) attn_bwd_dkv_kernel(const __gri
         const int st = i % KV_STAGES, u = i & 1;
         mbar_wait(q_full(st), (i / KV_STAGES) & 1);
         tc_fence_after();
+        DBG2(i, 0);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_bf16(tS(u), sdesc_sw128(sK + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
@@ -309,12 +322,14 @@ __global__ void __launch_bounds__(KV_THREADS, 1) attn_bwd_dkv_kernel(const __gri
         if (i + 1 < n_q) issue_s(i + 1);
         mbar_wait(p_full, i & 1);
         tc_fence_after();
+        DBG2(i, 1);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tdV, sdesc_sw128(sPt + k * 32, 16, 1024), sdesc_sw128(sdO(st) + k * 2048, 8192, 1024), id_a, (i | k) != 0);
         umma_commit(dv_done);
         mbar_wait(ds_full, i & 1);
         tc_fence_after();
+        DBG2(i, 2);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tdK, sdesc_sw128(sdSt + k * 32, 16, 1024), sdesc_sw128(sQ(st) + k * 2048, 8192, 1024), id_a, (i | k) != 0);
@@ -328,8 +343,8 @@ __global__ void __launch_bounds__(KV_THREADS, 1) attn_bwd_dkv_kernel(const __gri
     // per-query L and delta are per-COLUMN values, broadcast-read from smem
     if (active) {
       for (int i = 0; i < n_q; ++i) {
-        const int u = i & 1;
-        if (i >= 2) mbar_wait(ld_empty(u), ((i >> 1) - 1) & 1);
+        const int u = i % KV_LD;
+        if (i >= KV_LD) mbar_wait(ld_empty(u), ((i / KV_LD) - 1) & 1);
         for (int e = lane; e < 64; e += 32) {
           const int q = i * 64 + e;
           const bool ok = q < P.S;
@@ -350,12 +365,15 @@ __global__ void __launch_bounds__(KV_THREADS, 1) attn_bwd_dkv_kernel(const __gri
     const bool all_keys_ok = kv0 + 128 <= kv_len && !(txt_len < P.split && kv0 + 128 > txt_len && kv0 < P.split);
     if (active) {
       for (int i = 0; i < n_q; ++i) {
-        const int u = i & 1;
-        mbar_wait(ld_full(u), (i >> 1) & 1);
-        const float4* L4 = reinterpret_cast<const float4*>(ld_gen + u * 128 + half * 32);
-        const float4* D4 = reinterpret_cast<const float4*>(ld_gen + u * 128 + 64 + half * 32);
+        const int u = i & 1, ul = i % KV_LD;
+        if (threadIdx.x == 128) DBG2(i, 4);
+        mbar_wait(ld_full(ul), (i / KV_LD) & 1);
+        if (threadIdx.x == 128) DBG2(i, 5);
+        const float4* L4 = reinterpret_cast<const float4*>(ld_gen + ul * 128 + half * 32);
+        const float4* D4 = reinterpret_cast<const float4*>(ld_gen + ul * 128 + 64 + half * 32);
         mbar_wait(s_full(u), (i >> 1) & 1);
         tc_fence_after();
+        if (threadIdx.x == 128) DBG2(i, 6);
         float p[32];
         uint32_t pk[16];
         {
@@ -377,7 +395,9 @@ __global__ void __launch_bounds__(KV_THREADS, 1) attn_bwd_dkv_kernel(const __gri
 #pragma unroll
           for (int e = 0; e < 16; ++e) pk[e] = pack_bf16(p[2 * e], p[2 * e + 1]);
         }
+        if (threadIdx.x == 128) DBG2(i, 7);
         if (i > 0) mbar_wait(dv_done, (i - 1) & 1);  // P^T buffer consumed by the dV MMA of tile i-1
+        if (threadIdx.x == 128) DBG2(i, 8);
         {
           const uint32_t prow = sPt + row * 128;
 #pragma unroll
@@ -391,6 +411,7 @@ __global__ void __launch_bounds__(KV_THREADS, 1) attn_bwd_dkv_kernel(const __gri
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
+        if (threadIdx.x == 128) DBG2(i, 9);
         {
           uint32_t rp[32];
           tmem_ld32(tdP(u) + lane_off, rp);
@@ -406,7 +427,9 @@ __global__ void __launch_bounds__(KV_THREADS, 1) attn_bwd_dkv_kernel(const __gri
             pk[2 * v + 1] = pack_bf16(a2, a3);
           }
         }
+        if (threadIdx.x == 128) DBG2(i, 10);
         if (i > 0) mbar_wait(dk_done, (i - 1) & 1);  // dS^T buffer consumed by the dK MMA of tile i-1
+        if (threadIdx.x == 128) DBG2(i, 11);
         {
           const uint32_t drow = sdSt + row * 128;
 #pragma unroll
@@ -422,8 +445,9 @@ __global__ void __launch_bounds__(KV_THREADS, 1) attn_bwd_dkv_kernel(const __gri
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(ds_full);
-          mbar_arrive(ld_empty(u));
+          mbar_arrive(ld_empty(ul));
         }
+        if (threadIdx.x == 128) DBG2(i, 12);
       }
       mbar_wait(acc_full, 0);
       tc_fence_after();
@@ -481,6 +505,7 @@ int attn_bwd_two_kernel(const void* Q, const void* K, const void* V, const void*
     return rc;
   P.dQ = dQ; P.dK = (bf16*)dK; P.dV = (bf16*)dV; P.lse = lse; P.delta = delta; P.kv_len = kv_len; P.txt_len = txt_len;
   P.split = txt_len ? split : 0; P.S = S; P.H = H; P.scale = softmax_scale; P.scale_log2 = softmax_scale * 1.4426950408889634f;
+  P.dbg = ::g_qfx_attn_bwd_dbg;
   static bool attr_done = false;
   if (!attr_done) {
     QFX_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
