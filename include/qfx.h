@@ -40,7 +40,8 @@ int qfx_version(void);
 enum qfx_epilogue {
   QFX_EPI_BIAS = 0,       /* out = alpha*acc + bias                                                  (nn.Linear)            */
   QFX_EPI_GELU = 1,       /* out2 = u = acc + bias ; out = gelu_tanh(u)        (FeedForward "gelu-approximate" net.0)       */
-  QFX_EPI_RESID_GATE = 2, /* out = resid + gate[row / rows_per_batch, :] * (acc + bias)   (transformer_qwenimage.py:473,480) */
+  QFX_EPI_RESID_GATE = 2, /* out = resid + gate[row / rows_per_batch, :] * (acc + bias)   (transformer_qwenimage.py:473,480);
+                             out2 (optional) = acc + bias, the un-gated branch output (needed for d gate)                  */
   QFX_EPI_DGELU = 3,      /* out = acc * gelu_tanh'(aux)                                   (autograd of net.0's GELU)        */
   QFX_EPI_ADD = 4         /* out = resid + alpha*acc   (trans_b=1: sum of two dgrads, FLUX single block qkv + proj_mlp)      */
 };
@@ -55,7 +56,7 @@ typedef struct {
   int a2_col0;                   /* first column of A2 to use */
   const void* bias;              /* [N] or NULL */
   void* out;       int64_t ldo;  /* [M, N] */
-  void* out2;      int64_t ldo2; /* QFX_EPI_GELU: pre-activation u */
+  void* out2;      int64_t ldo2; /* QFX_EPI_GELU: pre-activation u;  QFX_EPI_RESID_GATE: optional un-gated branch output */
   const void* resid; int64_t ldr;/* QFX_EPI_RESID_GATE */
   const void* gate;  int64_t ldg; int rows_per_batch;
   const void* aux;   int64_t ldaux; /* QFX_EPI_DGELU: u */
@@ -98,6 +99,13 @@ int qfx_ln_modulate_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, const 
 int qfx_ln_modulate_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* mean, const float* rstd,
                         const void* scale, int64_t ldmod, int rows_per_batch, const void* dres, int64_t lddres, void* dx,
                         int64_t lddx, const void* gate, int64_t ldgate, void* dx_gated, int64_t lddxg, int M, int D, void* stream);
+/* Gradients of the AdaLN modulation vectors (autograd of transformer_qwenimage.py:420-423,443-448,473,480 when the modulation
+ * Linear carries LoRA):  per sample b (rows b*rows_per_batch ..) and column d, ACCUMULATED (+=) into fp32 [B, D] buffers:
+ *   sum_out[b,d]  += sum_t g[t,d]                       (d shift; NULL to skip)
+ *   prod_out[b,d] += sum_t g[t,d] * m[t,d]              (d scale with m = bf16(LN(x)) when mean/rstd are given (m = x),
+ *                                                        d gate with m = the un-gated branch output when mean == NULL) */
+int qfx_mod_grad(const void* g, int64_t ldg, const void* m, int64_t ldm, const float* mean, const float* rstd, int rows_per_batch,
+                 float* sum_out, float* prod_out, int64_t ldo, int M, int D, void* stream);
 int qfx_gate_mul(const void* a, int64_t lda, const void* gate, int64_t ldg, int rows_per_batch, void* out, int64_t ldo, int M,
                  int D, void* stream);
 /* out = bf16(a + b), n elements (sums of the [B, D] conditioning embeddings, transformer_flux.py time_text_embed) */

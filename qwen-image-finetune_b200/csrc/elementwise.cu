@@ -186,6 +186,60 @@ __global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const bf16* __rest
   }
 }
 
+// Column reductions over the tokens of each sample for the modulation gradients (see qfx_mod_grad in qfx.h).
+// grid (D/256, B, row splits): a CTA owns 256 columns (one uint4 per lane) of one sample's row range, its 8 warps stride over
+// the rows, partials meet in shared memory and leave as one fp32 atomic per column and CTA.
+__global__ void __launch_bounds__(256) mod_grad_kernel(const bf16* __restrict__ g, int64_t ldg, const bf16* __restrict__ m, int64_t ldm,
+                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                       int rows_per_batch, float* __restrict__ sum_out, float* __restrict__ prod_out,
+                                                       int64_t ldo, int D) {
+  __shared__ float red[2][8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const int b = blockIdx.y;
+  const int per = (rows_per_batch + gridDim.z - 1) / gridDim.z;
+  const int r0 = blockIdx.z * per, r1 = min(rows_per_batch, r0 + per);
+  float s[8], p[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = p[e] = 0.f;
+  if (col < D) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const int64_t row = (int64_t)b * rows_per_batch + r;
+      float fg[8], fm[8];
+      unpack8(*reinterpret_cast<const uint4*>(g + row * ldg + col), fg);
+      if (m != nullptr) {
+        unpack8(*reinterpret_cast<const uint4*>(m + row * ldm + col), fm);
+        if (mean != nullptr) {
+          const float mu = mean[row], rs = rstd[row];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) fm[e] = round_bf16((fm[e] - mu) * rs);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) p[e] += fg[e] * fm[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] += fg[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[0][warp][lane * 8 + e] = s[e];
+    red[1][warp][lane * 8 + e] = p[e];
+  }
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < D) {
+    float ts = 0.f, tp = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      ts += red[0][w][threadIdx.x];
+      tp += red[1][w][threadIdx.x];
+    }
+    if (sum_out != nullptr) atomicAdd(sum_out + (int64_t)b * ldo + c, ts);
+    if (prod_out != nullptr && m != nullptr) atomicAdd(prod_out + (int64_t)b * ldo + c, tp);
+  }
+}
+
 // out = a * gate[b]   (backward of the gated residual branch when no LN-bwd kernel precedes it)
 __global__ void __launch_bounds__(256) gate_mul_kernel(const bf16* __restrict__ a, int64_t lda, const bf16* __restrict__ gate,
                                                        int64_t ldg, int rows_per_batch, bf16* __restrict__ out, int64_t ldo,
@@ -635,6 +689,19 @@ extern "C" int qfx_ln_modulate_bwd(const void* dy, int64_t lddy, const void* x, 
         lddres, (bf16*)dx, lddx, (const bf16*)gate, ldgate, (bf16*)dx_gated, lddxg, M);
     LAUNCH_OK();
   });
+}
+
+extern "C" int qfx_mod_grad(const void* g, int64_t ldg, const void* m, int64_t ldm, const float* mean, const float* rstd,
+                            int rows_per_batch, float* sum_out, float* prod_out, int64_t ldo, int M, int D, void* stream) {
+  QFX_CHECK_ARG(D % 8 == 0 && ldg % 8 == 0 && (m == nullptr || ldm % 8 == 0) && rows_per_batch > 0 && M % rows_per_batch == 0,
+                "qfx_mod_grad: bad dims (D=%d, M=%d, rows_per_batch=%d)", D, M, rows_per_batch);
+  QFX_CHECK_ARG((mean == nullptr) == (rstd == nullptr) && (mean == nullptr || m != nullptr), "qfx_mod_grad: mean/rstd need m");
+  const int B = M / rows_per_batch, cb = (D + 255) / 256;
+  int splits = (4 * num_sms() + cb * B - 1) / (cb * B);  // about four CTAs per SM
+  splits = splits < 1 ? 1 : (splits > (rows_per_batch + 31) / 32 ? (rows_per_batch + 31) / 32 : splits);
+  mod_grad_kernel<<<dim3(cb, B, splits), 256, 0, (cudaStream_t)stream>>>((const bf16*)g, ldg, (const bf16*)m, ldm, mean, rstd,
+                                                                        rows_per_batch, sum_out, prod_out, ldo, D);
+  LAUNCH_OK();
 }
 
 extern "C" int qfx_gate_mul(const void* a, int64_t lda, const void* gate, int64_t ldg, int rows_per_batch, void* out,

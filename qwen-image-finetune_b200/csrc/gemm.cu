@@ -108,7 +108,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmProb& q, const GemmParam
               float z0 = round_bf16(bf16_lo(gw[e]) * y0);
               float z1 = round_bf16(bf16_hi(gw[e]) * y1);
               o[i] = pack_bf16(bf16_lo(rw[e]) + z0, bf16_hi(rw[e]) + z1);
+              if (q.out2 != nullptr) r[i] = pack_bf16(y0, y1);  // un-gated branch output (the accumulator registers are dead now)
             }
+          }
+          if (q.out2 != nullptr) {  // kept when the gate's AdaLN linear carries LoRA: d gate = sum_t dOut * y
+            uint4* dst2 = reinterpret_cast<uint4*>(q.out2 + (int64_t)row * q.ldo2 + n);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) dst2[v] = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
           }
         }
       } else if (EPI == QFX_EPI_ADD) {

@@ -88,6 +88,8 @@ class FluxB200(FusedMMDiTBase):
         }
 
     def _wb(self, l, grp, s):
+        if l < 0:
+            return self.w[grp + "_w"], self.w[grp + "_b"]
         if grp.startswith("s_"):
             return self.w[grp + "_w"][l], self.w[grp + "_b"][l]
         return self.w[grp + "_w"][l, s], self.w[grp + "_b"][l, s]
@@ -140,6 +142,18 @@ class FluxB200(FusedMMDiTBase):
                 t[f"single_transformer_blocks.{l}.{nm}"] = ((l, grp), (0, 1), slot, d_in, d_out, n)
         return t
 
+    def _mod_table(self) -> dict:
+        t = {}
+        for l in range(self.L):
+            t[f"transformer_blocks.{l}.norm1.linear"] = ("dbl", 2 * l, 6)
+            t[f"transformer_blocks.{l}.norm1_context.linear"] = ("dbl", 2 * l + 1, 6)
+        for l in range(self.Ls):
+            t[f"single_transformer_blocks.{l}.norm.linear"] = ("sgl", l, 3)
+        return t
+
+    def _embed_table(self) -> dict:
+        return {"x_embedder": ("x_in", 0, self.C_in), "context_embedder": ("ctx_in", 1, self.J)}
+
     # ------------------------------------------------------------------------------------------------ workspace
     def _workspace(self, B, T, Limg, train: bool):
         def build():
@@ -186,12 +200,17 @@ class FluxB200(FusedMMDiTBase):
                                  ws["V"], self._rpb(ws, s), T if s == 0 else 0, round_mid=False)
         lib.attn_fwd(ws["Q"], ws["K"], ws["V"], O[:Mt], O[Mt:], T, save["lse"], kv_len=ws.get("kv_len"), txt_len=ws.get("txt_len"))
         # x = x + gate * proj_out(cat[attn, gelu(mlp)]): attention wrote columns [0, D) and the GELU epilogue [D, 5D) of save["cat"]
-        self._grouped(ws, l, "s_out", save["cat"], Xout, D, 5 * D, lib.EPI_RESID_GATE, resid=Xin, gate=self._smod(ws, l, 2))
+        self._grouped(ws, l, "s_out", save["cat"], Xout, D, 5 * D, lib.EPI_RESID_GATE, resid=Xin, gate=self._smod(ws, l, 2),
+                      out2=save.get("y_out"))
 
     def _single_bwd(self, ws, l, Xin, dX, dXn, save, prev_gate):
         D, w = self.D, self.w
         st, qkv, O, u = save["stats"], save["qkv"], save["O"], save["u"]
         Wo = w["s_out_w"][l]
+        dsm = lambda j: self._dmod(ws, "sgl", l, j)  # d(shift, scale, gate): ONE vector per sample for text and image rows alike
+        if dsm(2) is not None:
+            for s in (0, 1):
+                lib.mod_grad(self._rows(ws, dX, s), self._rpb(ws, s), m=self._rows(ws, save["y_out"], s), prod_out=dsm(2))
         # d[attn | mlp] = dY . W_out (+ U . A_lora)   (dY = dX * gate is already in ws['dY']); the two column ranges of the
         # concatenated input go to different consumers (attention backward / GELU backward), so they are two contractions
         pa, pm = [], []
@@ -212,6 +231,9 @@ class FluxB200(FusedMMDiTBase):
         self._dgrad_grouped(ws, l, "s_qkv", ws["dqkv"], ws["dxm"], D, 3 * D, D, ws["xm"])
         self._dgrad_grouped(ws, l, "s_mlp", ws["dbig"], ws["dxm"], D, 4 * D, 4 * D, ws["xm"], epilogue=lib.EPI_ADD, resid=ws["dxm"])
         for s in (0, 1):
+            if dsm(0) is not None:
+                lib.mod_grad(self._rows(ws, ws["dxm"], s), self._rpb(ws, s), sum_out=dsm(0), m=self._rows(ws, Xin, s),
+                             prod_out=dsm(1), mean=self._rows(ws, st[0], s), rstd=self._rows(ws, st[1], s))
             lib.ln_modulate_bwd(self._rows(ws, ws["dxm"], s), self._rows(ws, Xin, s), self._rows(ws, st[0], s),
                                 self._rows(ws, st[1], s), self._smod(ws, l, 1)[s], self._rpb(ws, s), self._rows(ws, dXn, s),
                                 dres=self._rows(ws, dX, s), gate=prev_gate[s] if prev_gate else None,
@@ -225,24 +247,31 @@ class FluxB200(FusedMMDiTBase):
         lib.gemv_act(tmp, w[pre + "2_w"], w[pre + "2_b"], out, act=1)
 
     def _forward_impl(self, hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
-                      train: bool):
-        lib.require_cuda(hidden_states, encoder_hidden_states, pooled_projections, timestep)
+                      kv_len=None, train: bool = False):
+        """img_ids [L, 3] (shared) or [B, L, 3] together with kv_len (int32 [B] on the device: T + valid image tokens) for a
+        pad-to-max multi-resolution batch — per-sample RoPE tables and key masks (transformer_flux_custom.py:494-616)."""
+        lib.require_cuda(hidden_states, encoder_hidden_states, pooled_projections, timestep, kv_len)
         B, Limg, _ = hidden_states.shape
         T = encoder_hidden_states.shape[1]
         D, L, Ls, w = self.D, self.L, self.Ls, self.w
         ws = self._workspace(B, T, Limg, train)
         Mt = ws["Mt"]
-        if img_ids.ndim == 3:
-            img_ids = img_ids[0]
         if txt_ids.ndim == 3:
             txt_ids = txt_ids[0]
+        if img_ids.ndim == 3 and kv_len is None:
+            img_ids = img_ids[0]  # batched ids without a mask: every sample has the same layout (transformer_flux_custom.py:473-476)
         key = (img_ids.data_ptr(), txt_ids.data_ptr(), tuple(img_ids.shape), tuple(txt_ids.shape), img_ids._version)
         if key not in self._rope_cache:  # built with torch ops on the ids' device (no host sync); re-used while the ids tensor lives
             self._rope_cache.clear()
-            self._rope_cache[key] = flux_rope_table(torch.cat((txt_ids.to(self.dev), img_ids.to(self.dev)), dim=0),
-                                                    self.config.axes_dims_rope)
+            ti, ii = txt_ids.to(self.dev), img_ids.to(self.dev)
+            if ii.ndim == 3:  # zero-padded ids give position 0 on every axis = the identity rotation the reference pads with (:538-553)
+                self._rope_cache[key] = torch.stack([flux_rope_table(torch.cat((ti, ii[b]), dim=0), self.config.axes_dims_rope)
+                                                     for b in range(B)]).contiguous()
+            else:
+                self._rope_cache[key] = flux_rope_table(torch.cat((ti, ii), dim=0), self.config.axes_dims_rope)
         ws["rope"] = self._rope_cache[key]
-        assert ws["rope"].shape[0] == ws["S"]
+        ws["kv_len"] = kv_len
+        assert ws["rope"].shape[-3] == ws["S"]
         X0 = ws["X"][0]
         # --- conditioning: temb = MLP_t(sin(1000 t)) [+ MLP_g(sin(1000 g))] + MLP_p(pooled)   (bf16 products, like the model)
         t32 = (timestep.to(BF) * 1000).float().contiguous()
@@ -259,10 +288,10 @@ class FluxB200(FusedMMDiTBase):
         if Ls:
             lib.gemv_act(ws["temb"], w["s_mod_w"].view(Ls * 3 * D, D), w["s_mod_b"].view(-1), ws["smods"], act=1)
         lib.gemv_act(ws["temb"], w["norm_out_w"], w["norm_out_b"], ws["fmod"], act=1)
+        self._mod_lora_fwd(ws, ws["temb"])
         # --- embedders
-        hs = hidden_states.to(BF).reshape(B * Limg, self.C_in)
-        lib.gemm([lib.gemm_problem(hs, w["x_in_w"], X0[Mt:], bias=w["x_in_b"])], D, self.C_in)
-        lib.gemm([lib.gemm_problem(encoder_hidden_states.to(BF).reshape(Mt, self.J), w["ctx_in_w"], X0[:Mt], bias=w["ctx_in_b"])], D, self.J)
+        self._embed_fwd(ws, "x_in", 0, hidden_states.to(BF).reshape(B * Limg, self.C_in), X0[Mt:])
+        self._embed_fwd(ws, "ctx_in", 1, encoder_hidden_states.to(BF).reshape(Mt, self.J), X0[:Mt])
         # --- blocks
         nb = L + Ls
         xi = lambda i: ws["X"][i] if train else ws["X"][i & 1]
@@ -287,6 +316,7 @@ class FluxB200(FusedMMDiTBase):
         Limg, Mt = ws["Limg"], ws["Mt"]
         D, L, Ls, w = self.D, self.L, self.Ls, self.w
         nb = L + Ls
+        self._mod_grad_buffers(ws)
         lib.gemm([lib.gemm_problem(dpred, w["proj_out_w"], ws["dhn"])], D, self.C_out, trans_b=True)
         dX = ws["dX"][nb & 1]
         dX[:Mt].zero_()
@@ -301,13 +331,25 @@ class FluxB200(FusedMMDiTBase):
             else:
                 self._double_bwd(ws, blk, ws["X"][blk], dX, dXn, ws["dbl"][blk], self._mods(ws, blk), prev)
             dX = dXn
+        self._mod_lora_bwd(ws)
+        self._embed_bwd(ws, "x_in", 0, dX)
+        self._embed_bwd(ws, "ctx_in", 1, dX)
 
     # ------------------------------------------------------------------------------------------------ public API
     def forward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None, timestep=None, img_ids=None,
-                txt_ids=None, guidance=None, joint_attention_kwargs=None, return_dict=False):
-        args = (hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance)
+                txt_ids=None, guidance=None, joint_attention_kwargs=None, return_dict=False, attention_mask=None):
+        kv_len = None
+        if attention_mask is not None:  # [B, T + L] validity mask of a pad-to-max batch (prefix-valid per sample, tools.py:319-396)
+            kv_len = attention_mask.to(self.dev).sum(dim=1).to(torch.int32)
+            if img_ids.ndim == 2:
+                img_ids = img_ids[None].expand(hidden_states.shape[0], -1, -1)
+        args = (hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance, kv_len)
         if torch.is_grad_enabled() and self._lora_params:
             out = ModelFn.apply(self, args, *self._lora_params.values())
         else:
             out = self._forward_impl(*args, train=False).clone()
+        if kv_len is not None:  # padded image rows come back as exact zeros (transformer_flux_custom.py:724-735)
+            T = encoder_hidden_states.shape[1]
+            valid = torch.arange(out.shape[1], device=out.device)[None, :] < (kv_len[:, None] - T)
+            out = out * valid[..., None].to(out.dtype)
         return (out,)

@@ -110,6 +110,7 @@ _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _ln_fwd = _sig("qfx_ln_modulate_fwd", _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _vp, _vp, _i, _i, _f, _vp)
 _ln_bwd = _sig("qfx_ln_modulate_bwd", _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp, _i64, _vp, _i64, _vp, _i64, _vp,
                _i64, _i, _i, _vp)
+_mod_grad = _sig("qfx_mod_grad", _vp, _i64, _vp, _i64, _vp, _vp, _i, _vp, _vp, _i64, _i, _i, _vp)
 _gate_mul = _sig("qfx_gate_mul", _vp, _i64, _vp, _i64, _i, _vp, _i64, _i, _i, _vp)
 _rms_rows = _sig("qfx_rmsnorm_rows", _vp, _i64, _vp, _vp, _i64, _i, _i, _f, _vp)
 _qknr_fwd = _sig("qfx_qk_norm_rope_fwd", _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp)
@@ -139,6 +140,16 @@ def ln_modulate_bwd(dy, x, mean, rstd, scale, rows_per_batch, dx, dres=None, gat
     check(_ln_bwd(ptr(dy), dy.stride(0), ptr(x), x.stride(0), ptr(mean), ptr(rstd), ptr(scale), scale.stride(0),
                   rows_per_batch, ptr(dres), _ld(dres), ptr(dx), dx.stride(0), ptr(gate), _ld(gate), ptr(dx_gated),
                   _ld(dx_gated), x.shape[0], x.shape[1], cur_stream()), "qfx_ln_modulate_bwd")
+
+
+def mod_grad(g, rows_per_batch, sum_out=None, m=None, prod_out=None, mean=None, rstd=None):
+    """Modulation-vector gradients, accumulated (+=) into fp32 [B, D] views: sum_out += sum_t g ; prod_out += sum_t g * m',
+    m' = bf16((m - mean) * rstd) when the row statistics are given (d scale), else m itself (d gate)."""
+    require_cuda(g, m, sum_out, prod_out, mean, rstd)
+    o = sum_out if sum_out is not None else prod_out
+    assert o.dtype == torch.float32 and (sum_out is None or prod_out is None or sum_out.stride(0) == prod_out.stride(0))
+    check(_mod_grad(ptr(g), g.stride(0), ptr(m), _ld(m), ptr(mean), ptr(rstd), rows_per_batch, ptr(sum_out), ptr(prod_out),
+                    o.stride(0), g.shape[0], g.shape[1], cur_stream()), "qfx_mod_grad")
 
 
 def gate_mul(a, gate, rows_per_batch, out):

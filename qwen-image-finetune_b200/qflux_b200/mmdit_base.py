@@ -47,7 +47,18 @@ class FusedMMDiTBase(nn.Module):
         """full module name -> (site_key=(l, grp), streams tuple, slot, d_in, d_out, n_slots)"""
         raise NotImplementedError
 
+    def _mod_table(self) -> dict:
+        """full name of an AdaLN modulation Linear -> (kind, index, n_chunks): kind "dbl" indexes rows of ws["mods"] viewed
+        [B, L*2, 6D] (index = 2*l + stream), kind "sgl" rows of ws["smods"] viewed [B, Ls, 3D]."""
+        return {}
+
+    def _embed_table(self) -> dict:
+        """full name of an input embedder Linear -> (weight key prefix in self.w, stream, d_in)."""
+        return {}
+
     def _wb(self, l, grp, s):
+        if l < 0:  # input embedders: one weight, no block index
+            return self.w[grp + "_w"], self.w[grp + "_b"]
         return self.w[grp + "_w"][l, s], self.w[grp + "_b"][l, s]
 
     # -----------------------------------------------------------------------------------------------------------------
@@ -55,7 +66,8 @@ class FusedMMDiTBase(nn.Module):
         if not host_only and not torch.cuda.is_available():
             raise lib.QfxError(f"{type(self).__name__} needs a CUDA device (sm_100a); there is no CPU fallback")
         self.dev = torch.device(device)
-        self.sites = {}          # (l, grp, s) -> LoraSite
+        self.sites = {}          # (l, grp, s) -> LoraSite   (l = -1: input embedders)
+        self.mod_sites = {}      # kind -> dict(idx=[row indices], names=[...], A=[n, r, D], B=[n, C, r], ga, gb)  (AdaLN linears)
         self._lora_params = {}   # PEFT name -> nn.Parameter
         self.lora_scaling, self.lora_rank = 0.0, 0
         self.G32 = self.G16 = None
@@ -122,7 +134,11 @@ class FusedMMDiTBase(nn.Module):
             raise NotImplementedError(f"LoRA rank {r}: the fused kernels take r in (4, 8, 16, 32, 64)")
         if self._lora_params:
             raise lib.QfxError("an adapter is already attached")
-        table = self._linear_table()
+        table = dict(self._linear_table())
+        D = self.D
+        for full, (key, s_, d_in) in self._embed_table().items():
+            table[full] = ((-1, key), (s_,), 0, d_in, D, 1)
+        mod_table = self._mod_table()
 
         def match(full):
             if isinstance(target_modules, str):
@@ -132,9 +148,10 @@ class FusedMMDiTBase(nn.Module):
         wanted = [full for full in table if match(full)]
         for k, v in self._weight_views().items():  # modules PEFT would adapt but the fused path cannot: fail loudly
             mod = k.rsplit(".", 1)[0]
-            if k.endswith(".weight") and v.ndim == 2 and mod not in table and match(mod):
+            if k.endswith(".weight") and v.ndim == 2 and mod not in table and mod not in mod_table and match(mod):
                 raise NotImplementedError(f"LoRA on `{mod}` is outside the fused hot path (SURVEY.md §8a a12)")
-        if not wanted:
+        wanted_mods = [full for full in mod_table if match(full)]
+        if not wanted and not wanted_mods:
             raise lib.QfxError(f"no LoRA-capable module matches target_modules={target_modules!r}")
         self.lora_rank, self.lora_scaling = r, float(lora_alpha) / r
         g = torch.Generator(device=self.dev).manual_seed(seed)
@@ -161,6 +178,31 @@ class FusedMMDiTBase(nn.Module):
             site.members[slot] = (full, pA, pB, gA_off, gB_off, d_in, d_out)
             self._lora_params[full + ".lora_A.default.weight"] = pA
             self._lora_params[full + ".lora_B.default.weight"] = pB
+        # AdaLN modulation linears (M = batch rows only): factors stacked per kind so that forward and backward are a handful of
+        # batched [B, .] products; gradients come from per-sample column reductions in the block backward (qfx_mod_grad)
+        self._extra_members = []
+        for kind in ("dbl", "sgl"):
+            names = [f for f in wanted_mods if mod_table[f][0] == kind]
+            if not names:
+                continue
+            n, C = len(names), mod_table[names[0]][2] * D
+            A_all = torch.zeros(n, r, D, device=self.dev, dtype=BF)
+            B_all = torch.zeros(n, C, r, device=self.dev, dtype=BF)
+            if init_lora_weights == "gaussian":
+                A_all.copy_(torch.randn(n, r, D, device=self.dev, generator=g) / r)
+            else:
+                A_all.copy_((torch.rand(n, r, D, device=self.dev, generator=g) * 2 - 1) / math.sqrt(D))
+            if b_std > 0:
+                B_all.copy_(torch.randn(n, C, r, device=self.dev, generator=g) * b_std)
+            ga0, gb0 = off, off + n * r * D
+            off = gb0 + n * C * r
+            self.mod_sites[kind] = dict(idx=torch.tensor([mod_table[f][1] for f in names], device=self.dev), names=names, A=A_all,
+                                        B=B_all, ga=ga0, gb=gb0, C=C, rows={mod_table[f][1] for f in names})
+            for i, full in enumerate(names):
+                pA, pB = nn.Parameter(A_all[i]), nn.Parameter(B_all[i])
+                self._extra_members.append((full, pA, pB, ga0 + i * r * D, gb0 + i * C * r, D, C))
+                self._lora_params[full + ".lora_A.default.weight"] = pA
+                self._lora_params[full + ".lora_B.default.weight"] = pB
         self.G32 = torch.zeros(off, device=self.dev, dtype=torch.float32)
         self.G16 = torch.zeros(off, device=self.dev, dtype=BF)
         self._gnorm_sq = torch.zeros(1, device=self.dev, dtype=torch.float32)
@@ -175,23 +217,83 @@ class FusedMMDiTBase(nn.Module):
                 seen.add(id(site))
                 yield site
 
+    def _all_members(self):
+        """(name, A param, B param, grad offset of A, grad offset of B, d_in, d_out) of every adapted Linear."""
+        for site in self._unique_sites():
+            yield from site.members.values()
+        yield from getattr(self, "_extra_members", [])
+
     def bind_param_grads(self):
         """Point every LoRA `param.grad` at its slice of the flat bf16 gradient buffer (no copies)."""
         r = self.lora_rank
-        for site in self._unique_sites():
-            for slot, (full, pA, pB, ga, gb, d_in, d_out) in site.members.items():
-                pA.grad = self.G16[ga: ga + r * d_in].view(r, d_in)
-                pB.grad = self.G16[gb: gb + d_out * r].view(d_out, r)
+        for full, pA, pB, ga, gb, d_in, d_out in self._all_members():
+            pA.grad = self.G16[ga: ga + r * d_in].view(r, d_in)
+            pB.grad = self.G16[gb: gb + d_out * r].view(d_out, r)
 
     def lora_grad_views(self, flat=None):
         """{param name: view into a flat gradient buffer (default: the fp32 accumulator)}."""
         flat = self.G32 if flat is None else flat
         out, r = {}, self.lora_rank
-        for site in self._unique_sites():
-            for slot, (full, pA, pB, ga, gb, d_in, d_out) in site.members.items():
-                out[full + ".lora_A.default.weight"] = flat[ga: ga + r * d_in].view(r, d_in)
-                out[full + ".lora_B.default.weight"] = flat[gb: gb + d_out * r].view(d_out, r)
+        for full, pA, pB, ga, gb, d_in, d_out in self._all_members():
+            out[full + ".lora_A.default.weight"] = flat[ga: ga + r * d_in].view(r, d_in)
+            out[full + ".lora_B.default.weight"] = flat[gb: gb + d_out * r].view(d_out, r)
         return out
+
+    # ------------------------------------------------------------------------------------------------ AdaLN-linear LoRA
+    def _mods_view(self, ws, kind):
+        C = self.mod_sites[kind]["C"]
+        t = ws["mods"] if kind == "dbl" else ws["smods"]
+        return t.view(t.shape[0], -1, C)
+
+    def _mod_lora_fwd(self, ws, temb):
+        """mods += scaling * lora_B(lora_A(silu(temb))) for every adapted modulation Linear, with PEFT's bf16 rounding points
+        (lora_A output, lora_B output, the scaled product, the sum).  [B, .] operands: batched torch products, not a hot path."""
+        if not self.mod_sites:
+            return
+        x = torch.nn.functional.silu(temb.float()).to(BF)  # the same rounded activation the modulation GEMV consumes
+        ws["mod_x"] = x
+        for kind, ms in self.mod_sites.items():
+            t = torch.matmul(x.float()[None], ms["A"].float().transpose(1, 2)).to(BF)        # [n, B, r]
+            d = torch.bmm(t.float(), ms["B"].float().transpose(1, 2)).to(BF)                  # [n, B, C]
+            d = (d.float() * self.lora_scaling).to(BF)
+            mv = self._mods_view(ws, kind)
+            mv[:, ms["idx"]] = (mv[:, ms["idx"]].float() + d.float().permute(1, 0, 2)).to(BF)
+            ws["mod_t_" + kind] = t
+
+    def _mod_grad_buffers(self, ws):
+        """fp32 accumulators for d mods (same layout as the modulation vectors), zeroed at the start of every backward."""
+        for kind in self.mod_sites:
+            key = "dmods" if kind == "dbl" else "dsmods"
+            src = ws["mods"] if kind == "dbl" else ws["smods"]
+            if key not in ws:
+                ws[key] = torch.empty(src.shape, device=self.dev, dtype=torch.float32)
+            ws[key].zero_()
+
+    def _dmod(self, ws, kind, row, j):
+        """fp32 [B, D] view: gradient of chunk j of modulation row `row` (None when that Linear has no adapter)."""
+        ms = self.mod_sites.get(kind)
+        if ms is None or row not in ms["rows"]:
+            return None
+        D = self.D
+        t = ws["dmods" if kind == "dbl" else "dsmods"]
+        off = row * ms["C"] + j * D
+        return t[:, off: off + D]
+
+    def _mod_lora_bwd(self, ws):
+        """LoRA gradients of the modulation linears from the accumulated d mods:  dB = s * dmod^T t,  dA = s * (dmod B)^T x."""
+        if not self.mod_sites:
+            return
+        r, D, x = self.lora_rank, self.D, ws["mod_x"].float()
+        for kind, ms in self.mod_sites.items():
+            n, C = len(ms["names"]), ms["C"]
+            g = ws["dmods" if kind == "dbl" else "dsmods"]
+            dm = g.view(g.shape[0], -1, C)[:, ms["idx"]].to(BF).float()                       # [B, n, C]  (autograd hands bf16 grads on)
+            t = ws["mod_t_" + kind].float()                                                    # [n, B, r]
+            dB = torch.einsum("bnc,nbr->ncr", dm, t) * self.lora_scaling
+            u = (torch.einsum("bnc,ncr->nbr", dm, ms["B"].float()) * self.lora_scaling).to(BF).float()
+            dA = torch.einsum("nbr,bd->nrd", u, x)
+            self.G32[ms["ga"]: ms["ga"] + n * r * D].view(n, r, D).add_(dA)
+            self.G32[ms["gb"]: ms["gb"] + n * C * r].view(n, C, r).add_(dB)
 
     def zero_lora_grads(self):
         self.G32.zero_()
@@ -226,6 +328,19 @@ class FusedMMDiTBase(nn.Module):
         Tb = ws["loraT"][(l, grp, s)]
         lib.gemm([lib.gemm_problem(X, site.A_pad, Tb)], site.n * PAD, X.shape[1], alpha=self.lora_scaling)
         return site, Tb
+
+    def _embed_fwd(self, ws, key, s, X, dst):
+        """Input embedder `key` (x_embedder / context_embedder / img_in / txt_in) with its optional fused LoRA pair."""
+        W, b = self._wb(-1, key, s)
+        site, Tb = self._lora_T(ws, -1, key, s, X)
+        kw = dict(A2=Tb, B2=site.B_pad, kb2=1) if site is not None else {}
+        lib.gemm([lib.gemm_problem(X, W, dst, bias=b, **kw)], self.D, X.shape[1])
+        ws["embed_in_" + key] = X
+
+    def _embed_bwd(self, ws, key, s, dX0):
+        """LoRA gradients of an input embedder from the gradient at the first block's input (the embedder input is data)."""
+        if self._site(-1, key, s) is not None:
+            self._lora_bwd(ws, -1, key, s, self._rows(ws, dX0, s), ws["embed_in_" + key], self.D)
 
     def _grouped(self, ws, l, grp, src, dst, N, K, epilogue, **epi):
         """One grouped GEMM over (image, text) rows of block l for weight group `grp` with optional fused LoRA."""
@@ -278,7 +393,11 @@ class FusedMMDiTBase(nn.Module):
                 gB.append(self._gscratch)
                 gA.append(self._gscratch)
         lib.lora_wgrad_tc(dY, Tb, gB, r, 1, r, mode=1 if site.n > 1 else 0, Dg=n_out_each if site.n > 1 else 0)
-        lib.lora_wgrad_tc(Xsaved, U, gA, 1, Xsaved.shape[1], r, mode=0)
+        if Xsaved.shape[1] % 128 == 0:
+            lib.lora_wgrad_tc(Xsaved, U, gA, 1, Xsaved.shape[1], r, mode=0)
+        else:  # 64-channel latent embedder: too narrow for the tcgen05 tile, a [r, 64] result on the CUDA cores
+            for g in range(site.n):
+                lib.lora_wgrad(Xsaved, U[:, g * PAD:(g + 1) * PAD], gA[g], 1, Xsaved.shape[1], r)
         return U, site.A_pad, site.n
 
     def _dgrad_grouped(self, ws, l, grp, dY, dXout, N, K, n_out_each, Xsaved, epilogue=lib.EPI_BIAS, aux=None, resid=None):
@@ -314,13 +433,13 @@ class FusedMMDiTBase(nn.Module):
             lib.qk_norm_rope_fwd(self._rows(ws, qkv, s), w["qknorm_w"][l, 2 * s], w["qknorm_w"][l, 2 * s + 1], ws["rope"], Qs, Ks, Vs,
                                  self._rpb(ws, s), T if s == 0 else 0, round_mid=self.round_mid)
         lib.attn_fwd(Qs, Ks, Vs, O[:Mt], O[Mt:], T, save["lse"], kv_len=ws.get("kv_len"), txt_len=ws.get("txt_len"))
-        self._grouped(ws, l, "out", O, xmid, D, D, lib.EPI_RESID_GATE, resid=Xin, gate=mods(2))
+        self._grouped(ws, l, "out", O, xmid, D, D, lib.EPI_RESID_GATE, resid=Xin, gate=mods(2), out2=save.get("y_attn"))
         for s in (0, 1):
             lib.ln_modulate_fwd(self._rows(ws, xmid, s), self._rows(ws, ws["xm"], s), mods(3)[s], mods(4)[s], self._rpb(ws, s),
                                 self._rows(ws, st[2], s), self._rows(ws, st[3], s))
         h = save.get("h", ws["h"])  # kept per block only when ff.net.2 carries LoRA (its input is needed for dA)
         self._grouped(ws, l, "up", ws["xm"], h, 4 * D, D, lib.EPI_GELU, out2=u)
-        self._grouped(ws, l, "down", h, Xout, D, 4 * D, lib.EPI_RESID_GATE, resid=xmid, gate=mods(5))
+        self._grouped(ws, l, "down", h, Xout, D, 4 * D, lib.EPI_RESID_GATE, resid=xmid, gate=mods(5), out2=save.get("y_mlp"))
 
     def _attn_bwd_core(self, ws, qkv, O, lse, wq_wk, save=None):
         """dO (token-major, ws['dO']) -> dqkv (ws['dqkv']); wq_wk(s) -> (wq, wk) norm weights of stream s.
@@ -349,6 +468,10 @@ class FusedMMDiTBase(nn.Module):
         D = self.D
         st, qkv, O, xmid, u = save["stats"], save["qkv"], save["O"], save["xmid"], save["u"]
         w = self.w
+        dm = lambda s, j: self._dmod(ws, "dbl", 2 * l + s, j)  # fp32 [B, D] accumulators of d(shift1, scale1, gate1, shift2, scale2, gate2)
+        for s in (0, 1):
+            if dm(s, 5) is not None:  # d gate2 = sum_t dXout * mlp_out  (before dX is overwritten with dXmid below)
+                lib.mod_grad(self._rows(ws, dX, s), self._rpb(ws, s), m=self._rows(ws, save["y_mlp"], s), prod_out=dm(s, 5))
         # ---- MLP branch
         self._dgrad_grouped(ws, l, "down", ws["dY"], ws["dbig"], 4 * D, D, D, save.get("h"), epilogue=lib.EPI_DGELU, aux=u)
         if self._site(l, "up", 0) or self._site(l, "up", 1):  # LoRA input = xm2, recomputed from the statistics
@@ -357,9 +480,15 @@ class FusedMMDiTBase(nn.Module):
         self._dgrad_grouped(ws, l, "up", ws["dbig"], ws["dxm"], D, 4 * D, 4 * D, ws["xm"])
         # ---- norm2 backward: dXmid = dX + LN_bwd ; also emit dXmid * gate1 for the attention out-projection
         for s in (0, 1):
+            if dm(s, 3) is not None:  # d shift2 = sum_t dy ; d scale2 = sum_t dy * LN(xmid)
+                lib.mod_grad(self._rows(ws, ws["dxm"], s), self._rpb(ws, s), sum_out=dm(s, 3), m=self._rows(ws, xmid, s),
+                             prod_out=dm(s, 4), mean=self._rows(ws, st[2], s), rstd=self._rows(ws, st[3], s))
             lib.ln_modulate_bwd(self._rows(ws, ws["dxm"], s), self._rows(ws, xmid, s), self._rows(ws, st[2], s),
                                 self._rows(ws, st[3], s), mods(4)[s], self._rpb(ws, s), self._rows(ws, dX, s),
                                 dres=self._rows(ws, dX, s), gate=mods(2)[s], dx_gated=self._rows(ws, ws["dY"], s))
+        for s in (0, 1):
+            if dm(s, 2) is not None:  # d gate1 = sum_t dXmid * attn_out   (dX holds dXmid now)
+                lib.mod_grad(self._rows(ws, dX, s), self._rpb(ws, s), m=self._rows(ws, save["y_attn"], s), prod_out=dm(s, 2))
         # ---- attention output projection (LoRA input = O), attention, q|k|v projection (LoRA input = xm1, recomputed)
         self._dgrad_grouped(ws, l, "out", ws["dY"], ws["dO"], D, D, D, O)
         self._attn_bwd_core(ws, qkv, O, save["lse"], lambda s: (w["qknorm_w"][l, 2 * s], w["qknorm_w"][l, 2 * s + 1]), save)
@@ -372,6 +501,9 @@ class FusedMMDiTBase(nn.Module):
         self._dgrad_grouped(ws, l, "qkv", ws["dqkv"], ws["dxm"], D, 3 * D, D, xm1)
         # ---- norm1 backward: dXin = dXmid + LN_bwd ; emit dXin * (gate of the block before)
         for s in (0, 1):
+            if dm(s, 0) is not None:
+                lib.mod_grad(self._rows(ws, ws["dxm"], s), self._rpb(ws, s), sum_out=dm(s, 0), m=self._rows(ws, Xin, s),
+                             prod_out=dm(s, 1), mean=self._rows(ws, st[0], s), rstd=self._rows(ws, st[1], s))
             lib.ln_modulate_bwd(self._rows(ws, ws["dxm"], s), self._rows(ws, Xin, s), self._rows(ws, st[0], s),
                                 self._rows(ws, st[1], s), mods(1)[s], self._rpb(ws, s), self._rows(ws, dXn, s),
                                 dres=self._rows(ws, dX, s), gate=prev_gate[s] if prev_gate else None,
@@ -399,6 +531,9 @@ class FusedMMDiTBase(nn.Module):
             for l, blk in enumerate(ws["dbl"]):
                 if self._site(l, "down", 0) or self._site(l, "down", 1):
                     blk["h"] = e(M, 4 * D)
+                rows = self.mod_sites.get("dbl", {}).get("rows", ())
+                if 2 * l in rows or 2 * l + 1 in rows:  # un-gated branch outputs, needed for d gate
+                    blk["y_attn"], blk["y_mlp"] = e(M, D), e(M, D)
         # single blocks keep cat[attn | gelu(mlp)] — the input of proj_out — in ONE [M, 5D] buffer: attention and the GELU epilogue
         # write straight into its column ranges (no concat), proj_out is a plain K = 5D contraction, and the buffer is the LoRA
         # input of proj_out in the backward
@@ -406,6 +541,10 @@ class FusedMMDiTBase(nn.Module):
                           u=e(M, 4 * D)) for _ in range(ns)]
         for blk in ws["sgl"]:
             blk["O"], blk["h"] = blk["cat"][:, :D], blk["cat"][:, D:]
+        if train:
+            for l, blk in enumerate(ws["sgl"]):
+                if l in self.mod_sites.get("sgl", {}).get("rows", ()):
+                    blk["y_out"] = e(M, D)
         ws["hn"], ws["pred"] = e(Mi, D), e(Mi, self.C_out)
         ws["fstats"] = e(2, Mi, dt=torch.float32)
         self._alloc_lora_T(ws)

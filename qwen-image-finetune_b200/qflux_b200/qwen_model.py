@@ -117,6 +117,16 @@ class QwenImageB200(FusedMMDiTBase):
         return t
 
     # ------------------------------------------------------------------------------------------------ workspace
+    def _mod_table(self) -> dict:
+        t = {}
+        for l in range(self.L):
+            t[f"transformer_blocks.{l}.img_mod.1"] = ("dbl", 2 * l, 6)
+            t[f"transformer_blocks.{l}.txt_mod.1"] = ("dbl", 2 * l + 1, 6)
+        return t
+
+    def _embed_table(self) -> dict:
+        return {"img_in": ("img_in", 0, self.C_in), "txt_in": ("txt_in", 1, self.J)}
+
     def _workspace(self, B, T, Limg, train: bool):
         def build():
             ws = self._alloc_common({}, B, T, Limg, train, self.L)
@@ -187,11 +197,12 @@ class QwenImageB200(FusedMMDiTBase):
         lib.gemv_act(ws["t1"], w["t2_w"], w["t2_b"], ws["temb"], act=1)
         lib.gemv_act(ws["temb"], w["mod_w"].view(L * 2 * 6 * D, D), w["mod_b"].view(-1), ws["mods"], act=1)
         lib.gemv_act(ws["temb"], w["norm_out_w"], w["norm_out_b"], ws["fmod"], act=1)
+        self._mod_lora_fwd(ws, ws["temb"])
         # --- embedders
         hs = hidden_states.to(BF).reshape(B * Limg, self.C_in)
-        lib.gemm([lib.gemm_problem(hs, w["img_in_w"], X0[Mt:], bias=w["img_in_b"])], D, self.C_in)
+        self._embed_fwd(ws, "img_in", 0, hs, X0[Mt:])
         lib.rmsnorm_rows(encoder_hidden_states.to(BF).reshape(Mt, self.J), w["txt_norm_w"], ws["txt_n"])
-        lib.gemm([lib.gemm_problem(ws["txt_n"], w["txt_in_w"], X0[:Mt], bias=w["txt_in_b"])], D, self.J)
+        self._embed_fwd(ws, "txt_in", 1, ws["txt_n"], X0[:Mt])
         # --- blocks
         for l in range(L):
             Xin, Xout = (ws["X"][l], ws["X"][l + 1]) if train else (ws["X"][l & 1], ws["X"][(l + 1) & 1])
@@ -210,6 +221,7 @@ class QwenImageB200(FusedMMDiTBase):
         assert ws is not None and self._ws_key[3], "backward needs a training-mode forward first"
         Limg, Mt = ws["Limg"], ws["Mt"]
         D, L, w = self.D, self.L, self.w
+        self._mod_grad_buffers(ws)
         # --- head: proj_out dgrad -> final AdaLN backward.  Text rows of the last block output receive no gradient.
         lib.gemm([lib.gemm_problem(dpred, w["proj_out_w"], ws["dhn"])], D, self.C_out, trans_b=True)
         dX = ws["dX"][L & 1]
@@ -222,6 +234,9 @@ class QwenImageB200(FusedMMDiTBase):
             self._double_bwd(ws, l, ws["X"][l], dX, dXn, ws["dbl"][l], self._mods(ws, l),
                              self._mods(ws, l - 1)(5) if l > 0 else None)
             dX = dXn
+        self._mod_lora_bwd(ws)
+        self._embed_bwd(ws, "img_in", 0, dX)
+        self._embed_bwd(ws, "txt_in", 1, dX)
 
     # ------------------------------------------------------------------------------------------------ public API
     def forward(self, hidden_states, encoder_hidden_states=None, encoder_hidden_states_mask=None, timestep=None,

@@ -184,8 +184,11 @@ class FluxKontextStep:
         if t is None:
             t = embeddings["timestep"] if "timestep" in embeddings else torch.rand((B,), device=dev, dtype=BF)
         t = t.to(dev, BF)
-        ids = torch.cat([embeddings["image_ids"].to(dev), embeddings["control_ids"].to(dev)], dim=0)
         edit_mask = embeddings.get("edit_mask")
+        shapes = embeddings.get("img_shapes")
+        if shapes is not None and any(list(map(tuple, sh)) != list(map(tuple, shapes[0])) for sh in shapes):
+            return self._prepare_multi(embeddings, x0, ctrl, pe, pooled, noise.to(dev, BF), t, edit_mask, shapes)
+        ids = torch.cat([embeddings["image_ids"].to(dev), embeddings["control_ids"].to(dev)], dim=0)
         if self.loss_kind == "mse" and edit_mask is None:
             if (B, L) not in self._ones:
                 self._ones[(B, L)] = torch.ones(B, L, device=dev)
@@ -197,12 +200,51 @@ class FluxKontextStep:
         guidance = torch.ones(B, device=dev) if m.config.guidance_embeds else None
         return (x0, ctrl, pe, pooled, embeddings["text_ids"].to(dev), ids, noise.to(dev, BF), t, guidance, w, norm)
 
-    def _run(self, x0, ctrl, pe, pooled, text_ids, ids, noise, t, guidance, w, norm):
+    def _prepare_multi(self, embeddings, x0, ctrl, pe, pooled, noise, t, edit_mask, shapes):
+        """`_compute_loss_multi_resolution_mode` (flux_kontext_trainer.py:579-796): img_shapes is one list per sample of
+        latent-patch shapes [(1, h, w) target, (1, h, w) control_1, ...] (the trainer converts pixel shapes with
+        convert_img_shapes_to_latent first); image / control latents are zero-padded to the batch maximum.  Per-sample ids
+        (control j carries j in the first column, :635-650), sequences [target | controls] padded to the longest sample, key mask,
+        and a loss over the valid target tokens only.  All bookkeeping is host metadata: no device sync."""
+        m, dev = self.dit, self.dit.dev
+        B, L, C = x0.shape
+        T = pe.shape[1]
+        lt = [sh[0][1] * sh[0][2] for sh in shapes]
+        lc = [sum(h * w_ for (_, h, w_) in sh[1:]) for sh in shapes]
+        Ltot = max(a + b for a, b in zip(lt, lc))
+        ids = torch.zeros(B, Ltot, 3)
+        for b, sh in enumerate(shapes):
+            parts = [self.latent_image_ids(sh[0][1], sh[0][2], "cpu", 0.0)]
+            parts += [self.latent_image_ids(h, w_, "cpu", float(j + 1)) for j, (_, h, w_) in enumerate(sh[1:])]
+            cat = torch.cat(parts, dim=0)
+            ids[b, : cat.shape[0]] = cat
+        Lt = torch.tensor(lt, dtype=torch.int32).to(dev, non_blocking=True)
+        Lc = torch.tensor(lc, dtype=torch.int32).to(dev, non_blocking=True)
+        kv_len = torch.tensor([T + a + b for a, b in zip(lt, lc)], dtype=torch.int32).to(dev, non_blocking=True)
+        amask = (torch.arange(L)[None, :] < torch.tensor(lt)[:, None]).float()
+        w = amask
+        if edit_mask is not None and self.loss_kind != "mse":
+            em = edit_mask.float().cpu()
+            w = amask * (em * self.fg + (1 - em) * self.bg)
+        # MseLoss ignores the mask: mean over all B*L*C elements, padded ones contribute 0 (prediction and target are both zero
+        # there); AttentionMaskMseLoss divides by the valid-token count (attention_mask_loss.py:146-226)
+        norm = 1.0 / (C * (float(sum(lt)) + 1e-12)) if self.loss_kind == "attention_mask" else 1.0 / (B * L * C)
+        guidance = torch.ones(B, device=dev) if m.config.guidance_embeds else None
+        return (x0, ctrl, pe, pooled, embeddings["text_ids"].to(dev), ids.to(dev, non_blocking=True), noise, t, guidance,
+                w.to(dev).contiguous(), norm, (Lt, Lc, Ltot, kv_len))
+
+    def _run(self, x0, ctrl, pe, pooled, text_ids, ids, noise, t, guidance, w, norm, var=None):
         m = self.dit
         B, L, C = x0.shape
-        packed = torch.empty(B, L + ctrl.shape[1], C, device=m.dev, dtype=BF)
-        lib.flow_noisy_input(x0, noise, ctrl, t.float().contiguous(), packed)
-        pred = m._forward_impl(packed, pe, pooled, t, ids, text_ids, guidance, train=True)
+        if var is None:
+            packed = torch.empty(B, L + ctrl.shape[1], C, device=m.dev, dtype=BF)
+            lib.flow_noisy_input(x0, noise, ctrl, t.float().contiguous(), packed)
+            pred = m._forward_impl(packed, pe, pooled, t, ids, text_ids, guidance, train=True)
+        else:
+            Lt, Lc, Ltot, kv_len = var
+            packed = torch.empty(B, Ltot, C, device=m.dev, dtype=BF)
+            lib.flow_noisy_input_var(x0, noise, ctrl, t.float().contiguous(), Lt, Lc, packed)
+            pred = m._forward_impl(packed, pe, pooled, t, ids, text_ids, guidance, kv_len, train=True)
         ws = m._ws
         lib.flow_loss(pred, x0, noise, w, norm, ws["loss"], ws["dpred"])
         m.G32.zero_()

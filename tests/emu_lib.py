@@ -60,6 +60,8 @@ def gemm(problems, N, K, *, trans_b=False, epilogue=EPI_BIAS, alpha=1.0, lora_gr
             rpb = p.rows_per_batch or A.shape[0]
             g = p.gate.float().repeat_interleave(rpb, 0)
             p.out.copy_((p.resid.float() + (g * y).to(BF).float()).to(BF))
+            if p.out2 is not None:
+                p.out2.copy_(y.to(BF))
         elif epilogue == EPI_ADD:
             p.out.copy_((p.resid.float() + (acc * alpha).to(BF).float()).to(BF))
         elif epilogue == EPI_DGELU:
@@ -90,6 +92,18 @@ def ln_modulate_bwd(dy, x, mean, rstd, scale, rows_per_batch, dx, dres=None, gat
     if dx_gated is not None:
         dx_gated.copy_((o.float() * gate.float().repeat_interleave(rows_per_batch, 0)).to(BF))
     dx.copy_(o)
+
+
+def mod_grad(g, rows_per_batch, sum_out=None, m=None, prod_out=None, mean=None, rstd=None):
+    B = g.shape[0] // rows_per_batch
+    gf = g.float().view(B, rows_per_batch, -1)
+    if sum_out is not None:
+        sum_out += gf.sum(1)
+    if prod_out is not None:
+        mf = m.float()
+        if mean is not None:
+            mf = ((mf - mean[:, None]) * rstd[:, None]).to(BF).float()
+        prod_out += (gf * mf.view(B, rows_per_batch, -1)).sum(1)
 
 
 def gate_mul(a, gate, rows_per_batch, out):
@@ -269,7 +283,7 @@ def require_cuda(*tensors):
     return None
 
 
-_NAMES = ["gemm_problem", "gemm", "ln_modulate_fwd", "ln_modulate_bwd", "gate_mul", "add_bf16", "rmsnorm_rows", "qk_norm_rope_fwd",
+_NAMES = ["gemm_problem", "gemm", "ln_modulate_fwd", "ln_modulate_bwd", "mod_grad", "gate_mul", "add_bf16", "rmsnorm_rows", "qk_norm_rope_fwd",
           "qk_norm_rope_bwd", "gemv_act", "timestep_sinusoid", "flow_noisy_input", "flow_noisy_input_var", "flow_loss", "lora_wgrad", "lora_wgrad_tc", "attn_delta",
           "attn_fwd", "attn_bwd", "grad_finalize", "require_cuda"]
 

@@ -26,7 +26,7 @@ GEMM = ["basic_nt_bn64", "basic_nn_bn64", "basic_nt_bn128", "basic_nn_bn128", "b
         "basic_nt_bn256", "basic_nn_bn256", "basic_nt_alpha_nobias", "basic_nt_big", "basic_nn_big", "lora_nt_bn128",
         "lora_nn_bn128", "lora_nt_bn256", "lora_nn_bn256", "lora_nt_groups3", "lora_nt_kb2", "lora_nn_kb3",
         "epilogues_bn128", "epilogues_bn256", "grouped_nt", "grouped_nn"]
-OPS = ["wgrad_tc", "ln_mod_3072", "ln_mod_256", "rms_rows", "qk_norm_rope", "qk_norm_rope_h2", "gemv", "flow", "wgrad", "attn_small",
+OPS = ["wgrad_tc", "ln_mod_3072", "ln_mod_256", "mod_grad_3072", "mod_grad_256_ragged", "rms_rows", "qk_norm_rope", "qk_norm_rope_h2", "gemv", "flow", "wgrad", "attn_small",
        "attn_300", "attn_1tile_tail", "attn_ragged", "attn_txtgap", "attn_bwd_txtgap", "attn_bwd_small", "attn_bwd_300", "attn_bwd_tail", "attn_bwd_ragged"]
 
 
@@ -48,7 +48,9 @@ def test_attention_full_size_properties():
 
 
 @pytest.mark.parametrize("name", ["inference_tiny", "step_tiny", "step_tiny_nolora_targets_all_attn", "step_mid",
-                                  "step_full_width_1blk", "flux_tiny", "flux_tiny_regex_noguidance", "flux_full_width_1p1"])
+                                  "step_full_width_1blk", "flux_tiny", "flux_tiny_regex_noguidance", "flux_full_width_1p1",
+                                  "flux_tiny_mlp_out_targets", "step_tiny_mlp_down_targets", "flux_tiny_yaml_targets",
+                                  "step_tiny_mod_embed_targets"])
 def test_fused_step_vs_oracle(name):
     r = _cases("model_check")[name]()
     if "pred_vs_fp32" not in r:
@@ -60,8 +62,9 @@ def test_fused_step_vs_oracle(name):
     assert r["fast_vs_autograd"] < 5e-3
 
 
-def test_qwen_multi_resolution_vs_unpadded_oracle():
-    r = _cases("model_check")["qwen_multires"]()
+@pytest.mark.parametrize("name", ["qwen_multires", "flux_multires"])
+def test_multi_resolution_vs_unpadded_oracle(name):
+    r = _cases("model_check")[name]()
     assert r["pred_vs_fp32"] < 2e-2 and r["grad_vs_fp32"] < 3e-2 and r["loss_rel"] < 1e-2
 
 

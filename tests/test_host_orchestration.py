@@ -50,7 +50,8 @@ def _inputs(B, hw, T, J):
 
 @pytest.mark.parametrize("targets,r", [(("to_q", "to_k", "to_v", "to_out.0"), 4),
                                        (("to_q", "to_v", "add_k_proj", "to_add_out", "net.0.proj"), 8),
-                                       (("to_k", "img_mlp.net.2", "txt_mlp.net.0.proj", "txt_mlp.net.2"), 4)])
+                                       (("to_k", "img_mlp.net.2", "txt_mlp.net.0.proj", "txt_mlp.net.2"), 4),
+                                       (("to_q", "img_mod.1", "txt_mod.1", "img_in", "txt_in"), 4)])
 def test_step_matches_oracle_on_cpu(emu, targets, r):
     from qflux_b200.train_step import QwenImageEditStep
     orc, m = _pair(2, 2, 128, r, targets)
@@ -116,7 +117,7 @@ def test_lora_registry_and_errors():
     from qflux_b200.qwen_model import QwenB200Config, QwenImageB200
     m = QwenImageB200(QwenB200Config(num_layers=2, num_attention_heads=2, joint_attention_dim=128), device="cpu", _host_only=True)
     with pytest.raises(NotImplementedError):
-        m.add_adapter(4, 4, target_modules=r".*(img_mod\.1|attn\.to_q)")
+        m.add_adapter(4, 4, target_modules=r".*(norm_out\.linear|attn\.to_q)")
     m = QwenImageB200(QwenB200Config(num_layers=2, num_attention_heads=2, joint_attention_dim=128), device="cpu", _host_only=True)
     m.add_adapter(16, 16)
     names = [n for n, _ in m.named_parameters()]
@@ -132,6 +133,11 @@ def test_lora_registry_and_errors():
 
 
 # ------------------------------------------------------------------------------------------------------------------ FLUX
+# target_modules of BASELINE config 3 (/root/reference/configs/face_seg_flux_kontext_fp16.yaml:11): every Linear of every block incl. the
+# AdaLN modulation linears, plus x_embedder
+FLUX_YAML_TARGETS = (r"(.*x_embedder|.*transformer_blocks\.[0-9]+\.(norm|norm1)\.linear|.*transformer_blocks\.[0-9]+\.attn\.(to_k|to_q|to_v|to_add_out)|.*transformer_blocks\.[0-9]+\.attn\.to_out\.0|.*single_transformer_blocks\.[0-9]+\.attn\.to_out|.*single_transformer_blocks\.[0-9]+\.(proj_mlp|proj_out)|.*(?<!single_)transformer_blocks\.[0-9]+\.ff\.net\.2|.*(?<!single_)transformer_blocks\.[0-9]+\.ff\.net\.0\.proj|.*(?<!single_)transformer_blocks\.[0-9]+\.norm1_context\.linear|.*(?<!single_)transformer_blocks\.[0-9]+\.ff_context\.net\.0\.proj|.*(?<!single_)transformer_blocks\.[0-9]+\.ff_context\.net\.2|.*(?<!single_)transformer_blocks\.[0-9]+\.attn\.(to_add_out|add_k_proj|add_q_proj|add_v_proj))")
+
+
 def _flux_pair(r, targets, guidance=True):
     from qflux_b200.flux_model import FluxB200, FluxB200Config
     kw = dict(num_layers=2, num_single_layers=2, attention_head_dim=128, num_attention_heads=2, joint_attention_dim=64,
@@ -160,7 +166,8 @@ def _flux_pair(r, targets, guidance=True):
 
 @pytest.mark.parametrize("targets", [("to_q", "to_k", "to_v", "to_out.0"),
                                      r".*(attn\.(to_[qkv]|add_[qkv]_proj|to_add_out)|proj_mlp|ff\.net\.0\.proj)",
-                                     r".*(single_transformer_blocks\.[0-9]+\.(proj_mlp|proj_out)|ff\.net\.2|ff_context\.net\.(0\.proj|2)|attn\.to_out\.0)"])
+                                     r".*(single_transformer_blocks\.[0-9]+\.(proj_mlp|proj_out)|ff\.net\.2|ff_context\.net\.(0\.proj|2)|attn\.to_out\.0)",
+                                     FLUX_YAML_TARGETS])
 def test_flux_step_matches_oracle_on_cpu(emu, targets):
     """BASELINE config 3 family (FLUX-Kontext shared-resolution recipe) at tiny size: 2 double + 2 single blocks."""
     from qflux_b200.train_step import FluxKontextStep
@@ -275,3 +282,65 @@ def test_qwen_multi_resolution_matches_per_sample_oracle(emu):
         out = m(hidden_states=packed, timestep=sig, encoder_hidden_states=pe, encoder_hidden_states_mask=mask, img_shapes=shapes,
                 txt_seq_lens=txt)[0]
     assert out.shape == (2, 32, 64) and out[1, 16:].abs().max() == 0 and out[1, :16].abs().max() > 0
+
+
+def test_flux_multi_resolution_matches_per_sample_oracle(emu):
+    """FLUX-Kontext pad-to-max multi-resolution recipe (flux_kontext_trainer.py:579-796, transformer_flux_custom.py): samples of
+    different latent sizes in one padded batch with per-sample ids / RoPE, a key mask and a masked loss must equal running
+    every sample alone and un-padded (the reference's own check: tests/src/models/test_flux_per_sample_rope.py:481-486)."""
+    from qflux_b200.train_step import FluxKontextStep
+    orc, m = _flux_pair(4, ("to_q", "to_k", "to_v", "to_out.0", "proj_mlp"))
+    g = torch.Generator().manual_seed(21)
+    rn = lambda *s: torch.randn(*s, generator=g).bfloat16()
+    shapes = [[(1, 4, 4), (1, 4, 4)], [(1, 2, 4), (1, 4, 2)], [(1, 4, 2), (1, 2, 2), (1, 2, 4)]]
+    B, T = 3, 8
+    lt = [sh[0][1] * sh[0][2] for sh in shapes]
+    lc = [sum(h * w for (_, h, w) in sh[1:]) for sh in shapes]
+    Lm, Lcm = max(lt), max(lc)
+    x0, ctrl, noise = rn(B, Lm, 64), rn(B, Lcm, 64), rn(B, Lm, 64)
+    for b in range(B):
+        x0[b, lt[b]:] = 0
+        noise[b, lt[b]:] = 0
+        ctrl[b, lc[b]:] = 0
+    pe, pooled, t = rn(B, T, 64), rn(B, 64), torch.tensor([0.5, 0.25, 0.125])  # t * 1000 exact in bf16 (the model multiplies in bf16)
+    text_ids = torch.zeros(T, 3)
+    # ---- oracle: one un-padded run per sample; AttentionMaskMseLoss normalisation over all valid target tokens
+    preds, total = [], 0.0
+    for b in range(B):
+        ids = [FluxKontextStep.latent_image_ids(shapes[b][0][1], shapes[b][0][2], "cpu", 0.0)]
+        ids += [FluxKontextStep.latent_image_ids(h, w, "cpu", float(j + 1)) for j, (_, h, w) in enumerate(shapes[b][1:])]
+        noisy = (1 - t[b]) * x0[b, :lt[b]].float() + t[b] * noise[b, :lt[b]].float()
+        packed = torch.cat([noisy.bfloat16().float(), ctrl[b, :lc[b]].float()], 0)[None]
+        p = orc(hidden_states=packed, encoder_hidden_states=pe[b:b + 1].float(), pooled_projections=pooled[b:b + 1].float(),
+                timestep=t[b:b + 1], img_ids=torch.cat(ids, 0), txt_ids=text_ids, guidance=torch.ones(1))[0][0, :lt[b]]
+        preds.append(p)
+        total = total + ((p - (noise[b, :lt[b]].float() - x0[b, :lt[b]].float())) ** 2).mean(-1).sum()
+    loss_o = total / (sum(lt) + 1e-12)
+    loss_o.backward()
+    # ---- B200 (emulated kernels): one padded batch
+    step = FluxKontextStep(m, "attention_mask")
+    emb = dict(image_latents=x0, control_latents=ctrl, pooled_prompt_embeds=pooled, prompt_embeds=pe, text_ids=text_ids, img_shapes=shapes)
+    loss_b = step.compute_loss(emb, noise=noise, t=t)
+    Ltot = max(a + c for a, c in zip(lt, lc))
+    pred_b = m._ws["pred"].view(B, Ltot, 64).float().clone()
+    loss_b.backward()
+    for b in range(B):
+        assert ((pred_b[b, :lt[b]] - preds[b]).norm() / preds[b].norm()).item() < 1e-2
+    assert abs(loss_b.item() - loss_o.item()) < 1e-2
+    go = {n: (p.grad if p.grad is not None else torch.zeros_like(p)) for n, p in orc.named_parameters() if p.requires_grad}
+    num = sum(((p.grad.float() - go[n]) ** 2).sum() for n, p in m.named_parameters())
+    den = sum((v ** 2).sum() for v in go.values())
+    assert float((num / den).sqrt()) < 2e-2
+    # "mse" criterion in this mode: mean over the padded [B, Lmax, C] block, padded elements contribute zero
+    loss_m = FluxKontextStep(m, "mse").compute_loss(emb, noise=noise, t=t)
+    assert abs(loss_m.item() - (total / (B * Lm)).item()) < 1e-2
+    # module API (transformer_flux_custom.py signature): batched ids + attention_mask, padded rows come back as exact zeros
+    ids_b = torch.zeros(B, Ltot, 3)
+    am = torch.zeros(B, T + Ltot, dtype=torch.bool)
+    for b in range(B):
+        ids_b[b, :lt[b]] = FluxKontextStep.latent_image_ids(shapes[b][0][1], shapes[b][0][2], "cpu", 0.0)
+        am[b, : T + lt[b] + lc[b]] = True
+    with torch.no_grad():
+        out = m(hidden_states=rn(B, Ltot, 64), encoder_hidden_states=pe, pooled_projections=pooled, timestep=t, img_ids=ids_b,
+                txt_ids=text_ids, guidance=torch.ones(B), attention_mask=am)[0]
+    assert out.shape == (B, Ltot, 64) and out[1, lt[1] + lc[1]:].abs().max() == 0 and out[1, : lt[1]].abs().max() > 0

@@ -75,6 +75,11 @@ def epilogues(bn):
              epilogue=lib.EPI_RESID_GATE, block_n=bn)
     ref = resid.float() + gate.float().repeat_interleave(M // Bsz, 0) * ref_u
     res["resid_gate"] = rel_l2(out.float(), ref)
+    # RESID_GATE with the optional second output (un-gated branch, kept when the gate's AdaLN linear carries LoRA)
+    out_b, y = torch.zeros_like(out), torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    lib.gemm([lib.gemm_problem(A, W, out_b, bias=b, resid=resid, gate=gate, rows_per_batch=M // Bsz, out2=y)], N, K,
+             epilogue=lib.EPI_RESID_GATE, block_n=bn)
+    res["resid_gate_out2"] = max(rel_l2(y.float(), ref_u), float((out_b.float() - out.float()).abs().max()))
     # DGELU (trans_b)
     Wt = _mk(K, N, seed=8, scale=0.1)
     aux = _mk(M, N, seed=9)

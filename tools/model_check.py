@@ -120,12 +120,18 @@ def full_width_block():
     return r
 
 
-def flux_step_parity(H=2, L=2, Ls=2, J=64, Pp=64, B=2, hw=4, T=8, r=4,
-                     targets=("to_q", "to_k", "to_v", "to_out.0"), guidance=True):
-    """FLUX-Kontext shared-resolution recipe (flux_kontext_trainer.py:494-577) vs the oracle."""
+FLUX_YAML_TARGETS = (
+    r"(.*x_embedder|.*transformer_blocks\.[0-9]+\.(norm|norm1)\.linear|.*transformer_blocks\.[0-9]+\.attn\.(to_k|to_q|to_v|to_add_out)"
+    r"|.*transformer_blocks\.[0-9]+\.attn\.to_out\.0|.*single_transformer_blocks\.[0-9]+\.attn\.to_out"
+    r"|.*single_transformer_blocks\.[0-9]+\.(proj_mlp|proj_out)|.*(?<!single_)transformer_blocks\.[0-9]+\.ff\.net\.2"
+    r"|.*(?<!single_)transformer_blocks\.[0-9]+\.ff\.net\.0\.proj|.*(?<!single_)transformer_blocks\.[0-9]+\.norm1_context\.linear"
+    r"|.*(?<!single_)transformer_blocks\.[0-9]+\.ff_context\.net\.0\.proj|.*(?<!single_)transformer_blocks\.[0-9]+\.ff_context\.net\.2"
+    r"|.*(?<!single_)transformer_blocks\.[0-9]+\.attn\.(to_add_out|add_k_proj|add_q_proj|add_v_proj))")
+
+
+def build_flux_pair(H=2, L=2, Ls=2, J=64, Pp=64, r=4, targets=("to_q", "to_k", "to_v", "to_out.0"), guidance=True):
     from oracle import mmdit_oracle as mo
     from qflux_b200.flux_model import FluxB200, FluxB200Config
-    from qflux_b200.train_step import FluxKontextStep
     kw = dict(num_layers=L, num_single_layers=Ls, attention_head_dim=128, num_attention_heads=H, joint_attention_dim=J,
               pooled_projection_dim=Pp, guidance_embeds=guidance)
     orc = mo.init_synthetic_(mo.FluxOracle(mo.FluxConfig(**kw)), std=0.05 if H < 8 else 0.02)
@@ -144,6 +150,15 @@ def flux_step_parity(H=2, L=2, Ls=2, J=64, Pp=64, B=2, hw=4, T=8, r=4,
     m = FluxB200(FluxB200Config(**kw)).add_adapter(r, r, target_modules=targets)
     missing, unexpected = m.load_state_dict(orc.state_dict(), strict=True)
     assert not missing and not unexpected
+    return orc, m
+
+
+def flux_step_parity(H=2, L=2, Ls=2, J=64, Pp=64, B=2, hw=4, T=8, r=4,
+                     targets=("to_q", "to_k", "to_v", "to_out.0"), guidance=True):
+    """FLUX-Kontext shared-resolution recipe (flux_kontext_trainer.py:494-577) vs the oracle."""
+    from oracle import mmdit_oracle as mo
+    from qflux_b200.train_step import FluxKontextStep
+    orc, m = build_flux_pair(H, L, Ls, J, Pp, r, targets, guidance)
     gg = torch.Generator(device="cuda").manual_seed(3)
     rn = lambda *s: torch.randn(*s, device="cuda", generator=gg).bfloat16()
     Lt = hw * hw
@@ -227,6 +242,52 @@ def qwen_multires(H=2, L=2, J=128):
     return res
 
 
+def flux_multires(H=2, L=2, Ls=2, J=64, Pp=64):
+    """FLUX pad-to-max multi-resolution recipe (flux_kontext_trainer.py:579-796): per-sample ids / RoPE, key mask, masked loss —
+    against one un-padded oracle run per sample."""
+    from qflux_b200.train_step import FluxKontextStep
+    orc, m = build_flux_pair(H, L, Ls, J, Pp, 4, r".*(attn\.to_[qkv]|to_out\.0|proj_mlp|single_transformer_blocks\.[0-9]+\.proj_out)")
+    g = torch.Generator(device="cuda").manual_seed(21)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()
+    shapes = [[(1, 16, 12), (1, 16, 12)], [(1, 8, 10), (1, 10, 8)], [(1, 12, 8), (1, 6, 8), (1, 8, 12)]]
+    B, T = 3, 24
+    lt = [sh[0][1] * sh[0][2] for sh in shapes]
+    lc = [sum(h * w for (_, h, w) in sh[1:]) for sh in shapes]
+    Lm, Lcm = max(lt), max(lc)
+    x0, ctrl, noise = rn(B, Lm, 64), rn(B, Lcm, 64), rn(B, Lm, 64)
+    for b in range(B):
+        x0[b, lt[b]:] = 0; noise[b, lt[b]:] = 0; ctrl[b, lc[b]:] = 0
+    pe, pooled, t = rn(B, T, J), rn(B, Pp), torch.tensor([0.5, 0.25, 0.125], device="cuda")
+    text_ids = torch.zeros(T, 3, device="cuda")
+    preds, total = [], 0.0
+    for b in range(B):
+        ids = [FluxKontextStep.latent_image_ids(shapes[b][0][1], shapes[b][0][2], "cuda", 0.0)]
+        ids += [FluxKontextStep.latent_image_ids(h, w, "cuda", float(j + 1)) for j, (_, h, w) in enumerate(shapes[b][1:])]
+        noisy = (1 - t[b]) * x0[b, :lt[b]].float() + t[b] * noise[b, :lt[b]].float()
+        packed = torch.cat([noisy.bfloat16().float(), ctrl[b, :lc[b]].float()], 0)[None]
+        p = orc(hidden_states=packed, encoder_hidden_states=pe[b:b + 1].float(), pooled_projections=pooled[b:b + 1].float(),
+                timestep=t[b:b + 1], img_ids=torch.cat(ids, 0), txt_ids=text_ids, guidance=torch.ones(1, device="cuda"))[0][0, :lt[b]]
+        preds.append(p)
+        total = total + ((p - (noise[b, :lt[b]].float() - x0[b, :lt[b]].float())) ** 2).mean(-1).sum()
+    loss_o = total / (sum(lt) + 1e-12)
+    loss_o.backward()
+    step = FluxKontextStep(m, "attention_mask")
+    emb = dict(image_latents=x0, control_latents=ctrl, pooled_prompt_embeds=pooled, prompt_embeds=pe, text_ids=text_ids, img_shapes=shapes)
+    loss_b = step.compute_loss(emb, noise=noise, t=t)
+    pred_b = m._ws["pred"].view(B, -1, 64).float().clone()
+    loss_b.backward()
+    torch.cuda.synchronize()
+    res = dict(pred_vs_fp32=max(rel_l2(pred_b[b, :lt[b]], preds[b]) for b in range(B)), loss=loss_o.item(),
+               loss_abs=abs(loss_b.item() - loss_o.item()))
+    res["loss_rel"] = res["loss_abs"] / max(1.0, abs(loss_o.item()))
+    go = {n: (p.grad if p.grad is not None else torch.zeros_like(p)) for n, p in orc.named_parameters() if p.requires_grad}
+    num = sum(((p.grad.float() - go[n]).double() ** 2).sum() for n, p in m.named_parameters())
+    den = sum((v.double() ** 2).sum() for v in go.values())
+    res["grad_vs_fp32"] = float((num / den).sqrt())
+    res["err"] = max(res["pred_vs_fp32"], res["grad_vs_fp32"])
+    return res
+
+
 CASES = {
     "inference_tiny": inference_parity,
     "step_tiny": lambda: step_parity(),
@@ -237,6 +298,13 @@ CASES = {
     "flux_tiny": lambda: flux_step_parity(),
     "flux_tiny_regex_noguidance": lambda: flux_step_parity(guidance=False, r=8,
                                                            targets=r".*(attn\.(to_[qkv]|add_[qkv]_proj|to_add_out)|proj_mlp|ff\.net\.0\.proj)"),
+    "flux_tiny_mlp_out_targets": lambda: flux_step_parity(
+        r=8, targets=r".*(single_transformer_blocks\.[0-9]+\.(proj_mlp|proj_out)|ff\.net\.2|ff_context\.net\.(0\.proj|2)|attn\.to_out\.0)"),
+    "flux_multires": flux_multires,
+    # BASELINE config 3 target set (configs/face_seg_flux_kontext_fp16.yaml:11): every block Linear, the AdaLN linears, x_embedder
+    "flux_tiny_yaml_targets": lambda: flux_step_parity(r=8, targets=FLUX_YAML_TARGETS),
+    "step_tiny_mod_embed_targets": lambda: step_parity(targets=("to_q", "img_mod.1", "txt_mod.1", "img_in", "txt_in")),
+    "step_tiny_mlp_down_targets": lambda: step_parity(targets=("to_k", "img_mlp.net.2", "txt_mlp.net.0.proj", "txt_mlp.net.2")),
     "flux_full_width_1p1": lambda: flux_step_parity(H=24, L=1, Ls=1, J=4096, Pp=768, B=1, hw=32, T=512, r=16),
 }
 

@@ -47,6 +47,31 @@ def ln_mod(D=3072, M=1000, Bsz=4):
     return res
 
 
+def mod_grad(D=3072, rpb=1000, Bsz=4):
+    """d shift / d scale / d gate column reductions (qfx_mod_grad) vs fp32 torch, including accumulation into a non-zero buffer."""
+    from qflux_b200 import lib
+    M = rpb * Bsz
+    g, x, y = _mk(M, D, seed=1), _mk(M, D, seed=2, scale=2.0) + 0.5, _mk(M, D, seed=3)
+    mean, rstd = x.float().mean(1), torch.rsqrt(x.float().var(1, unbiased=False) + 1e-6)
+    buf = torch.randn(Bsz, 6 * D, device="cuda")
+    ref = buf.clone()
+    lib.mod_grad(g, rpb, sum_out=buf[:, :D], m=x, prod_out=buf[:, D:2 * D], mean=mean, rstd=rstd)
+    lib.mod_grad(g, rpb, m=y, prod_out=buf[:, 2 * D:3 * D])
+    lib.mod_grad(g, rpb, sum_out=buf[:, 3 * D:4 * D])
+    torch.cuda.synchronize()
+    gf = g.float().view(Bsz, rpb, D)
+    xh = ((x.float() - mean[:, None]) * rstd[:, None]).bfloat16().float().view(Bsz, rpb, D)
+    ref[:, :D] += gf.sum(1)
+    ref[:, D:2 * D] += (gf * xh).sum(1)
+    ref[:, 2 * D:3 * D] += (gf * y.float().view(Bsz, rpb, D)).sum(1)
+    ref[:, 3 * D:4 * D] += gf.sum(1)
+    res = dict(shift=rel_l2(buf[:, :D], ref[:, :D]), scale=rel_l2(buf[:, D:2 * D], ref[:, D:2 * D]),
+               gate=rel_l2(buf[:, 2 * D:3 * D], ref[:, 2 * D:3 * D]), sum_only=rel_l2(buf[:, 3 * D:4 * D], ref[:, 3 * D:4 * D]),
+               untouched=float((buf[:, 4 * D:] - ref[:, 4 * D:]).abs().max()))
+    res["err"] = max(res.values())
+    return res
+
+
 def rms_rows():
     from qflux_b200 import lib
     from oracle.mmdit_oracle import diffusers_rms_norm
@@ -306,6 +331,8 @@ def attn_bwd(Bsz=2, H=3, S=300, split=44, ragged=False, perf=False, txt_gap=Fals
 CASES = {
     "ln_mod_3072": lambda: ln_mod(3072),
     "ln_mod_256": lambda: ln_mod(256, M=96, Bsz=3),
+    "mod_grad_3072": mod_grad,
+    "mod_grad_256_ragged": lambda: mod_grad(256, 37, 3),
     "rms_rows": rms_rows,
     "qk_norm_rope": qk_norm_rope,
     "qk_norm_rope_h2": lambda: qk_norm_rope(H=2, Bsz=3, T=7, L=33),
