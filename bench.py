@@ -191,7 +191,8 @@ def run_b200(args):
     torch.manual_seed(1234 + rank)
     m = build_model(dev, args.layers)
     step = QwenImageEditStep(m, "mse", max_grad_norm=1.0)
-    opt = torch.optim.AdamW(list(m.parameters()), lr=1e-4, foreach=True)
+    from qflux_b200.optim import FusedLoraAdamW
+    opt = FusedLoraAdamW(m, lr=1e-4)  # clip + AdamW fused over the flat fp32 LoRA gradient (torch AdamW semantics, fp32 moments)
     B, L, T, hw = CFG["B"], CFG["hw"] ** 2, CFG["T"], CFG["hw"]
     host = dict(image_latents=torch.randn(B, L, 64).half().pin_memory(), control_latents=torch.randn(B, L, 64).half().pin_memory(),
                 prompt_embeds=(torch.randn(B, T, CFG["joint"]) * 3).bfloat16().pin_memory(),
@@ -265,7 +266,7 @@ def run_b200(args):
             "config": {"workload": f"Qwen-Image-Edit LoRA r=16 bf16 512x512 cached embeds, {args.layers} blocks D=3072 H=24, "
                                    f"S=352 txt + 2x1024 img tokens", "global_batch": B * world, "batch_per_gpu": B,
                        "parallelism": f"dp{world}", "l2": "inputs > L2: 41 GB weights + 35 GB activations stream through 126 MB L2",
-                       "optimizer": "torch AdamW(foreach) on LoRA params", "loss": loss_val},
+                       "optimizer": "qfx_fused_adamw: global-norm clip 1.0 + AdamW on the LoRA params, one kernel over the flat fp32 gradient", "loss": loss_val},
             "clocks": clk, "gpu_launches": launches, "host_issue_ms_per_step": host_issue_ms,
             "e2e": {"value": e2e_ips, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel<256,false,GELU> grouped img+txt MLP-up [8192+1408,3072]x[12288,3072]",

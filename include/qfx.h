@@ -145,6 +145,24 @@ int qfx_lora_wgrad(const void* P, int64_t ldp, const void* Q, int64_t ldq, float
  * sumsq receives ||g*pre_scale||^2.  max_norm <= 0 disables clipping. */
 int qfx_grad_finalize(const float* g, int64_t n, float pre_scale, float max_norm, float* sumsq, void* out_bf16, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused clip + AdamW over the flat fp32 LoRA gradient buffer (replaces clip_gradients + optimizer.step(),
+ * base_trainer.py:449-455,528-533 with the default torch.optim.AdamW of :884-916).  `tensors` (device) describes every bf16
+ * parameter: row-major [numel / cols, cols] with row stride ld elements, its gradient / moments at grad_offset in the flat
+ * buffers.  `chunks` (device, int pairs {tensor index, first element}) tiles each tensor in pieces of <= QFX_ADAMW_CHUNK.
+ * grad has been summed over ranks; pre_scale = 1/world; max_norm <= 0 disables clipping; sumsq receives ||grad*pre_scale||^2;
+ * step >= 1 is the Adam step count (bias correction).  Moments are fp32.  All on `stream`, no host synchronisation. */
+#define QFX_ADAMW_CHUNK 4096
+typedef struct {
+  void* param;
+  int64_t grad_offset;
+  int numel, cols;
+  int64_t ld;
+} qfx_adamw_tensor;
+int qfx_fused_adamw(const qfx_adamw_tensor* tensors, const int* chunks, int n_chunks, const float* grad, int64_t n_grad,
+                    float* exp_avg, float* exp_avg_sq, float* sumsq, float pre_scale, float max_norm, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

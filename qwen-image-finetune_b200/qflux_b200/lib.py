@@ -228,6 +228,37 @@ def flow_loss(pred, x0, noise, w, norm, loss, dpred=None, grad_scale=1.0):
                  cur_stream()), "qfx_flow_loss")
 
 
+class AdamWTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad_offset", C.c_int64), ("numel", C.c_int), ("cols", C.c_int), ("ld", C.c_int64)]
+
+
+ADAMW_CHUNK = 4096
+_adamw = _sig("qfx_fused_adamw", _vp, _vp, _i, _vp, _i64, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _f, _i, _vp)
+
+
+def adamw_tables(members, device):
+    """members: iterable of (param tensor [rows, cols] bf16 with unit column stride, grad offset).  Returns the device tables
+    (tensor descriptors as a uint8 tensor, chunk list int32 [n, 2]) qfx_fused_adamw walks."""
+    members = list(members)
+    arr = (AdamWTensor * len(members))()
+    chunks = []
+    for i, (p, off) in enumerate(members):
+        assert p.dtype == torch.bfloat16 and p.dim() == 2 and p.stride(1) == 1
+        arr[i] = AdamWTensor(p.data_ptr(), off, p.numel(), p.shape[1], p.stride(0))
+        chunks += [(i, e) for e in range(0, p.numel(), ADAMW_CHUNK)]
+    raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().to(device)
+    return raw, torch.tensor(chunks, dtype=torch.int32).to(device)
+
+
+def fused_adamw(tables, grad, exp_avg, exp_avg_sq, sumsq, pre_scale, max_norm, lr, beta1, beta2, eps, weight_decay, step):
+    """Clip (global L2 norm of grad * pre_scale) + AdamW on every tensor of `tables` in place; fp32 grad / moments."""
+    raw, chunks = tables
+    require_cuda(raw, chunks, grad, exp_avg, exp_avg_sq, sumsq)
+    check(_adamw(ptr(raw), ptr(chunks), chunks.shape[0], ptr(grad), grad.numel(), ptr(exp_avg), ptr(exp_avg_sq), ptr(sumsq),
+                 float(pre_scale), float(max_norm), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+                 int(step), cur_stream()), "qfx_fused_adamw")
+
+
 def lora_wgrad(P, Q, G, gs_i, gs_j, r):
     """G[i*gs_i + j*gs_j] += sum_m P[m,i] Q[m,j], j < r.  G fp32."""
     require_cuda(P, Q, G)

@@ -1,0 +1,56 @@
+"""Fused clip + AdamW for the LoRA parameters of a fused MMDiT.
+
+Mirrors what the reference's step body does after `accelerator.backward(loss)`
+(/root/reference/src/qflux/trainer/base_trainer.py:528-533): `clip_gradients()` (:449-455, global L2 norm over the trainable
+parameters, max_grad_norm) -> `optimizer.step()` (torch.optim.AdamW by default, :884-916 / config.py:534) -> `zero_grad()`.
+The gradient is the model's flat fp32 accumulator (all-reduced by the caller for data parallel runs); nothing synchronises
+with the host.  Moments are kept in fp32 (torch keeps them in the parameter dtype, bf16) — documented deviation, DESIGN.md.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import lib
+
+
+class FusedLoraAdamW:
+    def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
+                 max_grad_norm: float = 1.0):
+        if model.G32 is None:
+            raise lib.QfxError("attach a LoRA adapter (model.add_adapter) before building the optimizer")
+        self.model = model
+        self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
+        self.param_groups = [dict(self.defaults, params=list(model.parameters()))]  # torch-scheduler compatible view
+        self.max_grad_norm = max_grad_norm
+        self.step_count = 0
+        n = model.G32.numel()
+        self.exp_avg = torch.zeros(n, device=model.dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(n, device=model.dev, dtype=torch.float32)
+        self.grad_norm_sq = torch.zeros(1, device=model.dev, dtype=torch.float32)
+        members = []
+        for full, pA, pB, ga, gb, d_in, d_out in model._all_members():
+            members += [(pA.data, ga), (pB.data, gb)]
+        self._tables = lib.adamw_tables(members, model.dev)
+
+    @torch.no_grad()
+    def step(self, world_size: int = 1):
+        """grad = model.G32 (sum over ranks) / world_size, clipped to max_grad_norm; returns the device tensor ||grad||^2."""
+        g = self.param_groups[0]
+        self.step_count += 1
+        lib.fused_adamw(self._tables, self.model.G32, self.exp_avg, self.exp_avg_sq, self.grad_norm_sq, 1.0 / world_size,
+                        self.max_grad_norm, g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.step_count)
+        return self.grad_norm_sq
+
+    def zero_grad(self, set_to_none: bool = True):
+        self.model.G32.zero_()
+
+    def state_dict(self):
+        return dict(step=self.step_count, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq,
+                    param_groups=[{k: v for k, v in g.items() if k != "params"} for g in self.param_groups])
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        for g, s in zip(self.param_groups, sd["param_groups"]):
+            g.update(s)

@@ -43,6 +43,24 @@ def token_weights_and_norm(kind, B, L, C, weighting=None, attention_mask=None, e
     raise ValueError(f"unknown loss kind {kind!r}")
 
 
+def _sync_and_step(dit, optimizer, max_grad_norm):
+    """Data-parallel tail of a step (base_trainer.py:383-388, 449-455, 528-533): ONE all-reduce(sum) of the flat fp32 LoRA
+    gradient, then either the fused clip + AdamW kernel (FusedLoraAdamW reads the accumulator directly) or, for any torch
+    optimizer, mean + clip + cast into the bf16 `.grad` views followed by `optimizer.step()`."""
+    from .optim import FusedLoraAdamW
+    world = 1
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        world = dist.get_world_size()
+        dist.all_reduce(dit.G32)
+    if isinstance(optimizer, FusedLoraAdamW):
+        optimizer.max_grad_norm = max_grad_norm
+        optimizer.step(world)
+        return
+    dit.finalize_grads(world, max_grad_norm)
+    if optimizer is not None:
+        optimizer.step()
+
+
 class _StepFn(torch.autograd.Function):
     """loss = fused(forward -> flow loss -> backward); autograd backward only scales the already computed gradients."""
 
@@ -143,13 +161,7 @@ class QwenImageEditStep:
         clip -> bf16 grads -> optimizer.step().  Returns the (device) loss tensor; nothing here syncs with the host."""
         args = self._prepare(embeddings, noise, u)
         loss = self._run(*args)
-        world = 1
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            world = dist.get_world_size()
-            dist.all_reduce(self.dit.G32)
-        self.dit.finalize_grads(world, self.max_grad_norm)
-        if optimizer is not None:
-            optimizer.step()
+        _sync_and_step(self.dit, optimizer, self.max_grad_norm)
         return loss
 
 
@@ -258,11 +270,5 @@ class FluxKontextStep:
     @torch.no_grad()
     def train_step(self, embeddings: dict, optimizer=None, noise=None, t=None):
         loss = self._run(*self._prepare(embeddings, noise, t))
-        world = 1
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            world = dist.get_world_size()
-            dist.all_reduce(self.dit.G32)
-        self.dit.finalize_grads(world, self.max_grad_norm)
-        if optimizer is not None:
-            optimizer.step()
+        _sync_and_step(self.dit, optimizer, self.max_grad_norm)
         return loss

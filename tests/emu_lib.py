@@ -225,6 +225,29 @@ def lora_wgrad_tc(A, B, G_list, gs_i, gs_j, r, mode=0, Dg=0):
         view += res
 
 
+def adamw_tables(members, device):
+    return list(members), None
+
+
+def fused_adamw(tables, grad, exp_avg, exp_avg_sq, sumsq, pre_scale, max_norm, lr, beta1, beta2, eps, weight_decay, step):
+    members, _ = tables
+    g = grad * pre_scale
+    sumsq.copy_((g ** 2).sum().reshape(1))
+    coef = 1.0
+    if max_norm > 0:
+        coef = min(1.0, max_norm / (float(sumsq.sqrt()) + 1e-6))
+    g = g * coef
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    for p, off in members:
+        n = p.numel()
+        gi = g[off: off + n].view(p.shape)
+        m, v = exp_avg[off: off + n].view(p.shape), exp_avg_sq[off: off + n].view(p.shape)
+        w = p.float() * (1 - lr * weight_decay)
+        m.mul_(beta1).add_(gi, alpha=1 - beta1)
+        v.mul_(beta2).addcmul_(gi, gi, value=1 - beta2)
+        p.copy_((w - (lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps)).to(BF))
+
+
 def attn_delta(O, dO, delta, tokens_per_sample, s_offset, dO_joint=None):
     B, H, S = delta.shape
     n = tokens_per_sample
@@ -285,7 +308,7 @@ def require_cuda(*tensors):
 
 _NAMES = ["gemm_problem", "gemm", "ln_modulate_fwd", "ln_modulate_bwd", "mod_grad", "gate_mul", "add_bf16", "rmsnorm_rows", "qk_norm_rope_fwd",
           "qk_norm_rope_bwd", "gemv_act", "timestep_sinusoid", "flow_noisy_input", "flow_noisy_input_var", "flow_loss", "lora_wgrad", "lora_wgrad_tc", "attn_delta",
-          "attn_fwd", "attn_bwd", "grad_finalize", "require_cuda"]
+          "attn_fwd", "attn_bwd", "grad_finalize", "adamw_tables", "fused_adamw", "require_cuda"]
 
 
 def install(lib_module):

@@ -344,3 +344,79 @@ def test_flux_multi_resolution_matches_per_sample_oracle(emu):
         out = m(hidden_states=rn(B, Ltot, 64), encoder_hidden_states=pe, pooled_projections=pooled, timestep=t, img_ids=ids_b,
                 txt_ids=text_ids, guidance=torch.ones(B), attention_mask=am)[0]
     assert out.shape == (B, Ltot, 64) and out[1, lt[1] + lc[1]:].abs().max() == 0 and out[1, : lt[1]].abs().max() > 0
+
+
+def test_fused_adamw_matches_torch_adamw(emu):
+    """FusedLoraAdamW (clip + AdamW on the flat fp32 gradient) against clip_grad_norm_ + torch.optim.AdamW run on
+    fp32 master copies of the same parameters, three steps; bf16 parameters agree to one rounding."""
+    from qflux_b200.optim import FusedLoraAdamW
+    from qflux_b200.train_step import QwenImageEditStep
+    orc, m = _pair(2, 2, 128, 4, ("to_q", "to_out.0", "img_mod.1", "net.2"))
+    x = _inputs(2, 4, 24, 128)
+    emb = {k: x[k] for k in ("image_latents", "control_latents", "prompt_embeds", "prompt_embeds_mask", "img_shapes")}
+    step = QwenImageEditStep(m, "mse", max_grad_norm=0.05)  # small enough that clipping is active
+    opt = FusedLoraAdamW(m, lr=1e-2, weight_decay=0.1)
+    master = {n: p.detach().float().clone().requires_grad_(True) for n, p in m.named_parameters()}
+    ref = torch.optim.AdamW(list(master.values()), lr=1e-2, weight_decay=0.1)
+    for it in range(3):
+        before = {n: p.detach().float().clone() for n, p in m.named_parameters()}
+        step.train_step(emb, opt, noise=x["noise"], u=x["u"])
+        gv = m.lora_grad_views()  # the fp32 accumulator the fused kernel consumed
+        for n, p in master.items():
+            p.data.copy_(before[n])  # same starting point as the bf16 parameters of this step
+            p.grad = gv[n].clone()
+        norm = torch.nn.utils.clip_grad_norm_(list(master.values()), 0.05)
+        assert abs(float(opt.grad_norm_sq.sqrt()) - float(norm)) < 1e-4 * float(norm) and float(norm) > 0.05
+        ref.step()
+        for n, p in m.named_parameters():
+            assert torch.equal(p.detach(), master[n].detach().to(torch.bfloat16)) or \
+                (p.detach().float() - master[n].detach()).abs().max() <= 2 * 2 ** -8 * master[n].detach().abs().max(), n
+    assert opt.step_count == 3 and set(opt.state_dict()) == {"step", "exp_avg", "exp_avg_sq", "param_groups"}
+
+
+def test_sampling_loops_match_oracle(emu):
+    """Inference sampler: the same Euler / true-CFG loop driven by the fused model (emulated kernels) and by the
+    oracle must agree; schedule sanity: decreasing sigmas from the shifted 1.0 to 0, more shift for longer sequences."""
+    from qflux_b200 import sampler
+    sig = sampler.flow_match_sigmas(8, 1024)
+    assert sig.shape == (9,) and sig[-1] == 0 and abs(float(sig[0]) - 1.0) < 1e-6 and bool((sig[1:] < sig[:-1]).all())
+    assert float(sampler.flow_match_sigmas(8, 4096)[4]) > float(sig[4]) > float(sampler.flow_match_sigmas(8, 256)[4])
+    assert abs(sampler.calculate_shift(256) - 0.5) < 1e-9 and abs(sampler.calculate_shift(4096) - 1.15) < 1e-9
+    g = torch.Generator().manual_seed(5)
+    rn = lambda *s: torch.randn(*s, generator=g).bfloat16()
+    # ---- Qwen, true CFG with norm rescaling
+    orc, m = _pair(2, 2, 128, 4, ("to_q", "to_k", "to_v", "to_out.0"))
+    B, hw, T = 2, 4, 8
+    emb = dict(latents=rn(B, hw * hw, 64), control_latents=rn(B, hw * hw, 64), prompt_embeds=rn(B, T, 128) * 3,
+               prompt_embeds_mask=torch.ones(B, T, dtype=torch.int64), negative_prompt_embeds=rn(B, T, 128) * 3,
+               negative_prompt_embeds_mask=torch.ones(B, T, dtype=torch.int64), img_shapes=[[(1, hw, hw), (1, hw, hw)]] * B,
+               num_inference_steps=3, true_cfg_scale=2.5)
+
+    class F32:  # the oracle behind the module signature, bf16 in / bf16 out like a bf16 model
+        def __init__(self, net):
+            self.net, self.device = net, torch.device("cpu")
+
+        def __call__(self, **kw):
+            if "pooled_projections" in kw:  # a bf16 FLUX model multiplies timestep / guidance by 1000 IN bf16 (transformer_flux.py:707-710)
+                for k in ("timestep", "guidance"):
+                    kw[k] = (kw[k].bfloat16() * 1000).float() / 1000
+            kw = {k: (v.float() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in kw.items()}
+            if "txt_seq_lens" in kw and kw["txt_seq_lens"] is None:
+                kw["txt_seq_lens"] = kw["encoder_hidden_states_mask"].sum(1).tolist()
+            with torch.no_grad():
+                return (self.net(**kw)[0].bfloat16(),)
+
+    out_b = sampler.sample_qwen(m, emb)
+    out_o = sampler.sample_qwen(F32(orc), emb)
+    assert out_b.shape == (B, hw * hw, 64) and ((out_b.float() - out_o.float()).norm() / out_o.float().norm()).item() < 2e-2
+    # ---- FLUX
+    from qflux_b200.train_step import FluxKontextStep
+    forc, fm = _flux_pair(4, ("to_q", "to_k", "to_v", "to_out.0"))
+    femb = dict(latents=rn(B, hw * hw, 64), latent_ids=FluxKontextStep.latent_image_ids(hw, hw, "cpu", 0.0),
+                control_latents=rn(B, hw * hw, 64), control_ids=FluxKontextStep.latent_image_ids(hw, hw, "cpu", 1.0),
+                pooled_prompt_embeds=rn(B, 64), prompt_embeds=rn(B, T, 64), text_ids=torch.zeros(T, 3), guidance=3.5,
+                negative_pooled_prompt_embeds=rn(B, 64), negative_prompt_embeds=rn(B, T, 64), negative_text_ids=torch.zeros(T, 3),
+                num_inference_steps=3, true_cfg_scale=1.5)
+    fo_b = sampler.sample_flux(fm, femb)
+    fo_o = sampler.sample_flux(F32(forc), femb)
+    assert ((fo_b.float() - fo_o.float()).norm() / fo_o.float().norm()).item() < 2e-2

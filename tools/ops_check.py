@@ -72,6 +72,45 @@ def mod_grad(D=3072, rpb=1000, Bsz=4):
     return res
 
 
+def fused_adamw():
+    """qfx_fused_adamw (clip + AdamW, strided bf16 parameters, fp32 moments) vs clip_grad_norm_ + torch.optim.AdamW on fp32 masters."""
+    from qflux_b200 import lib
+    g = torch.Generator(device="cuda").manual_seed(5)
+    pad = torch.zeros(3 * 3072, 64, device="cuda", dtype=BF)            # a padded B-factor buffer: [out, 64] with rank-16 views
+    shapes = [(16, 3072), (3072, 16), (16, 12288), (5000, 16), (7, 33)]
+    params, off, members = [], 0, []
+    for i, (r_, c_) in enumerate(shapes):
+        if c_ == 16:
+            p = pad[i * 100: i * 100 + r_, :16]                          # row-strided view (ld = 64)
+        else:
+            p = torch.empty(r_, c_, device="cuda", dtype=BF)
+        p.copy_(torch.randn(r_, c_, device="cuda", generator=g) * 0.1)
+        params.append(p)
+        members.append((p, off))
+        off += p.numel()
+    tables = lib.adamw_tables(members, "cuda")
+    m32, v32, ss = torch.zeros(off, device="cuda"), torch.zeros(off, device="cuda"), torch.zeros(1, device="cuda")
+    master = [p.float().clone().requires_grad_(True) for p in params]
+    ref = torch.optim.AdamW(master, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.05)
+    errs, nerr = [], []
+    for step in range(1, 4):
+        G = torch.randn(off, device="cuda", generator=g) * (2.0 if step == 2 else 0.01)  # step 2 is clipped, the others are not
+        for q, p in zip(master, params):
+            q.data.copy_(p.float())
+        lib.fused_adamw(tables, G, m32, v32, ss, 0.5, 1.0, 3e-3, 0.9, 0.99, 1e-8, 0.05, step)
+        for q, (p, o) in zip(master, members):
+            q.grad = (G[o: o + p.numel()] * 0.5).view(p.shape).clone()
+        norm = torch.nn.utils.clip_grad_norm_(master, 1.0)
+        ref.step()
+        torch.cuda.synchronize()
+        nerr.append(abs(float(ss.sqrt()) - float(norm)) / float(norm))
+        errs.append(max(float((p.float() - q.detach()).abs().max() / q.detach().abs().max()) for p, q in zip(params, master)))
+    untouched = float(pad[:, 16:].abs().max())  # the padding columns of the factor buffer must stay zero
+    res = dict(param_rel=max(errs), norm_rel=max(nerr), untouched=untouched)
+    res["err"] = max(res["param_rel"] / 2, res["norm_rel"], untouched)  # bf16 parameters: one rounding (2^-8 relative) allowed
+    return res
+
+
 def rms_rows():
     from qflux_b200 import lib
     from oracle.mmdit_oracle import diffusers_rms_norm
@@ -333,6 +372,7 @@ CASES = {
     "ln_mod_256": lambda: ln_mod(256, M=96, Bsz=3),
     "mod_grad_3072": mod_grad,
     "mod_grad_256_ragged": lambda: mod_grad(256, 37, 3),
+    "fused_adamw": fused_adamw,
     "rms_rows": rms_rows,
     "qk_norm_rope": qk_norm_rope,
     "qk_norm_rope_h2": lambda: qk_norm_rope(H=2, Bsz=3, T=7, L=33),
