@@ -78,10 +78,11 @@ def fused_adamw():
     g = torch.Generator(device="cuda").manual_seed(5)
     pad = torch.zeros(3 * 3072, 64, device="cuda", dtype=BF)            # a padded B-factor buffer: [out, 64] with rank-16 views
     shapes = [(16, 3072), (3072, 16), (16, 12288), (5000, 16), (7, 33)]
-    params, off, members = [], 0, []
+    params, off, members, row0 = [], 0, [], 0
     for i, (r_, c_) in enumerate(shapes):
         if c_ == 16:
-            p = pad[i * 100: i * 100 + r_, :16]                          # row-strided view (ld = 64)
+            p = pad[row0: row0 + r_, :16]                                # row-strided view (ld = 64), disjoint row ranges
+            row0 += r_
         else:
             p = torch.empty(r_, c_, device="cuda", dtype=BF)
         p.copy_(torch.randn(r_, c_, device="cuda", generator=g) * 0.1)
