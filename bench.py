@@ -137,7 +137,7 @@ def run_reference(args):
             "config": {"workload": "Qwen-Image-Edit LoRA r=16, 512x512 cached embeds (CPU path, extrapolated)", "global_batch": 1},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": vals[-1]["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ====================================================================================================== B200 arm
@@ -275,12 +275,27 @@ def run_b200(args):
                          "peak_source": f"{which} MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)", "kernel_ms": g_ms,
                          "step_algorithmic_tflops_per_gpu": step_tf, "step_frac_of_sustained": step_tf / sustained},
             "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def _emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL's version banner, library chatter) was
+    re-routed to stderr in main() so that stdout carries nothing but this line."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)  # fd 1 -> stderr for the rest of the run (C libraries print to it directly)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
