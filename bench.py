@@ -190,6 +190,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(1234 + rank)
     m = build_model(dev, args.layers)
+    if args.shard_weights:
+        m.shard_frozen_weights()
     step = QwenImageEditStep(m, "mse", max_grad_norm=1.0)
     from qflux_b200.optim import FusedLoraAdamW
     opt = FusedLoraAdamW(m, lr=1e-4)  # clip + AdamW fused over the flat fp32 LoRA gradient (torch AdamW semantics, fp32 moments)
@@ -265,7 +267,7 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": f"Qwen-Image-Edit LoRA r=16 bf16 512x512 cached embeds, {args.layers} blocks D=3072 H=24, "
                                    f"S=352 txt + 2x1024 img tokens", "global_batch": B * world, "batch_per_gpu": B,
-                       "parallelism": f"dp{world}", "l2": "inputs > L2: 41 GB weights + 35 GB activations stream through 126 MB L2",
+                       "parallelism": f"dp{world}" + ("+sharded-frozen-weights" if args.shard_weights else ""), "l2": "inputs > L2: 41 GB weights + 35 GB activations stream through 126 MB L2",
                        "optimizer": "qfx_fused_adamw: global-norm clip 1.0 + AdamW on the LoRA params, one kernel over the flat fp32 gradient", "loss": loss_val},
             "clocks": clk, "gpu_launches": launches, "host_issue_ms_per_step": host_issue_ms,
             "e2e": {"value": e2e_ips, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -303,6 +305,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--layers", type=int, default=CFG["layers"], help="debug only: fewer blocks (INVALID as a bench value)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--shard-weights", action="store_true",
+                    help="BASELINE config 4 layout: frozen block weights sharded 1/N per rank, all-gathered per block (not the headline config)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -74,6 +74,7 @@ class FusedMMDiTBase(nn.Module):
         self._ws = self._ws_key = None
         self._rope_cache = {}
         self.gradient_checkpointing = False  # accepted for interface compatibility; HBM holds the activations
+        self._sharded = None     # sharding.ShardedBlocks once shard_frozen_weights() has run
 
     @property
     def device(self):
@@ -196,7 +197,8 @@ class FusedMMDiTBase(nn.Module):
                 B_all.copy_(torch.randn(n, C, r, device=self.dev, generator=g) * b_std)
             ga0, gb0 = off, off + n * r * D
             off = gb0 + n * C * r
-            self.mod_sites[kind] = dict(idx=torch.tensor([mod_table[f][1] for f in names], device=self.dev), names=names, A=A_all,
+            self.mod_sites[kind] = dict(idx=torch.tensor([mod_table[f][1] for f in names], device=self.dev),
+                                        idx_list=[mod_table[f][1] for f in names], names=names, A=A_all,
                                         B=B_all, ga=ga0, gb=gb0, C=C, rows={mod_table[f][1] for f in names})
             for i, full in enumerate(names):
                 pA, pB = nn.Parameter(A_all[i]), nn.Parameter(B_all[i])
@@ -245,20 +247,30 @@ class FusedMMDiTBase(nn.Module):
         t = ws["mods"] if kind == "dbl" else ws["smods"]
         return t.view(t.shape[0], -1, C)
 
-    def _mod_lora_fwd(self, ws, temb):
+    def _mod_lora_fwd(self, ws, temb, kind_rows=None):
         """mods += scaling * lora_B(lora_A(silu(temb))) for every adapted modulation Linear, with PEFT's bf16 rounding points
-        (lora_A output, lora_B output, the scaled product, the sum).  [B, .] operands: batched torch products, not a hot path."""
+        (lora_A output, lora_B output, the scaled product, the sum).  [B, .] operands: batched torch products, not a hot path.
+        kind_rows = (kind, rows): only those rows (sharded weights produce the base modulation vectors block by block)."""
         if not self.mod_sites:
             return
         x = torch.nn.functional.silu(temb.float()).to(BF)  # the same rounded activation the modulation GEMV consumes
         ws["mod_x"] = x
         for kind, ms in self.mod_sites.items():
-            t = torch.matmul(x.float()[None], ms["A"].float().transpose(1, 2)).to(BF)        # [n, B, r]
-            d = torch.bmm(t.float(), ms["B"].float().transpose(1, 2)).to(BF)                  # [n, B, C]
+            sel = list(range(len(ms["names"])))
+            if kind_rows is not None:
+                sel = [i for i in sel if kind == kind_rows[0] and ms["idx_list"][i] in kind_rows[1]]
+                if not sel:
+                    continue
+            A, Bm, idx = ms["A"][sel], ms["B"][sel], ms["idx"][sel]
+            t = torch.matmul(x.float()[None], A.float().transpose(1, 2)).to(BF)               # [n, B, r]
+            d = torch.bmm(t.float(), Bm.float().transpose(1, 2)).to(BF)                       # [n, B, C]
             d = (d.float() * self.lora_scaling).to(BF)
             mv = self._mods_view(ws, kind)
-            mv[:, ms["idx"]] = (mv[:, ms["idx"]].float() + d.float().permute(1, 0, 2)).to(BF)
-            ws["mod_t_" + kind] = t
+            mv[:, idx] = (mv[:, idx].float() + d.float().permute(1, 0, 2)).to(BF)
+            key = "mod_t_" + kind
+            if key not in ws or ws[key].shape[1] != t.shape[1]:
+                ws[key] = torch.zeros(len(ms["names"]), t.shape[1], t.shape[2], device=self.dev, dtype=BF)
+            ws[key][sel] = t
 
     def _mod_grad_buffers(self, ws):
         """fp32 accumulators for d mods (same layout as the modulation vectors), zeroed at the start of every backward."""

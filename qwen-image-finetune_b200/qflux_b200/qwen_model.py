@@ -93,7 +93,7 @@ class QwenImageB200(FusedMMDiTBase):
         out[p + "linear_2.weight"], out[p + "linear_2.bias"] = w["t2_w"], w["t2_b"]
         out["norm_out.linear.weight"], out["norm_out.linear.bias"] = w["norm_out_w"], w["norm_out_b"]
         out["proj_out.weight"], out["proj_out.bias"] = w["proj_out_w"], w["proj_out_b"]
-        for l in range(self.L):
+        for l in range(self.L if self._sharded is None else 0):  # sharded block weights are not addressable as full tensors
             b = f"transformer_blocks.{l}."
             for s, nm in ((0, "img_mod.1"), (1, "txt_mod.1")):
                 out[b + nm + ".weight"], out[b + nm + ".bias"] = w["mod_w"][l, s], w["mod_b"][l, s]
@@ -105,6 +105,24 @@ class QwenImageB200(FusedMMDiTBase):
                     W, Bv = W[slot * D:(slot + 1) * D], Bv[slot * D:(slot + 1) * D]
                 out[b + nm + ".weight"], out[b + nm + ".bias"] = W, Bv
         return out
+
+    _PER_LAYER = ("mod_w", "mod_b", "qkv_w", "qkv_b", "out_w", "out_b", "up_w", "up_b", "down_w", "down_b", "qknorm_w")
+
+    def shard_frozen_weights(self, group=None):
+        """BASELINE config 4 ("FSDP"): keep 1/world of every block's frozen weights on this rank; a block's full weights are
+        all-gathered into one of two ring buffers right before it runs (sharding.py).  Call after the weights are loaded.
+        LoRA factors stay replicated; `state_dict()` then only carries the replicated tensors and the LoRA parameters."""
+        from .sharding import ShardedBlocks
+        if self._sharded is not None:
+            return self
+        stacked = {k: self.w[k] for k in self._PER_LAYER}
+        self._sharded = ShardedBlocks(stacked, self.L, group)
+        for k in self._PER_LAYER:
+            self.w[k] = self._sharded.rings[k]
+        del stacked
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+        return self
 
     def _linear_table(self) -> dict:
         D = self.D
@@ -195,9 +213,11 @@ class QwenImageB200(FusedMMDiTBase):
         lib.timestep_sinusoid(t32, 1000.0, ws["sin"])
         lib.gemv_act(ws["sin"], w["t1_w"], w["t1_b"], ws["t1"], act=0)
         lib.gemv_act(ws["t1"], w["t2_w"], w["t2_b"], ws["temb"], act=1)
-        lib.gemv_act(ws["temb"], w["mod_w"].view(L * 2 * 6 * D, D), w["mod_b"].view(-1), ws["mods"], act=1)
+        sh = self._sharded
+        if sh is None:  # all 2L modulation linears in one launch
+            lib.gemv_act(ws["temb"], w["mod_w"].view(L * 2 * 6 * D, D), w["mod_b"].view(-1), ws["mods"], act=1)
+            self._mod_lora_fwd(ws, ws["temb"])
         lib.gemv_act(ws["temb"], w["norm_out_w"], w["norm_out_b"], ws["fmod"], act=1)
-        self._mod_lora_fwd(ws, ws["temb"])
         # --- embedders
         hs = hidden_states.to(BF).reshape(B * Limg, self.C_in)
         self._embed_fwd(ws, "img_in", 0, hs, X0[Mt:])
@@ -206,7 +226,14 @@ class QwenImageB200(FusedMMDiTBase):
         # --- blocks
         for l in range(L):
             Xin, Xout = (ws["X"][l], ws["X"][l + 1]) if train else (ws["X"][l & 1], ws["X"][(l + 1) & 1])
+            if sh is not None:  # block l's weights arrive by all-gather (block l+1's gather starts now, on the side stream)
+                sh.acquire(l, then_prefetch=l + 1)
+                lib.gemv_act(ws["temb"], w["mod_w"][l].view(2 * 6 * D, D), w["mod_b"][l].view(-1),
+                             ws["mods"][:, l * 12 * D:(l + 1) * 12 * D], act=1)
+                self._mod_lora_fwd(ws, ws["temb"], ("dbl", (2 * l, 2 * l + 1)))
             self._double_fwd(ws, l, Xin, Xout, ws["dbl"][l if train else 0], self._mods(ws, l))
+            if sh is not None:
+                sh.release(l)
         Xl = ws["X"][L] if train else ws["X"][L & 1]
         ws["Xlast"] = Xl
         # --- output head: AdaLayerNormContinuous (scale, shift) + proj_out, image stream only
@@ -229,10 +256,15 @@ class QwenImageB200(FusedMMDiTBase):
         ws["dY"][:Mt].zero_()
         lib.ln_modulate_bwd(ws["dhn"], ws["Xlast"][Mt:], ws["fstats"][0], ws["fstats"][1], ws["fmod"][:, :D], Limg, dX[Mt:],
                             gate=self._mods(ws, L - 1)(5)[0], dx_gated=ws["dY"][Mt:])
+        sh = self._sharded
         for l in range(L - 1, -1, -1):
             dXn = ws["dX"][l & 1]
+            if sh is not None:
+                sh.acquire(l, then_prefetch=l - 1)
             self._double_bwd(ws, l, ws["X"][l], dX, dXn, ws["dbl"][l], self._mods(ws, l),
                              self._mods(ws, l - 1)(5) if l > 0 else None)
+            if sh is not None:
+                sh.release(l)
             dX = dXn
         self._mod_lora_bwd(ws)
         self._embed_bwd(ws, "img_in", 0, dX)

@@ -70,3 +70,66 @@ def test_dp2_gradient_exchange(tmp_path):
     assert r["differs"], "ranks must see different batches"
     assert r["ok_mean"], "every rank must hold the mean LoRA gradient after the exchange step"
     assert r["ok_sync"], "replicas must stay bit-identical after the optimizer step"
+
+
+def _worker_sharded(rank, world, port, out):
+    """BASELINE config 4 semantics on 2 ranks: frozen block weights sharded 1/world (all-gathered block by block into a two-slot
+    ring), LoRA replicated, gradients all-reduced — must reproduce the un-sharded model's loss and gradients exactly."""
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "qwen-image-finetune_b200"))
+    import emu_lib
+    from qflux_b200 import lib
+    emu_lib.install(lib)
+    from qflux_b200.qwen_model import QwenB200Config, QwenImageB200
+    from qflux_b200.train_step import QwenImageEditStep
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def build():
+        torch.manual_seed(7)
+        m = QwenImageB200(QwenB200Config(num_layers=3, num_attention_heads=2, joint_attention_dim=128), device="cpu", _host_only=True)
+        for k, t in m.w.items():
+            if k.endswith("_w") and t.ndim >= 2:
+                t.copy_((torch.randn(t.shape) * 0.05).bfloat16())
+            elif k.endswith("_b"):
+                t.copy_((torch.randn(t.shape) * 0.02).bfloat16())
+        m.add_adapter(4, 4, target_modules=("to_q", "to_out.0", "img_mod.1", "net.2"), b_std=0.05)
+        return m
+
+    full, sh = build(), build().shard_frozen_weights()
+    per_rank = sh._sharded.shard.numel()
+    total = sum(full.w[k].numel() for k in type(full)._PER_LAYER)
+    g = torch.Generator().manual_seed(100 + rank)  # per-rank data (data parallel on top of the sharding)
+    rn = lambda *s: torch.randn(*s, generator=g).bfloat16()
+    emb = dict(image_latents=rn(1, 16, 64), control_latents=rn(1, 16, 64), prompt_embeds=rn(1, 8, 128), img_shapes=[[(1, 4, 4), (1, 4, 4)]])
+    noise, u = rn(1, 16, 64), torch.tensor([0.5])
+    res = {}
+    for name, m in (("full", full), ("sharded", sh)):
+        step = QwenImageEditStep(m, max_grad_norm=0.0)
+        loss = step._run(*step._prepare(emb, noise, u))
+        res[name] = (float(loss), m.G32.clone())
+        step._run(*step._prepare(emb, noise, u))  # a second step re-uses the ring (block 0 is resident in slot 0 after the backward)
+        assert torch.equal(m.G32, res[name][1])
+    # inference path with the ring (two-slot activations, no saved blocks)
+    with torch.no_grad():
+        kw = dict(hidden_states=rn(1, 32, 64), timestep=torch.tensor([0.5]), encoder_hidden_states=emb["prompt_embeds"],
+                  encoder_hidden_states_mask=torch.ones(1, 8, dtype=torch.int64), img_shapes=emb["img_shapes"], txt_seq_lens=[8])
+        same_fwd = torch.equal(full(**kw)[0], sh(**kw)[0])
+    ok = dict(loss=res["full"][0] == res["sharded"][0], grads=torch.equal(res["full"][1], res["sharded"][1]), fwd=same_fwd,
+              shard_fraction=per_rank / total, lora_only_state=all("lora" in k or "transformer_blocks" not in k for k in sh.state_dict()))
+    allr = [None] * world
+    dist.all_gather_object(allr, ok)
+    if rank == 0:
+        torch.save(allr, out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_frozen_weights_match_replicated(tmp_path):
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker_sharded, args=(2, _free_port(), out), nprocs=2, join=True)
+    for r in torch.load(out):
+        assert r["loss"] and r["grads"] and r["fwd"], r
+        assert 0.5 <= r["shard_fraction"] < 0.51, "each of 2 ranks keeps half of the block weights (plus alignment padding)"
+        assert r["lora_only_state"]
