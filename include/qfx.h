@@ -141,6 +141,16 @@ int qfx_flow_loss(const void* pred, const void* x0, const void* noise, const flo
 /* G[i*gs_i + j*gs_j] += sum_m P[m,i] Q[m,j], j < r  (LoRA dB = dY^T (sXA^T), dA = (s dY B)^T X); fp32 atomics */
 int qfx_lora_wgrad(const void* P, int64_t ldp, const void* Q, int64_t ldq, float* G, int64_t gs_i, int64_t gs_j, int M, int Dp,
                    int r, void* stream);
+/* The same LoRA weight gradients on the tensor cores (tcgen05, both operands MN-major straight from HBM, rows split over CTAs,
+ * fp32 atomics).  A [M, Na] (lda), B [M, 64*G] (ldb), both bf16 row-major; Gp: G device pointers to fp32 gradients.
+ *   mode 0: for every group g < G and j < r:  Gp[g][i*gs_i + j*gs_j] += sum_m A[m,i] * B[m, g*64 + j]            (dA, or 1-group dB)
+ *   mode 1 (Na = G*Dg): Gp[g][(i - g*Dg)*gs_i + j*gs_j] += sum_m A[m,i] * B[m, g*64 + j]  for g = i / Dg   (dB of a fused q|k|v site)
+ * Na % 128 == 0. */
+int qfx_lora_wgrad_tc(const void* A, int64_t lda, int Na, const void* B, int64_t ldb, int G, int M, int mode, int Dg,
+                      float* const* Gp, int64_t gs_i, int64_t gs_j, int r, void* stream);
+/* Debugging aid for tools/attn_timeline.py: device buffer of >= 16 * n_query_tiles int64 that receives clock64 stamps of one
+ * backward CTA (NULL disables, the default). */
+void qfx_attn_bwd_set_debug(long long* buf);
 /* out = bf16(g * pre_scale * min(1, max_norm / (||g * pre_scale|| + 1e-6)))  (clip_grad_norm_, base_trainer.py:449-455);
  * sumsq receives ||g*pre_scale||^2.  max_norm <= 0 disables clipping. */
 int qfx_grad_finalize(const float* g, int64_t n, float pre_scale, float max_norm, float* sumsq, void* out_bf16, void* stream);
