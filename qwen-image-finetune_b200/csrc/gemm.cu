@@ -37,6 +37,12 @@ struct GemmParams {
   int nprob, N, K, lora_group_n;
   int tiles_m0, tiles_m_total, tiles_n, total_tiles;
   float alpha;
+  // split-K of the last, partial wave of the CTA-pair kernel (tail_split > 1): tiles >= tail_first are cut into tail_split
+  // K ranges that run on otherwise idle CTA pairs; partial sums meet in tail_ws (fp32, zeroed by a memset node in front of the
+  // launch) and the CTA whose arrival completes tail_cnt runs the epilogue of its half tile
+  int tail_first, tail_split;
+  float* tail_ws;
+  int* tail_cnt;
 };
 
 template <int BN>
@@ -50,15 +56,26 @@ struct GemmCfg {
 };
 
 // Epilogue of one [128 x BN] accumulator tile: thread = output row (TMEM lane), 32 columns per tcgen05.ld.
+// ws_row != nullptr: the accumulator row comes from the split-K workspace (fp32, global) instead of tensor memory
 template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_tile(const GemmProb& q, const GemmParams& P, uint32_t t_row, int row, bool row_ok, int n0) {
+__device__ __forceinline__ void epilogue_tile(const GemmProb& q, const GemmParams& P, uint32_t t_row, int row, bool row_ok, int n0,
+                                              float* ws_row = nullptr) {
     const bf16* gate_row = nullptr;
     if (EPI == QFX_EPI_RESID_GATE && row_ok) gate_row = q.gate + (int64_t)(row / q.rows_per_batch) * q.ldg;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t r[32];
-      tmem_ld32(t_row + c, r);
-      tmem_ld_wait();
+      if (ws_row == nullptr) {
+        tmem_ld32(t_row + c, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const float4 f = __ldcg(reinterpret_cast<const float4*>(ws_row + c) + v);  // written by other SMs' reds: read at L2
+          r[4 * v] = __float_as_uint(f.x); r[4 * v + 1] = __float_as_uint(f.y);
+          r[4 * v + 2] = __float_as_uint(f.z); r[4 * v + 3] = __float_as_uint(f.w);
+        }
+      }
       const int n = n0 + c;
       uint32_t o[16];
       uint4 bias4[4];
@@ -315,6 +332,9 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
 // 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x BN tile.  Each CTA stages its own 128 rows of A and
 // HALF of the B tile, so per-SM shared-memory traffic drops by a third and the ring holds 6 stages instead of 4 for the
 // same 192 KB; the leader CTA issues tcgen05.mma.cta_group::2 (M = 256), completion is multicast to both CTAs' barriers.
+// floats of padding per split-K workspace row: with a power-of-two row stride (1024 B) the row-per-thread reads of the final
+// epilogue camp on a few L2 slices (measured: +40 us per GEMM)
+constexpr int WS_PAD = 8;
 template <int BN>
 struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -368,20 +388,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm2_kernel
     m0 = (prob ? mm - P.tiles_m0 : mm) * 256 + (int)rank * BM;
     n0 = n_blk * BN;
   };
+  // Work units of this CTA pair, in order: whole tiles cluster_id, cluster_id + n_clusters, ... below tail_first, then (split-K of
+  // the last partial wave) at most ONE K range of a tail tile.  All three roles walk the same list.
+  struct Unit {
+    int tile, kb_lo, kb_hi;
+    bool lora, split;
+  };
+  auto unit_at = [&](int i, Unit& u) -> bool {
+    const int tile = cluster_id + i * n_clusters;
+    if (tile < P.tail_first) {
+      u.tile = tile; u.kb_lo = 0; u.kb_hi = nkb; u.lora = true; u.split = false;
+      return true;
+    }
+    const int idx = tile - P.tail_first, R = P.total_tiles - P.tail_first;
+    if (P.tail_split <= 1 || idx >= R * P.tail_split) return false;
+    const int part = idx / R;
+    u.tile = P.tail_first + idx - part * R;
+    u.kb_lo = part * nkb / P.tail_split;
+    u.kb_hi = (part + 1) * nkb / P.tail_split;
+    u.lora = part == P.tail_split - 1;  // the LoRA k-blocks ride with the last K range
+    u.split = true;
+    return true;
+  };
+  __shared__ int tail_last;
 
   if (warp == 0) {
     // =============================================================== TMA producer (both CTAs)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < P.total_tiles; tile += n_clusters) {
+      Unit u;
+      for (int i = 0; unit_at(i, u); ++i) {
         int prob, m0, n0;
-        decode(tile, prob, m0, n0);
+        decode(u.tile, prob, m0, n0);
         const GemmProb& q = P.p[prob];
-        const int kb_total = nkb + q.kb2;
+        const int kb_end = u.lora ? nkb + q.kb2 : nkb;  // kb in [kb_lo, kb_hi) are base k-blocks, [nkb, kb_end) the LoRA ones
         const int grp = (!TRANS_B && P.lora_group_n > 0) ? n0 / P.lora_group_n : 0;
         const int nh = n0 + (int)rank * (BN / 2);  // this CTA's half of the B columns
-        for (int kb = 0; kb < kb_total; ++kb) {
+        for (int kb = u.kb_lo; kb < kb_end; kb = (kb + 1 == u.kb_hi ? nkb : kb + 1)) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_dst = a_dst + C::A_BYTES;
@@ -415,11 +459,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm2_kernel
       constexpr uint32_t idesc = idesc_bf16(256, BN, 0, TRANS_B ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = cluster_id; tile < P.total_tiles; tile += n_clusters, ++it) {
+      Unit u;
+      for (int it = 0; unit_at(it, u); ++it) {
         int prob, m0, n0;
-        decode(tile, prob, m0, n0);
-        const int kb_total = nkb + P.p[prob].kb2;
+        decode(u.tile, prob, m0, n0);
+        const int kb_total = (u.kb_hi - u.kb_lo) + (u.lora ? P.p[prob].kb2 : 0);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -445,10 +489,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm2_kernel
   } else if (warp >= 4) {
     // =============================================================== epilogue (both CTAs, own 128 rows)
     const int q4 = warp & 3;
-    int it = 0;
-    for (int tile = cluster_id; tile < P.total_tiles; tile += n_clusters, ++it) {
+    Unit u;
+    for (int it = 0; unit_at(it, u); ++it) {
       int prob, m0, n0;
-      decode(tile, prob, m0, n0);
+      decode(u.tile, prob, m0, n0);
       const GemmProb& q = P.p[prob];
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -457,12 +501,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm2_kernel
       const int row = m0 + q4 * 32 + lane;
       const bool row_ok = row < q.M;
       const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * BN;
-      epilogue_tile<BN, EPI>(q, P, t_row, row, row_ok, n0);
+      float* ws_row = nullptr;
+      if (!u.split) {
+        epilogue_tile<BN, EPI>(q, P, t_row, row, row_ok, n0);
+      } else {  // partial sum over [kb_lo, kb_hi): add it into the workspace row of this (tile, CTA half)
+        const int slot = (u.tile - P.tail_first) * 2 + (int)rank;
+        ws_row = P.tail_ws + ((int64_t)slot * BM + q4 * 32 + lane) * (BN + WS_PAD);  // padded rows: a power-of-two row stride camps on L2 slices
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int v = 0; v < 8; ++v) red_add_v4(ws_row + c + 4 * v, r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (leader) mbar_arrive(tempty_bar(acc));
         else mbar_arrive_remote(tempty_bar(acc), 0);
+      }
+      if (u.split) {
+        // the CTA whose arrival completes the count owns the epilogue of this half tile (threadfence + counter pattern)
+        const int slot = (u.tile - P.tail_first) * 2 + (int)rank;
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 128) {
+          const int old = atomicAdd(P.tail_cnt + slot, 1);
+          tail_last = old == P.tail_split - 1;
+          if (tail_last) P.tail_cnt[slot] = 0;  // ready for the next launch
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tail_last) {
+          __threadfence();
+          epilogue_tile<BN, EPI>(q, P, 0u, row, row_ok, n0, ws_row);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // tail_last is re-used only after everyone has read it
       }
     }
   }
@@ -510,7 +585,36 @@ static int launch2(const GemmParams& P, cudaStream_t stream) {
   }
   int clusters = num_sms() / 2;
   if (P.total_tiles < clusters) clusters = P.total_tiles;
-  kern<<<2 * clusters, 256, C::SMEM_BYTES, stream>>>(P);
+  GemmParams Q = P;
+  Q.tail_first = P.total_tiles;
+  Q.tail_split = 1;
+  // Split-K of the last partial wave: R leftover tiles leave clusters - R pairs idle for a whole tile time; with long K (the
+  // D<->4D and 3D->D contractions) each leftover tile is cut into floor(clusters / R) K ranges instead.  QFX_GEMM_NO_SPLITK=1
+  // disables it (A/B).  The workspace is process-wide: GEMMs are issued from one stream at a time.
+  static const bool no_split = getenv("QFX_GEMM_NO_SPLITK") != nullptr;
+  const int nkb = P.K / BK, R = P.total_tiles % clusters;
+  if (!no_split && P.total_tiles > clusters && R > 0 && nkb >= 64) {
+    int S = clusters / R;
+    if (S > nkb / 8) S = nkb / 8;  // at least 8 k-blocks per range
+    if (S >= 2) {
+      static float* ws = nullptr;
+      static int* cnt = nullptr;
+      if (ws == nullptr) {
+        const size_t bytes = (size_t)(num_sms() / 2) * 256 * (256 + WS_PAD) * sizeof(float);
+        QFX_CUDA(cudaMalloc(&ws, bytes));
+        QFX_CUDA(cudaMemset(ws, 0, bytes));
+        QFX_CUDA(cudaMalloc(&cnt, num_sms() * sizeof(int)));
+        QFX_CUDA(cudaMemset(cnt, 0, num_sms() * sizeof(int)));
+      }
+      // (zeroing the rows inside the kernel after the final read was measured at ~100 us per GEMM; a memset of the 3 MB in use is ~2)
+      QFX_CUDA(cudaMemsetAsync(ws, 0, (size_t)R * 256 * (BN + WS_PAD) * sizeof(float), stream));
+      Q.tail_first = P.total_tiles - R;
+      Q.tail_split = S;
+      Q.tail_ws = ws;
+      Q.tail_cnt = cnt;
+    }
+  }
+  kern<<<2 * clusters, 256, C::SMEM_BYTES, stream>>>(Q);
   QFX_CUDA(cudaGetLastError());
   return 0;
 }

@@ -221,6 +221,12 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_
 }
 
 // ------------------------------------------------------------------------------------------------ numerics
+// fp32 vector reduction into global memory (no return value): 16 bytes per lane
+__device__ __forceinline__ void red_add_v4(float* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)),
+               "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+               : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -25,7 +25,11 @@ def _cases(mod):
 GEMM = ["basic_nt_bn64", "basic_nn_bn64", "basic_nt_bn128", "basic_nn_bn128", "basic_nt_bn192", "basic_nn_bn192",
         "basic_nt_bn256", "basic_nn_bn256", "basic_nt_alpha_nobias", "basic_nt_big", "basic_nn_big", "lora_nt_bn128",
         "lora_nn_bn128", "lora_nt_bn256", "lora_nn_bn256", "lora_nt_groups3", "lora_nt_kb2", "lora_nn_kb3",
-        "epilogues_bn128", "epilogues_bn256", "grouped_nt", "grouped_nn"]
+        "epilogues_bn128", "epilogues_bn256", "grouped_nt", "grouped_nn",
+        # CTA-pair kernel (cta_group::2), incl. the split-K tail wave (workspace + last-arriver epilogue)
+        "cta2_basic_nt_bn1256", "cta2_basic_nn_bn1256", "cta2_lora_nt_bn1256", "cta2_lora_nn_bn1256", "cta2_basic_nt_bn1128",
+        "cta2_lora_nn_bn1128", "cta2_epilogues", "cta2_grouped_nt", "cta2_grouped_nn", "cta2_splitk_epilogues", "cta2_splitk_lora_nt",
+        "cta2_splitk_lora_nn", "cta2_splitk_grouped_nn"]
 OPS = ["wgrad_tc", "ln_mod_3072", "ln_mod_256", "mod_grad_3072", "mod_grad_256_ragged", "fused_adamw", "rms_rows", "qk_norm_rope", "qk_norm_rope_h2", "gemv", "flow", "wgrad", "attn_small",
        "attn_300", "attn_1tile_tail", "attn_ragged", "attn_txtgap", "attn_bwd_txtgap", "attn_bwd_small", "attn_bwd_300", "attn_bwd_tail", "attn_bwd_ragged"]
 
