@@ -271,9 +271,9 @@ def run_b200(args):
                        "optimizer": "qfx_fused_adamw: global-norm clip 1.0 + AdamW on the LoRA params, one kernel over the flat fp32 gradient", "loss": loss_val},
             "clocks": clk, "gpu_launches": launches, "host_issue_ms_per_step": host_issue_ms,
             "e2e": {"value": e2e_ips, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-            "roofline": {"bound": "tensor", "kernel": "gemm_kernel<256,false,GELU> grouped img+txt MLP-up [8192+1408,3072]x[12288,3072]",
-                         "achieved": g_tf, "peak": burst, "unit": "TFLOP/s", "frac": g_tf / burst, "traffic": 1.363e9,
-                         "traffic_source": "dram__bytes_read+write per launch, profiles/r01_ncu_full_gemm_kernel.md (algorithmic 0.68e9)",
+            "roofline": {"bound": "tensor", "kernel": "gemm2_kernel<256,false,BIAS> (CTA pair, cta_group::2) grouped img+txt MLP-up [8192+1408,3072]x[12288,3072]",
+                         "achieved": g_tf, "peak": burst, "unit": "TFLOP/s", "frac": g_tf / burst, "traffic": 0.880e9,
+                         "traffic_source": "dram__bytes_read+write per launch, profiles/r01_ncu_full_gemm2_kernel.md (algorithmic 0.446e9: A 59 MB + 2 x 75.5 MB weights + 236 MB out)",
                          "peak_source": f"{which} MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)", "kernel_ms": g_ms,
                          "step_algorithmic_tflops_per_gpu": step_tf, "step_frac_of_sustained": step_tf / sustained},
             "cpu_baseline": cpu}

@@ -41,6 +41,7 @@ struct GemmParams {
   // K ranges that run on otherwise idle CTA pairs; partial sums meet in tail_ws (fp32, zeroed by a memset node in front of the
   // launch) and the CTA whose arrival completes tail_cnt runs the epilogue of its half tile
   int tail_first, tail_split;
+  int n_fast;  // CTA-pair kernel: consecutive tiles walk N first (A rows stay in L2) instead of M first (B tile stays)
   float* tail_ws;
   int* tail_cnt;
 };
@@ -382,8 +383,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm2_kernel
 
   const int nkb = P.K / BK;
   auto decode = [&](int tile, int& prob, int& m0, int& n0) {  // tiles are 256 rows tall here
-    int n_blk = tile / P.tiles_m_total;
-    int mm = tile - n_blk * P.tiles_m_total;
+    int n_blk, mm;
+    if (P.n_fast) {
+      mm = tile / P.tiles_n;
+      n_blk = tile - mm * P.tiles_n;
+    } else {
+      n_blk = tile / P.tiles_m_total;
+      mm = tile - n_blk * P.tiles_m_total;
+    }
     prob = mm >= P.tiles_m0 ? 1 : 0;
     m0 = (prob ? mm - P.tiles_m0 : mm) * 256 + (int)rank * BM;
     n0 = n_blk * BN;
@@ -588,6 +595,16 @@ static int launch2(const GemmParams& P, cudaStream_t stream) {
   GemmParams Q = P;
   Q.tail_first = P.total_tiles;
   Q.tail_split = 1;
+  // Tile order.  M-first re-reads all of A once per wave of N blocks: fine while A (rows x K) stays in the 126 MB L2, but for the
+  // K = 3D / 4D contractions A is 177-236 MB and ncu showed 1.8 GB of DRAM reads for 0.39 GB of operands.  N-first keeps a few
+  // row blocks of A resident and re-reads the (per-stream 57-75 MB) weight instead.
+  {
+    double a_bytes = 0;
+    for (int i = 0; i < P.nprob; ++i) a_bytes += 2.0 * P.p[i].M * P.K;
+    const double w_bytes = 2.0 * P.N * P.K;  // per stream
+    static const int force = getenv("QFX_GEMM_NFAST") ? atoi(getenv("QFX_GEMM_NFAST")) : -1;
+    Q.n_fast = force >= 0 ? force : (a_bytes > 96e6 && w_bytes < 96e6);
+  }
   // Split-K of the last partial wave: R leftover tiles leave clusters - R pairs idle for a whole tile time; with long K (the
   // D<->4D and 3D->D contractions) each leftover tile is cut into floor(clusters / R) K ranges instead.  QFX_GEMM_NO_SPLITK=1
   // disables it (A/B).  The workspace is process-wide: GEMMs are issued from one stream at a time.
