@@ -13,6 +13,7 @@
 // The same 128B-swizzled shared-memory tile serves as K-major or MN-major operand — only the descriptor changes — so
 // nothing is transposed in memory.  dQ_i is staged fp32 in the (free) P/dS buffers and added to the global fp32
 // accumulator with one TMA reduce-add (cp.reduce.async.bulk.tensor) per 32-column slab instead of 16K scalar atomics.
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/qfx.h"
@@ -363,11 +364,21 @@ extern "C" void qfx_attn_bwd_set_debug(long long* buf) { g_qfx_attn_bwd_dbg = bu
 
 /* All of Q, K, V, dO, dK, dV: [B, H, S, 128] bf16; dQ_accum: [B, H, S, 128] fp32, MUST be zeroed by the caller (it is the
  * target of TMA reduce-adds from every key tile).  lse: log2-domain logsumexp from qfx_attn_fwd; delta = rowsum(dO*O). */
+namespace qfx {
+int attn_bwd_transposed(const void* Q, const void* K, const void* V, const void* dO, const float* lse, const float* delta, float* dQ,
+                        void* dK, void* dV, const int* kv_len, const int* txt_len, int split, int B, int H, int S, float softmax_scale,
+                        cudaStream_t stream);  // attention_bwd2.cu
+}
+
 extern "C" int qfx_attn_bwd(const void* Q, const void* K, const void* V, const void* dO, const float* lse, const float* delta,
                             float* dQ_accum, void* dK, void* dV, const int* kv_len, const int* txt_len, int split, int B, int H,
                             int S, float softmax_scale, void* stream) {
   extern long long* g_qfx_attn_bwd_dbg;
   QFX_CHECK_ARG(B > 0 && H > 0 && S > 0 && dQ_accum && dK && dV && lse && delta, "qfx_attn_bwd: bad arguments");
+  static const bool transposed = getenv("QFX_ATTN_BWD2") != nullptr;  // A/B switch: the transposed formulation (attention_bwd2.cu)
+  if (transposed)
+    return qfx::attn_bwd_transposed(Q, K, V, dO, lse, delta, dQ_accum, dK, dV, kv_len, txt_len, split, B, H, S, softmax_scale,
+                                    (cudaStream_t)stream);
   AttnBwdParams P;
   memset(&P, 0, sizeof(P));
   int rc;
