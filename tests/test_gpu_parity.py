@@ -89,3 +89,28 @@ def test_attention_backward_transposed_variant(name):
     res = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
     assert r.returncode == 0 and res, r.stdout[-500:] + r.stderr[-500:]
     assert json.loads(res[-1][7:])["err"] < 5e-3
+
+
+def test_cache_loader_cuda_path(tmp_path):
+    """CachedEmbeddingLoader on the device: pinned ping-pong staging + side-stream upload must hand out complete, un-clobbered batches."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_cache_loader import _write_cache
+    from qflux_b200.cache_loader import CachedEmbeddingLoader
+    truth = _write_cache(str(tmp_path), n=5)
+    ld = CachedEmbeddingLoader(str(tmp_path), batch_size=1, device="cuda", shuffle=False, drop_last=False)
+    got = []
+    for b in ld:  # keep every batch alive while later ones are staged and uploaded
+        assert b["image_latents"].is_cuda and b["prompt_embeds_mask"].is_cuda
+        got.append(b)
+    import torch
+    torch.cuda.synchronize()
+    assert len(got) == 5
+    for i, b in enumerate(got):
+        assert torch.equal(b["image_latents"][0].cpu(), truth[i]["image_latents"])
+        assert torch.equal(b["prompt_embeds"][0].cpu(), truth[i]["prompt_embeds"])
+        assert b["img_shapes"] == [[(1,) + truth[i]["hw"], (1,) + truth[i]["hw"]]]
+
+
+def test_sampler_on_device_matches_oracle():
+    r = _cases("model_check")["sampler_tiny"]()
+    assert r["qwen"] < 2e-2 and r["flux"] < 2e-2

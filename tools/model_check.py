@@ -288,6 +288,45 @@ def flux_multires(H=2, L=2, Ls=2, J=64, Pp=64):
     return res
 
 
+def sampler_tiny():
+    """Euler / true-CFG sampling loops (qflux_b200/sampler.py) on the fused forward against the same loop driven by the fp32 oracle."""
+    from qflux_b200 import sampler
+    from qflux_b200.train_step import FluxKontextStep
+
+    class F32:  # the oracle behind the module signature, bf16 in / bf16 out like a bf16 model
+        def __init__(self, net):
+            self.net, self.device = net, torch.device("cuda")
+
+        def __call__(self, **kw):
+            if "pooled_projections" in kw:  # a bf16 FLUX model multiplies timestep / guidance by 1000 in bf16 (transformer_flux.py:707-710)
+                for k in ("timestep", "guidance"):
+                    kw[k] = (kw[k].bfloat16() * 1000).float() / 1000
+            kw = {k: (v.float() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in kw.items()}
+            if "txt_seq_lens" in kw and kw["txt_seq_lens"] is None:
+                kw["txt_seq_lens"] = kw["encoder_hidden_states_mask"].sum(1).tolist()
+            with torch.no_grad():
+                return (self.net(**kw)[0].bfloat16(),)
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()
+    B, hw, T = 2, 8, 24
+    orc, m = build_pair(2, 2, 128, 4, ("to_q", "to_k", "to_v", "to_out.0"))
+    emb = dict(latents=rn(B, hw * hw, 64), control_latents=rn(B, hw * hw, 64), prompt_embeds=rn(B, T, 128) * 3,
+               prompt_embeds_mask=torch.ones(B, T, dtype=torch.int64, device="cuda"), negative_prompt_embeds=rn(B, T, 128) * 3,
+               negative_prompt_embeds_mask=torch.ones(B, T, dtype=torch.int64, device="cuda"), img_shapes=[[(1, hw, hw), (1, hw, hw)]] * B,
+               num_inference_steps=4, true_cfg_scale=2.5)
+    res = dict(qwen=rel_l2(sampler.sample_qwen(m, emb).float(), sampler.sample_qwen(F32(orc), emb).float()))
+    forc, fm = build_flux_pair()
+    femb = dict(latents=rn(B, hw * hw, 64), latent_ids=FluxKontextStep.latent_image_ids(hw, hw, "cuda", 0.0),
+                control_latents=rn(B, hw * hw, 64), control_ids=FluxKontextStep.latent_image_ids(hw, hw, "cuda", 1.0),
+                pooled_prompt_embeds=rn(B, 64), prompt_embeds=rn(B, T, 64), text_ids=torch.zeros(T, 3, device="cuda"), guidance=3.5,
+                negative_pooled_prompt_embeds=rn(B, 64), negative_prompt_embeds=rn(B, T, 64), negative_text_ids=torch.zeros(T, 3, device="cuda"),
+                num_inference_steps=4, true_cfg_scale=1.5)
+    res["flux"] = rel_l2(sampler.sample_flux(fm, femb).float(), sampler.sample_flux(F32(forc), femb).float())
+    res["err"] = max(res.values())
+    return res
+
+
 CASES = {
     "inference_tiny": inference_parity,
     "step_tiny": lambda: step_parity(),
@@ -301,6 +340,7 @@ CASES = {
     "flux_tiny_mlp_out_targets": lambda: flux_step_parity(
         r=8, targets=r".*(single_transformer_blocks\.[0-9]+\.(proj_mlp|proj_out)|ff\.net\.2|ff_context\.net\.(0\.proj|2)|attn\.to_out\.0)"),
     "flux_multires": flux_multires,
+    "sampler_tiny": sampler_tiny,
     # BASELINE config 3 target set (configs/face_seg_flux_kontext_fp16.yaml:11): every block Linear, the AdaLN linears, x_embedder
     "flux_tiny_yaml_targets": lambda: flux_step_parity(r=8, targets=FLUX_YAML_TARGETS),
     "step_tiny_mod_embed_targets": lambda: step_parity(targets=("to_q", "img_mod.1", "txt_mod.1", "img_in", "txt_in")),
