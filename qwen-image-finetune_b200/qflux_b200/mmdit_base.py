@@ -84,6 +84,10 @@ class FusedMMDiTBase(nn.Module):
     def dtype(self):
         return BF
 
+    def shard_frozen_weights(self, group=None):
+        """FSDP-style sharding of the frozen block weights (sharding.py); implemented for the Qwen-Image model (BASELINE config 4)."""
+        raise NotImplementedError(f"{type(self).__name__}: sharded frozen weights are implemented for QwenImageB200 only")
+
     def enable_gradient_checkpointing(self):
         self.gradient_checkpointing = True
 
