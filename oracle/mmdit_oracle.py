@@ -21,6 +21,8 @@ Reference files followed (paths relative to /root/reference/src/qflux):
   models/transformer_qwenimage.py:257-354  QwenDoubleStreamAttnProcessor2_0 (joint [txt; img] attention)
   models/transformer_qwenimage.py:377-494  QwenImageTransformerBlock (AdaLN-Zero x2 streams, GELU-tanh MLP)
   models/transformer_qwenimage.py:497-672  QwenImageTransformer2DModel.forward
+  models/transformer_qwen_custom.py:86-216,384-573   per-sample RoPE, padded-row zeroing and additive key mask of the custom Qwen forward
+  models/transformer_flux_custom.py:84-160,372-741   the same for FLUX (per-sample ids, identity rotation on padding)
   models/transformer_flux.py:102-166       FluxAttnProcessor (RoPE applied after concat)
   models/transformer_flux.py:385-523       FluxSingleTransformerBlock / FluxTransformerBlock
   models/transformer_flux.py:526-554       FluxPosEmbed
@@ -230,6 +232,25 @@ class QwenEmbedRope:
         return torch.cat(vid, dim=0).to(device), txt.to(device)
 
 
+def qwen_rope_per_sample(q, k, rope_list, T, img_offset="aligned"):
+    """QwenDoubleStreamAttnProcessorPerSample._apply_rope_per_sample (transformer_qwen_custom.py:167-216) on the joint [text; image]
+    sequence: sample b rotates its first txt_len_b positions with its text table and L_b positions with its image table; all other
+    positions (padding) keep the identity rotation.
+    img_offset: where the image table is applied.  "reference" = joint positions [txt_len_b, txt_len_b + L_b) — what the reference does
+    (:199-208: `seq_txt` is the per-sample text length, not the padded one), which is mis-aligned by T - txt_len_b whenever a sample's
+    text is padded; "aligned" = [T, T + L_b), the positions the image tokens actually occupy.  The two agree when no text is padded
+    (the only case the reference's tests cover, tests/src/models/test_qwen_per_sample_rope.py); the B200 path implements "aligned",
+    which is what makes a padded batch equal the per-sample un-padded runs."""
+    qo, ko = q.clone(), k.clone()
+    for b, (img_f, txt_f) in enumerate(rope_list):
+        nt, ni = txt_f.shape[0], img_f.shape[0]
+        i0 = T if img_offset == "aligned" else nt
+        for src, dst in ((q, qo), (k, ko)):
+            dst[b:b + 1, :nt] = apply_rotary_emb_qwen(src[b:b + 1, :nt], txt_f)
+            dst[b:b + 1, i0:i0 + ni] = apply_rotary_emb_qwen(src[b:b + 1, i0:i0 + ni], img_f)
+    return qo, ko
+
+
 class QwenBlock(nn.Module):
     def __init__(self, dim, heads, head_dim, eps=1e-6):
         super().__init__()
@@ -247,7 +268,9 @@ class QwenBlock(nn.Module):
         shift, scale, gate = mod.chunk(3, dim=-1)
         return x * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1), gate.unsqueeze(1)
 
-    def forward(self, hidden, enc, temb, rope):
+    def forward(self, hidden, enc, temb, rope, attn_mask=None, img_offset="aligned"):
+        """rope: (img_freqs, txt_freqs) shared by the batch, or a LIST of such pairs, one per sample (custom model,
+        transformer_qwen_custom.py:167-216).  attn_mask: additive [B,1,1,S] key mask (:507-517)."""
         a = self.attn
         img_mod1, img_mod2 = self.img_mod(temb).chunk(2, dim=-1)
         txt_mod1, txt_mod2 = self.txt_mod(temb).chunk(2, dim=-1)
@@ -258,11 +281,15 @@ class QwenBlock(nn.Module):
         iq, ik, iv = (f(img_m).unflatten(-1, (H, -1)) for f in (a.to_q, a.to_k, a.to_v))
         tq, tk, tv = (f(txt_m).unflatten(-1, (H, -1)) for f in (a.add_q_proj, a.add_k_proj, a.add_v_proj))
         iq, ik, tq, tk = a.norm_q(iq), a.norm_k(ik), a.norm_added_q(tq), a.norm_added_k(tk)
-        img_f, txt_f = rope
-        iq, ik = apply_rotary_emb_qwen(iq, img_f), apply_rotary_emb_qwen(ik, img_f)
-        tq, tk = apply_rotary_emb_qwen(tq, txt_f), apply_rotary_emb_qwen(tk, txt_f)
-        q, k, v = torch.cat([tq, iq], 1), torch.cat([tk, ik], 1), torch.cat([tv, iv], 1)
-        o = sdpa(q, k, v).flatten(2, 3).to(q.dtype)  # NB: encoder_hidden_states_mask is never used (:276)
+        if isinstance(rope, list):
+            q, k, v = torch.cat([tq, iq], 1), torch.cat([tk, ik], 1), torch.cat([tv, iv], 1)
+            q, k = qwen_rope_per_sample(q, k, rope, T, img_offset)
+        else:
+            img_f, txt_f = rope
+            iq, ik = apply_rotary_emb_qwen(iq, img_f), apply_rotary_emb_qwen(ik, img_f)
+            tq, tk = apply_rotary_emb_qwen(tq, txt_f), apply_rotary_emb_qwen(tk, txt_f)
+            q, k, v = torch.cat([tq, iq], 1), torch.cat([tk, ik], 1), torch.cat([tv, iv], 1)
+        o = sdpa(q, k, v, attn_mask).flatten(2, 3).to(q.dtype)  # NB: encoder_hidden_states_mask is never used (:276)
         txt_o, img_o = a.to_add_out(o[:, :T]), a.to_out[0](o[:, T:])
         hidden = hidden + img_g1 * img_o
         enc = enc + txt_g1 * txt_o
@@ -319,15 +346,36 @@ class QwenImageOracle(nn.Module):
         self.proj_out = LoraLinear(D, cfg.patch_size ** 2 * cfg.out_channels)
 
     def forward(self, hidden_states, encoder_hidden_states=None, encoder_hidden_states_mask=None, timestep=None,
-                img_shapes=None, txt_seq_lens=None, guidance=None, attention_kwargs=None, return_dict=False):
+                img_shapes=None, txt_seq_lens=None, guidance=None, attention_kwargs=None, return_dict=False, attention_mask=None,
+                img_offset="aligned"):
+        """The stock forward (transformer_qwenimage.py:570-672) and, with `attention_mask` [B, T + L] / per-sample `img_shapes`
+        (a list of lists whose entries differ), the custom multi-resolution forward (transformer_qwen_custom.py:384-573): per-sample
+        RoPE, padded rows zeroed after the embedders and after every block, additive -inf key mask, padded output rows zeroed."""
         h = self.img_in(hidden_states)
         timestep = timestep.to(h.dtype)  # bf16 rounding of sigma happens HERE (:624)
         enc = self.txt_in(self.txt_norm(encoder_hidden_states))
         temb = self.time_text_embed.timestep_embedder(timestep_sinusoid(timestep, 256, scale=1000.0).to(h.dtype))
-        rope = self.pos_embed(img_shapes, txt_seq_lens, h.device)
+        nested = isinstance(img_shapes, list) and len(img_shapes) > 0 and isinstance(img_shapes[0], list)
+        if nested and not all(sh == img_shapes[0] for sh in img_shapes):  # :458-474 per-sample mode only when the samples differ
+            lens = txt_seq_lens if isinstance(txt_seq_lens, list) else [txt_seq_lens] * len(img_shapes)
+            rope = [self.pos_embed([sh], [n], h.device) for sh, n in zip(img_shapes, lens)]
+        else:
+            rope = self.pos_embed(img_shapes, txt_seq_lens, h.device)
+        add_mask = img_valid = None
+        if attention_mask is not None:
+            m = attention_mask.to(h.device) > 0
+            T = enc.shape[1]
+            img_valid = m[:, T:T + h.shape[1]]
+            enc = enc.masked_fill(~m[:, :T].unsqueeze(-1), 0)
+            h = h.masked_fill(~img_valid.unsqueeze(-1), 0)
+            add_mask = torch.zeros(m.shape[0], 1, 1, m.shape[1], dtype=h.dtype, device=h.device).masked_fill(~m[:, None, None, :], float("-inf"))
         for blk in self.transformer_blocks:
-            enc, h = blk(h, enc, temb, rope)
+            enc, h = blk(h, enc, temb, rope, add_mask, img_offset)
+            if img_valid is not None:
+                h = h * img_valid.unsqueeze(-1)  # :545-560
         out = self.proj_out(self.norm_out(h, temb))
+        if img_valid is not None:
+            out = out.masked_fill(~img_valid.unsqueeze(-1), 0)
         return (out,)
 
 
@@ -348,7 +396,7 @@ def flux_rope(ids: torch.Tensor, axes_dim, theta=10000):
 
 def apply_rotary_emb_real(x, cos, sin):
     """diffusers apply_rotary_emb(use_real=True, unbind_dim=-1, sequence_dim=1); x [B,S,H,d], cos/sin [S,d]."""
-    cos, sin = cos[None, :, None, :], sin[None, :, None, :]
+    cos, sin = (cos[None, :, None, :], sin[None, :, None, :]) if cos.ndim == 2 else (cos[:, :, None, :], sin[:, :, None, :])  # [B,S,d]: per sample
     xr, xi = x.reshape(*x.shape[:-1], -1, 2).unbind(-1)
     xrot = torch.stack([-xi, xr], dim=-1).flatten(3)
     return (x.float() * cos + xrot.float() * sin).to(x.dtype)
@@ -375,7 +423,7 @@ class FluxDoubleBlock(nn.Module):
         self.attn = JointAttention(dim, heads, head_dim, torch_rms=True)
         self.ff, self.ff_context = FeedForward(dim), FeedForward(dim)
 
-    def forward(self, hidden, enc, temb, rope):
+    def forward(self, hidden, enc, temb, rope, attn_mask=None):
         a, H = self.attn, self.attn.heads
         nh, gate_msa, shift_mlp, scale_mlp, gate_mlp = self.norm1(hidden, temb)
         ne, c_gate_msa, c_shift_mlp, c_scale_mlp, c_gate_mlp = self.norm1_context(enc, temb)
@@ -385,7 +433,7 @@ class FluxDoubleBlock(nn.Module):
         eq, ek = a.norm_added_q(eq), a.norm_added_k(ek)
         q, k, v = torch.cat([eq, q], 1), torch.cat([ek, k], 1), torch.cat([ev, v], 1)
         q, k = apply_rotary_emb_real(q, *rope), apply_rotary_emb_real(k, *rope)
-        o = sdpa(q, k, v).flatten(2, 3).to(q.dtype)
+        o = sdpa(q, k, v, attn_mask).flatten(2, 3).to(q.dtype)
         T = enc.shape[1]
         ctx_o, img_o = a.to_add_out(o[:, :T]), a.to_out[0](o[:, T:])
         hidden = hidden + gate_msa.unsqueeze(1) * img_o
@@ -405,7 +453,7 @@ class FluxSingleBlock(nn.Module):
         self.proj_out = LoraLinear(dim + int(dim * mlp_ratio), dim)
         self.attn = JointAttention(dim, heads, head_dim, added=False, pre_only=True, torch_rms=True)
 
-    def forward(self, hidden, enc, temb, rope):
+    def forward(self, hidden, enc, temb, rope, attn_mask=None):
         T = enc.shape[1]
         x = torch.cat([enc, hidden], dim=1)
         n, gate = self.norm(x, temb)
@@ -413,7 +461,7 @@ class FluxSingleBlock(nn.Module):
         a, H = self.attn, self.attn.heads
         q, k, v = (f(n).unflatten(-1, (H, -1)) for f in (a.to_q, a.to_k, a.to_v))
         q, k = apply_rotary_emb_real(a.norm_q(q), *rope), apply_rotary_emb_real(a.norm_k(k), *rope)
-        o = sdpa(q, k, v).flatten(2, 3).to(q.dtype)
+        o = sdpa(q, k, v, attn_mask).flatten(2, 3).to(q.dtype)
         x = x + gate.unsqueeze(1) * self.proj_out(torch.cat([o, mlp], dim=2))
         return x[:, :T], x[:, T:]
 
@@ -455,8 +503,19 @@ class FluxOracle(nn.Module):
         self.proj_out = LoraLinear(D, cfg.patch_size ** 2 * (cfg.out_channels or cfg.in_channels))
 
     def forward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None, timestep=None, img_ids=None,
-                txt_ids=None, guidance=None, joint_attention_kwargs=None, return_dict=False):
+                txt_ids=None, guidance=None, joint_attention_kwargs=None, return_dict=False, attention_mask=None):
+        """The stock forward (transformer_flux.py:641-828) and, with `attention_mask` [B, T + L] and batched `img_ids` [B, L, 3], the
+        custom multi-resolution forward (transformer_flux_custom.py:372-741): per-sample RoPE from each sample's valid ids with the
+        identity rotation on padded positions (:494-553), padded image rows zeroed after x_embedder (:423-442), after every block
+        (:645-661, 693-709) and in the output (:724-735), additive -inf key mask (:604-616)."""
         h = self.x_embedder(hidden_states)
+        img_valid = add_mask = None
+        if attention_mask is not None:
+            T0 = txt_ids.shape[-2]
+            m = attention_mask.to(h.device) > 0
+            img_valid = m[:, T0:T0 + h.shape[1]]
+            h = h.masked_fill(~img_valid.unsqueeze(-1), 0)
+            add_mask = torch.zeros(m.shape[0], 1, 1, m.shape[1], dtype=h.dtype, device=h.device).masked_fill(~m[:, None, None, :], float("-inf"))
         t = timestep.to(h.dtype) * 1000
         tte = self.time_text_embed
         temb = tte.timestep_embedder(timestep_sinusoid(t, 256).to(pooled_projections.dtype))
@@ -465,12 +524,33 @@ class FluxOracle(nn.Module):
             temb = temb + tte.guidance_embedder(timestep_sinusoid(g, 256).to(pooled_projections.dtype))
         temb = temb + tte.text_embedder(pooled_projections)
         enc = self.context_embedder(encoder_hidden_states)
-        rope = flux_rope(torch.cat((txt_ids, img_ids), dim=0), self.config.axes_dims_rope)
+        if img_ids.ndim == 3 and attention_mask is None:
+            img_ids = img_ids[0]  # batched ids without a mask: shared layout (transformer_flux_custom.py:473-476)
+        if txt_ids.ndim == 3:
+            txt_ids = txt_ids[0]
+        if img_ids.ndim == 3:
+            cs, sn = [], []
+            for b in range(img_ids.shape[0]):
+                nv = int(img_valid[b].sum())
+                c, s_ = flux_rope(torch.cat((txt_ids, img_ids[b, :nv]), dim=0), self.config.axes_dims_rope)
+                pad = img_ids.shape[1] - nv
+                cs.append(torch.cat([c, torch.ones(pad, c.shape[1], device=c.device)], 0))   # identity rotation on the padding
+                sn.append(torch.cat([s_, torch.zeros(pad, c.shape[1], device=c.device)], 0))
+            rope = (torch.stack(cs), torch.stack(sn))
+        else:
+            rope = flux_rope(torch.cat((txt_ids, img_ids), dim=0), self.config.axes_dims_rope)
         for blk in self.transformer_blocks:
-            enc, h = blk(h, enc, temb, rope)
+            enc, h = blk(h, enc, temb, rope, add_mask)
+            if img_valid is not None:
+                h = h * img_valid.unsqueeze(-1)
         for blk in self.single_transformer_blocks:
-            enc, h = blk(h, enc, temb, rope)
-        return (self.proj_out(self.norm_out(h, temb)),)
+            enc, h = blk(h, enc, temb, rope, add_mask)
+            if img_valid is not None:
+                h = h * img_valid.unsqueeze(-1)
+        out = self.proj_out(self.norm_out(h, temb))
+        if img_valid is not None:
+            out = out.masked_fill(~img_valid.unsqueeze(-1), 0)
+        return (out,)
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -260,16 +260,14 @@ class FluxB200(FusedMMDiTBase):
             txt_ids = txt_ids[0]
         if img_ids.ndim == 3 and kv_len is None:
             img_ids = img_ids[0]  # batched ids without a mask: every sample has the same layout (transformer_flux_custom.py:473-476)
-        key = (img_ids.data_ptr(), txt_ids.data_ptr(), tuple(img_ids.shape), tuple(txt_ids.shape), img_ids._version)
-        if key not in self._rope_cache:  # built with torch ops on the ids' device (no host sync); re-used while the ids tensor lives
-            self._rope_cache.clear()
-            ti, ii = txt_ids.to(self.dev), img_ids.to(self.dev)
-            if ii.ndim == 3:  # zero-padded ids give position 0 on every axis = the identity rotation the reference pads with (:538-553)
-                self._rope_cache[key] = torch.stack([flux_rope_table(torch.cat((ti, ii[b]), dim=0), self.config.axes_dims_rope)
-                                                     for b in range(B)]).contiguous()
-            else:
-                self._rope_cache[key] = flux_rope_table(torch.cat((ti, ii), dim=0), self.config.axes_dims_rope)
-        ws["rope"] = self._rope_cache[key]
+        # The table is rebuilt on every call (a few small device kernels, no host sync): the ids are data, and a cache keyed on the
+        # tensor's address goes stale when the allocator hands the same block to the next batch's ids.
+        ti, ii = txt_ids.to(self.dev), img_ids.to(self.dev)
+        if ii.ndim == 3:  # zero-padded ids give position 0 on every axis = the identity rotation the reference pads with (:538-553)
+            ws["rope"] = torch.stack([flux_rope_table(torch.cat((ti, ii[b]), dim=0), self.config.axes_dims_rope)
+                                      for b in range(B)]).contiguous()
+        else:
+            ws["rope"] = flux_rope_table(torch.cat((ti, ii), dim=0), self.config.axes_dims_rope)
         ws["kv_len"] = kv_len
         assert ws["rope"].shape[-3] == ws["S"]
         X0 = ws["X"][0]

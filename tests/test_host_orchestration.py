@@ -282,6 +282,13 @@ def test_qwen_multi_resolution_matches_per_sample_oracle(emu):
         out = m(hidden_states=packed, timestep=sig, encoder_hidden_states=pe, encoder_hidden_states_mask=mask, img_shapes=shapes,
                 txt_seq_lens=txt)[0]
     assert out.shape == (2, 32, 64) and out[1, 16:].abs().max() == 0 and out[1, :16].abs().max() > 0
+    # ... and the whole padded batch equals the oracle's restatement of the custom forward (transformer_qwen_custom.py:384-573)
+    am = torch.zeros(2, 8 + 32, dtype=torch.bool)
+    am[0], am[1, :5], am[1, 8:8 + 16] = True, True, True
+    with torch.no_grad():
+        ref = orc(hidden_states=packed.float(), timestep=sig, encoder_hidden_states=pe.float(), img_shapes=shapes, txt_seq_lens=txt,
+                  attention_mask=am)[0]
+    assert ((out.float() - ref).norm() / ref.norm()).item() < 1e-2 and ref[1, 16:].abs().max() == 0
 
 
 def test_flux_multi_resolution_matches_per_sample_oracle(emu):
@@ -340,10 +347,15 @@ def test_flux_multi_resolution_matches_per_sample_oracle(emu):
     for b in range(B):
         ids_b[b, :lt[b]] = FluxKontextStep.latent_image_ids(shapes[b][0][1], shapes[b][0][2], "cpu", 0.0)
         am[b, : T + lt[b] + lc[b]] = True
+    hs_in = rn(B, Ltot, 64)
     with torch.no_grad():
-        out = m(hidden_states=rn(B, Ltot, 64), encoder_hidden_states=pe, pooled_projections=pooled, timestep=t, img_ids=ids_b,
+        out = m(hidden_states=hs_in, encoder_hidden_states=pe, pooled_projections=pooled, timestep=t, img_ids=ids_b,
                 txt_ids=text_ids, guidance=torch.ones(B), attention_mask=am)[0]
+        # the oracle's restatement of the custom forward (transformer_flux_custom.py:372-741) on the same padded batch
+        ref = orc(hidden_states=hs_in.float(), encoder_hidden_states=pe.float(), pooled_projections=pooled.float(), timestep=t, img_ids=ids_b,
+                  txt_ids=text_ids, guidance=torch.ones(B), attention_mask=am)[0]
     assert out.shape == (B, Ltot, 64) and out[1, lt[1] + lc[1]:].abs().max() == 0 and out[1, : lt[1]].abs().max() > 0
+    assert ((out.float() - ref).norm() / ref.norm()).item() < 1e-2 and ref[1, lt[1] + lc[1]:].abs().max() == 0
 
 
 def test_fused_adamw_matches_torch_adamw(emu):

@@ -123,3 +123,70 @@ def test_lora_regex_targets():
     m = tiny_flux()
     t = mo.lora_targets(m, r".*single_transformer_blocks\.\d+\.(proj_mlp|proj_out|attn\.to_[qkv])")
     assert sorted(n.split(".", 2)[2] for n, _ in t) == ["attn.to_k", "attn.to_q", "attn.to_v", "proj_mlp", "proj_out"]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# custom multi-resolution forwards (transformer_qwen_custom.py:384-573, transformer_flux_custom.py:372-741): the self-checks
+# the reference's own tests run on them
+# ------------------------------------------------------------------------------------------------------------------
+def test_qwen_custom_padded_equals_unpadded_per_sample():
+    """tests/src/models/test_qwen_per_sample_rope.py:417 (rel-L2 < 1e-4), test_qwen_custom.py:672-692 (padded rows exactly 0)."""
+    m = tiny_qwen()
+    g = torch.Generator().manual_seed(1)
+    shapes = [[(1, 4, 4), (1, 4, 4)], [(1, 2, 4), (1, 4, 2)], [(1, 2, 2), (1, 2, 2)]]
+    B, T, J = 3, 6, 512
+    L = [sum(f * h * w for f, h, w in sh) for sh in shapes]
+    txt = [6, 4, 5]
+    Lmax = max(L)
+    hs, enc = torch.zeros(B, Lmax, 64), torch.zeros(B, T, J)
+    am = torch.zeros(B, T + Lmax, dtype=torch.bool)
+    for b in range(B):
+        hs[b, :L[b]] = torch.randn(L[b], 64, generator=g)
+        enc[b, :txt[b]] = torch.randn(txt[b], J, generator=g)
+        am[b, :txt[b]] = True
+        am[b, T:T + L[b]] = True
+    t = torch.tensor([0.5, 0.25, 0.75])
+    with torch.no_grad():
+        out = m(hidden_states=hs, encoder_hidden_states=enc, timestep=t, img_shapes=shapes, txt_seq_lens=txt, attention_mask=am)[0]
+        out_ref_quirk = m(hidden_states=hs, encoder_hidden_states=enc, timestep=t, img_shapes=shapes, txt_seq_lens=txt, attention_mask=am,
+                          img_offset="reference")[0]
+        for b in range(B):
+            solo = m(hidden_states=hs[b:b + 1, :L[b]], encoder_hidden_states=enc[b:b + 1, :txt[b]], timestep=t[b:b + 1],
+                     img_shapes=[shapes[b]], txt_seq_lens=[txt[b]])[0][0]
+            assert ((out[b, :L[b]] - solo).norm() / solo.norm()).item() < 1e-4
+            assert out[b, L[b]:].abs().max() == 0 if L[b] < Lmax else True
+            if txt[b] == T:  # no text padding: the reference's placement of the image table coincides with the aligned one
+                torch.testing.assert_close(out_ref_quirk[b], out[b])
+            else:            # padded text: the reference applies the image table T - txt_len positions early (documented quirk)
+                assert ((out_ref_quirk[b, :L[b]] - solo).norm() / solo.norm()).item() > 1e-3
+        # identical shape lists -> the shared path, bit-identical to the stock forward (transformer_qwen_custom.py:458-469)
+        same = [shapes[0]] * 2
+        a = m(hidden_states=hs[:2], encoder_hidden_states=enc[:2], timestep=t[:2], img_shapes=same, txt_seq_lens=[T, T])[0]
+        b_ = m(hidden_states=hs[:2], encoder_hidden_states=enc[:2], timestep=t[:2], img_shapes=[shapes[0]], txt_seq_lens=[T, T])[0]
+        assert torch.equal(a, b_)
+
+
+def test_flux_custom_padded_equals_unpadded_per_sample():
+    """tests/src/models/test_flux_per_sample_rope.py:481-486 (rel-L2 < 1e-4), test_flux_transformer_padding.py:91 (atol 1e-5)."""
+    m = tiny_flux()
+    g = torch.Generator().manual_seed(2)
+    hw = [(4, 4), (2, 4), (4, 2)]
+    B, T = 3, 5
+    L = [2 * h * w for h, w in hw]  # target + one control of the same size
+    Lmax = max(L)
+    hs, ids = torch.zeros(B, Lmax, 64), torch.zeros(B, Lmax, 3)
+    am = torch.ones(B, T + Lmax, dtype=torch.bool)
+    for b, (h, w) in enumerate(hw):
+        hs[b, :L[b]] = torch.randn(L[b], 64, generator=g)
+        ids[b, :L[b]] = torch.cat([mo.flux_latent_image_ids(h, w, 0.0), mo.flux_latent_image_ids(h, w, 1.0)], 0)
+        am[b, T + L[b]:] = False
+    enc, pooled, t, txt_ids = torch.randn(B, T, 32, generator=g), torch.randn(B, 16, generator=g), torch.tensor([0.5, 0.25, 0.75]), torch.zeros(T, 3)
+    with torch.no_grad():
+        out = m(hidden_states=hs, encoder_hidden_states=enc, pooled_projections=pooled, timestep=t, img_ids=ids, txt_ids=txt_ids,
+                guidance=torch.ones(B), attention_mask=am)[0]
+        for b in range(B):
+            solo = m(hidden_states=hs[b:b + 1, :L[b]], encoder_hidden_states=enc[b:b + 1], pooled_projections=pooled[b:b + 1],
+                     timestep=t[b:b + 1], img_ids=ids[b, :L[b]], txt_ids=txt_ids, guidance=torch.ones(1))[0][0]
+            assert ((out[b, :L[b]] - solo).norm() / solo.norm()).item() < 1e-4
+            torch.testing.assert_close(out[b, :L[b]], solo, atol=1e-5, rtol=1e-4)
+            assert L[b] == Lmax or out[b, L[b]:].abs().max() == 0
