@@ -176,6 +176,8 @@ class QwenImageB200(FusedMMDiTBase):
         (cos 1, sin 0 — transformer_flux_custom.py:148-154), their keys are masked anyway.  Returns (table, kv_len int32 [B])."""
         key = ("multi", tuple(tuple(tuple(s) for s in sh) for sh in img_shapes), T, Limg)
         if key not in self._rope_cache:
+            if len(self._rope_cache) >= 64:  # bucketed multi-resolution training meets a bounded set of shape combinations; stay bounded anyway
+                self._rope_cache.pop(next(iter(self._rope_cache)))
             tabs, lens = [], []
             for sh in img_shapes:
                 t = qwen_rope_table(sh, T, self.config.axes_dims_rope)
