@@ -13,14 +13,16 @@ import torch
 from . import lib
 
 
-class FusedLoraAdamW:
+class FusedLoraAdamW(torch.optim.Optimizer):
+    """A `torch.optim.Optimizer` over the model's LoRA parameters (so `get_scheduler(...)` / any `LRScheduler` drives `param_groups`
+    exactly as with the reference's AdamW), whose `step()` is one fused kernel reading the model's flat fp32 gradient."""
+
     def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
                  max_grad_norm: float = 1.0):
         if model.G32 is None:
             raise lib.QfxError("attach a LoRA adapter (model.add_adapter) before building the optimizer")
+        super().__init__(list(model.parameters()), dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self.model = model
-        self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
-        self.param_groups = [dict(self.defaults, params=list(model.parameters()))]  # torch-scheduler compatible view
         self.max_grad_norm = max_grad_norm
         self.step_count = 0
         n = model.G32.numel()
@@ -33,7 +35,7 @@ class FusedLoraAdamW:
         self._tables = lib.adamw_tables(members, model.dev)
 
     @torch.no_grad()
-    def step(self, world_size: int = 1):
+    def step(self, world_size: int = 1, closure=None):
         """grad = model.G32 (sum over ranks) / world_size, clipped to max_grad_norm; returns the device tensor ||grad||^2."""
         g = self.param_groups[0]
         self.step_count += 1
@@ -45,12 +47,14 @@ class FusedLoraAdamW:
         self.model.G32.zero_()
 
     def state_dict(self):
-        return dict(step=self.step_count, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq,
-                    param_groups=[{k: v for k, v in g.items() if k != "params"} for g in self.param_groups])
+        sd = super().state_dict()
+        sd["fused"] = dict(step=self.step_count, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq)
+        return sd
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        for g, s in zip(self.param_groups, sd["param_groups"]):
-            g.update(s)
+        sd = dict(sd)
+        fused = sd.pop("fused")
+        super().load_state_dict(sd)
+        self.step_count = int(fused["step"])
+        self.exp_avg.copy_(fused["exp_avg"])
+        self.exp_avg_sq.copy_(fused["exp_avg_sq"])

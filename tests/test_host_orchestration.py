@@ -383,7 +383,16 @@ def test_fused_adamw_matches_torch_adamw(emu):
         for n, p in m.named_parameters():
             assert torch.equal(p.detach(), master[n].detach().to(torch.bfloat16)) or \
                 (p.detach().float() - master[n].detach()).abs().max() <= 2 * 2 ** -8 * master[n].detach().abs().max(), n
-    assert opt.step_count == 3 and set(opt.state_dict()) == {"step", "exp_avg", "exp_avg_sq", "param_groups"}
+    # it is a torch Optimizer: LR schedulers drive it, and its state round-trips
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda k: 0.5 ** k)
+    step.train_step(emb, opt, noise=x["noise"], u=x["u"])
+    sched.step()
+    assert abs(opt.param_groups[0]["lr"] - 0.5e-2) < 1e-12 and opt.step_count == 4
+    sd = opt.state_dict()
+    assert set(sd) == {"state", "param_groups", "fused"} and sd["fused"]["step"] == 4
+    opt2 = FusedLoraAdamW(m, lr=1.0)
+    opt2.load_state_dict(sd)
+    assert opt2.step_count == 4 and opt2.param_groups[0]["lr"] == opt.param_groups[0]["lr"] and torch.equal(opt2.exp_avg, opt.exp_avg)
 
 
 def test_sampling_loops_match_oracle(emu):
