@@ -36,7 +36,7 @@ checkpoints load unchanged when they become available.
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import torch
 import torch.nn as nn
