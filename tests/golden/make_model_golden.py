@@ -4,6 +4,7 @@
   * flux_ref_tiny : BASELINE config 1 (2 double + 1 single, heads 2x64 = hidden 128, joint 32, pooled 16, LoRA r=4, 64x64-px latents;
                     /root/reference/tests/src/models/test_flux_per_sample_rope.py:264-278)        -> pins the oracle (regression)
   * qwen_b200_tiny / flux_b200_tiny : head_dim-128 siblings (hidden 256) that the sm_100a kernels can run -> GPU parity fixtures
+  * flux_b200_yaml_targets : the same FLUX sibling with the LoRA target regex of BASELINE config 3 (every block Linear, AdaLN linears, x_embedder)
 All fp32, CPU, torch.manual_seed-free (explicit generators).  Run:  python tests/golden/make_model_golden.py
 The oracle is parity-UNPINNED against diffusers (not installable offline); these vectors pin the oracle against drift and give the
 GPU box an oracle-free reference.
@@ -47,11 +48,22 @@ def qwen_case(heads, hd, joint, axes, seed):
                 loss=loss.detach(), grads={n: p.grad.clone() for n, p in orc.named_parameters() if p.requires_grad})
 
 
-def flux_case(heads, hd, joint, pooled, axes, seed):
+# target_modules of BASELINE config 3 (/root/reference/configs/face_seg_flux_kontext_fp16.yaml:11): every block Linear, the AdaLN
+# modulation linears and x_embedder
+FLUX_YAML_TARGETS = (
+    r"(.*x_embedder|.*transformer_blocks\.[0-9]+\.(norm|norm1)\.linear|.*transformer_blocks\.[0-9]+\.attn\.(to_k|to_q|to_v|to_add_out)"
+    r"|.*transformer_blocks\.[0-9]+\.attn\.to_out\.0|.*single_transformer_blocks\.[0-9]+\.attn\.to_out"
+    r"|.*single_transformer_blocks\.[0-9]+\.(proj_mlp|proj_out)|.*(?<!single_)transformer_blocks\.[0-9]+\.ff\.net\.2"
+    r"|.*(?<!single_)transformer_blocks\.[0-9]+\.ff\.net\.0\.proj|.*(?<!single_)transformer_blocks\.[0-9]+\.norm1_context\.linear"
+    r"|.*(?<!single_)transformer_blocks\.[0-9]+\.ff_context\.net\.0\.proj|.*(?<!single_)transformer_blocks\.[0-9]+\.ff_context\.net\.2"
+    r"|.*(?<!single_)transformer_blocks\.[0-9]+\.attn\.(to_add_out|add_k_proj|add_q_proj|add_v_proj))")
+
+
+def flux_case(heads, hd, joint, pooled, axes, seed, targets=mo.DEFAULT_TARGETS):
     cfg = mo.FluxConfig(num_layers=2, num_single_layers=1, attention_head_dim=hd, num_attention_heads=heads, joint_attention_dim=joint,
                         pooled_projection_dim=pooled, axes_dims_rope=axes, guidance_embeds=True)
     orc = mo.init_synthetic_(mo.FluxOracle(cfg), seed=seed, std=0.05)
-    mo.add_lora_adapter(orc, r=4, alpha=4, b_std=0.05, seed=seed)
+    mo.add_lora_adapter(orc, r=4, alpha=4, target_modules=targets, b_std=0.05, seed=seed)
     _perturb(orc, seed + 1)
     g = torch.Generator().manual_seed(seed + 2)
     rn = lambda *s: torch.randn(*s, generator=g).bfloat16().float()
@@ -75,21 +87,23 @@ def build_qwen(heads, hd, joint, axes, seed):
     return orc
 
 
-def build_flux(heads, hd, joint, pooled, axes, seed):
+def build_flux(heads, hd, joint, pooled, axes, seed, targets=mo.DEFAULT_TARGETS):
     cfg = mo.FluxConfig(num_layers=2, num_single_layers=1, attention_head_dim=hd, num_attention_heads=heads, joint_attention_dim=joint,
                         pooled_projection_dim=pooled, axes_dims_rope=axes, guidance_embeds=True)
     orc = mo.init_synthetic_(mo.FluxOracle(cfg), seed=seed, std=0.05)
-    mo.add_lora_adapter(orc, r=4, alpha=4, b_std=0.05, seed=seed)
+    mo.add_lora_adapter(orc, r=4, alpha=4, target_modules=targets, b_std=0.05, seed=seed)
     _perturb(orc, seed + 1)
     return orc
 
 
 CASES = dict(qwen_ref_tiny=("qwen", (4, 64, 512, (8, 28, 28), 100)), flux_ref_tiny=("flux", (2, 64, 32, 16, (8, 28, 28), 200)),
-             qwen_b200_tiny=("qwen", (2, 128, 128, (16, 56, 56), 300)), flux_b200_tiny=("flux", (2, 128, 64, 64, (16, 56, 56), 400)))
+             qwen_b200_tiny=("qwen", (2, 128, 128, (16, 56, 56), 300)), flux_b200_tiny=("flux", (2, 128, 64, 64, (16, 56, 56), 400)),
+             flux_b200_yaml_targets=("flux", (2, 128, 64, 64, (16, 56, 56), 500, FLUX_YAML_TARGETS)))
 
 def main():
   out = dict(qwen_ref_tiny=qwen_case(4, 64, 512, (8, 28, 28), 100), flux_ref_tiny=flux_case(2, 64, 32, 16, (8, 28, 28), 200),
-             qwen_b200_tiny=qwen_case(2, 128, 128, (16, 56, 56), 300), flux_b200_tiny=flux_case(2, 128, 64, 64, (16, 56, 56), 400))
+             qwen_b200_tiny=qwen_case(2, 128, 128, (16, 56, 56), 300), flux_b200_tiny=flux_case(2, 128, 64, 64, (16, 56, 56), 400),
+             flux_b200_yaml_targets=flux_case(2, 128, 64, 64, (16, 56, 56), 500, FLUX_YAML_TARGETS))
   # keep the fixture small: weights are rebuilt from the seeds; only a checksum is stored
   for c in out.values():
       sd = c.pop("state_dict")
