@@ -43,7 +43,26 @@ def token_weights_and_norm(kind, B, L, C, weighting=None, attention_mask=None, e
     raise ValueError(f"unknown loss kind {kind!r}")
 
 
-def _sync_and_step(dit, optimizer, max_grad_norm):
+class _Accumulation:
+    """Gradient accumulation (`accelerator.accumulate(...)` around training_step, base_trainer.py:518-533, train.gradient_accumulation_steps):
+    micro-steps add into the same flat fp32 LoRA gradient; the exchange + clip + optimizer step run on the last one with the mean over
+    micro-steps and ranks (accelerate divides the loss by the number of accumulation steps)."""
+
+    def _init_accumulation(self, steps: int):
+        self.gradient_accumulation_steps, self._micro = max(1, int(steps)), 0
+
+    def _fused_micro_step(self, args, optimizer):
+        self._accumulating = self._micro > 0  # read by _run: keep the gradient of the earlier micro-steps
+        loss = self._run(*args)
+        self._accumulating = False
+        self._micro += 1
+        if self._micro >= self.gradient_accumulation_steps:
+            _sync_and_step(self.dit, optimizer, self.max_grad_norm, self._micro)
+            self._micro = 0
+        return loss
+
+
+def _sync_and_step(dit, optimizer, max_grad_norm, micro_steps: int = 1):
     """Data-parallel tail of a step (base_trainer.py:383-388, 449-455, 528-533): ONE all-reduce(sum) of the flat fp32 LoRA
     gradient, then either the fused clip + AdamW kernel (FusedLoraAdamW reads the accumulator directly) or, for any torch
     optimizer, mean + clip + cast into the bf16 `.grad` views followed by `optimizer.step()`."""
@@ -54,9 +73,9 @@ def _sync_and_step(dit, optimizer, max_grad_norm):
         dist.all_reduce(dit.G32)
     if isinstance(optimizer, FusedLoraAdamW):
         optimizer.max_grad_norm = max_grad_norm
-        optimizer.step(world)
+        optimizer.step(world * micro_steps)  # divisor of the summed gradient
         return
-    dit.finalize_grads(world, max_grad_norm)
+    dit.finalize_grads(world * micro_steps, max_grad_norm)
     if optimizer is not None:
         optimizer.step()
 
@@ -78,12 +97,14 @@ class _StepFn(torch.autograd.Function):
         return (None, None) + grads
 
 
-class QwenImageEditStep:
+class QwenImageEditStep(_Accumulation):
     def __init__(self, dit: QwenImageB200, loss_kind: str = "mse", fg: float = 2.0, bg: float = 1.0,
-                 num_train_timesteps: int = 1000, max_grad_norm: float = 1.0):
+                 num_train_timesteps: int = 1000, max_grad_norm: float = 1.0, gradient_accumulation_steps: int = 1):
         self.dit, self.loss_kind, self.fg, self.bg = dit, loss_kind, fg, bg
         self.num_train_timesteps, self.max_grad_norm = num_train_timesteps, max_grad_norm
         self._ones = {}
+        self._accumulating = False
+        self._init_accumulation(gradient_accumulation_steps)
 
     # --------------------------------------------------------------------------------------------- internals
     def _sigmas(self, B, u=None):
@@ -107,7 +128,8 @@ class QwenImageEditStep:
             pred = m._forward_impl(packed, prompt_embeds, sigma, img_shapes, txt_len, train=True)
         ws = m._ws
         lib.flow_loss(pred, image_latents, noise, w, norm, ws["loss"], ws["dpred"])
-        m.G32.zero_()
+        if not self._accumulating:
+            m.G32.zero_()
         m._backward_impl(ws["dpred"])
         return ws["loss"]
 
@@ -159,20 +181,20 @@ class QwenImageEditStep:
     def train_step(self, embeddings: dict, optimizer=None, noise=None, u=None):
         """Fast path (no autograd graph): fused fwd/loss/bwd -> NCCL mean all-reduce of the flat LoRA gradient ->
         clip -> bf16 grads -> optimizer.step().  Returns the (device) loss tensor; nothing here syncs with the host."""
-        args = self._prepare(embeddings, noise, u)
-        loss = self._run(*args)
-        _sync_and_step(self.dit, optimizer, self.max_grad_norm)
-        return loss
+        return self._fused_micro_step(self._prepare(embeddings, noise, u), optimizer)
 
 
-class FluxKontextStep:
+class FluxKontextStep(_Accumulation):
     """Mirror of `FluxKontextLoraTrainer._compute_loss_shared_mode`
     (/root/reference/src/qflux/trainer/flux_kontext_trainer.py:494-577): t ~ U(0,1) in bf16 on the device, x_t = (1-t) x0 + t eps,
     ids = [target ids ; control ids], guidance = 1 when the model has guidance embeddings, target = eps - x0, MSE."""
 
-    def __init__(self, dit, loss_kind: str = "mse", fg: float = 2.0, bg: float = 1.0, max_grad_norm: float = 1.0):
+    def __init__(self, dit, loss_kind: str = "mse", fg: float = 2.0, bg: float = 1.0, max_grad_norm: float = 1.0,
+                 gradient_accumulation_steps: int = 1):
         self.dit, self.loss_kind, self.fg, self.bg, self.max_grad_norm = dit, loss_kind, fg, bg, max_grad_norm
         self._ones = {}
+        self._accumulating = False
+        self._init_accumulation(gradient_accumulation_steps)
 
     @staticmethod
     def latent_image_ids(h2, w2, device, first=0.0):
@@ -259,7 +281,8 @@ class FluxKontextStep:
             pred = m._forward_impl(packed, pe, pooled, t, ids, text_ids, guidance, kv_len, train=True)
         ws = m._ws
         lib.flow_loss(pred, x0, noise, w, norm, ws["loss"], ws["dpred"])
-        m.G32.zero_()
+        if not self._accumulating:
+            m.G32.zero_()
         m._backward_impl(ws["dpred"])
         return ws["loss"]
 
@@ -269,6 +292,4 @@ class FluxKontextStep:
 
     @torch.no_grad()
     def train_step(self, embeddings: dict, optimizer=None, noise=None, t=None):
-        loss = self._run(*self._prepare(embeddings, noise, t))
-        _sync_and_step(self.dit, optimizer, self.max_grad_norm)
-        return loss
+        return self._fused_micro_step(self._prepare(embeddings, noise, t), optimizer)

@@ -441,3 +441,34 @@ def test_sampling_loops_match_oracle(emu):
     fo_b = sampler.sample_flux(fm, femb)
     fo_o = sampler.sample_flux(F32(forc), femb)
     assert ((fo_b.float() - fo_o.float()).norm() / fo_o.float().norm()).item() < 2e-2
+
+
+def test_gradient_accumulation_equals_one_big_batch(emu):
+    """train.gradient_accumulation_steps (accelerator.accumulate, base_trainer.py:518-533): two micro-steps of B=1 accumulate into the same
+    flat gradient and step once with the mean — the same update as one step on the B=2 batch (MSE: mean over samples)."""
+    from qflux_b200.optim import FusedLoraAdamW
+    from qflux_b200.train_step import QwenImageEditStep
+    res = {}
+    x = _inputs(2, 4, 24, 128)
+    keys = ("image_latents", "control_latents", "prompt_embeds", "prompt_embeds_mask")
+    for mode in ("big", "accum"):
+        orc, m = _pair(2, 2, 128, 4, ("to_q", "to_out.0"))
+        opt = FusedLoraAdamW(m, lr=1e-2, weight_decay=0.0)
+        if mode == "big":
+            step = QwenImageEditStep(m, "mse", max_grad_norm=0.0)
+            step.train_step({**{k: x[k] for k in keys}, "img_shapes": x["img_shapes"]}, opt, noise=x["noise"], u=x["u"])
+        else:
+            step = QwenImageEditStep(m, "mse", max_grad_norm=0.0, gradient_accumulation_steps=2)
+            p0 = [p.detach().clone() for p in m.parameters()]
+            for b in range(2):
+                emb = {**{k: x[k][b:b + 1] for k in keys}, "img_shapes": x["img_shapes"][b:b + 1]}
+                step.train_step(emb, opt, noise=x["noise"][b:b + 1], u=x["u"][b:b + 1])
+                if b == 0:  # no optimizer step after the first micro-step
+                    assert all(torch.equal(p, q) for p, q in zip(m.parameters(), p0)) and opt.step_count == 0
+            assert opt.step_count == 1
+        res[mode] = (m.G32.clone(), [p.detach().float().clone() for p in m.parameters()])
+    g_big, g_acc = res["big"][0], res["accum"][0] / 2  # the accumulator holds the SUM over micro-steps; the optimizer divides
+    assert ((g_big - g_acc).norm() / g_big.norm()).item() < 2e-2
+    num = sum(((a - b) ** 2).sum() for a, b in zip(res["big"][1], res["accum"][1]))
+    den = sum((a ** 2).sum() for a in res["big"][1])
+    assert float((num / den).sqrt()) < 1e-3
