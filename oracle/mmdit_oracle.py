@@ -1,18 +1,22 @@
-"""ORACLE — test infrastructure only. PARITY UNPINNED for the transformer forward/backward.
+"""ORACLE — test infrastructure only.  PARITY PINNED to the reference's own code through leaf restatements of diffusers / peft.
 
 CPU/GPU-agnostic pure-torch restatement of the reference's hot path:
 
     noise-predict forward (Qwen-Image / FLUX MMDiT) -> flow-matching MSE -> backward (LoRA grads)
 
-Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` / library-baseline legs may
 import this file.  The product path (qflux_b200) never routes through it.
 
-Why "parity unpinned": the arithmetic of this path lives in `diffusers` / `peft`, which are not vendored in
-/root/reference and are not installed in this image (no network) — see SURVEY.md §8c.  No golden tensor of the
-transformer path is reachable offline (the reference's fixtures live on the HF Hub).  The restatement therefore
-follows the reference's vendored model files line by line and the *published* semantics of the diffusers
-building blocks they import; what IS pinned offline is the loss functions (the reference's own
-tests/src/losses/* pass against `oracle.losses_oracle`, see tests/test_oracle_losses.py).
+How it is pinned: the arithmetic of this path lives partly in `diffusers` / `peft`, which are not vendored in /root/reference and
+are not installable here (no network).  tests/shims/ restates ONLY the leaf layers those packages contribute (RMSNorm, AdaLayerNorm*,
+FeedForward, Timesteps/TimestepEmbedding, Attention container, SDPA dispatch, rotary helpers, PEFT LoRA Linear, scheduler tables);
+with them, tests/golden/make_ref_model_golden.py runs the REFERENCE'S OWN `qflux.models.transformer_qwenimage`, `transformer_flux`,
+`transformer_qwen_custom`, `transformer_flux_custom`, `BaseTrainer.add_lora_adapter`, `QwenImageEditTrainer._compute_loss` and
+`FluxKontextLoraTrainer._compute_loss` (shared + multi-resolution) and commits their outputs (tests/golden/ref_model_golden.pt).
+tests/test_reference_goldens.py holds this file to those vectors at fp32 round-off (pred / loss 1e-5, every LoRA gradient 1e-4) on
+ten cases (stock + custom models, Edit-Plus 3-image RoPE, every LoRA target set, all three losses).  What remains un-pinned is the
+dozen leaf ops of tests/shims (no diffusers wheel exists offline to check them against); the loss functions are pinned directly to
+`qflux.losses` (tests/test_oracle_losses.py).
 
 Reference files followed (paths relative to /root/reference/src/qflux):
   models/transformer_qwenimage.py:93-140   apply_rotary_emb_qwen (complex, pairs (2i,2i+1))

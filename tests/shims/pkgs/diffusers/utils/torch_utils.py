@@ -1,0 +1,15 @@
+def maybe_allow_in_graph(cls):
+    return cls
+
+
+def is_compiled_module(module):
+    return hasattr(module, "_orig_mod")
+
+
+def randn_tensor(shape, generator=None, device=None, dtype=None, layout=None):
+    """diffusers.utils.torch_utils.randn_tensor for a single (or no) generator: torch.randn on the generator's device, then moved."""
+    import torch
+    rand_device = device
+    if generator is not None and hasattr(generator, "device") and generator.device.type != getattr(torch.device(device or "cpu"), "type", "cpu"):
+        rand_device = "cpu"
+    return torch.randn(shape, generator=generator, device=rand_device, dtype=dtype, layout=layout or torch.strided).to(device)
