@@ -52,7 +52,18 @@ class CachedEmbeddingLoader:
         metas = sorted(glob.glob(os.path.join(self.root, "metadata", "*.json")))
         if not metas:
             raise FileNotFoundError(f"no cache metadata under {self.root}/metadata (EmbeddingCacheManager.exist would be False)")
-        self.samples = metas[rank::world_size]  # data parallel: disjoint strided shards, like the DataLoader sharding of accelerate
+        # data parallel: disjoint strided shards.  Every rank must yield the SAME number of batches (a rank with one batch more would
+        # block forever in the gradient all-reduce), so the global list is first cut (drop_last) or wrapped around (like accelerate's
+        # even_batches) to a multiple of world_size * batch_size
+        unit = world_size * batch_size
+        if world_size > 1 and len(metas) % unit:
+            if drop_last:
+                metas = metas[: len(metas) - len(metas) % unit]
+            else:
+                metas = metas + metas[: unit - len(metas) % unit]
+        if not metas:
+            raise ValueError(f"{self.root}: fewer cached samples than world_size * batch_size = {unit}")
+        self.samples = metas[rank::world_size]
         self.epoch = 0
         self._stage = [dict(), dict()]  # two sets of pinned staging buffers: one being filled while the other uploads
 

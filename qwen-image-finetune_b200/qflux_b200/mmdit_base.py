@@ -35,6 +35,26 @@ class LoraSite:
         self.r = 0
 
 
+class _LoraConfigLike:
+    """The attributes of `peft.LoraConfig` this path reads and `get_peft_model_state_dict` inspects (used when peft is not installed
+    or the short `add_adapter(r, alpha)` form is used)."""
+    peft_type = "LORA"
+    bias = "none"
+    use_dora = False
+    lora_dropout = 0.0
+    layer_replication = None
+    rank_pattern: dict = {}
+    alpha_pattern: dict = {}
+    is_prompt_learning = False
+
+    def __init__(self, r, lora_alpha, target_modules, init_lora_weights="gaussian"):
+        self.r, self.lora_alpha, self.target_modules, self.init_lora_weights = r, lora_alpha, target_modules, init_lora_weights
+
+    def to_dict(self):
+        return dict(r=self.r, lora_alpha=self.lora_alpha, target_modules=self.target_modules, init_lora_weights=self.init_lora_weights,
+                    peft_type=self.peft_type, bias=self.bias)
+
+
 class FusedMMDiTBase(nn.Module):
     # subclasses fill these -------------------------------------------------------------------------------------------
     round_mid = True  # diffusers RMSNorm (Qwen) rounds before the weight multiply; torch.nn.RMSNorm (FLUX) does not
@@ -70,6 +90,7 @@ class FusedMMDiTBase(nn.Module):
         self.mod_sites = {}      # kind -> dict(idx=[row indices], names=[...], A=[n, r, D], B=[n, C, r], ga, gb)  (AdaLN linears)
         self._lora_params = {}   # PEFT name -> nn.Parameter
         self.lora_scaling, self.lora_rank = 0.0, 0
+        self.adapter_name, self.peft_config = "default", {}
         self.G32 = self.G16 = None
         self._ws = self._ws_key = None
         self._rope_cache = {}
@@ -88,8 +109,25 @@ class FusedMMDiTBase(nn.Module):
         """FSDP-style sharding of the frozen block weights (sharding.py); implemented for the Qwen-Image model (BASELINE config 4)."""
         raise NotImplementedError(f"{type(self).__name__}: sharded frozen weights are implemented for QwenImageB200 only")
 
-    def enable_gradient_checkpointing(self):
+    def enable_gradient_checkpointing(self, *args, **kwargs):
         self.gradient_checkpointing = True
+
+    def _apply(self, fn, recurse=True):
+        """`dit.to(accelerator.device)` / `.cuda()` / `.bfloat16()` (base_trainer.py:388, qwen_image_edit_trainer.py:300-330) are accepted
+        when they are no-ops; the HBM layout (fused, layer-stacked weights; LoRA parameters that are views into padded buffers) cannot be
+        moved or re-typed tensor by tensor, so anything else fails loudly instead of silently detaching the views."""
+        probe = torch.empty(0, device=self.dev, dtype=BF)
+        moved = fn(probe)
+        if moved.device != probe.device or (moved.dtype != BF and moved.is_floating_point()):
+            raise lib.QfxError(f"{type(self).__name__} lives on {self.dev} in bf16; construct it on the target device instead of "
+                               f"moving it (requested {moved.device}, {moved.dtype})")
+        return self
+
+    def zero_grad(self, set_to_none: bool = True):
+        if self.G32 is not None:
+            self.G32.zero_()
+        for p in self.parameters():
+            p.grad = None
 
     # ------------------------------------------------------------------------------------------------ state dict
     def state_dict(self, *args, **kwargs):
@@ -100,7 +138,9 @@ class FusedMMDiTBase(nn.Module):
             mod, leaf = k.rsplit(".", 1)
             sd[(mod + ".base_layer." + leaf) if mod in lora_mods else k] = v
         for k, p in self._lora_params.items():
-            sd[k] = p.detach()
+            # lora_B parameters are strided views into the padded factor buffer: hand out compact copies (safetensors refuses
+            # non-contiguous tensors, torch.save would serialise the whole padded storage)
+            sd[k] = p.detach().contiguous().clone()
         return sd
 
     @torch.no_grad()
@@ -109,18 +149,32 @@ class FusedMMDiTBase(nn.Module):
         unexpected, seen = [], set()
         for k, v in sd.items():
             kk = k.replace(".base_layer.", ".")
+            lk = self._canonical_lora_key(k)
             if kk in views:
                 views[kk].copy_(v.to(self.dev, BF))
                 seen.add(kk)
-            elif k in self._lora_params:
-                self._lora_params[k].copy_(v.to(self.dev, BF))
-                seen.add(k)
+            elif lk in self._lora_params:
+                self._lora_params[lk].copy_(v.to(self.dev, BF))
+                seen.add(lk)
             else:
                 unexpected.append(k)
         missing = [k for k in list(views) + list(self._lora_params) if k not in seen]
         if strict and (unexpected or [m for m in missing if "lora" not in m]):
             raise KeyError(f"load_state_dict: missing {missing[:5]}..., unexpected {unexpected[:5]}...")
         return missing, unexpected
+
+    def _canonical_lora_key(self, k: str) -> str:
+        """Spellings a LoRA tensor name arrives in -> this model's parameter name `<module>.lora_X.<adapter>.weight`:
+        the PEFT state-dict form (identical), the diffusers LoRA-file form written by `save_lora`
+        (`transformer.<module>.lora_X.weight`, base_trainer.py:858-875) and the adapter-less `get_peft_model_state_dict` form."""
+        if ".lora_" not in k:
+            return k
+        if k.startswith("transformer."):
+            k = k[len("transformer."):]
+        head, _, tail = k.rpartition(".")
+        if head.endswith(".lora_A") or head.endswith(".lora_B"):
+            k = f"{head}.{self.adapter_name}.{tail}"
+        return k
 
     def named_parameters(self, prefix="", recurse=True, remove_duplicate=True):
         for k, p in self._lora_params.items():
@@ -131,10 +185,36 @@ class FusedMMDiTBase(nn.Module):
             yield p
 
     # ------------------------------------------------------------------------------------------------ LoRA registry
-    def add_adapter(self, r: int, lora_alpha: float, target_modules=DEFAULT_TARGETS, init_lora_weights="gaussian",
-                    seed: int = 0, b_std: float = 0.0):
-        """PEFT-equivalent of `dit.add_adapter(LoraConfig(...))` (/root/reference/src/qflux/trainer/base_trainer.py:929-941).
+    def add_adapter(self, adapter_config, lora_alpha: float | None = None, target_modules=None, init_lora_weights=None,
+                    seed: int = 0, b_std: float = 0.0, adapter_name: str = "default"):
+        """`dit.add_adapter(LoraConfig(r=, lora_alpha=, init_lora_weights=, target_modules=), adapter_name=...)` exactly as the reference
+        calls it (/root/reference/src/qflux/trainer/base_trainer.py:929-941) — `adapter_config` is any object with those attributes (a real
+        `peft.LoraConfig` included; it is kept in `self.peft_config[adapter_name]` for `get_peft_model_state_dict`).  The short form
+        `add_adapter(r, lora_alpha, target_modules=...)` is kept for scripts and tests.
         target_modules: list of name suffixes or one full regex (PEFT matching rules)."""
+        if isinstance(adapter_config, int):
+            r = adapter_config
+            cfg = _LoraConfigLike(r=r, lora_alpha=lora_alpha if lora_alpha is not None else r,
+                                  target_modules=list(DEFAULT_TARGETS) if target_modules is None else target_modules,
+                                  init_lora_weights="gaussian" if init_lora_weights is None else init_lora_weights)
+        else:
+            cfg = adapter_config
+            for attr, val in (("lora_dropout", 0.0), ("bias", "none"), ("use_dora", False), ("use_rslora", False)):
+                if getattr(cfg, attr, val) not in (val, None):
+                    raise NotImplementedError(f"LoraConfig.{attr}={getattr(cfg, attr)!r}: the fused path implements plain LoRA (dropout 0, no bias)")
+            if getattr(cfg, "rank_pattern", None) or getattr(cfg, "alpha_pattern", None):
+                raise NotImplementedError("per-module rank / alpha patterns are not supported by the fused path")
+        r, lora_alpha = int(cfg.r), float(cfg.lora_alpha)
+        target_modules = cfg.target_modules
+        if isinstance(target_modules, (set, tuple)):
+            target_modules = list(target_modules)
+        init_lora_weights = cfg.init_lora_weights
+        if init_lora_weights not in (True, "gaussian") and not (isinstance(init_lora_weights, str) and init_lora_weights.lower() == "gaussian"):
+            raise NotImplementedError(f"init_lora_weights={init_lora_weights!r} (supported: True = kaiming-uniform A, 'gaussian')")
+        init_lora_weights = "gaussian" if init_lora_weights is not True else True
+        self.adapter_name = adapter_name
+        self.peft_config = {adapter_name: cfg}
+        self._hf_peft_config_loaded = True
         if r not in (4, 8, 16, 32, 64):
             raise NotImplementedError(f"LoRA rank {r}: the fused kernels take r in (4, 8, 16, 32, 64)")
         if self._lora_params:
@@ -181,8 +261,7 @@ class FusedMMDiTBase(nn.Module):
             gA_off, gB_off = off, off + r * d_in
             off = gB_off + d_out * r
             site.members[slot] = (full, pA, pB, gA_off, gB_off, d_in, d_out)
-            self._lora_params[full + ".lora_A.default.weight"] = pA
-            self._lora_params[full + ".lora_B.default.weight"] = pB
+            self._register_lora(full, pA, pB)
         # AdaLN modulation linears (M = batch rows only): factors stacked per kind so that forward and backward are a handful of
         # batched [B, .] products; gradients come from per-sample column reductions in the block backward (qfx_mod_grad)
         self._extra_members = []
@@ -207,14 +286,64 @@ class FusedMMDiTBase(nn.Module):
             for i, full in enumerate(names):
                 pA, pB = nn.Parameter(A_all[i]), nn.Parameter(B_all[i])
                 self._extra_members.append((full, pA, pB, ga0 + i * r * D, gb0 + i * C * r, D, C))
-                self._lora_params[full + ".lora_A.default.weight"] = pA
-                self._lora_params[full + ".lora_B.default.weight"] = pB
+                self._register_lora(full, pA, pB)
         self.G32 = torch.zeros(off, device=self.dev, dtype=torch.float32)
         self.G16 = torch.zeros(off, device=self.dev, dtype=BF)
         self._gnorm_sq = torch.zeros(1, device=self.dev, dtype=torch.float32)
         self._gscratch = torch.zeros(5 * self.D * PAD, device=self.dev, dtype=torch.float32)
         self._ws = self._ws_key = None  # per-block saved tensors depend on which sites exist
         return self
+
+    def _register_lora(self, full: str, pA: nn.Parameter, pB: nn.Parameter):
+        """Publish the factors of module `full` under PEFT's names — in the flat name table AND as a real child-module path
+        `<full>.lora_A.<adapter>` / `<full>.lora_B.<adapter>` so that module scans see them: `get_lora_layers(dit)` (what
+        `accelerator_prepare` wraps / lists as FSDP `ignored_modules`, utils/lora_utils.py:25-38, base_trainer.py:340-342,383-387)."""
+        a = self.adapter_name
+        self._lora_params[f"{full}.lora_A.{a}.weight"] = pA
+        self._lora_params[f"{full}.lora_B.{a}.weight"] = pB
+        node = self
+        for part in full.split("."):
+            if part not in node._modules:
+                node.add_module(part, nn.Module())
+            node = node._modules[part]
+        for which, p in (("lora_A", pA), ("lora_B", pB)):
+            md = nn.ModuleDict()
+            leaf = nn.Module()
+            leaf.weight = p
+            md[a] = leaf
+            node.add_module(which, md)
+
+    def set_adapter(self, adapter_name):
+        """`transformer.set_adapter(adapter_name)` (base_trainer.py:941): one adapter is attached at a time."""
+        names = [adapter_name] if isinstance(adapter_name, str) else list(adapter_name)
+        if not self._lora_params or names != [self.adapter_name]:
+            raise lib.QfxError(f"set_adapter({adapter_name!r}): attached adapter is {getattr(self, 'adapter_name', None)!r}")
+
+    def active_adapters(self):
+        return [self.adapter_name] if self._lora_params else []
+
+    def load_lora_adapter(self, pretrained_model_name_or_path_or_dict, prefix="transformer", adapter_name="default", **kwargs):
+        """`transformer.load_lora_adapter(path, adapter_name=...)` (base_trainer.py:983): a diffusers-format LoRA file
+        (`pytorch_lora_weights.safetensors`, keys `transformer.<module>.lora_A.weight`, what `save_lora` writes).  The rank is read from
+        the tensors, alpha = rank (the format carries no alpha), targets = the modules present."""
+        sd = pretrained_model_name_or_path_or_dict
+        if not isinstance(sd, dict):
+            import os
+            import safetensors.torch
+            path = sd if not os.path.isdir(sd) else os.path.join(sd, "pytorch_lora_weights.safetensors")
+            sd = safetensors.torch.load_file(path)
+        if prefix and any(k.startswith(prefix + ".") for k in sd):
+            sd = {k[len(prefix) + 1:]: v for k, v in sd.items() if k.startswith(prefix + ".")}
+        mods = sorted({k.rsplit(".lora_", 1)[0] for k in sd if ".lora_" in k})
+        ranks = {v.shape[0] for k, v in sd.items() if ".lora_A" in k}
+        if not mods or len(ranks) != 1:
+            raise lib.QfxError(f"load_lora_adapter: expected LoRA tensors of one rank, found ranks {sorted(ranks)} in {len(sd)} tensors")
+        r = ranks.pop()
+        self.add_adapter(_LoraConfigLike(r=r, lora_alpha=r, target_modules="(" + "|".join(re.escape(m) for m in mods) + ")",
+                                         init_lora_weights=True), adapter_name=adapter_name)
+        missing, unexpected = self.load_state_dict(sd, strict=False)
+        if unexpected or any("lora" in m for m in missing):
+            raise lib.QfxError(f"load_lora_adapter: unexpected {unexpected[:3]}, missing {[m for m in missing if 'lora' in m][:3]}")
 
     def _unique_sites(self):
         seen = set()
@@ -241,8 +370,8 @@ class FusedMMDiTBase(nn.Module):
         flat = self.G32 if flat is None else flat
         out, r = {}, self.lora_rank
         for full, pA, pB, ga, gb, d_in, d_out in self._all_members():
-            out[full + ".lora_A.default.weight"] = flat[ga: ga + r * d_in].view(r, d_in)
-            out[full + ".lora_B.default.weight"] = flat[gb: gb + d_out * r].view(d_out, r)
+            out[f"{full}.lora_A.{self.adapter_name}.weight"] = flat[ga: ga + r * d_in].view(r, d_in)
+            out[f"{full}.lora_B.{self.adapter_name}.weight"] = flat[gb: gb + d_out * r].view(d_out, r)
         return out
 
     # ------------------------------------------------------------------------------------------------ AdaLN-linear LoRA

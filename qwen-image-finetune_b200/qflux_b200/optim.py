@@ -24,6 +24,7 @@ class FusedLoraAdamW(torch.optim.Optimizer):
         super().__init__(list(model.parameters()), dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self.model = model
         self.max_grad_norm = max_grad_norm
+        self.grad_divisor = 1  # how many per-rank / per-micro-step gradients were SUMMED into model.G32 (set by _sync_and_step)
         self.step_count = 0
         n = model.G32.numel()
         self.exp_avg = torch.zeros(n, device=model.dev, dtype=torch.float32)
@@ -35,13 +36,21 @@ class FusedLoraAdamW(torch.optim.Optimizer):
         self._tables = lib.adamw_tables(members, model.dev)
 
     @torch.no_grad()
-    def step(self, world_size: int = 1, closure=None):
-        """grad = model.G32 (sum over ranks) / world_size, clipped to max_grad_norm; returns the device tensor ||grad||^2."""
+    def step(self, closure=None, *, grad_divisor=None):
+        """torch.optim contract: the first positional argument is `closure` (accelerate's AcceleratedOptimizer calls `step(closure)`).
+        grad = model.G32 / divisor, clipped to max_grad_norm, where the divisor (ranks x accumulated micro-steps, i.e. the SUM in G32 ->
+        the mean) is `grad_divisor` if given, else what `_sync_and_step` stored in `self.grad_divisor` after the all-reduce, else 1.
+        Returns the closure's loss (None without one); ||grad||^2 stays on the device in `self.grad_norm_sq`."""
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        div = grad_divisor if grad_divisor is not None else self.grad_divisor
         g = self.param_groups[0]
         self.step_count += 1
-        lib.fused_adamw(self._tables, self.model.G32, self.exp_avg, self.exp_avg_sq, self.grad_norm_sq, 1.0 / world_size,
+        lib.fused_adamw(self._tables, self.model.G32, self.exp_avg, self.exp_avg_sq, self.grad_norm_sq, 1.0 / float(div),
                         self.max_grad_norm, g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.step_count)
-        return self.grad_norm_sq
+        return loss
 
     def zero_grad(self, set_to_none: bool = True):
         self.model.G32.zero_()

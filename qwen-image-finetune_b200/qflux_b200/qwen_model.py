@@ -52,6 +52,29 @@ _BLOCK_LINEARS = {
 }
 
 
+class _QwenPosEmbed:
+    """`dit.pos_embed(img_shapes, txt_seq_lens, device=)` as the reference's trainer calls it for per-sample tables
+    (/root/reference/src/qflux/trainer/qwen_image_edit_trainer.py:734; QwenEmbedRope.forward, transformer_qwenimage.py:197-235):
+    returns (vid_freqs [sum f*h*w, 64], txt_freqs [max(txt_seq_lens), 64]) as complex64, from the same table the kernels use."""
+
+    def __init__(self, axes_dim, theta=10000):
+        self.axes_dim, self.theta = tuple(axes_dim), theta
+
+    def __call__(self, video_fhw, txt_seq_lens, device=None):
+        if isinstance(video_fhw, list) and video_fhw and isinstance(video_fhw[0], (list,)):
+            video_fhw = video_fhw[0]  # only the first sample's shapes are used in shared mode (:206-207)
+        if not isinstance(video_fhw, list):
+            video_fhw = [video_fhw]
+        T = int(max(txt_seq_lens)) if isinstance(txt_seq_lens, (list, tuple)) else int(txt_seq_lens)
+        tab = qwen_rope_table([tuple(s) for s in video_fhw], T, self.axes_dim, float(self.theta))
+        cis = torch.complex(tab[..., 0], tab[..., 1])
+        if device is not None:
+            cis = cis.to(device)
+        return cis[T:], cis[:T]
+
+    forward = __call__
+
+
 class QwenImageB200(FusedMMDiTBase):
     round_mid = True
 
@@ -62,6 +85,7 @@ class QwenImageB200(FusedMMDiTBase):
         self._init_common(device, _host_only)
         assert cfg.attention_head_dim == 128, "the sm_100a attention kernels are specialised for head_dim 128"
         self.config = cfg
+        self.pos_embed = _QwenPosEmbed(cfg.axes_dims_rope)
         D = cfg.num_attention_heads * cfg.attention_head_dim
         self.D, self.H, self.L, self.J = D, cfg.num_attention_heads, cfg.num_layers, cfg.joint_attention_dim
         self.C_in, self.C_out = cfg.in_channels, cfg.patch_size ** 2 * cfg.out_channels

@@ -35,6 +35,14 @@ def flow_match_sigmas(num_inference_steps: int, image_seq_len: int, *, base_seq_
     return torch.cat([s, torch.zeros(1, dtype=torch.float64)]).float()
 
 
+def _euler_step(lat, v, sig, i):
+    """FlowMatchEulerDiscreteScheduler.step: sample.float() + (sigma_next - sigma) * model_output, cast to the model-output dtype.  The
+    step size is a 0-dim fp32 tensor, so its product with the bf16 model output is ROUNDED TO bf16 before the fp32 add (torch type
+    promotion) — reproduced here so the trajectories match the reference's scheduler bit for bit."""
+    dt = sig[i + 1] - sig[i]
+    return (lat.float() + dt * v).to(v.dtype)
+
+
 def _model_sigma(sigma: float, B: int, device) -> torch.Tensor:
     """What the trainers hand to `dit(timestep=...)`: t = sigma*1000 cast to the weight dtype, then `/ 1000` in that dtype."""
     t = torch.full((B,), sigma * 1000.0, device=device).to(BF)
@@ -67,7 +75,7 @@ def sample_qwen(dit, embeddings: dict, *, scheduler_kwargs: dict | None = None) 
                      txt_seq_lens=None)[0][:, :L]
             comb = vn + cfg * (v - vn)
             v = comb * (torch.norm(v, dim=-1, keepdim=True) / torch.norm(comb, dim=-1, keepdim=True))
-        lat = (lat.float() + (float(sig[i + 1]) - float(sig[i])) * v.float()).to(v.dtype)  # scheduler.step: fp32 update, model dtype out
+        lat = _euler_step(lat, v, sig, i)
     return lat
 
 
@@ -96,5 +104,5 @@ def sample_flux(dit, embeddings: dict, *, scheduler_kwargs: dict | None = None) 
                      encoder_hidden_states=embeddings["negative_prompt_embeds"].to(dev, BF),
                      txt_ids=embeddings["negative_text_ids"].to(dev), img_ids=ids)[0][:, :L]
             v = vn + cfg * (v - vn)
-        lat = (lat.float() + (float(sig[i + 1]) - float(sig[i])) * v.float()).to(v.dtype)
+        lat = _euler_step(lat, v, sig, i)
     return lat

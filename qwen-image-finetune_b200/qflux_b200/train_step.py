@@ -71,9 +71,11 @@ def _sync_and_step(dit, optimizer, max_grad_norm, micro_steps: int = 1):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         world = dist.get_world_size()
         dist.all_reduce(dit.G32)
-    if isinstance(optimizer, FusedLoraAdamW):
-        optimizer.max_grad_norm = max_grad_norm
-        optimizer.step(world * micro_steps)  # divisor of the summed gradient
+    inner = getattr(optimizer, "optimizer", optimizer)  # accelerate hands the trainer an AcceleratedOptimizer wrapper (.optimizer)
+    if isinstance(inner, FusedLoraAdamW):
+        inner.max_grad_norm = max_grad_norm
+        inner.grad_divisor = world * micro_steps  # G32 holds the SUM over ranks and micro-steps
+        optimizer.step()                          # through the wrapper when there is one (step(closure=None) contract)
         return
     dit.finalize_grads(world * micro_steps, max_grad_norm)
     if optimizer is not None:
@@ -140,8 +142,10 @@ class QwenImageEditStep(_Accumulation):
         ctrl = embeddings["control_latents"].to(dev, BF, non_blocking=True).contiguous()
         pe = embeddings["prompt_embeds"].to(dev, BF, non_blocking=True).contiguous()
         B, L, C = x0.shape
-        if noise is None:
-            noise = torch.randn(x0.shape, device=dev, dtype=BF)
+        if noise is None:  # like the FLUX trainer (flux_kontext_trainer.py:515-522) the batch may carry its own noise / draw
+            noise = embeddings["noise"] if "noise" in embeddings else torch.randn(x0.shape, device=dev, dtype=BF)
+        if u is None and "u" in embeddings:
+            u = embeddings["u"]
         sigma = self._sigmas(B, u).to(dev, non_blocking=True)
         edit_mask = embeddings.get("edit_mask")
         shapes = embeddings["img_shapes"]

@@ -51,7 +51,14 @@ def test_loader_pads_like_the_reference_collate(tmp_path):
     # data-parallel sharding is disjoint and complete; shuffling is per-epoch deterministic
     r0 = CachedEmbeddingLoader(str(tmp_path), 1, device="cpu", shuffle=False, drop_last=False, rank=0, world_size=2)
     r1 = CachedEmbeddingLoader(str(tmp_path), 1, device="cpu", shuffle=False, drop_last=False, rank=1, world_size=2)
-    assert len(r0.samples) == 3 and len(r1.samples) == 2 and not set(r0.samples) & set(r1.samples)
+    # ... and EVEN: every rank yields the same number of batches (a rank with one batch more would hang in the gradient all-reduce);
+    # without drop_last the global list wraps around (like accelerate's even_batches), with it the remainder is cut
+    assert len(r0) == len(r1) == 3 and set(r0.samples) | set(r1.samples) == set(ld.samples) and len(set(r0.samples) & set(r1.samples)) == 1
+    d0 = CachedEmbeddingLoader(str(tmp_path), 1, device="cpu", shuffle=False, drop_last=True, rank=0, world_size=2)
+    d1 = CachedEmbeddingLoader(str(tmp_path), 1, device="cpu", shuffle=False, drop_last=True, rank=1, world_size=2)
+    assert len(d0) == len(d1) == 2 and not set(d0.samples) & set(d1.samples)
+    lens = {len(CachedEmbeddingLoader(str(tmp_path), 1, device="cpu", drop_last=dl, rank=r, world_size=4)) for r in range(4) for dl in (True,)}
+    assert lens == {1}
     s = CachedEmbeddingLoader(str(tmp_path), 1, device="cpu", shuffle=True, drop_last=False, seed=3)
     e0 = [b["prompt_embeds"].shape[1] for b in s]
     e1 = [b["prompt_embeds"].shape[1] for b in s]

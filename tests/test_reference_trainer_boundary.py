@@ -1,0 +1,287 @@
+"""Row (b) of SURVEY.md §8 — the drop-in boundary — exercised with the REFERENCE'S OWN trainer code (build container only: needs
+/root/reference; `diffusers` / `peft` / `accelerate` come from tests/shims).  The fused model runs on CPU with emulated kernels
+(tests/emu_lib.py): what is under test is the interface, not the arithmetic.
+
+Driven reference code: `BaseTrainer.add_lora_adapter`, `.load_pretrain_lora_model`, `.save_lora`, `.clip_gradients`, `.forward_loss`,
+`QwenImageEditTrainer._compute_loss`, `utils.lora_utils.get_lora_layers / classify_lora_weight`, `QwenEmbedRope`,
+the loop body of `train_epoch` (base_trainer.py:518-533)."""
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/src/qflux"), reason="needs /root/reference (build container)")
+
+sys.path.insert(0, os.path.join(HERE, "golden"))
+sys.path.insert(0, os.path.join(HERE, "shims"))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    import stub_importer
+    stub_importer.install()
+    if "/root/reference/src" not in sys.path:
+        sys.path.insert(0, "/root/reference/src")
+    import make_ref_model_golden as mg
+    return mg
+
+
+@pytest.fixture()
+def emu():
+    import emu_lib
+    from qflux_b200 import lib
+    restore = emu_lib.install(lib)
+    yield
+    restore()
+
+
+def _cfg(r=4, alpha=8, targets=("to_q", "to_k", "to_v", "to_out.0"), pretrained=None):
+    lora = types.SimpleNamespace(r=r, lora_alpha=alpha, init_lora_weights="gaussian", target_modules=list(targets), pretrained_weight=pretrained)
+    return types.SimpleNamespace(model=types.SimpleNamespace(lora=lora), train=types.SimpleNamespace(max_grad_norm=0.5, gradient_accumulation_steps=1))
+
+
+def _fused(host_only=True):
+    import ref_common as rc
+    from qflux_b200.qwen_model import QwenB200Config, QwenImageB200
+    c = rc.QWEN_HD128
+    return QwenImageB200(QwenB200Config(num_layers=c["num_layers"], num_attention_heads=c["num_attention_heads"],
+                                        joint_attention_dim=c["joint_attention_dim"]), device="cpu", _host_only=host_only)
+
+
+def test_reference_add_lora_adapter_and_module_scan(ref, emu):
+    """base_trainer.py:929-941 on the fused model: LoraConfig object + adapter_name; get_lora_layers (lora_utils.py:25-38) finds child
+    modules whose parameters are exactly the trainable LoRA parameters (what accelerator_prepare wraps / FSDP ignores)."""
+    from qflux.trainer.base_trainer import BaseTrainer
+    from qflux.utils.lora_utils import get_lora_layers
+    m = _fused()
+    BaseTrainer.add_lora_adapter(m, _cfg(), "lora_edit")
+    names = [n for n, _ in m.named_parameters()]
+    assert len(names) == 2 * 4 * 2 and all(".lora_A.lora_edit.weight" in n or ".lora_B.lora_edit.weight" in n for n in names)
+    assert all(p.requires_grad for p in m.parameters()) and all("lora" in n for n in names)  # qwen_image_edit_trainer.py:314-318
+    assert set(m.peft_config) == {"lora_edit"} and m.peft_config["lora_edit"].r == 4
+    layers = get_lora_layers(m)
+    assert layers and all(isinstance(v, torch.nn.Module) for v in layers.values())
+    found = {id(p) for v in layers.values() for p in v.parameters()}
+    assert found == {id(p) for p in m.parameters()}
+    with pytest.raises(Exception):
+        m.set_adapter("other")
+    m.set_adapter("lora_edit")
+    assert m.to("cpu") is m and m.to(torch.bfloat16) is m  # no-op moves are accepted (base_trainer.py:388) ...
+    with pytest.raises(Exception):
+        m.to(torch.float32)                                  # ... re-typing the fused HBM layout is refused loudly
+
+
+def test_pos_embed_matches_reference_rope(ref):
+    """`dit.pos_embed([shapes], [T], device)` (qwen_image_edit_trainer.py:734) vs the reference's QwenEmbedRope (scale_rope=True)."""
+    from qflux.models.transformer_qwenimage import QwenEmbedRope
+    m = _fused()
+    r = QwenEmbedRope(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+    for shapes, T in (([(1, 4, 4), (1, 4, 4)], 7), ([(1, 4, 6), (1, 4, 6), (1, 2, 8)], 11)):
+        a_v, a_t = m.pos_embed([shapes], [T], device=torch.device("cpu"))
+        b_v, b_t = r([shapes], [T], device=torch.device("cpu"))
+        assert a_v.shape == b_v.shape and a_t.shape == b_t.shape
+        assert (a_v - b_v).abs().max() < 2e-5 and (a_t - b_t).abs().max() < 2e-5
+
+
+def test_patch_trainer_runs_the_reference_loop_body(ref, emu):
+    """patch_trainer on a reference trainer object: the reference's own loop body (training_step -> accelerator.backward -> clip_gradients
+    -> optimizer.step -> zero_grad) runs unmodified on the fused model and tracks the un-patched reference run."""
+    import ref_common as rc
+    from accelerate import Accelerator
+    from qflux.losses import MseLoss
+    from qflux.trainer.qwen_image_edit_trainer import QwenImageEditTrainer
+    import qflux.trainer.qwen_image_edit_trainer as qt
+    from qflux_b200 import patch_trainer
+    from qflux_b200.mmdit_base import FusedMMDiTBase
+    spec = rc.CASES["qwen_hd128"]
+    x = rc.rand_inputs(spec)
+    emb = {k: v for k, v in x.items() if k != "u"}
+    orig = qt.compute_density_for_timestep_sampling
+    qt.compute_density_for_timestep_sampling = lambda **kw: x["u"].clone()
+    try:
+        results = {}
+        for which in ("reference", "b200"):
+            dit, _ = ref.build_reference(spec)
+            tr = ref._trainer(QwenImageEditTrainer, dit, MseLoss(reduction="mean"))
+            tr.config = _cfg()
+            tr.adapter_name = "default"
+            if which == "b200":
+                patch_trainer(tr, _host_only=True)
+                assert isinstance(tr.dit, FusedMMDiTBase) and tr.dit.peft_config["default"].r == 4
+            tr.optimizer = torch.optim.AdamW([p for p in tr.dit.parameters() if p.requires_grad], lr=1e-2, weight_decay=0.0)
+            losses = []
+            for it in range(3):  # base_trainer.py:518-533
+                with tr.accelerator.accumulate(tr.dit):
+                    torch.manual_seed(100 + it)
+                    e = dict(emb)
+                    if which == "b200":  # the reference draws randn_like(image_latents) in fp32 on the CPU: hand the fused step the same draw
+                        e["noise"] = torch.randn_like(emb["image_latents"])
+                        e["u"] = x["u"]
+                    loss = tr._compute_loss(e)
+                    tr.accelerator.backward(loss)
+                    tr.clip_gradients()
+                    tr.optimizer.step()
+                    tr.optimizer.zero_grad()
+                losses.append(float(loss))
+            results[which] = (losses, {n: p.detach().float().clone() for n, p in tr.dit.named_parameters() if p.requires_grad}, tr)
+    finally:
+        qt.compute_density_for_timestep_sampling = orig
+    (l_r, p_r, _), (l_b, p_b, tr_b) = results["reference"], results["b200"]
+    assert all(abs(a - b) < 2e-2 for a, b in zip(l_r, l_b)), (l_r, l_b)
+    assert l_b[-1] < l_b[0]  # the optimizer actually moved the LoRA parameters in the right direction
+    assert set(p_r) == set(p_b)
+    num = sum(((p_b[n] - p_r[n]) ** 2).sum() for n in p_r)
+    den = sum((p_r[n] ** 2).sum() for n in p_r)
+    assert float((num / den).sqrt()) < 2e-2  # bf16 parameters vs the fp32 reference run after three AdamW steps
+
+
+def test_save_lora_roundtrip_through_reference_code(ref, emu, tmp_path):
+    """save_lora (base_trainer.py:858-875: unwrap -> get_peft_model_state_dict -> convert_state_dict_to_diffusers ->
+    pipeline.save_lora_weights -> safetensors) on the fused model; the file loads back into the fused model AND into the reference model
+    (`load_lora_adapter`, :983), and `load_pretrain_lora_model` (:943-1002) resumes from it."""
+    import ref_common as rc
+    import safetensors.torch
+    from accelerate import Accelerator
+    from diffusers import FluxKontextPipeline
+    from qflux.models.transformer_qwenimage import QwenImageTransformer2DModel
+    from qflux.trainer.base_trainer import BaseTrainer
+    from qflux.trainer.qwen_image_edit_trainer import QwenImageEditTrainer
+    from qflux.utils.lora_utils import classify_lora_weight
+    m = _fused()
+    BaseTrainer.add_lora_adapter(m, _cfg(), "default")
+    rc.det_fill_(type("B", (), {"named_parameters": lambda s: iter(m._lora_params.items())})(), 5)
+    tr = object.__new__(QwenImageEditTrainer)
+    tr.accelerator, tr.dit, tr.adapter_name, tr.pipeline_class = Accelerator(), m, "default", FluxKontextPipeline
+    folder = str(tmp_path / "ckpt")
+    tr.save_lora(folder)
+    path = os.path.join(folder, "pytorch_lora_weights.safetensors")
+    sd = safetensors.torch.load_file(path)
+    assert len(sd) == 16 and all(k.startswith("transformer.") and (k.endswith(".lora_A.weight") or k.endswith(".lora_B.weight")) for k in sd)
+    assert classify_lora_weight(path) == "PEFT"
+    want = {n: p.detach().clone() for n, p in m.named_parameters()}
+    # (1) into a fresh fused model through the diffusers entry point
+    m2 = _fused()
+    m2.load_lora_adapter(path, adapter_name="default")
+    assert m2.lora_rank == 4 and all(torch.equal(p, want[n]) for n, p in m2.named_parameters())
+    # (2) into the reference model through ITS load_lora_adapter
+    refm = QwenImageTransformer2DModel(**rc.QWEN_HD128)
+    refm.load_lora_adapter(path, adapter_name="default")
+    got = {n: p for n, p in refm.named_parameters() if "lora_" in n}
+    assert set(got) == set(want) and all(torch.equal(got[n].to(torch.bfloat16), want[n]) for n in want)
+    # (3) the trainer's resume path: classify -> add_lora_adapter -> load_state_dict(strict=False) -> no unexpected keys
+    m3 = _fused()
+    BaseTrainer.load_pretrain_lora_model(m3, _cfg(pretrained=path), "default")
+    assert all(torch.equal(p, want[n]) for n, p in m3.named_parameters())
+    # state_dict() hands out compact tensors (safetensors refuses views), torch.save stays small
+    assert all(v.is_contiguous() for v in m.state_dict().values() if v.ndim == 2 and v.shape[1] == 4)
+
+
+def test_fused_adamw_honours_the_optimizer_contract(emu):
+    """`step(closure=None)` positional contract, AcceleratedOptimizer-style wrappers (`.optimizer`), mean over ranks x micro-steps."""
+    import ref_common as rc
+    from qflux_b200.optim import FusedLoraAdamW
+    from qflux_b200.train_step import QwenImageEditStep, _sync_and_step
+    sys.path.insert(0, HERE)
+    from test_reference_goldens import _b200_model
+    m, _ = _b200_model(rc.CASES["qwen_hd128"], "cpu", True)  # name-derived non-zero weights (an all-zero model has zero LoRA gradients)
+    opt = FusedLoraAdamW(m, lr=1e-2)
+
+    class Wrapped:  # accelerate.optimizer.AcceleratedOptimizer: forwards step(closure) to .optimizer
+        def __init__(self, o):
+            self.optimizer = o
+
+        def step(self, closure=None):
+            return self.optimizer.step(closure)
+    x = rc.rand_inputs(rc.CASES["qwen_hd128"])
+    emb = {k: x[k] for k in ("image_latents", "control_latents", "prompt_embeds", "img_shapes")}
+    step = QwenImageEditStep(m, "mse", max_grad_norm=1.0)
+    before = [p.detach().clone() for p in m.parameters()]
+    step.train_step(emb, Wrapped(opt), noise=torch.randn(2, 16, 64).bfloat16(), u=x["u"])
+    assert opt.step_count == 1 and any(not torch.equal(a, b) for a, b in zip(before, m.parameters()))
+    assert opt.step(None) is None and opt.step_count == 2          # positional closure slot accepts None
+    assert opt.step(lambda: torch.tensor(3.0)).item() == 3.0        # and a real closure
+    # the divisor set by the sync (world x micro-steps) is what a later plain step() uses: a summed gradient is never applied as-is
+    m.G32.fill_(2.0)
+    _sync_and_step(m, opt, 0.0, micro_steps=4)
+    assert opt.grad_divisor == 4 and abs(float(opt.grad_norm_sq.sqrt()) - 0.5 * m.G32.numel() ** 0.5) < 1e-2 * m.G32.numel() ** 0.5
+
+
+def test_patch_trainer_flux_shared_and_multires(ref, emu):
+    """patch_trainer on the FLUX-Kontext trainer: the reference's `embeddings` dict (pixel `image`, pixel-space `img_shapes`, `control_ids`)
+    goes through the fused step unchanged, in shared mode (flux_kontext_trainer.py:494-577) and in multi-resolution mode (:579-796)."""
+    import ref_common as rc
+    from qflux.losses import AttentionMaskMseLoss, MseLoss
+    from qflux.trainer.flux_kontext_trainer import FluxKontextLoraTrainer
+    from qflux_b200 import patch_trainer
+    for case, crit in (("flux_hd128", MseLoss(reduction="mean")), ("flux_custom_multires", AttentionMaskMseLoss(reduction="mean"))):
+        spec = rc.CASES[case]
+        x = rc.rand_inputs(spec)
+        emb = {k: v for k, v in x.items() if k not in ("img_shapes_latent", "hw")}
+        if spec["kind"] == "flux":
+            h_, w_ = x["hw"]
+            emb["control_ids"] = FluxKontextLoraTrainer._prepare_latent_image_ids(1, h_, w_, torch.device("cpu"), torch.float32)
+            emb["control_ids"][..., 0] = 1
+            emb["img_shapes"] = [[(3, h_ * 16, w_ * 16), (3, h_ * 16, w_ * 16)]] * spec["B"]
+        else:
+            emb["timestep"] = x["timestep"].view(-1, 1)
+        out = {}
+        for which in ("reference", "b200"):
+            dit, _ = ref.build_reference(spec)
+            tr = ref._trainer(FluxKontextLoraTrainer, dit, crit)
+            tr.config = _cfg()
+            e = dict(emb)
+            if which == "b200":
+                patch_trainer(tr, _host_only=True)
+                if spec["kind"] == "flux_multi":  # the fused step takes one padded noise tensor and a flat timestep vector
+                    lt = [s[0][1] * s[0][2] for s in x["img_shapes_latent"]]
+                    nz = torch.zeros(len(lt), max(lt), 64)
+                    for b, n in enumerate(lt):
+                        nz[b, :n] = x["noise"][b]
+                    e["noise"], e["timestep"] = nz, x["timestep"]
+            loss = tr._compute_loss(e)
+            loss.backward()
+            out[which] = (float(loss), {n: p.grad.float().clone() for n, p in tr.dit.named_parameters() if p.requires_grad and p.grad is not None})
+        (l_r, g_r), (l_b, g_b) = out["reference"], out["b200"]
+        assert abs(l_r - l_b) < 1e-2, (case, l_r, l_b)
+        num = sum(((g_b[n] - g_r[n]) ** 2).sum() for n in g_r)
+        den = sum((g_r[n] ** 2).sum() for n in g_r)
+        assert set(g_r) <= set(g_b) and float((num / den).sqrt()) < 2e-2, case
+
+
+def test_sampler_schedule_matches_reference_prepare_predict_timesteps(ref):
+    """§8 f2: `flow_match_sigmas` vs the reference's `BaseTrainer.prepare_predict_timesteps` (base_trainer.py:1009-1043 -> calculate_shift,
+    retrieve_timesteps -> FlowMatchEulerDiscreteScheduler.set_timesteps(sigmas=, mu=)), for the Qwen-Image and the FLUX scheduler configs,
+    and the Euler update vs `scheduler.step`."""
+    import contextlib
+    import io
+    from diffusers.schedulers.scheduling_flow_match_euler_discrete import FlowMatchEulerDiscreteScheduler
+    from qflux.trainer.base_trainer import BaseTrainer
+    from qflux.utils.sampling import calculate_shift as ref_shift
+    from qflux_b200.sampler import calculate_shift, flow_match_sigmas
+    qwen = dict(num_train_timesteps=1000, shift=1.0, use_dynamic_shifting=True, base_shift=0.5, max_shift=0.9, base_image_seq_len=256,
+                max_image_seq_len=8192, shift_terminal=0.02)
+    flux = dict(num_train_timesteps=1000, shift=3.0, use_dynamic_shifting=True, base_shift=0.5, max_shift=1.15, base_image_seq_len=256,
+                max_image_seq_len=4096)
+    for conf in (qwen, flux):
+        for steps, seq in ((20, 1024), (8, 4096), (50, 400)):
+            tr = types.SimpleNamespace(sampling_scheduler=FlowMatchEulerDiscreteScheduler(**conf), scheduler=None,
+                                       dit=torch.nn.Linear(1, 1))
+            with contextlib.redirect_stdout(io.StringIO()):  # the reference prints the shift arguments
+                ts, n = BaseTrainer.prepare_predict_timesteps(tr, steps, seq)
+                assert abs(calculate_shift(seq, conf["base_image_seq_len"], conf["max_image_seq_len"], conf["base_shift"], conf["max_shift"])
+                           - ref_shift(seq, conf["base_image_seq_len"], conf["max_image_seq_len"], conf["base_shift"], conf["max_shift"])) < 1e-12
+            sig = flow_match_sigmas(steps, seq, base_seq_len=conf["base_image_seq_len"], max_seq_len=conf["max_image_seq_len"],
+                                    base_shift=conf["base_shift"], max_shift=conf["max_shift"], shift_terminal=conf.get("shift_terminal"))
+            assert n == steps and sig.numel() == steps + 1 and sig[-1] == 0
+            assert torch.allclose(sig[:-1] * 1000, ts.cpu(), rtol=2e-6, atol=1e-4), (conf, steps, seq)
+            assert torch.allclose(sig, tr.sampling_scheduler.sigmas.cpu(), rtol=2e-6, atol=1e-7)
+            # one Euler step of the loop in sampler.py == scheduler.step (fp32 update, model dtype out)
+            x, v = torch.randn(2, 8, 64).bfloat16(), torch.randn(2, 8, 64).bfloat16()
+            tr.sampling_scheduler.set_begin_index(0)
+            want = tr.sampling_scheduler.step(v, ts[0], x, return_dict=False)[0]
+            from qflux_b200.sampler import _euler_step
+            got = _euler_step(x, v, sig, 0)
+            assert torch.equal(want, got)
