@@ -368,6 +368,9 @@ namespace qfx {
 int attn_bwd_transposed(const void* Q, const void* K, const void* V, const void* dO, const float* lse, const float* delta, float* dQ,
                         void* dK, void* dV, const int* kv_len, const int* txt_len, int split, int B, int H, int S, float softmax_scale,
                         cudaStream_t stream);  // attention_bwd2.cu
+int attn_bwd_pipelined(const void* Q, const void* K, const void* V, const void* dO, const float* lse, const float* delta, float* dQ,
+                       void* dK, void* dV, const int* kv_len, const int* txt_len, int split, int B, int H, int S, float softmax_scale,
+                       cudaStream_t stream);  // attention_bwd3.cu
 }
 
 extern "C" int qfx_attn_bwd(const void* Q, const void* K, const void* V, const void* dO, const float* lse, const float* delta,
@@ -375,7 +378,13 @@ extern "C" int qfx_attn_bwd(const void* Q, const void* K, const void* V, const v
                             int S, float softmax_scale, void* stream) {
   extern long long* g_qfx_attn_bwd_dbg;
   QFX_CHECK_ARG(B > 0 && H > 0 && S > 0 && dQ_accum && dK && dV && lse && delta, "qfx_attn_bwd: bad arguments");
-  static const bool transposed = getenv("QFX_ATTN_BWD2") != nullptr;  // A/B switch: the transposed formulation (attention_bwd2.cu)
+  // default: the software-pipelined transposed kernel (attention_bwd3.cu).  A/B switches: QFX_ATTN_BWD1=1 the round-1 serial-chain
+  // kernel below, QFX_ATTN_BWD2=1 the 64-query transposed kernel (attention_bwd2.cu)
+  static const bool transposed = getenv("QFX_ATTN_BWD2") != nullptr;
+  static const bool serial = getenv("QFX_ATTN_BWD1") != nullptr;
+  if (!transposed && !serial)
+    return qfx::attn_bwd_pipelined(Q, K, V, dO, lse, delta, dQ_accum, dK, dV, kv_len, txt_len, split, B, H, S, softmax_scale,
+                                   (cudaStream_t)stream);
   if (transposed)
     return qfx::attn_bwd_transposed(Q, K, V, dO, lse, delta, dQ_accum, dK, dV, kv_len, txt_len, split, B, H, S, softmax_scale,
                                     (cudaStream_t)stream);
