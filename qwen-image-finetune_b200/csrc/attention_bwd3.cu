@@ -75,6 +75,12 @@ __device__ __forceinline__ void b3_mma_ts(uint32_t d, uint32_t a_tmem, uint32_t 
       : "memory");
 }
 
+__device__ __forceinline__ uint32_t b3_mul_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
 constexpr int B3_TILE = 128 * 128 * 2;  // 32 KB: [128 rows x 128] bf16, two 64-column swizzle atoms of 16 KB
 constexpr int B3_ATOM = 128 * 128;      // 16 KB
 constexpr int B3_RING = 2;              // L / delta ring depth (tile i -> slot i & 1)
@@ -212,6 +218,8 @@ __global__ void __launch_bounds__(B3_THREADS, 1) attn_bwd3_kernel(const __grid_c
           umma_commit_w(do_empty(i & 1));
           if (lane == 0) B3_DBG(i, 7);
         };
+        // (Measured and rejected: issuing dP_{i+1} between two halves of dK_i shortens the dS-pass dependency loop by one dK/2, but Q_i is
+        // then released one dP later and the ~1700-clk TMA latency of Q_{i+2} lands on the S_{i+2} issue: 0.757 -> 0.773 ms.)
         auto issue_dq_dk = [&](int i) {
           const uint32_t mQ = b3_lo_mnmaj(sQ(i & 1));
           mbar_wait(ds_full, i & 1);
@@ -231,8 +239,8 @@ __global__ void __launch_bounds__(B3_THREADS, 1) attn_bwd3_kernel(const __grid_c
         issue_dp(0);
         issue_dv(0);
         for (int i = 1; i < n_q; ++i) {
-          issue_s(i);
-          issue_dq_dk(i - 1);
+          issue_s(i);          // runs under the dS pass of tile i-1
+          issue_dq_dk(i - 1);  // run under the P pass of tile i
           issue_dp(i);
           issue_dv(i);
         }
@@ -341,8 +349,7 @@ __global__ void __launch_bounds__(B3_THREADS, 1) attn_bwd3_kernel(const __grid_c
         float* dst = base + (int64_t)q0 * 128;
 #pragma unroll
         for (int j = 0; j < 64; ++j)
-          if (j < nq) atomicAdd(dst + j * 128, __uint_as_float(r[j]));
-        if (warp == 12 && lane == 0) B3_DBG(i, 14);
+          if (j < nq && P.rotate != 2) atomicAdd(dst + j * 128, __uint_as_float(r[j]));
       }
     }
   } else if (warp >= 4) {
@@ -364,21 +371,22 @@ __global__ void __launch_bounds__(B3_THREADS, 1) attn_bwd3_kernel(const __grid_c
         tc_fence_after();
         if (warp == 4 && lane == 0) B3_DBG(i, 8);
         uint32_t pk[32];
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t rs[32];
-          tmem_ld32(tS + lane_off + half * 64 + cc * 32, rs);
+        {
+          // both 32-column loads are in flight before the first exponential (one exposed tensor-memory latency per pass instead of two)
+          uint32_t rs[64];
+          tmem_ld32(tS + lane_off + half * 64, rs);
+          tmem_ld32(tS + lane_off + half * 64 + 32, rs + 32);
           tmem_ld_wait();
+          if (warp == 4 && lane == 0) B3_DBG(i, 14);
 #pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            const float4 l = L4[cc * 8 + v];
-            float p0 = exp2f(__uint_as_float(rs[4 * v]) * P.scale_log2 - l.x);  // L = +inf for queries past S -> 0
-            float p1 = exp2f(__uint_as_float(rs[4 * v + 1]) * P.scale_log2 - l.y);
-            float p2 = exp2f(__uint_as_float(rs[4 * v + 2]) * P.scale_log2 - l.z);
-            float p3 = exp2f(__uint_as_float(rs[4 * v + 3]) * P.scale_log2 - l.w);
-            if (!key_ok) p0 = p1 = p2 = p3 = 0.f;
-            pk[cc * 16 + 2 * v] = pack_bf16(p0, p1);
-            pk[cc * 16 + 2 * v + 1] = pack_bf16(p2, p3);
+          for (int v = 0; v < 16; ++v) {
+            const float4 l = L4[v];  // L = +inf for queries past S -> P = 0
+            pk[2 * v] = pack_bf16(exp2f(__uint_as_float(rs[4 * v]) * P.scale_log2 - l.x), exp2f(__uint_as_float(rs[4 * v + 1]) * P.scale_log2 - l.y));
+            pk[2 * v + 1] = pack_bf16(exp2f(__uint_as_float(rs[4 * v + 2]) * P.scale_log2 - l.z), exp2f(__uint_as_float(rs[4 * v + 3]) * P.scale_log2 - l.w));
+          }
+          if (!key_ok) {  // masked key ROW (last key tile / text padding only): no per-element select in the common path
+#pragma unroll
+            for (int e = 0; e < 32; ++e) pk[e] = 0u;
           }
         }
         // the packed P^T columns of column-half 1 ([32, 64)) lie over S^T columns that column-half 0 reads: both warps of the pair
@@ -402,15 +410,16 @@ __global__ void __launch_bounds__(B3_THREADS, 1) attn_bwd3_kernel(const __grid_c
           uint32_t rp[32];
           tmem_ld32(tdP + lane_off + half * 64 + cc * 32, rp);
           tmem_ld_wait();
+          if (cc == 0 && warp == 4 && lane == 0) B3_DBG(i, 15);
           uint32_t ds[16];
 #pragma unroll
           for (int v = 0; v < 8; ++v) {
             const float4 d = D4[cc * 8 + v];
             const uint32_t pa = pk[cc * 16 + 2 * v], pb = pk[cc * 16 + 2 * v + 1];
-            ds[2 * v] = pack_bf16(bf16_lo(pa) * (__uint_as_float(rp[4 * v]) * P.scale - d.x),
-                                  bf16_hi(pa) * (__uint_as_float(rp[4 * v + 1]) * P.scale - d.y));
-            ds[2 * v + 1] = pack_bf16(bf16_lo(pb) * (__uint_as_float(rp[4 * v + 2]) * P.scale - d.z),
-                                      bf16_hi(pb) * (__uint_as_float(rp[4 * v + 3]) * P.scale - d.w));
+            // dS = P o (dP c - delta c): the bracket in fp32, rounded to bf16 and multiplied by the bf16 P as a packed pair (one HMUL2 for
+            // two elements instead of unpack + 2 FMUL + pack; dS is stored in bf16 either way)
+            ds[2 * v] = b3_mul_bf16x2(pa, pack_bf16(__uint_as_float(rp[4 * v]) * P.scale - d.x, __uint_as_float(rp[4 * v + 1]) * P.scale - d.y));
+            ds[2 * v + 1] = b3_mul_bf16x2(pb, pack_bf16(__uint_as_float(rp[4 * v + 2]) * P.scale - d.z, __uint_as_float(rp[4 * v + 3]) * P.scale - d.w));
           }
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
@@ -488,6 +497,7 @@ int attn_bwd_pipelined(const void* Q, const void* K, const void* V, const void* 
   P.dbg = g_qfx_attn_bwd_dbg;
   static const bool no_rotate = getenv("QFX_ATTN_BWD3_NO_ROTATE") != nullptr;
   P.rotate = no_rotate ? 0 : 1;
+  if (getenv("QFX_ATTN_BWD3_NO_RED")) P.rotate = 2;  // EXPERIMENT ONLY (wrong dQ): how much of the kernel time is the dQ red traffic?
   static const bool lane_issue = getenv("QFX_ATTN_BWD3_LANE_ISSUE") != nullptr;  // A/B: single-lane issue region (lane-serialising loops)
   static bool attr_done = false;
   if (!attr_done) {

@@ -39,8 +39,8 @@ lib._lib.qfx_attn_bwd_set_debug(C.c_void_p(0))
 d = dbg.view(19, 16).cpu()
 t0 = int(d[0, 0])
 names = ["mma:S s", "mma:S e", "mma:dQdK s", "mma:dQdK e", "mma:dP s", "mma:dP e", "mma:dV s", "mma:dV e", "cmp:S rdy", "cmp:P done", "cmp:dP rdy",
-         "cmp:dS done", "drn:dQ rdy", "drn:drained", "drn:reds done"]
+         "cmp:dS done", "drn:dQ rdy", "drn:drained", "cmp:S in reg", "cmp:dP in reg"]
 print("iter " + " ".join(f"{n:>12s}" for n in names))
 for i in range(19):
-    print(f"{i:4d} " + " ".join(f"{int(d[i, k]) - t0:12d}" for k in range(15)))
+    print(f"{i:4d} " + " ".join(f"{int(d[i, k]) - t0:12d}" for k in range(16)))
 print("period (mma:S s):", [int(d[i + 1, 0] - d[i, 0]) for i in range(18)])
