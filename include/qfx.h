@@ -122,6 +122,28 @@ int qfx_qk_norm_rope_fwd(const void* qkv, int64_t ldqkv, const void* wq, const v
 int qfx_qk_norm_rope_bwd(const void* dQ, const void* dK, const void* dV, const void* qkv, int64_t ldqkv, const void* wq,
                          const void* wk, const float* rope, int64_t rope_bstride, void* dqkv, int64_t lddqkv, int tokens,
                          int tokens_per_sample, int s_offset, int S, int H, float eps, int round_mid, void* stream);
+/* Stream-pair variants of the glue above: ONE launch over a stream-major activation buffer whose rows [0, split) (text stream) and
+ * [split, M) (image stream) carry different per-stream operands — modulation vectors / q-k norm weights / sample length / joint
+ * offset — exactly as the reference applies img_mod vs txt_mod, norm_q vs norm_added_q (transformer_qwenimage.py:437-448, 305-312).
+ * Arguments without suffix describe the first group, `...1` the second; split >= M degenerates to the single-group call. */
+int qfx_ln_modulate_fwd_pair(const void* x, int64_t ldx, void* y, int64_t ldy, const void* shift, const void* scale, int64_t ldmod,
+                             int rows_per_batch, float* mean, float* rstd, int M, int D, float eps, int split, const void* shift1,
+                             const void* scale1, int rows_per_batch1, void* stream);
+int qfx_ln_modulate_bwd_pair(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* mean, const float* rstd,
+                             const void* scale, int64_t ldmod, int rows_per_batch, const void* dres, int64_t lddres, void* dx,
+                             int64_t lddx, const void* gate, int64_t ldgate, void* dx_gated, int64_t lddxg, int M, int D, int split,
+                             const void* scale1, const void* gate1, int rows_per_batch1, void* stream);
+int qfx_qk_norm_rope_fwd_pair(const void* qkv, int64_t ldqkv, const void* wq, const void* wk, const float* rope,
+                              int64_t rope_bstride, void* Q, void* K, void* V, int tokens, int tokens_per_sample, int s_offset, int S,
+                              int H, float eps, int round_mid, int split, const void* wq1, const void* wk1, int tokens_per_sample1,
+                              int s_offset1, void* stream);
+int qfx_qk_norm_rope_bwd_pair(const void* dQ, const void* dK, const void* dV, const void* qkv, int64_t ldqkv, const void* wq,
+                              const void* wk, const float* rope, int64_t rope_bstride, void* dqkv, int64_t lddqkv, int tokens,
+                              int tokens_per_sample, int s_offset, int S, int H, float eps, int round_mid, int split, const void* wq1,
+                              const void* wk1, int tokens_per_sample1, int s_offset1, void* stream);
+int qfx_attn_delta_pair(const void* O, int64_t ldo, const void* dO, int64_t lddo, float* delta, void* dO_joint, int tokens,
+                        int tokens_per_sample, int s_offset, int S, int H, int split, int tokens_per_sample1, int s_offset1,
+                        void* stream);
 /* y[b,:] = act(x[b,:]) . W^T + bias, b < 8; act 0 none / 1 SiLU  (timestep MLP, img_mod/txt_mod, norm_out.linear) */
 int qfx_gemv_act(const void* x, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* y, int64_t ldy, int B, int N,
                  int K, int act, void* stream);

@@ -67,7 +67,11 @@ __global__ void __launch_bounds__(256) ln_modulate_fwd_kernel(const bf16* __rest
                                                               int64_t ldy, const bf16* __restrict__ shift,
                                                               const bf16* __restrict__ scale, int64_t ldmod,
                                                               int rows_per_batch, float* __restrict__ mean_out,
-                                                              float* __restrict__ rstd_out, int M, float eps) {
+                                                              float* __restrict__ rstd_out, int M, float eps, int split,
+                                                              const bf16* __restrict__ shift1, const bf16* __restrict__ scale1,
+                                                              int rows_per_batch1) {
+  // rows >= split form a second row group with its own modulation vectors (the image stream behind the text stream of a
+  // stream-major activation buffer): one launch serves both streams
   constexpr int T = W * 32, D = T * VPT * 8, RPC = 8 / W;
   __shared__ float red[RPC][4 * W];
   const int rl = (threadIdx.x >> 5) / W;
@@ -98,9 +102,10 @@ __global__ void __launch_bounds__(256) ln_modulate_fwd_kernel(const bf16* __rest
     mean_out[row] = mean;
     rstd_out[row] = rstd;
   }
-  const int b = row / rows_per_batch;
-  const uint4* sh = reinterpret_cast<const uint4*>(shift + (int64_t)b * ldmod);
-  const uint4* sc = reinterpret_cast<const uint4*>(scale + (int64_t)b * ldmod);
+  const bool g1 = row >= split;
+  const int b = g1 ? (row - split) / rows_per_batch1 : row / rows_per_batch;
+  const uint4* sh = reinterpret_cast<const uint4*>((g1 ? shift1 : shift) + (int64_t)b * ldmod);
+  const uint4* sc = reinterpret_cast<const uint4*>((g1 ? scale1 : scale) + (int64_t)b * ldmod);
   uint4* yr = reinterpret_cast<uint4*>(y + (int64_t)row * ldy);
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
@@ -127,13 +132,20 @@ __global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const bf16* __rest
                                                               int rows_per_batch, const bf16* __restrict__ dres,
                                                               int64_t lddres, bf16* __restrict__ dx, int64_t lddx,
                                                               const bf16* __restrict__ gate, int64_t ldgate,
-                                                              bf16* __restrict__ dx_gated, int64_t lddxg, int M) {
+                                                              bf16* __restrict__ dx_gated, int64_t lddxg, int M, int split,
+                                                              const bf16* __restrict__ scale1, const bf16* __restrict__ gate1,
+                                                              int rows_per_batch1) {
   constexpr int T = W * 32, D = T * VPT * 8, RPC = 8 / W;
   __shared__ float red[RPC][2 * W];
   const int rl = (threadIdx.x >> 5) / W;
   const int row = min(blockIdx.x * RPC + rl, M - 1);
   const int t = threadIdx.x % T;
-  const int b = row / rows_per_batch;
+  const bool g1 = row >= split;  // second row group (see ln_modulate_fwd_kernel)
+  const int b = g1 ? (row - split) / rows_per_batch1 : row / rows_per_batch;
+  if (g1) {
+    scale = scale1;
+    gate = gate1;
+  }
   const float mean = mean_in[row], rstd = rstd_in[row];
   const uint4* dyr = reinterpret_cast<const uint4*>(dy + (int64_t)row * lddy);
   const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * ldx);
@@ -304,12 +316,22 @@ __global__ void __launch_bounds__(256) qk_norm_rope_fwd_kernel(const bf16* __res
                                                                const float2* __restrict__ rope, int64_t rope_bstride,
                                                                bf16* __restrict__ Q, bf16* __restrict__ K, bf16* __restrict__ V,
                                                                int tokens, int tokens_per_sample, int s_offset, int S, int H,
-                                                               float eps) {
+                                                               float eps, int split, const bf16* __restrict__ wq1,
+                                                               const bf16* __restrict__ wk1, int tokens_per_sample1, int s_offset1) {
   const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (gw >= tokens * H) return;
   const int tok = gw / H, h = gw - tok * H;
-  const int b = tok / tokens_per_sample, s = s_offset + tok - b * tokens_per_sample;
+  int b, s;
+  if (tok >= split) {  // second token group: its own norm weights, sample length and joint-sequence offset (image stream behind text)
+    b = (tok - split) / tokens_per_sample1;
+    s = s_offset1 + (tok - split) - b * tokens_per_sample1;
+    wq = wq1;
+    wk = wk1;
+  } else {
+    b = tok / tokens_per_sample;
+    s = s_offset + tok - b * tokens_per_sample;
+  }
   const int D = H * 128;
   const bf16* base = qkv + (int64_t)tok * ldqkv + h * 128 + lane * 4;
   const int64_t dst = (((int64_t)b * H + h) * S + s) * 128 + lane * 4;
@@ -343,12 +365,22 @@ __global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(const float* __re
                                                                const bf16* __restrict__ wk, const float2* __restrict__ rope,
                                                                int64_t rope_bstride, bf16* __restrict__ dqkv, int64_t lddqkv,
                                                                int tokens, int tokens_per_sample, int s_offset, int S, int H,
-                                                               float eps) {
+                                                               float eps, int split, const bf16* __restrict__ wq1,
+                                                               const bf16* __restrict__ wk1, int tokens_per_sample1, int s_offset1) {
   const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (gw >= tokens * H) return;
   const int tok = gw / H, h = gw - tok * H;
-  const int b = tok / tokens_per_sample, s = s_offset + tok - b * tokens_per_sample;
+  int b, s;
+  if (tok >= split) {
+    b = (tok - split) / tokens_per_sample1;
+    s = s_offset1 + (tok - split) - b * tokens_per_sample1;
+    wq = wq1;
+    wk = wk1;
+  } else {
+    b = tok / tokens_per_sample;
+    s = s_offset + tok - b * tokens_per_sample;
+  }
   const int D = H * 128;
   const bf16* base = qkv + (int64_t)tok * ldqkv + h * 128 + lane * 4;
   bf16* obase = dqkv + (int64_t)tok * lddqkv + h * 128 + lane * 4;
@@ -599,12 +631,20 @@ __global__ void __launch_bounds__(128) lora_wgrad_kernel(const bf16* __restrict_
 // delta[b,h,s] = sum_d dO * O over one head (token-major [tokens, H*128] operands) — softmax-backward row term.
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ O, int64_t ldo, const bf16* __restrict__ dO,
                                                          int64_t lddo, float* __restrict__ delta, bf16* __restrict__ dOj,
-                                                         int tokens, int tokens_per_sample, int s_offset, int S, int H) {
+                                                         int tokens, int tokens_per_sample, int s_offset, int S, int H, int split,
+                                                         int tokens_per_sample1, int s_offset1) {
   const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (gw >= tokens * H) return;
   const int tok = gw / H, h = gw - tok * H;
-  const int b = tok / tokens_per_sample, s = s_offset + tok - b * tokens_per_sample;
+  int b, s;
+  if (tok >= split) {
+    b = (tok - split) / tokens_per_sample1;
+    s = s_offset1 + (tok - split) - b * tokens_per_sample1;
+  } else {
+    b = tok / tokens_per_sample;
+    s = s_offset + tok - b * tokens_per_sample;
+  }
   const uint2 a = *reinterpret_cast<const uint2*>(O + (int64_t)tok * ldo + h * 128 + lane * 4);
   const uint2 g = *reinterpret_cast<const uint2*>(dO + (int64_t)tok * lddo + h * 128 + lane * 4);
   float d = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) + bf16_hi(a.y) * bf16_hi(g.y);
@@ -665,14 +705,41 @@ static int dispatch_nv(int D, F&& f) {
   return -1;
 }
 
-extern "C" int qfx_ln_modulate_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, const void* shift, const void* scale,
-                                   int64_t ldmod, int rows_per_batch, float* mean, float* rstd, int M, int D, float eps,
-                                   void* stream) {
+extern "C" int qfx_ln_modulate_fwd_pair(const void* x, int64_t ldx, void* y, int64_t ldy, const void* shift, const void* scale,
+                                        int64_t ldmod, int rows_per_batch, float* mean, float* rstd, int M, int D, float eps,
+                                        int split, const void* shift1, const void* scale1, int rows_per_batch1, void* stream) {
   QFX_CHECK_ARG(D % 256 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldmod % 8 == 0, "qfx_ln_modulate_fwd: bad dims");
+  QFX_CHECK_ARG(split >= M || (shift1 && scale1 && rows_per_batch1 > 0), "qfx_ln_modulate_fwd_pair: second group needs shift/scale/rows_per_batch");
   return dispatch_nv(D, [&](auto w, auto vpt) {
     constexpr int W = decltype(w)::value, RPC = 8 / W;
     ln_modulate_fwd_kernel<W, decltype(vpt)::value><<<(M + RPC - 1) / RPC, 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)shift, (const bf16*)scale, ldmod, rows_per_batch, mean, rstd, M, eps);
+        (const bf16*)x, ldx, (bf16*)y, ldy, (const bf16*)shift, (const bf16*)scale, ldmod, rows_per_batch, mean, rstd, M, eps, split,
+        (const bf16*)shift1, (const bf16*)scale1, rows_per_batch1);
+    LAUNCH_OK();
+  });
+}
+
+extern "C" int qfx_ln_modulate_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, const void* shift, const void* scale,
+                                   int64_t ldmod, int rows_per_batch, float* mean, float* rstd, int M, int D, float eps,
+                                   void* stream) {
+  return qfx_ln_modulate_fwd_pair(x, ldx, y, ldy, shift, scale, ldmod, rows_per_batch, mean, rstd, M, D, eps, M, nullptr, nullptr, 1,
+                                  stream);
+}
+
+extern "C" int qfx_ln_modulate_bwd_pair(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* mean,
+                                        const float* rstd, const void* scale, int64_t ldmod, int rows_per_batch, const void* dres,
+                                        int64_t lddres, void* dx, int64_t lddx, const void* gate, int64_t ldgate, void* dx_gated,
+                                        int64_t lddxg, int M, int D, int split, const void* scale1, const void* gate1,
+                                        int rows_per_batch1, void* stream) {
+  QFX_CHECK_ARG(D % 256 == 0, "qfx_ln_modulate_bwd: bad dims");
+  QFX_CHECK_ARG(split >= M || (scale1 && rows_per_batch1 > 0 && ((gate1 != nullptr) == (gate != nullptr))),
+                "qfx_ln_modulate_bwd_pair: second group needs scale (and a gate iff the first group has one)");
+  return dispatch_nv(D, [&](auto w, auto vpt) {
+    constexpr int W = decltype(w)::value, RPC = 8 / W;
+    ln_modulate_bwd_kernel<W, decltype(vpt)::value><<<(M + RPC - 1) / RPC, 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)dy, lddy, (const bf16*)x, ldx, mean, rstd, (const bf16*)scale, ldmod, rows_per_batch, (const bf16*)dres,
+        lddres, (bf16*)dx, lddx, (const bf16*)gate, ldgate, (bf16*)dx_gated, lddxg, M, split, (const bf16*)scale1,
+        (const bf16*)gate1, rows_per_batch1);
     LAUNCH_OK();
   });
 }
@@ -681,14 +748,8 @@ extern "C" int qfx_ln_modulate_bwd(const void* dy, int64_t lddy, const void* x, 
                                    const float* rstd, const void* scale, int64_t ldmod, int rows_per_batch, const void* dres,
                                    int64_t lddres, void* dx, int64_t lddx, const void* gate, int64_t ldgate, void* dx_gated,
                                    int64_t lddxg, int M, int D, void* stream) {
-  QFX_CHECK_ARG(D % 256 == 0, "qfx_ln_modulate_bwd: bad dims");
-  return dispatch_nv(D, [&](auto w, auto vpt) {
-    constexpr int W = decltype(w)::value, RPC = 8 / W;
-    ln_modulate_bwd_kernel<W, decltype(vpt)::value><<<(M + RPC - 1) / RPC, 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)dy, lddy, (const bf16*)x, ldx, mean, rstd, (const bf16*)scale, ldmod, rows_per_batch, (const bf16*)dres,
-        lddres, (bf16*)dx, lddx, (const bf16*)gate, ldgate, (bf16*)dx_gated, lddxg, M);
-    LAUNCH_OK();
-  });
+  return qfx_ln_modulate_bwd_pair(dy, lddy, x, ldx, mean, rstd, scale, ldmod, rows_per_batch, dres, lddres, dx, lddx, gate, ldgate,
+                                  dx_gated, lddxg, M, D, M, nullptr, nullptr, 1, stream);
 }
 
 extern "C" int qfx_mod_grad(const void* g, int64_t ldg, const void* m, int64_t ldm, const float* mean, const float* rstd,
@@ -724,18 +785,47 @@ extern "C" int qfx_rmsnorm_rows(const void* x, int64_t ldx, const void* w, void*
   LAUNCH_OK();
 }
 
-extern "C" int qfx_qk_norm_rope_fwd(const void* qkv, int64_t ldqkv, const void* wq, const void* wk, const float* rope,
-                                    int64_t rope_bstride, void* Q, void* K, void* V, int tokens, int tokens_per_sample,
-                                    int s_offset, int S, int H, float eps, int round_mid, void* stream) {
+extern "C" int qfx_qk_norm_rope_fwd_pair(const void* qkv, int64_t ldqkv, const void* wq, const void* wk, const float* rope,
+                                         int64_t rope_bstride, void* Q, void* K, void* V, int tokens, int tokens_per_sample,
+                                         int s_offset, int S, int H, float eps, int round_mid, int split, const void* wq1,
+                                         const void* wk1, int tokens_per_sample1, int s_offset1, void* stream) {
+  QFX_CHECK_ARG(split >= tokens || (wq1 && wk1 && tokens_per_sample1 > 0), "qfx_qk_norm_rope_fwd_pair: second group incomplete");
   const int blocks = (tokens * H + 7) / 8;
   if (round_mid)
     qk_norm_rope_fwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(
         (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk, (const float2*)rope, rope_bstride, (bf16*)Q, (bf16*)K, (bf16*)V,
-        tokens, tokens_per_sample, s_offset, S, H, eps);
+        tokens, tokens_per_sample, s_offset, S, H, eps, split, (const bf16*)wq1, (const bf16*)wk1, tokens_per_sample1, s_offset1);
   else
     qk_norm_rope_fwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(
         (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk, (const float2*)rope, rope_bstride, (bf16*)Q, (bf16*)K, (bf16*)V,
-        tokens, tokens_per_sample, s_offset, S, H, eps);
+        tokens, tokens_per_sample, s_offset, S, H, eps, split, (const bf16*)wq1, (const bf16*)wk1, tokens_per_sample1, s_offset1);
+  LAUNCH_OK();
+}
+
+extern "C" int qfx_qk_norm_rope_fwd(const void* qkv, int64_t ldqkv, const void* wq, const void* wk, const float* rope,
+                                    int64_t rope_bstride, void* Q, void* K, void* V, int tokens, int tokens_per_sample,
+                                    int s_offset, int S, int H, float eps, int round_mid, void* stream) {
+  return qfx_qk_norm_rope_fwd_pair(qkv, ldqkv, wq, wk, rope, rope_bstride, Q, K, V, tokens, tokens_per_sample, s_offset, S, H, eps,
+                                   round_mid, tokens, nullptr, nullptr, 1, 0, stream);
+}
+
+extern "C" int qfx_qk_norm_rope_bwd_pair(const void* dQ, const void* dK, const void* dV, const void* qkv, int64_t ldqkv,
+                                         const void* wq, const void* wk, const float* rope, int64_t rope_bstride, void* dqkv,
+                                         int64_t lddqkv, int tokens, int tokens_per_sample, int s_offset, int S, int H, float eps,
+                                         int round_mid, int split, const void* wq1, const void* wk1, int tokens_per_sample1,
+                                         int s_offset1, void* stream) {
+  QFX_CHECK_ARG(split >= tokens || (wq1 && wk1 && tokens_per_sample1 > 0), "qfx_qk_norm_rope_bwd_pair: second group incomplete");
+  const int blocks = (tokens * H + 7) / 8;
+  if (round_mid)
+    qk_norm_rope_bwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const float*)dQ, (const bf16*)dK, (const bf16*)dV, (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk,
+        (const float2*)rope, rope_bstride, (bf16*)dqkv, lddqkv, tokens, tokens_per_sample, s_offset, S, H, eps, split,
+        (const bf16*)wq1, (const bf16*)wk1, tokens_per_sample1, s_offset1);
+  else
+    qk_norm_rope_bwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const float*)dQ, (const bf16*)dK, (const bf16*)dV, (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk,
+        (const float2*)rope, rope_bstride, (bf16*)dqkv, lddqkv, tokens, tokens_per_sample, s_offset, S, H, eps, split,
+        (const bf16*)wq1, (const bf16*)wk1, tokens_per_sample1, s_offset1);
   LAUNCH_OK();
 }
 
@@ -743,16 +833,8 @@ extern "C" int qfx_qk_norm_rope_bwd(const void* dQ, const void* dK, const void* 
                                     const void* wq, const void* wk, const float* rope, int64_t rope_bstride, void* dqkv,
                                     int64_t lddqkv, int tokens, int tokens_per_sample, int s_offset, int S, int H, float eps,
                                     int round_mid, void* stream) {
-  const int blocks = (tokens * H + 7) / 8;
-  if (round_mid)
-    qk_norm_rope_bwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-        (const float*)dQ, (const bf16*)dK, (const bf16*)dV, (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk,
-        (const float2*)rope, rope_bstride, (bf16*)dqkv, lddqkv, tokens, tokens_per_sample, s_offset, S, H, eps);
-  else
-    qk_norm_rope_bwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-        (const float*)dQ, (const bf16*)dK, (const bf16*)dV, (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk,
-        (const float2*)rope, rope_bstride, (bf16*)dqkv, lddqkv, tokens, tokens_per_sample, s_offset, S, H, eps);
-  LAUNCH_OK();
+  return qfx_qk_norm_rope_bwd_pair(dQ, dK, dV, qkv, ldqkv, wq, wk, rope, rope_bstride, dqkv, lddqkv, tokens, tokens_per_sample,
+                                   s_offset, S, H, eps, round_mid, tokens, nullptr, nullptr, 1, 0, stream);
 }
 
 extern "C" int qfx_gemv_act(const void* x, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* y, int64_t ldy,
@@ -827,12 +909,19 @@ extern "C" int qfx_lora_wgrad(const void* P, int64_t ldp, const void* Q, int64_t
   LAUNCH_OK();
 }
 
-extern "C" int qfx_attn_delta(const void* O, int64_t ldo, const void* dO, int64_t lddo, float* delta, void* dO_joint,
-                              int tokens, int tokens_per_sample, int s_offset, int S, int H, void* stream) {
+extern "C" int qfx_attn_delta_pair(const void* O, int64_t ldo, const void* dO, int64_t lddo, float* delta, void* dO_joint,
+                                   int tokens, int tokens_per_sample, int s_offset, int S, int H, int split, int tokens_per_sample1,
+                                   int s_offset1, void* stream) {
+  QFX_CHECK_ARG(split >= tokens || tokens_per_sample1 > 0, "qfx_attn_delta_pair: second group incomplete");
   attn_delta_kernel<<<(tokens * H + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const bf16*)O, ldo, (const bf16*)dO, lddo, delta,
                                                                             (bf16*)dO_joint, tokens, tokens_per_sample, s_offset,
-                                                                            S, H);
+                                                                            S, H, split, tokens_per_sample1, s_offset1);
   LAUNCH_OK();
+}
+
+extern "C" int qfx_attn_delta(const void* O, int64_t ldo, const void* dO, int64_t lddo, float* delta, void* dO_joint,
+                              int tokens, int tokens_per_sample, int s_offset, int S, int H, void* stream) {
+  return qfx_attn_delta_pair(O, ldo, dO, lddo, delta, dO_joint, tokens, tokens_per_sample, s_offset, S, H, tokens, 1, 0, stream);
 }
 
 extern "C" int qfx_grad_finalize(const float* g, int64_t n, float pre_scale, float max_norm, float* sumsq, void* out_bf16,

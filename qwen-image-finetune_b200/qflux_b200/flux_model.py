@@ -190,14 +190,12 @@ class FluxB200(FusedMMDiTBase):
         D, w = self.D, self.w
         T, Mt = ws["T"], ws["Mt"]
         st, qkv, O, h, u = save["stats"], save["qkv"], save["O"], save["h"], save["u"]
-        for s in (0, 1):
-            lib.ln_modulate_fwd(self._rows(ws, Xin, s), self._rows(ws, ws["xm"], s), self._smod(ws, l, 0)[s], self._smod(ws, l, 1)[s],
-                                self._rpb(ws, s), self._rows(ws, st[0], s), self._rows(ws, st[1], s))
+        self._ln_fwd2(ws, Xin, ws["xm"], self._smod(ws, l, 0), self._smod(ws, l, 1), st[0], st[1])
         self._grouped(ws, l, "s_qkv", ws["xm"], qkv, 3 * D, D, lib.EPI_BIAS)
         self._grouped(ws, l, "s_mlp", ws["xm"], h, 4 * D, D, lib.EPI_GELU, out2=u)
-        for s in (0, 1):
-            lib.qk_norm_rope_fwd(self._rows(ws, qkv, s), w["s_qknorm_w"][l, 0], w["s_qknorm_w"][l, 1], ws["rope"], ws["Q"], ws["K"],
-                                 ws["V"], self._rpb(ws, s), T if s == 0 else 0, round_mid=False)
+        qn = w["s_qknorm_w"][l]
+        lib.qk_norm_rope_fwd_pair(qkv, (qn[0], qn[1], T, 0), (qn[0], qn[1], ws["Limg"], T), Mt, ws["rope"], ws["Q"], ws["K"], ws["V"],
+                                  round_mid=False)
         lib.attn_fwd(ws["Q"], ws["K"], ws["V"], O[:Mt], O[Mt:], T, save["lse"], kv_len=ws.get("kv_len"), txt_len=ws.get("txt_len"))
         # x = x + gate * proj_out(cat[attn, gelu(mlp)]): attention wrote columns [0, D) and the GELU epilogue [D, 5D) of save["cat"]
         self._grouped(ws, l, "s_out", save["cat"], Xout, D, 5 * D, lib.EPI_RESID_GATE, resid=Xin, gate=self._smod(ws, l, 2),
@@ -225,19 +223,14 @@ class FluxB200(FusedMMDiTBase):
         lib.gemm(pm, 4 * D, D, trans_b=True, epilogue=lib.EPI_DGELU)
         self._attn_bwd_core(ws, qkv, O, save["lse"], lambda s: (w["s_qknorm_w"][l, 0], w["s_qknorm_w"][l, 1]))
         if self._site(l, "s_qkv", 0) or self._site(l, "s_mlp", 0):  # LoRA input = modulated norm output (recomputed)
-            for s in (0, 1):
-                lib.ln_modulate_fwd(self._rows(ws, Xin, s), self._rows(ws, ws["xm"], s), self._smod(ws, l, 0)[s],
-                                    self._smod(ws, l, 1)[s], self._rpb(ws, s))
+            self._ln_fwd2(ws, Xin, ws["xm"], self._smod(ws, l, 0), self._smod(ws, l, 1))
         self._dgrad_grouped(ws, l, "s_qkv", ws["dqkv"], ws["dxm"], D, 3 * D, D, ws["xm"])
         self._dgrad_grouped(ws, l, "s_mlp", ws["dbig"], ws["dxm"], D, 4 * D, 4 * D, ws["xm"], epilogue=lib.EPI_ADD, resid=ws["dxm"])
         for s in (0, 1):
             if dsm(0) is not None:
                 lib.mod_grad(self._rows(ws, ws["dxm"], s), self._rpb(ws, s), sum_out=dsm(0), m=self._rows(ws, Xin, s),
                              prod_out=dsm(1), mean=self._rows(ws, st[0], s), rstd=self._rows(ws, st[1], s))
-            lib.ln_modulate_bwd(self._rows(ws, ws["dxm"], s), self._rows(ws, Xin, s), self._rows(ws, st[0], s),
-                                self._rows(ws, st[1], s), self._smod(ws, l, 1)[s], self._rpb(ws, s), self._rows(ws, dXn, s),
-                                dres=self._rows(ws, dX, s), gate=prev_gate[s] if prev_gate else None,
-                                dx_gated=self._rows(ws, ws["dY"], s) if prev_gate else None)
+        self._ln_bwd2(ws, ws["dxm"], Xin, st[0], st[1], self._smod(ws, l, 1), dXn, dres=dX, gate=prev_gate, dx_gated=ws["dY"])
 
     # ------------------------------------------------------------------------------------------------ forward
     def _mlp2(self, x, pre, out, tmp):

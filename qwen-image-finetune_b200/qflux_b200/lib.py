@@ -127,6 +127,63 @@ _gfin = _sig("qfx_grad_finalize", _vp, _i64, _f, _f, _vp, _vp, _vp)
 _attn_fwd = _sig("qfx_attn_fwd", _vp, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp)
 
 
+_ln_fwd2 = _sig("qfx_ln_modulate_fwd_pair", _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _vp, _vp, _i, _i, _f, _i, _vp, _vp, _i, _vp)
+_ln_bwd2 = _sig("qfx_ln_modulate_bwd_pair", _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp, _i64, _vp, _i64, _vp, _i64, _vp,
+                _i64, _i, _i, _i, _vp, _vp, _i, _vp)
+_qknr_fwd2 = _sig("qfx_qk_norm_rope_fwd_pair", _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _vp,
+                  _i, _i, _vp)
+_qknr_bwd2 = _sig("qfx_qk_norm_rope_bwd_pair", _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _f, _i, _i,
+                  _vp, _vp, _i, _i, _vp)
+_delta2 = _sig("qfx_attn_delta_pair", _vp, _i64, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp)
+
+
+# ---- stream-pair launches: rows [0, split) of a stream-major buffer are group 0 (text), rows [split, M) group 1 (image); g0 / g1 carry
+# the per-stream operands.  One launch instead of two (the text launch alone is too small to fill 148 SMs).
+def ln_modulate_fwd_pair(x, y, g0, g1, split, mean=None, rstd=None, eps=1e-6):
+    """g = (shift, scale, rows_per_batch)"""
+    require_cuda(x, y, g0[0], g0[1], g1[0], g1[1])
+    assert g0[0].stride(0) == g0[1].stride(0) == g1[0].stride(0) == g1[1].stride(0)
+    check(_ln_fwd2(ptr(x), x.stride(0), ptr(y), y.stride(0), ptr(g0[0]), ptr(g0[1]), g0[0].stride(0), g0[2], ptr(mean), ptr(rstd),
+                   x.shape[0], x.shape[1], eps, split, ptr(g1[0]), ptr(g1[1]), g1[2], cur_stream()), "qfx_ln_modulate_fwd_pair")
+
+
+def ln_modulate_bwd_pair(dy, x, mean, rstd, g0, g1, split, dx, dres=None, dx_gated=None):
+    """g = (scale, rows_per_batch, gate or None); the gates (both or neither) produce dx_gated = dx * gate"""
+    require_cuda(dy, x, mean, rstd, g0[0], g1[0], dx)
+    assert g0[0].stride(0) == g1[0].stride(0) and (g0[2] is None) == (g1[2] is None) == (dx_gated is None)
+    assert g0[2] is None or g0[2].stride(0) == g1[2].stride(0)
+    check(_ln_bwd2(ptr(dy), dy.stride(0), ptr(x), x.stride(0), ptr(mean), ptr(rstd), ptr(g0[0]), g0[0].stride(0), g0[1], ptr(dres),
+                   _ld(dres), ptr(dx), dx.stride(0), ptr(g0[2]), _ld(g0[2]), ptr(dx_gated), _ld(dx_gated), x.shape[0], x.shape[1], split,
+                   ptr(g1[0]), ptr(g1[2]), g1[1], cur_stream()), "qfx_ln_modulate_bwd_pair")
+
+
+def qk_norm_rope_fwd_pair(qkv, g0, g1, split, rope, Q, K, V, eps=1e-6, round_mid=True):
+    """g = (wq, wk, tokens_per_sample, s_offset)"""
+    require_cuda(qkv, g0[0], g0[1], g1[0], g1[1], rope, Q, K, V)
+    B, H, S, _ = Q.shape
+    bstride = 0 if rope.dim() == 3 else S
+    check(_qknr_fwd2(ptr(qkv), qkv.stride(0), ptr(g0[0]), ptr(g0[1]), ptr(rope), bstride, ptr(Q), ptr(K), ptr(V), qkv.shape[0], g0[2],
+                     g0[3], S, H, eps, int(round_mid), split, ptr(g1[0]), ptr(g1[1]), g1[2], g1[3], cur_stream()),
+          "qfx_qk_norm_rope_fwd_pair")
+
+
+def qk_norm_rope_bwd_pair(dQ, dK, dV, qkv, g0, g1, split, rope, dqkv, eps=1e-6, round_mid=True):
+    require_cuda(dQ, dK, dV, qkv, g0[0], g0[1], g1[0], g1[1], rope, dqkv)
+    B, H, S, _ = dK.shape
+    bstride = 0 if rope.dim() == 3 else S
+    check(_qknr_bwd2(ptr(dQ), ptr(dK), ptr(dV), ptr(qkv), qkv.stride(0), ptr(g0[0]), ptr(g0[1]), ptr(rope), bstride, ptr(dqkv),
+                     dqkv.stride(0), qkv.shape[0], g0[2], g0[3], S, H, eps, int(round_mid), split, ptr(g1[0]), ptr(g1[1]), g1[2], g1[3],
+                     cur_stream()), "qfx_qk_norm_rope_bwd_pair")
+
+
+def attn_delta_pair(O, dO, delta, g0, g1, split, dO_joint=None):
+    """g = (tokens_per_sample, s_offset)"""
+    require_cuda(O, dO, delta, dO_joint)
+    B, H, S = delta.shape
+    check(_delta2(ptr(O), O.stride(0), ptr(dO), dO.stride(0), ptr(delta), ptr(dO_joint), O.shape[0], g0[0], g0[1], S, H, split, g1[0],
+                  g1[1], cur_stream()), "qfx_attn_delta_pair")
+
+
 def ln_modulate_fwd(x, y, shift, scale, rows_per_batch, mean=None, rstd=None, eps=1e-6):
     """shift/scale: [B, D] views (row stride = stride(0)) of the modulation tensor."""
     require_cuda(x, y, shift, scale)

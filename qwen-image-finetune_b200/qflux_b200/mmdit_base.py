@@ -460,6 +460,16 @@ class FusedMMDiTBase(nn.Module):
     def _site(self, l, grp, s):
         return self.sites.get((l, grp, s))
 
+    # one launch over both streams of a stream-major buffer (rows [0, Mt) text = stream 1, rows [Mt, M) image = stream 0);
+    # `shift` / `scale` / `gate` are (image view, text view) pairs as returned by the mods(j) accessors
+    def _ln_fwd2(self, ws, X, Y, shift, scale, mean=None, rstd=None):
+        lib.ln_modulate_fwd_pair(X, Y, (shift[1], scale[1], ws["T"]), (shift[0], scale[0], ws["Limg"]), ws["Mt"], mean, rstd)
+
+    def _ln_bwd2(self, ws, dy, x, mean, rstd, scale, dx, dres=None, gate=None, dx_gated=None):
+        g = gate if gate else (None, None)
+        lib.ln_modulate_bwd_pair(dy, x, mean, rstd, (scale[1], ws["T"], g[1]), (scale[0], ws["Limg"], g[0]), ws["Mt"], dx, dres=dres,
+                                 dx_gated=dx_gated if gate else None)
+
     def _alloc_lora_T(self, ws):
         ws["loraT"] = {}
         for (l, grp, s), site in self.sites.items():
@@ -570,18 +580,14 @@ class FusedMMDiTBase(nn.Module):
         w = self.w
         xm1 = save.get("xm1", ws["xm"])  # kept per block in training: it is the LoRA input of the q|k|v sites in the backward
         Qs, Ks, Vs = save.get("Q", ws["Q"]), save.get("K", ws["K"]), save.get("V", ws["V"])
-        for s in (0, 1):
-            lib.ln_modulate_fwd(self._rows(ws, Xin, s), self._rows(ws, xm1, s), mods(0)[s], mods(1)[s], self._rpb(ws, s),
-                                self._rows(ws, st[0], s), self._rows(ws, st[1], s))
+        # stream-major rows: text (stream 1) first, image (stream 0) behind it -> ONE launch per op covers both streams
+        lib.ln_modulate_fwd_pair(Xin, xm1, (mods(0)[1], mods(1)[1], T), (mods(0)[0], mods(1)[0], Limg), Mt, st[0], st[1])
         self._grouped(ws, l, "qkv", xm1, qkv, 3 * D, D, lib.EPI_BIAS)
-        for s in (0, 1):
-            lib.qk_norm_rope_fwd(self._rows(ws, qkv, s), w["qknorm_w"][l, 2 * s], w["qknorm_w"][l, 2 * s + 1], ws["rope"], Qs, Ks, Vs,
-                                 self._rpb(ws, s), T if s == 0 else 0, round_mid=self.round_mid)
+        qn = w["qknorm_w"][l]
+        lib.qk_norm_rope_fwd_pair(qkv, (qn[2], qn[3], T, 0), (qn[0], qn[1], Limg, T), Mt, ws["rope"], Qs, Ks, Vs, round_mid=self.round_mid)
         lib.attn_fwd(Qs, Ks, Vs, O[:Mt], O[Mt:], T, save["lse"], kv_len=ws.get("kv_len"), txt_len=ws.get("txt_len"))
         self._grouped(ws, l, "out", O, xmid, D, D, lib.EPI_RESID_GATE, resid=Xin, gate=mods(2), out2=save.get("y_attn"))
-        for s in (0, 1):
-            lib.ln_modulate_fwd(self._rows(ws, xmid, s), self._rows(ws, ws["xm"], s), mods(3)[s], mods(4)[s], self._rpb(ws, s),
-                                self._rows(ws, st[2], s), self._rows(ws, st[3], s))
+        lib.ln_modulate_fwd_pair(xmid, ws["xm"], (mods(3)[1], mods(4)[1], T), (mods(3)[0], mods(4)[0], Limg), Mt, st[2], st[3])
         h = save.get("h", ws["h"])  # kept per block only when ff.net.2 carries LoRA (its input is needed for dA)
         self._grouped(ws, l, "up", ws["xm"], h, 4 * D, D, lib.EPI_GELU, out2=u)
         self._grouped(ws, l, "down", h, Xout, D, 4 * D, lib.EPI_RESID_GATE, resid=xmid, gate=mods(5), out2=save.get("y_mlp"))
@@ -589,23 +595,17 @@ class FusedMMDiTBase(nn.Module):
     def _attn_bwd_core(self, ws, qkv, O, lse, wq_wk, save=None):
         """dO (token-major, ws['dO']) -> dqkv (ws['dqkv']); wq_wk(s) -> (wq, wk) norm weights of stream s.
         The normalised / rotated Q, K, V come from the block's saved tensors when present, else they are regenerated."""
-        T = ws["T"]
+        T, Limg, Mt = ws["T"], ws["Limg"], ws["Mt"]
         have = save is not None and "Q" in save
         Qs, Ks, Vs = (save["Q"], save["K"], save["V"]) if have else (ws["Q"], ws["K"], ws["V"])
-        for s in (0, 1):
-            wq, wk = wq_wk(s)
-            lib.attn_delta(self._rows(ws, O, s), self._rows(ws, ws["dO"], s), ws["delta"], self._rpb(ws, s), T if s == 0 else 0,
-                           ws["dOj"])
-            if not have:
-                lib.qk_norm_rope_fwd(self._rows(ws, qkv, s), wq, wk, ws["rope"], Qs, Ks, Vs, self._rpb(ws, s),
-                                     T if s == 0 else 0, round_mid=self.round_mid)
+        g_txt, g_img = (*wq_wk(1), T, 0), (*wq_wk(0), Limg, T)  # (wq, wk, tokens per sample, joint offset) of the two row groups
+        lib.attn_delta_pair(O, ws["dO"], ws["delta"], (T, 0), (Limg, T), Mt, ws["dOj"])
+        if not have:
+            lib.qk_norm_rope_fwd_pair(qkv, g_txt, g_img, Mt, ws["rope"], Qs, Ks, Vs, round_mid=self.round_mid)
         ws["dQ"].zero_()
         lib.attn_bwd(Qs, Ks, Vs, ws["dOj"], lse, ws["delta"], ws["dQ"], ws["dK"], ws["dV"], kv_len=ws.get("kv_len"),
                      txt_len=ws.get("txt_len"), split=T)
-        for s in (0, 1):
-            wq, wk = wq_wk(s)
-            lib.qk_norm_rope_bwd(ws["dQ"], ws["dK"], ws["dV"], self._rows(ws, qkv, s), wq, wk, ws["rope"],
-                                 self._rows(ws, ws["dqkv"], s), self._rpb(ws, s), T if s == 0 else 0, round_mid=self.round_mid)
+        lib.qk_norm_rope_bwd_pair(ws["dQ"], ws["dK"], ws["dV"], qkv, g_txt, g_img, Mt, ws["rope"], ws["dqkv"], round_mid=self.round_mid)
 
     def _double_bwd(self, ws, l, Xin, dX, dXn, save, mods, prev_gate):
         """dX: grad wrt the block output (ws['dY'] already holds dX * gate2).  Writes the grad wrt the block input to dXn
@@ -620,17 +620,16 @@ class FusedMMDiTBase(nn.Module):
         # ---- MLP branch
         self._dgrad_grouped(ws, l, "down", ws["dY"], ws["dbig"], 4 * D, D, D, save.get("h"), epilogue=lib.EPI_DGELU, aux=u)
         if self._site(l, "up", 0) or self._site(l, "up", 1):  # LoRA input = xm2, recomputed from the statistics
-            for s in (0, 1):
-                lib.ln_modulate_fwd(self._rows(ws, xmid, s), self._rows(ws, ws["xm"], s), mods(3)[s], mods(4)[s], self._rpb(ws, s))
+            self._ln_fwd2(ws, xmid, ws["xm"], mods(3), mods(4))
         self._dgrad_grouped(ws, l, "up", ws["dbig"], ws["dxm"], D, 4 * D, 4 * D, ws["xm"])
         # ---- norm2 backward: dXmid = dX + LN_bwd ; also emit dXmid * gate1 for the attention out-projection
         for s in (0, 1):
             if dm(s, 3) is not None:  # d shift2 = sum_t dy ; d scale2 = sum_t dy * LN(xmid)
                 lib.mod_grad(self._rows(ws, ws["dxm"], s), self._rpb(ws, s), sum_out=dm(s, 3), m=self._rows(ws, xmid, s),
                              prod_out=dm(s, 4), mean=self._rows(ws, st[2], s), rstd=self._rows(ws, st[3], s))
-            lib.ln_modulate_bwd(self._rows(ws, ws["dxm"], s), self._rows(ws, xmid, s), self._rows(ws, st[2], s),
-                                self._rows(ws, st[3], s), mods(4)[s], self._rpb(ws, s), self._rows(ws, dX, s),
-                                dres=self._rows(ws, dX, s), gate=mods(2)[s], dx_gated=self._rows(ws, ws["dY"], s))
+        T, Limg, Mt = ws["T"], ws["Limg"], ws["Mt"]
+        lib.ln_modulate_bwd_pair(ws["dxm"], xmid, st[2], st[3], (mods(4)[1], T, mods(2)[1]), (mods(4)[0], Limg, mods(2)[0]), Mt, dX,
+                                 dres=dX, dx_gated=ws["dY"])
         for s in (0, 1):
             if dm(s, 2) is not None:  # d gate1 = sum_t dXmid * attn_out   (dX holds dXmid now)
                 lib.mod_grad(self._rows(ws, dX, s), self._rpb(ws, s), m=self._rows(ws, save["y_attn"], s), prod_out=dm(s, 2))
@@ -641,18 +640,16 @@ class FusedMMDiTBase(nn.Module):
         if xm1 is None:
             xm1 = ws["xm"]
             if self._site(l, "qkv", 0) or self._site(l, "qkv", 1):
-                for s in (0, 1):
-                    lib.ln_modulate_fwd(self._rows(ws, Xin, s), self._rows(ws, xm1, s), mods(0)[s], mods(1)[s], self._rpb(ws, s))
+                self._ln_fwd2(ws, Xin, xm1, mods(0), mods(1))
         self._dgrad_grouped(ws, l, "qkv", ws["dqkv"], ws["dxm"], D, 3 * D, D, xm1)
         # ---- norm1 backward: dXin = dXmid + LN_bwd ; emit dXin * (gate of the block before)
         for s in (0, 1):
             if dm(s, 0) is not None:
                 lib.mod_grad(self._rows(ws, ws["dxm"], s), self._rpb(ws, s), sum_out=dm(s, 0), m=self._rows(ws, Xin, s),
                              prod_out=dm(s, 1), mean=self._rows(ws, st[0], s), rstd=self._rows(ws, st[1], s))
-            lib.ln_modulate_bwd(self._rows(ws, ws["dxm"], s), self._rows(ws, Xin, s), self._rows(ws, st[0], s),
-                                self._rows(ws, st[1], s), mods(1)[s], self._rpb(ws, s), self._rows(ws, dXn, s),
-                                dres=self._rows(ws, dX, s), gate=prev_gate[s] if prev_gate else None,
-                                dx_gated=self._rows(ws, ws["dY"], s) if prev_gate else None)
+        pg = prev_gate if prev_gate else (None, None)
+        lib.ln_modulate_bwd_pair(ws["dxm"], Xin, st[0], st[1], (mods(1)[1], T, pg[1]), (mods(1)[0], Limg, pg[0]), Mt, dXn, dres=dX,
+                                 dx_gated=ws["dY"] if prev_gate else None)
 
     # ------------------------------------------------------------------------------------------------ workspace pieces
     def _alloc_common(self, ws, B, T, Limg, train, n_double, n_single=0):

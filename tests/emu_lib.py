@@ -302,13 +302,41 @@ def grad_finalize(g_f32, pre_scale, max_norm, sumsq, out_bf16):
     out_bf16.copy_((g * coef).to(BF))
 
 
+# ---- stream-pair launches (one CUDA launch over both row groups of a stream-major buffer): emulated as the two single-group calls
+def ln_modulate_fwd_pair(x, y, g0, g1, split, mean=None, rstd=None, eps=1e-6):
+    for (sh, sc, rpb), sl in ((g0, slice(0, split)), (g1, slice(split, None))):
+        ln_modulate_fwd(x[sl], y[sl], sh, sc, rpb, None if mean is None else mean[sl], None if rstd is None else rstd[sl], eps)
+
+
+def ln_modulate_bwd_pair(dy, x, mean, rstd, g0, g1, split, dx, dres=None, dx_gated=None):
+    for (sc, rpb, gate), sl in ((g0, slice(0, split)), (g1, slice(split, None))):
+        ln_modulate_bwd(dy[sl], x[sl], mean[sl], rstd[sl], sc, rpb, dx[sl], dres=None if dres is None else dres[sl], gate=gate,
+                        dx_gated=None if dx_gated is None else dx_gated[sl])
+
+
+def qk_norm_rope_fwd_pair(qkv, g0, g1, split, rope, Q, K, V, eps=1e-6, round_mid=True):
+    for (wq, wk, tps, so), sl in ((g0, slice(0, split)), (g1, slice(split, None))):
+        qk_norm_rope_fwd(qkv[sl], wq, wk, rope, Q, K, V, tps, so, eps=eps, round_mid=round_mid)
+
+
+def qk_norm_rope_bwd_pair(dQ, dK, dV, qkv, g0, g1, split, rope, dqkv, eps=1e-6, round_mid=True):
+    for (wq, wk, tps, so), sl in ((g0, slice(0, split)), (g1, slice(split, None))):
+        qk_norm_rope_bwd(dQ, dK, dV, qkv[sl], wq, wk, rope, dqkv[sl], tps, so, eps=eps, round_mid=round_mid)
+
+
+def attn_delta_pair(O, dO, delta, g0, g1, split, dO_joint=None):
+    for (tps, so), sl in ((g0, slice(0, split)), (g1, slice(split, None))):
+        attn_delta(O[sl], dO[sl], delta, tps, so, dO_joint)
+
+
 def require_cuda(*tensors):
     return None
 
 
 _NAMES = ["gemm_problem", "gemm", "ln_modulate_fwd", "ln_modulate_bwd", "mod_grad", "gate_mul", "add_bf16", "rmsnorm_rows", "qk_norm_rope_fwd",
           "qk_norm_rope_bwd", "gemv_act", "timestep_sinusoid", "flow_noisy_input", "flow_noisy_input_var", "flow_loss", "lora_wgrad", "lora_wgrad_tc", "attn_delta",
-          "attn_fwd", "attn_bwd", "grad_finalize", "adamw_tables", "fused_adamw", "require_cuda"]
+          "attn_fwd", "attn_bwd", "grad_finalize", "adamw_tables", "fused_adamw", "require_cuda", "ln_modulate_fwd_pair", "ln_modulate_bwd_pair",
+          "qk_norm_rope_fwd_pair", "qk_norm_rope_bwd_pair", "attn_delta_pair"]
 
 
 def install(lib_module):
