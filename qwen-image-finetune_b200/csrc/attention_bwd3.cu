@@ -45,35 +45,13 @@ struct AttnBwd3Params {
   long long* dbg;  // optional clock64 stamps of CTA (1, 0): [iteration][16] (tools/attn_timeline3.py)
 };
 
-// Descriptor halves for the warp-converged issue path: hi word = SBO (1024 B) | version 1 | 128B swizzle; lo word = start address >> 4
-// | LBO >> 4 << 16.  Stepping K by 16 only ever adds a compile-time constant to the lo word.
-constexpr uint32_t B3_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
-__device__ __forceinline__ uint32_t b3_lo_kmaj(uint32_t base) { return ((base & 0x3ffffu) >> 4) | (1u << 16); }
-__device__ __forceinline__ uint32_t b3_lo_mnmaj(uint32_t base) { return ((base & 0x3ffffu) >> 4) | ((16384u >> 4) << 16); }
+// warp-converged issue with split descriptors (sm100.cuh: sdesc_lo / umma_ss_w / umma_ts_w)
+__device__ __forceinline__ uint32_t b3_lo_kmaj(uint32_t base) { return sdesc_lo(base, 16); }
+__device__ __forceinline__ uint32_t b3_lo_mnmaj(uint32_t base) { return sdesc_lo(base, 16384); }
 __host__ __device__ constexpr uint32_t b3_inc_kmaj(int k) { return (uint32_t)((k >> 2) * 1024 + (k & 3) * 2); }  // (k>>2) * 16 KB atom + (k&3) * 32 B, in 16-B units
 __host__ __device__ constexpr uint32_t b3_inc_mnmaj(int k) { return (uint32_t)(k * 128); }                        // 16 rows of 128 B
-// All 32 lanes execute these with identical operands; one elected lane issues (no lane-serialising loop, no R2UR per operand).
-__device__ __forceinline__ void b3_mma_ss(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %5};\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
-      ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(B3_DESC_HI)
-      : "memory");
-}
-__device__ __forceinline__ void b3_mma_ts(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
-      ::"r"(d), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(acc), "r"(B3_DESC_HI)
-      : "memory");
-}
+__device__ __forceinline__ void b3_mma_ss(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) { umma_ss_w(d, a_lo, b_lo, idesc, acc); }
+__device__ __forceinline__ void b3_mma_ts(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t acc) { umma_ts_w(d, a_tmem, b_lo, idesc, acc); }
 
 __device__ __forceinline__ uint32_t b3_mul_bf16x2(uint32_t a, uint32_t b) {
   uint32_t r;

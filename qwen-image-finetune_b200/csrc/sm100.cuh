@@ -60,6 +60,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Pure spin on mbarrier.test_wait (never suspends the thread): lower wake-up latency than try_wait for the one or two waits that sit on a
+// kernel's critical loop, at the price of issue slots while spinning.  Bounded like mbar_wait.
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  uint64_t t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((it & 0xffff) == 0xffff) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA / UMMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -277,6 +298,37 @@ __device__ __forceinline__ uint64_t sdesc_sw128(uint32_t saddr, uint32_t lbo_byt
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- warp-converged issue with split descriptors.  The 64-bit shared-memory descriptor is (lo, hi): hi = SBO >> 4 | version 1 << 14 |
+// 128B swizzle << 29 is a constant for SBO = 1024; lo = (address >> 4) | (LBO >> 4) << 16, so stepping K by 16 elements only ever
+// adds a compile-time constant to lo.  ALL 32 lanes execute these with identical operands and one elected lane issues: no
+// lane-serialising loop around the instruction and no per-operand R2UR (measured on the attention backward: 19 -> 3-8 SASS
+// instructions per tcgen05.mma).
+constexpr uint32_t SDESC_HI_SBO1024 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t sdesc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3ffffu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ void umma_ss_w(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(SDESC_HI_SBO1024)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_w(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+      ::"r"(d), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(acc), "r"(SDESC_HI_SBO1024)
+      : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ numerics
