@@ -316,7 +316,10 @@ __global__ void __launch_bounds__(192, 2) attn_fwd64_kernel(const __grid_constan
   auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto v_full = [&](int s) { return bar_base + 8u * (3 + s); };
   auto s_full = [&](int s) { return bar_base + 8u * (5 + s); };
-  const uint32_t p_full = bar_base + 8u * 7;
+  // ONE barrier per S/P buffer: S(j+1) is issued before P V(j), so with a single barrier a fast softmax warp could arrive for tile j+1
+  // before a slow one has arrived for tile j, completing tile j's phase without it — the P V(j) MMA then read fp32 score bits as bf16 P
+  // (round-2 finding: a latent race of the round-1 kernel, exposed as sporadic NaNs once the MMA issue got faster)
+  auto p_full = [&](int s) { return bar_base + 8u * (14 + s); };
   auto pv_done = [&](int s) { return bar_base + 8u * (8 + s); };
   const uint32_t o_full = bar_base + 8u * 10;
   auto k_empty = [&](int s) { return bar_base + 8u * (11 + s); };
@@ -340,7 +343,8 @@ __global__ void __launch_bounds__(192, 2) attn_fwd64_kernel(const __grid_constan
       mbar_init(pv_done(s), 1);
       mbar_init(k_empty(s), 1);
     }
-    mbar_init(p_full, 4);
+    mbar_init(p_full(0), 4);
+    mbar_init(p_full(1), 4);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -377,35 +381,39 @@ __global__ void __launch_bounds__(192, 2) attn_fwd64_kernel(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ================================================================= MMA issuer
-    if (lane == 0) {
+    // ================================================================= MMA issuer: the whole warp runs the loop with identical values and an
+    // elected lane issues (sm100.cuh umma_ss_w / umma_ts_w): a 64-key S instruction is only 32 clk of tensor work, and the single-lane issue
+    // region of round 1 spent ~19 SASS instructions (lane-serialising loop, R2UR per operand) on each
+    {
       constexpr uint32_t idesc_qk = idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_pv = idesc_bf16(128, 128, 0, 1);
+      const uint32_t kQ = sdesc_lo(sQ, 16);
       mbar_wait(q_full, 0);
       auto issue_pv = [&](int j) {
         const int s = j & 1;
-        mbar_wait(p_full, j & 1);
+        const uint32_t mV = sdesc_lo(sV(s), 8192);
+        mbar_wait(p_full(s), (j >> 1) & 1);
         mbar_wait(v_full(s), (j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // K = 64 keys: P in TMEM (8 packed columns per 16 keys), V MN-major (two 64-wide d atoms, 8 KB apart)
-          umma_bf16_ts(tO, tS0 + s * 64 + k * 8, sdesc_sw128(sV(s) + k * 2048, 8192, 1024), idesc_pv, (j | k) != 0);
-        umma_commit(pv_done(s));
+          umma_ts_w(tO, tS0 + s * 64 + k * 8, mV + (uint32_t)(k * 128), idesc_pv, (j | k) != 0);
+        umma_commit_w(pv_done(s));
       };
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j & 1;
+        const uint32_t kK = sdesc_lo(sK(s), 16);
         mbar_wait(k_full(s), (j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_bf16(tS0 + s * 64, sdesc_sw128(sQ + (k >> 2) * ATOM_BYTES + (k & 3) * 32, 16, 1024),
-                    sdesc_sw128(sK(s) + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024), idesc_qk, k != 0);
-        umma_commit(s_full(s));
-        umma_commit(k_empty(s));
+          umma_ss_w(tS0 + s * 64, kQ + (uint32_t)((k >> 2) * 1024 + (k & 3) * 2), kK + (uint32_t)((k >> 2) * 512 + (k & 3) * 2), idesc_qk, k != 0);
+        umma_commit_w(s_full(s));
+        umma_commit_w(k_empty(s));
         if (j > 0) issue_pv(j - 1);
       }
       issue_pv(n_tiles - 1);
-      umma_commit(o_full);
+      umma_commit_w(o_full);
     }
   } else {
     // ================================================================= softmax warps (thread = query row)
@@ -470,7 +478,7 @@ __global__ void __launch_bounds__(192, 2) attn_fwd64_kernel(const __grid_constan
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(p_full(s));
     }
     // ----------------------------------------------------------------- epilogue
     mbar_wait(o_full, 0);

@@ -44,6 +44,11 @@ def test_ops(name):
     assert _cases("ops_check")[name]()["err"] < 5e-3
 
 
+def test_attention_forward_is_race_free_at_full_size():
+    r = _cases("ops_check")["attn_stress"]()
+    assert r["non_finite"] == 0 and r["max_launch_to_launch_diff"] == 0.0
+
+
 def test_attention_full_size_properties():
     """BASELINE full size (B=4, H=24, S=2400): parity with fp32 SDPA forward and backward."""
     c = _cases("ops_check")

@@ -368,6 +368,32 @@ def attn_bwd(Bsz=2, H=3, S=300, split=44, ragged=False, perf=False, txt_gap=Fals
     return res
 
 
+def attn_stress(n=8):
+    """Full-size forward launched repeatedly: every launch must be finite and bit-identical (the forward has no atomics).  Guards the
+    round-2 finding: with one P-ready barrier for both S/P buffers a fast softmax warp could complete a tile's phase on behalf of a slow
+    one and P.V read fp32 score bits as bf16 P — sporadic NaNs in a handful of rows, never in the small cases."""
+    from qflux_b200 import lib
+    Bsz, H, S, split = 4, 24, 2400, 352
+    Q, K, V = (_mk(Bsz, H, S, 128, seed=i, scale=1.0) for i in (1, 2, 3))
+    Q = Q * 2.0
+    ot = torch.zeros(Bsz * split, H * 128, device="cuda", dtype=BF)
+    oi = torch.zeros(Bsz * (S - split), H * 128, device="cuda", dtype=BF)
+    lse = torch.zeros(Bsz, H, S, device="cuda")
+    first, bad, diff = None, 0, 0.0
+    for _ in range(n):
+        ot.zero_()
+        oi.zero_()
+        lib.attn_fwd(Q, K, V, ot, oi, split, lse)
+        torch.cuda.synchronize()
+        cur = torch.cat([ot.flatten(), oi.flatten()]).float()
+        bad += int((~torch.isfinite(cur)).sum())
+        if first is None:
+            first = cur
+        else:
+            diff = max(diff, float((cur - first).abs().max()))
+    return dict(non_finite=bad, max_launch_to_launch_diff=diff, err=float(bad) + diff)
+
+
 CASES = {
     "ln_mod_3072": lambda: ln_mod(3072),
     "ln_mod_256": lambda: ln_mod(256, M=96, Bsz=3),
@@ -389,6 +415,7 @@ CASES = {
     "attn_txtgap": lambda: attn(3, 2, 700, 300, ragged=True, txt_gap=True),
     "attn_bwd_txtgap": lambda: attn_bwd(3, 2, 700, 300, ragged=True, txt_gap=True),
     "attn_qwen_perf": lambda: attn(4, 24, 2400, 352, perf=True),
+    "attn_stress": attn_stress,
     "attn_bwd_small": lambda: attn_bwd(1, 2, 128, 32),
     "attn_bwd_300": lambda: attn_bwd(2, 3, 300, 44),
     "attn_bwd_tail": lambda: attn_bwd(1, 1, 70, 10),
