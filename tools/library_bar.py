@@ -89,7 +89,7 @@ def attn_library(B=4, H=24, S=2400, d=128):
     return out
 
 
-def _eager_step(layers, B, ckpt, steps=3, warmup=2):
+def _eager_step(layers, B, ckpt, steps=3, warmup=2, T=352, imgs=((1, 32, 32), (1, 32, 32))):
     """One eager training step of the oracle model in bf16 on the GPU: fwd + flow-matching loss + autograd bwd + clip + AdamW."""
     from oracle import mmdit_oracle as mo
     from torch.utils.checkpoint import checkpoint
@@ -113,11 +113,12 @@ def _eager_step(layers, B, ckpt, steps=3, warmup=2):
             blk.forward = (lambda f: (lambda *a, **k: checkpoint(f, *a, use_reentrant=False, **k)))(fwd)
     params = [p for p in m.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-4)
-    L, T, hw = 1024, 352, 32
+    imgs = [tuple(s) for s in imgs]
+    L, Lc = imgs[0][1] * imgs[0][2], sum(f * h * w for f, h, w in imgs[1:])
     g = torch.Generator(device="cuda").manual_seed(1)
-    x = dict(image_latents=torch.randn(B, L, 64, device="cuda", generator=g).to(BF), control_latents=torch.randn(B, L, 64, device="cuda", generator=g).to(BF),
+    x = dict(image_latents=torch.randn(B, L, 64, device="cuda", generator=g).to(BF), control_latents=torch.randn(B, Lc, 64, device="cuda", generator=g).to(BF),
              prompt_embeds=(torch.randn(B, T, 3584, device="cuda", generator=g) * 3).to(BF),
-             prompt_embeds_mask=torch.ones(B, T, dtype=torch.int64, device="cuda"), img_shapes=[[(1, hw, hw), (1, hw, hw)]] * B)
+             prompt_embeds_mask=torch.ones(B, T, dtype=torch.int64, device="cuda"), img_shapes=[list(imgs)] * B)
 
     def step():
         noise = torch.randn(B, L, 64, device="cuda", dtype=BF)
