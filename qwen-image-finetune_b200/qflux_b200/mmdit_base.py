@@ -394,7 +394,10 @@ class FusedMMDiTBase(nn.Module):
                 sel = [i for i in sel if kind == kind_rows[0] and ms["idx_list"][i] in kind_rows[1]]
                 if not sel:
                     continue
-            A, Bm, idx = ms["A"][sel], ms["B"][sel], ms["idx"][sel]
+            if len(sel) == len(ms["names"]):  # everything (the un-sharded path): no list indexing -> no host-to-device index upload, which
+                A, Bm, idx = ms["A"], ms["B"], ms["idx"]  # would be illegal inside the CUDA-graph capture of the step
+            else:
+                A, Bm, idx = ms["A"][sel], ms["B"][sel], ms["idx"][sel]
             t = torch.matmul(x.float()[None], A.float().transpose(1, 2)).to(BF)               # [n, B, r]
             d = torch.bmm(t.float(), Bm.float().transpose(1, 2)).to(BF)                       # [n, B, C]
             d = (d.float() * self.lora_scaling).to(BF)
@@ -403,7 +406,10 @@ class FusedMMDiTBase(nn.Module):
             key = "mod_t_" + kind
             if key not in ws or ws[key].shape[1] != t.shape[1]:
                 ws[key] = torch.zeros(len(ms["names"]), t.shape[1], t.shape[2], device=self.dev, dtype=BF)
-            ws[key][sel] = t
+            if len(sel) == len(ms["names"]):
+                ws[key].copy_(t)
+            else:
+                ws[key][sel] = t
 
     def _mod_grad_buffers(self, ws):
         """fp32 accumulators for d mods (same layout as the modulation vectors), zeroed at the start of every backward."""

@@ -37,9 +37,20 @@ def qwen_rope_table(img_shapes, txt_len: int, axes_dim=(16, 56, 56), theta: floa
     return torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()
 
 
+_FREQ_CACHE = {}
+
+
+def _device_freqs(d: int, theta: float, device) -> torch.Tensor:
+    """float64 axis frequencies resident on `device` (uploaded once: the table is rebuilt inside the CUDA-graph-captured step, where a
+    host-to-device copy is not allowed)."""
+    key = (d, float(theta), str(device))
+    if key not in _FREQ_CACHE:
+        _FREQ_CACHE[key] = _axis_freqs(d, theta, torch.float64).to(device)
+    return _FREQ_CACHE[key]
+
+
 def flux_rope_table(ids: torch.Tensor, axes_dim=(16, 56, 56), theta: float = 10000.0) -> torch.Tensor:
     """ids: [S, n_axes] (text ids first, as the model concatenates them). Returns [S, sum(axes)/2, 2]."""
     pos = ids.detach().double()  # stays on the ids' device: no host synchronisation inside the training step
-    ang = torch.cat([torch.outer(pos[:, i], _axis_freqs(d, theta, torch.float64).to(pos.device)) for i, d in enumerate(axes_dim)],
-                    dim=-1)
+    ang = torch.cat([torch.outer(pos[:, i], _device_freqs(d, theta, pos.device)) for i, d in enumerate(axes_dim)], dim=-1)
     return torch.stack([ang.cos().float(), ang.sin().float()], dim=-1).contiguous()

@@ -48,12 +48,74 @@ class _Accumulation:
     micro-steps add into the same flat fp32 LoRA gradient; the exchange + clip + optimizer step run on the last one with the mean over
     micro-steps and ranks (accelerate divides the loss by the number of accumulation steps)."""
 
-    def _init_accumulation(self, steps: int):
+    def _init_accumulation(self, steps: int, use_cuda_graph: bool = True):
         self.gradient_accumulation_steps, self._micro = max(1, int(steps)), 0
+        self.use_cuda_graph, self._graphs = bool(use_cuda_graph), {}
+
+    # ------------------------------------------------------------------------------------------------ CUDA graph of fwd + loss + bwd
+    # The fused step is ~1,300 (Qwen) to ~3,400 (FLUX with the YAML target set) kernel launches issued from Python through ctypes:
+    # 170-210 ms of host time per step, close to (FLUX: above) the device time.  All of it is shape-static, so the second step of a given
+    # shape is captured into a CUDA graph (inputs copied into static buffers, kernel arguments — TMA descriptors included — baked in) and
+    # every later step is a handful of small copies plus one graph launch.  The exchange + clip + optimizer stay outside (NCCL, and the
+    # optimizer's step count is a kernel argument).  Sharded frozen weights (side-stream all-gathers) run eagerly.
+    @staticmethod
+    def _sig(a):
+        if torch.is_tensor(a):
+            return ("t", tuple(a.shape), str(a.dtype))
+        if isinstance(a, (tuple, list)):
+            return tuple(_Accumulation._sig(x) for x in a)
+        return repr(a)
+
+    def _run_maybe_graphed(self, args):
+        m = self.dit
+        if not self.use_cuda_graph or m._sharded is not None or not torch.cuda.is_available() or not m.dev.type == "cuda":
+            return self._run(*args)
+        key = (self._sig(args), self._accumulating)
+        ent = self._graphs.get(key)
+        if ent is None:  # first step of this shape: eager (allocates the workspace, RoPE tables, split-K scratch, sets kernel attributes)
+            self._graphs[key] = "warm"
+            return self._run(*args)
+        if ent != "warm" and ent["ws"] is not m._ws:  # the model re-allocated its workspace (another shape ran in between): stale pointers
+            ent = "warm"
+        if ent == "warm":
+            static = self._clone_args(args)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = lib.LAUNCHES
+            try:
+                with torch.cuda.graph(g):
+                    loss = self._run(*static)
+            except Exception as e:  # something on this path is not capturable: say so once and stay eager (never silently wrong)
+                import warnings
+                warnings.warn(f"qflux_b200: CUDA-graph capture of the fused step failed ({type(e).__name__}: {e}); running eagerly")
+                torch.cuda.synchronize()
+                self.use_cuda_graph = False
+                lib.LAUNCHES = n0
+                return self._run(*args)
+            ent = dict(graph=g, static=static, loss=loss, launches=lib.LAUNCHES - n0, ws=m._ws)
+            lib.LAUNCHES = n0  # capture launches nothing
+            self._graphs[key] = ent
+        self._copy_args(ent["static"], args)
+        ent["graph"].replay()
+        lib.LAUNCHES += ent["launches"]
+        return ent["loss"]
+
+    @staticmethod
+    def _clone_args(args):
+        return tuple(a.clone() if torch.is_tensor(a) else (_Accumulation._clone_args(a) if isinstance(a, tuple) else a) for a in args)
+
+    @staticmethod
+    def _copy_args(static, args):
+        for s_, a in zip(static, args):
+            if torch.is_tensor(s_):
+                if s_.data_ptr() != a.data_ptr():
+                    s_.copy_(a, non_blocking=True)
+            elif isinstance(s_, tuple):
+                _Accumulation._copy_args(s_, a)
 
     def _fused_micro_step(self, args, optimizer):
         self._accumulating = self._micro > 0  # read by _run: keep the gradient of the earlier micro-steps
-        loss = self._run(*args)
+        loss = self._run_maybe_graphed(args)
         self._accumulating = False
         self._micro += 1
         if self._micro >= self.gradient_accumulation_steps:
@@ -101,12 +163,13 @@ class _StepFn(torch.autograd.Function):
 
 class QwenImageEditStep(_Accumulation):
     def __init__(self, dit: QwenImageB200, loss_kind: str = "mse", fg: float = 2.0, bg: float = 1.0,
-                 num_train_timesteps: int = 1000, max_grad_norm: float = 1.0, gradient_accumulation_steps: int = 1):
+                 num_train_timesteps: int = 1000, max_grad_norm: float = 1.0, gradient_accumulation_steps: int = 1,
+                 use_cuda_graph: bool = True):
         self.dit, self.loss_kind, self.fg, self.bg = dit, loss_kind, fg, bg
         self.num_train_timesteps, self.max_grad_norm = num_train_timesteps, max_grad_norm
         self._ones = {}
         self._accumulating = False
-        self._init_accumulation(gradient_accumulation_steps)
+        self._init_accumulation(gradient_accumulation_steps, use_cuda_graph)
 
     # --------------------------------------------------------------------------------------------- internals
     def _sigmas(self, B, u=None):
@@ -194,11 +257,11 @@ class FluxKontextStep(_Accumulation):
     ids = [target ids ; control ids], guidance = 1 when the model has guidance embeddings, target = eps - x0, MSE."""
 
     def __init__(self, dit, loss_kind: str = "mse", fg: float = 2.0, bg: float = 1.0, max_grad_norm: float = 1.0,
-                 gradient_accumulation_steps: int = 1):
+                 gradient_accumulation_steps: int = 1, use_cuda_graph: bool = True):
         self.dit, self.loss_kind, self.fg, self.bg, self.max_grad_norm = dit, loss_kind, fg, bg, max_grad_norm
         self._ones = {}
         self._accumulating = False
-        self._init_accumulation(gradient_accumulation_steps)
+        self._init_accumulation(gradient_accumulation_steps, use_cuda_graph)
 
     @staticmethod
     def latent_image_ids(h2, w2, device, first=0.0):

@@ -71,6 +71,26 @@ def test_fused_step_vs_oracle(name):
     assert r["fast_vs_autograd"] < 5e-3
 
 
+def test_fused_step_at_the_benchmark_point():
+    """6 full-width blocks, B=4, T=352, 2 x 1024 image tokens, LoRA r=16 (the benchmark config at reduced depth) vs fp32 / bf16 oracle;
+    the ragged text mask must not change the stock forward (reference semantics), on either implementation."""
+    r = _cases("model_check")["bench_point_6blk"]()
+    assert r["pred_vs_fp32"] < 2e-2 and r["pred_vs_fp32"] < 1.25 * r["bf16oracle_pred_vs_fp32"] + 1e-3
+    assert r["grad_vs_fp32"] < 3e-2 and r["loss_rel"] < 1e-2 and r["fast_vs_autograd"] < 5e-3
+    assert r["ragged_mask_oracle_diff"] == 0.0 and r["ragged_mask_b200_diff"] == 0.0 and r["ragged_b200_vs_bf16oracle"] < 2e-2
+
+
+def test_cuda_graph_replay_equals_eager_step():
+    r = _cases("model_check")["graph_replay"]()
+    assert r["err"] < 1e-4, r
+
+
+def test_five_optimizer_steps_track_the_oracle():
+    """fused step + fused clip/AdamW vs fp32 oracle + clip_grad_norm_ + torch.optim.AdamW: loss trajectory within 1e-2 (relative)."""
+    r = _cases("model_check")["train_trajectory_5steps"]()
+    assert r["loss_max_rel"] < 1e-2 and r["decreased"] and r["param_rel"] < 5e-2, r
+
+
 @pytest.mark.parametrize("name", ["qwen_multires", "flux_multires"])
 def test_multi_resolution_vs_unpadded_oracle(name):
     r = _cases("model_check")[name]()

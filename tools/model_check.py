@@ -120,6 +120,125 @@ def full_width_block():
     return r
 
 
+def bench_point_6blk():
+    """The benchmark point (SURVEY.md §8d cfg 2) at reduced DEPTH only: 6 full-width Qwen blocks (D=3072, H=24), B=4, T=352, 2 x 1024
+    image tokens, LoRA r=16 — fused step vs the fp32 and the bf16 oracle (cross-block strides, the B=4 batch indexing of the modulation
+    vectors, the grouped text+image launches at their real sizes).  Also the ragged-mask variant [352, 300, 352, 257]: the stock Qwen
+    forward hands `attention_mask=None` to SDPA and uses only max(txt_seq_lens) for the RoPE table (transformer_qwenimage.py:226-232,
+    332-339), so its result must EQUAL the all-ones-mask result — checked on the oracle and on the B200 module path."""
+    from oracle import mmdit_oracle as mo
+    t0 = time.time()
+    r = step_parity(H=24, L=6, J=3584, B=4, hw=32, T=352, r=16, bf16_oracle=True)
+    torch.cuda.empty_cache()
+    # ragged text mask through the public module signature (2 blocks are enough: the mask never reaches a kernel in this mode)
+    orc, m = build_pair(24, 2, 3584, 0, None)
+    x = inputs(4, 32, 352, 3584)
+    packed = torch.cat([x["image_latents"], x["control_latents"]], 1)
+    t = torch.tensor([0.75, 0.25, 0.5, 0.125], device="cuda")
+    ragged = torch.zeros(4, 352, dtype=torch.int64, device="cuda")
+    for b, n in enumerate([352, 300, 352, 257]):
+        ragged[b, :n] = 1
+    with torch.no_grad():
+        outs = {}
+        for name, mask in (("ones", x["prompt_embeds_mask"]), ("ragged", ragged)):
+            lens = mask.sum(1).tolist()
+            outs["orc_" + name] = orc.bfloat16()(hidden_states=packed, timestep=t, encoder_hidden_states=x["prompt_embeds"],
+                                                  encoder_hidden_states_mask=mask, img_shapes=x["img_shapes"], txt_seq_lens=lens)[0].float()
+            outs["b200_" + name] = m(hidden_states=packed, timestep=t, guidance=None, encoder_hidden_states_mask=mask,
+                                     encoder_hidden_states=x["prompt_embeds"], img_shapes=x["img_shapes"], txt_seq_lens=lens,
+                                     return_dict=False)[0].float()
+    r["ragged_mask_oracle_diff"] = float((outs["orc_ragged"] - outs["orc_ones"]).abs().max())
+    r["ragged_mask_b200_diff"] = float((outs["b200_ragged"] - outs["b200_ones"]).abs().max())
+    r["ragged_b200_vs_bf16oracle"] = rel_l2(outs["b200_ragged"], outs["orc_ragged"])
+    r["secs"] = round(time.time() - t0, 1)
+    return r
+
+
+def train_trajectory(steps=5, H=4, L=4, J=256, B=4, hw=8, T=40, r=8):
+    """`steps` optimizer steps: fused step + FusedLoraAdamW (clip 1.0) on the B200 path vs the fp32 oracle + clip_grad_norm_ +
+    torch.optim.AdamW with the same noise / timestep draws — loss trajectory and final LoRA parameters."""
+    from oracle import mmdit_oracle as mo
+    from qflux_b200.optim import FusedLoraAdamW
+    from qflux_b200.train_step import QwenImageEditStep
+    orc, m = build_pair(H, L, J, r, ("to_q", "to_k", "to_v", "to_out.0"))
+    x = inputs(B, hw, T, J)
+    xf = {k: (v.float() if torch.is_tensor(v) and v.is_floating_point() and k != "u" else v) for k, v in x.items()}
+    emb = {k: x[k] for k in ("image_latents", "control_latents", "prompt_embeds", "img_shapes")}
+    lr, wd = 2e-3, 1e-2
+    params = [p for p in orc.parameters() if p.requires_grad]
+    ref_opt = torch.optim.AdamW(params, lr=lr, weight_decay=wd)
+    step, opt = QwenImageEditStep(m, max_grad_norm=1.0), FusedLoraAdamW(m, lr=lr, weight_decay=wd)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    us = [torch.tensor([0.5, 0.25, 0.125, 0.75]), torch.tensor([0.75, 0.5, 0.25, 0.125]), torch.tensor([0.125, 0.75, 0.5, 0.25])]
+    lo, lb = [], []
+    for it in range(steps):
+        noise = torch.randn(B, hw * hw, 64, device="cuda", generator=g).bfloat16()
+        u = us[it % 3][:B]
+        loss_o, _ = mo.qwen_compute_loss(orc, **{**xf, "noise": noise.float(), "u": u})
+        ref_opt.zero_grad()
+        loss_o.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        ref_opt.step()
+        lo.append(loss_o.item())
+        lb.append(float(step.train_step(emb, opt, noise=noise, u=u).item()))
+    torch.cuda.synchronize()
+    po = {n: p.detach() for n, p in orc.named_parameters() if p.requires_grad}
+    num = sum(((p.detach().float() - po[n]).double() ** 2).sum() for n, p in m.named_parameters())
+    den = sum((v.double() ** 2).sum() for v in po.values())
+    return dict(loss_oracle=lo, loss_b200=lb, loss_max_rel=max(abs(a - b) / max(1.0, abs(a)) for a, b in zip(lo, lb)),
+                param_rel=float((num / den).sqrt()), decreased=lb[-1] < lb[0], err=max(abs(a - b) / max(1.0, abs(a)) for a, b in zip(lo, lb)))
+
+
+def graph_replay():
+    """The CUDA-graph-captured step (second and later calls of `train_step`) must reproduce the eager step: same loss and LoRA gradients
+    for the same inputs (the attention backward accumulates dQ with atomics, so 'same' is to a few fp32 ulps of reordering), new inputs
+    must be picked up through the static buffers, and the launch counter must keep counting.  Qwen and FLUX (YAML target set: the path
+    with AdaLN-linear LoRA, whose index bookkeeping must stay off the host inside the capture)."""
+    from qflux_b200 import lib
+    from qflux_b200.train_step import FluxKontextStep, QwenImageEditStep
+    res = {}
+    orc, m = build_pair(2, 2, 128, 4, ("to_q", "to_k", "to_v", "to_out.0", "img_mod.1"))
+    x = inputs(2, 4, 24, 128)
+    emb = {k: x[k] for k in ("image_latents", "control_latents", "prompt_embeds", "img_shapes")}
+    eager, graphed = QwenImageEditStep(m, use_cuda_graph=False), QwenImageEditStep(m, use_cuda_graph=True)
+    l_e = float(eager.train_step(emb, noise=x["noise"], u=x["u"]))
+    g_e = m.G32.clone()
+    n0 = lib.LAUNCHES
+    l1 = float(graphed.train_step(emb, noise=x["noise"], u=x["u"]))   # eager warm-up of the graphed step object
+    per_step = lib.LAUNCHES - n0
+    l2 = float(graphed.train_step(emb, noise=x["noise"], u=x["u"]))   # capture + first replay
+    g2 = m.G32.clone()
+    l3 = float(graphed.train_step(emb, noise=x["noise"], u=x["u"]))   # replay
+    res["qwen_loss"] = max(abs(l_e - l1), abs(l_e - l2), abs(l_e - l3))
+    res["qwen_grad"] = max(rel_l2(g2, g_e), rel_l2(m.G32, g_e))
+    res["launch_count_ok"] = float(lib.LAUNCHES - n0 != 3 * per_step)
+    noise2 = (x["noise"].float() * 0.5).bfloat16()
+    l_new_e = float(eager.train_step(emb, noise=noise2, u=x["u"]))
+    g_new_e = m.G32.clone()
+    l_new_g = float(graphed.train_step(emb, noise=noise2, u=x["u"]))
+    res["qwen_new_inputs"] = max(abs(l_new_e - l_new_g), rel_l2(m.G32, g_new_e))
+    assert abs(l_new_e - l_e) > 1e-3, "the second input set must actually differ"
+    assert len(graphed._graphs) == 1 and isinstance(next(iter(graphed._graphs.values())), dict), "no graph was captured"
+    # FLUX with the YAML target regex
+    orc, mf = build_flux_pair(targets=FLUX_YAML_TARGETS, r=4)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()
+    B, hw, T = 2, 4, 8
+    embf = dict(image_latents=rn(B, hw * hw, 64), control_latents=rn(B, hw * hw, 64), pooled_prompt_embeds=rn(B, 64), prompt_embeds=rn(B, T, 64),
+                text_ids=torch.zeros(T, 3, device="cuda"), image_ids=FluxKontextStep.latent_image_ids(hw, hw, "cuda", 0.0),
+                control_ids=FluxKontextStep.latent_image_ids(hw, hw, "cuda", 1.0))
+    nz, t = rn(B, hw * hw, 64), torch.tensor([0.5, 0.25], device="cuda")
+    fe, fg = FluxKontextStep(mf, use_cuda_graph=False), FluxKontextStep(mf, use_cuda_graph=True)
+    le = float(fe.train_step(embf, noise=nz, t=t))
+    ge = mf.G32.clone()
+    ls = [float(fg.train_step(embf, noise=nz, t=t)) for _ in range(3)]
+    res["flux_loss"] = max(abs(le - v) for v in ls)
+    res["flux_grad"] = rel_l2(mf.G32, ge)
+    assert len(fg._graphs) == 1 and isinstance(next(iter(fg._graphs.values())), dict), "no FLUX graph was captured"
+    res["err"] = max(res.values())
+    return res
+
+
 FLUX_YAML_TARGETS = (
     r"(.*x_embedder|.*transformer_blocks\.[0-9]+\.(norm|norm1)\.linear|.*transformer_blocks\.[0-9]+\.attn\.(to_k|to_q|to_v|to_add_out)"
     r"|.*transformer_blocks\.[0-9]+\.attn\.to_out\.0|.*single_transformer_blocks\.[0-9]+\.attn\.to_out"
@@ -346,6 +465,9 @@ CASES = {
     "step_tiny_mod_embed_targets": lambda: step_parity(targets=("to_q", "img_mod.1", "txt_mod.1", "img_in", "txt_in")),
     "step_tiny_mlp_down_targets": lambda: step_parity(targets=("to_k", "img_mlp.net.2", "txt_mlp.net.0.proj", "txt_mlp.net.2")),
     "flux_full_width_1p1": lambda: flux_step_parity(H=24, L=1, Ls=1, J=4096, Pp=768, B=1, hw=32, T=512, r=16),
+    "bench_point_6blk": bench_point_6blk,
+    "train_trajectory_5steps": train_trajectory,
+    "graph_replay": graph_replay,
 }
 
 if __name__ == "__main__":
