@@ -331,7 +331,8 @@ def run_b200(args):
     if cfg["model"] == "qwen":
         m = build_model(dev, args.layers or cfg["blocks"], cfg)
         if shard:
-            m.shard_frozen_weights()
+            m.shard_frozen_weights(gather=args.shard_gather)
+            shard_gather = m._sharded.gather
         step = QwenImageEditStep(m, "attention_mask" if name == "qwen_multires" else "mse", max_grad_norm=1.0)
     else:
         m = build_flux(dev, cfg, scale)
@@ -440,7 +441,7 @@ def run_b200(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": cfg["workload"], "name": name, "blocks": n_blocks, "global_batch": B * world, "batch_per_gpu": B,
-                       "parallelism": f"dp{world}" + ("+sharded-frozen-weights" if shard else ""),
+                       "parallelism": f"dp{world}" + (f"+sharded-frozen-weights({shard_gather}-gather)" if shard else ""),
                        "l2": "inputs > L2: tens of GB of weights + activations stream through 126 MB L2",
                        "optimizer": "qfx_fused_adamw: global-norm clip 1.0 + AdamW on the LoRA params, one kernel over the flat fp32 gradient",
                        "loss": loss_val},
@@ -477,6 +478,8 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer blocks (INVALID as a bench value)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-library", action="store_true", help="skip the library_baseline leg (eager PyTorch on the same GPU)")
+    ap.add_argument("--shard-gather", default="auto", choices=["auto", "peer", "nccl"],
+                    help="how a sharded block is assembled: copy-engine pulls from IPC-mapped peer shards (one node) or NCCL all-gather")
     ap.add_argument("--shard-weights", action="store_true",
                     help="frozen block weights sharded 1/N per rank, all-gathered per block (default for --config qwen_plus_sharded at N > 1)")
     args = ap.parse_args()

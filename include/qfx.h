@@ -195,6 +195,18 @@ int qfx_fused_adamw(const qfx_adamw_tensor* tensors, const int* chunks, int n_ch
                     float* exp_avg, float* exp_avg_sq, float* sumsq, float pre_scale, float max_norm, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int step, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Peer memory for sharded frozen weights (replaces FSDP's per-module all-gather, base_trainer.py:333-382, for the frozen block
+ * weights).  A rank's weight shard lives in an allocation made by qfx_peer_alloc; its 64-byte handle is sent to the other ranks
+ * of the node (any host transport), which map it with qfx_peer_open.  qfx_peer_copy_async then pulls bytes from a mapped peer
+ * pointer into local memory with the copy engines over NVLink (cudaMemcpyAsync on `stream`, no SM work, no collective). */
+#define QFX_PEER_HANDLE_BYTES 64
+int qfx_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle /* [QFX_PEER_HANDLE_BYTES] */);
+int qfx_peer_free(void* ptr);
+int qfx_peer_open(const unsigned char* handle, void** ptr);
+int qfx_peer_close(void* ptr);
+int qfx_peer_copy_async(void* dst, const void* src, int64_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

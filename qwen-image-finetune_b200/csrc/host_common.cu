@@ -84,3 +84,52 @@ int num_sms() {
 
 extern "C" const char* qfx_last_error(void) { return qfx::g_err; }
 extern "C" int qfx_version(void) { return 1; }
+
+// ---------------------------------------------------------------------------------------------------- peer memory
+// Sharded frozen weights: each rank exports its shard through CUDA IPC; a block's weights are assembled with copy-engine pulls.
+static_assert(sizeof(cudaIpcMemHandle_t) == QFX_PEER_HANDLE_BYTES, "handle size");
+
+#define QFX_RT(call)                                                            \
+  do {                                                                          \
+    cudaError_t e_ = (call);                                                    \
+    if (e_ != cudaSuccess) {                                                    \
+      qfx::set_error("%s: %s", #call, cudaGetErrorString(e_));                  \
+      return -1;                                                                \
+    }                                                                           \
+  } while (0)
+
+extern "C" int qfx_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle) {
+  if (bytes <= 0 || !ptr || !handle) {
+    qfx::set_error("qfx_peer_alloc: bad arguments");
+    return -1;
+  }
+  QFX_RT(cudaMalloc(ptr, (size_t)bytes));  // a dedicated allocation: the handle maps exactly this range (offset 0)
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) {
+    qfx::set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    return -1;
+  }
+  memcpy(handle, &h, sizeof(h));
+  return 0;
+}
+extern "C" int qfx_peer_free(void* ptr) {
+  QFX_RT(cudaFree(ptr));
+  return 0;
+}
+extern "C" int qfx_peer_open(const unsigned char* handle, void** ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  QFX_RT(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+extern "C" int qfx_peer_close(void* ptr) {
+  QFX_RT(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+extern "C" int qfx_peer_copy_async(void* dst, const void* src, int64_t bytes, void* stream) {
+  QFX_RT(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}

@@ -367,3 +367,58 @@ def attn_fwd(Q, K, V, out_txt, out_img, split, lse=None, kv_len=None, scale=None
     scale = scale if scale is not None else d ** -0.5
     check(_attn_fwd(ptr(Q), ptr(K), ptr(V), ptr(out_txt), _ld(out_txt), split, ptr(out_img), _ld(out_img), S - split, split,
                     ptr(lse), ptr(kv_len), ptr(txt_len), B, H, S, scale, cur_stream()), "qfx_attn_fwd")
+
+
+# ---------------------------------------------------------------------------------------------------- peer memory (sharding.py)
+PEER_HANDLE_BYTES = 64
+for _f in ("qfx_peer_alloc", "qfx_peer_free", "qfx_peer_open", "qfx_peer_close", "qfx_peer_copy_async"):
+    getattr(_lib, _f).restype = C.c_int
+_lib.qfx_peer_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]
+_lib.qfx_peer_free.argtypes = [C.c_void_p]
+_lib.qfx_peer_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+_lib.qfx_peer_close.argtypes = [C.c_void_p]
+_lib.qfx_peer_copy_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+
+
+def _rc(rc: int, what: str):  # like check(), but these are not kernel launches
+    if rc != 0:
+        raise QfxError(f"{what} failed (rc={rc}): {_lib.qfx_last_error().decode()}")
+
+
+class PeerBuffer:
+    """A device allocation other ranks of the node can map (CUDA IPC).  `.tensor(dtype, shape)` views it as a torch tensor."""
+
+    def __init__(self, nbytes: int, device):
+        self.nbytes, self.device = int(nbytes), torch.device(device)
+        p, h = C.c_void_p(), C.create_string_buffer(PEER_HANDLE_BYTES)
+        with torch.cuda.device(self.device):
+            _rc(_lib.qfx_peer_alloc(self.nbytes, C.byref(p), h), "qfx_peer_alloc")
+        self.ptr, self.handle = p.value, h.raw
+
+    @property
+    def __cuda_array_interface__(self):
+        return dict(shape=(self.nbytes,), typestr="|u1", data=(self.ptr, False), version=2)
+
+    def tensor(self, dtype, shape):
+        return torch.as_tensor(self, device=self.device).view(dtype).view(shape)
+
+    def free(self):
+        if self.ptr:
+            _rc(_lib.qfx_peer_free(C.c_void_p(self.ptr)), "qfx_peer_free")
+            self.ptr = 0
+
+
+def peer_open(handle: bytes, device) -> int:
+    p = C.c_void_p()
+    with torch.cuda.device(device):
+        _rc(_lib.qfx_peer_open(handle, C.byref(p)), "qfx_peer_open")
+    return p.value
+
+
+def peer_close(p: int):
+    _rc(_lib.qfx_peer_close(C.c_void_p(p)), "qfx_peer_close")
+
+
+def peer_copy_async(dst_ptr: int, src_ptr: int, nbytes: int, stream=None):
+    s = cur_stream() if stream is None else C.c_void_p(stream.cuda_stream)
+    _rc(_lib.qfx_peer_copy_async(C.c_void_p(dst_ptr), C.c_void_p(src_ptr), int(nbytes), s), "qfx_peer_copy_async")

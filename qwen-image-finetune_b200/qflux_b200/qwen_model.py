@@ -132,15 +132,16 @@ class QwenImageB200(FusedMMDiTBase):
 
     _PER_LAYER = ("mod_w", "mod_b", "qkv_w", "qkv_b", "out_w", "out_b", "up_w", "up_b", "down_w", "down_b", "qknorm_w")
 
-    def shard_frozen_weights(self, group=None):
+    def shard_frozen_weights(self, group=None, gather="auto"):
         """BASELINE config 4 ("FSDP"): keep 1/world of every block's frozen weights on this rank; a block's full weights are
-        all-gathered into one of two ring buffers right before it runs (sharding.py).  Call after the weights are loaded.
+        assembled in one of two ring buffers right before it runs — by copy-engine pulls from the peers' shards on one node, by
+        an NCCL all-gather otherwise (sharding.py).  Call after the weights are loaded.
         LoRA factors stay replicated; `state_dict()` then only carries the replicated tensors and the LoRA parameters."""
         from .sharding import ShardedBlocks
         if self._sharded is not None:
             return self
         stacked = {k: self.w[k] for k in self._PER_LAYER}
-        self._sharded = ShardedBlocks(stacked, self.L, group)
+        self._sharded = ShardedBlocks(stacked, self.L, group, gather=gather)
         for k in self._PER_LAYER:
             self.w[k] = self._sharded.rings[k]
         del stacked

@@ -2,8 +2,8 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/sharded_check.py
 
-Every rank builds the same replicated model and a sharded twin (1/world of each block's frozen weights per rank, NCCL all-gather
-per block into a two-slot ring, prefetched on a side stream), runs the fused training step on per-rank data with both and
+Every rank builds the same replicated model and a sharded twin (1/world of each block's frozen weights per rank; a block is assembled in a
+two-slot ring on a side stream — once with copy-engine pulls from the peers' IPC-mapped shards, once with an NCCL all-gather), runs the fused training step on per-rank data with both and
 compares loss and the flat LoRA gradient (to rounding: the loss sum, LoRA wgrad and dQ use fp32 atomics, so two runs of the SAME
 model differ in the last bits too — `self_*` reports that floor); rank 0 prints one JSON line."""
 import json
@@ -36,7 +36,7 @@ def main():
         m.add_adapter(16, 16, target_modules=("to_q", "to_k", "to_v", "to_out.0", "img_mod.1", "net.2"), b_std=0.05)
         return m
 
-    full, sh = build(), build().shard_frozen_weights()
+    full, sh, sh_nccl = build(), build().shard_frozen_weights(gather="peer"), build().shard_frozen_weights(gather="nccl")
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     rn = lambda *s: torch.randn(*s, device=dev, generator=g).bfloat16()
     B, hw, T = 2, 16, 40
@@ -54,10 +54,14 @@ def main():
     lf, gf = run(full)
     lf2, gf2 = run(full)
     ls, gs = run(sh)
+    ln, gn = run(sh_nccl)
     ok = dict(rank=rank, loss_full=lf, loss_sharded=ls, loss_rel=abs(ls - lf) / abs(lf), grad_rel=rel(gs, gf), self_loss_rel=abs(lf2 - lf) / abs(lf),
               self_grad_rel=rel(gf2, gf), grad_norm=float(gf.norm()), shard_mb=sh._sharded.shard.numel() * 2 / 2 ** 20,
               block_mb=sh._sharded.n_blk * 2 / 2 ** 20)
-    ok["pass"] = ok["loss_rel"] < 1e-5 and ok["grad_rel"] < max(1e-4, 10 * ok["self_grad_rel"])
+    ok.update(gather=sh._sharded.gather, nccl_loss_rel=abs(ln - lf) / abs(lf), nccl_grad_rel=rel(gn, gf))
+    tol = max(1e-4, 10 * ok["self_grad_rel"])
+    ok["pass"] = ok["loss_rel"] < 1e-5 and ok["grad_rel"] < tol and ok["nccl_loss_rel"] < 1e-5 and ok["nccl_grad_rel"] < tol and ok["gather"] == "peer"
+    sh._sharded.close()
     allr = [None] * world
     dist.all_gather_object(allr, ok)
     if rank == 0:
