@@ -77,7 +77,7 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.first = [], None, index, 0
 
     def start(self):
         try:
@@ -87,6 +87,11 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """Rows sampled before this point (the sampler is started ahead of the barrier: spawning nvidia-smi takes tens of ms, which
+        would otherwise delay rank 0's first step and be charged to every rank through the all-reduce) are not part of the result."""
+        self.first = len(self.rows)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
@@ -95,6 +100,7 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
+        self.rows = self.rows[self.first:] or self.rows[-1:]
         sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -336,6 +342,9 @@ def run_b200(args):
         step = QwenImageEditStep(m, "attention_mask" if name == "qwen_multires" else "mse", max_grad_norm=1.0)
     else:
         m = build_flux(dev, cfg, scale)
+        if shard:
+            m.shard_frozen_weights(gather=args.shard_gather)
+            shard_gather = m._sharded.gather
         step = FluxKontextStep(m, "mse", max_grad_norm=1.0)
     n_blocks = (args.layers or cfg["blocks"]) if cfg["model"] == "qwen" else (m.L + m.Ls)
     opt = FusedLoraAdamW(m, lr=1e-4)  # clip + AdamW fused over the flat fp32 LoRA gradient (torch AdamW semantics, fp32 moments)
@@ -361,10 +370,11 @@ def run_b200(args):
     # ---------------- device-resident arm
     for _ in range(args.warmup):
         step.train_step(devd, opt)
-    sync()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    sync()
+    clocks.mark()
     n0 = lib.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -401,6 +411,24 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_ips = B * world * args.steps / dt.item()
+    # the step's only data-path collective, timed alone: all-reduce(sum) of the flat fp32 LoRA gradient (train_step._sync_and_step)
+    allreduce = None
+    if world > 1:
+        g = torch.zeros_like(m.G32)
+        for _ in range(3):
+            dist.all_reduce(g)
+        sync()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            dist.all_reduce(g)
+        a1.record()
+        torch.cuda.synchronize()
+        ar = torch.tensor([a0.elapsed_time(a1) / 10], device=dev)
+        dist.all_reduce(ar, op=dist.ReduceOp.MAX)
+        allreduce = {"bytes": g.numel() * 4, "ms": round(ar.item(), 4), "share_of_step": round(ar.item() / ms_step, 5),
+                     "note": "one NCCL all-reduce of the flat fp32 LoRA gradient per optimizer step, after the backward"}
+        del g
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -445,7 +473,7 @@ def run_b200(args):
                        "l2": "inputs > L2: tens of GB of weights + activations stream through 126 MB L2",
                        "optimizer": "qfx_fused_adamw: global-norm clip 1.0 + AdamW on the LoRA params, one kernel over the flat fp32 gradient",
                        "loss": loss_val},
-            "clocks": clk, "gpu_launches": launches, "host_issue_ms_per_step": host_issue_ms, "ms_per_step_per_rank": per_rank,
+            "clocks": clk, "gpu_launches": launches, "host_issue_ms_per_step": host_issue_ms, "ms_per_step_per_rank": per_rank, "allreduce": allreduce,
             "e2e": {"value": e2e_ips, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "roofline": roof, "cpu_baseline": cpu, "library_baseline": lib_base}
     _emit(line)

@@ -115,7 +115,8 @@ class FluxB200(FusedMMDiTBase):
             out[p + "linear_2.weight"], out[p + "linear_2.bias"] = w[pre + "2_w"], w[pre + "2_b"]
         out["norm_out.linear.weight"], out["norm_out.linear.bias"] = w["norm_out_w"], w["norm_out_b"]
         out["proj_out.weight"], out["proj_out.bias"] = w["proj_out_w"], w["proj_out_b"]
-        for l in range(self.L):
+        sharded = self._sharded is not None  # sharded block weights are not addressable as full tensors
+        for l in range(0 if sharded else self.L):
             b = f"transformer_blocks.{l}."
             for s, nm in ((0, "norm1.linear"), (1, "norm1_context.linear")):
                 out[b + nm + ".weight"], out[b + nm + ".bias"] = w["mod_w"][l, s], w["mod_b"][l, s]
@@ -126,7 +127,7 @@ class FluxB200(FusedMMDiTBase):
                 if grp == "qkv":
                     W, Bv = W[slot * D:(slot + 1) * D], Bv[slot * D:(slot + 1) * D]
                 out[b + nm + ".weight"], out[b + nm + ".bias"] = W, Bv
-        for l in range(self.Ls):
+        for l in range(0 if sharded else self.Ls):
             b = f"single_transformer_blocks.{l}."
             out[b + "norm.linear.weight"], out[b + "norm.linear.bias"] = w["s_mod_w"][l], w["s_mod_b"][l]
             out[b + "attn.norm_q.weight"], out[b + "attn.norm_k.weight"] = w["s_qknorm_w"][l, 0], w["s_qknorm_w"][l, 1]
@@ -136,6 +137,55 @@ class FluxB200(FusedMMDiTBase):
                     W, Bv = W[slot * D:(slot + 1) * D], Bv[slot * D:(slot + 1) * D]
                 out[b + nm + ".weight"], out[b + nm + ".bias"] = W, Bv
         return out
+
+    _PER_LAYER = ("mod_w", "mod_b", "qkv_w", "qkv_b", "out_w", "out_b", "up_w", "up_b", "down_w", "down_b", "qknorm_w")
+    _PER_SINGLE = ("s_mod_w", "s_mod_b", "s_qkv_w", "s_qkv_b", "s_mlp_w", "s_mlp_b", "s_out_w", "s_out_b", "s_qknorm_w")
+
+    def shard_frozen_weights(self, group=None, gather="auto"):
+        """The reference's FSDP branch (base_trainer.py:333-382) for FLUX: 1/world of every double and every single block's frozen
+        weights per rank, a block assembled right before it runs (sharding.py; one two-slot ring per block kind).  LoRA factors
+        and the embedders / head stay replicated.  Call after the weights are loaded."""
+        from .sharding import ShardedBlocks
+        if self._sharded is not None:
+            return self
+        self._sharded = ShardedBlocks({k: self.w[k] for k in self._PER_LAYER}, self.L, group, gather=gather)
+        for k in self._PER_LAYER:
+            self.w[k] = self._sharded.rings[k]
+        self._sharded_s = None
+        if self.Ls:
+            self._sharded_s = ShardedBlocks({k: self.w[k] for k in self._PER_SINGLE}, self.Ls, group, gather=gather)
+            for k in self._PER_SINGLE:
+                self.w[k] = self._sharded_s.rings[k]
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+        return self
+
+    def _ring(self, blk):
+        """(ring, local index) of global block `blk` (double blocks first, then single blocks)."""
+        return (self._sharded, blk) if blk < self.L else (self._sharded_s, blk - self.L)
+
+    def _acquire(self, ws, blk, nxt):
+        """Sharded weights: make block `blk` resident, start fetching `nxt`, and produce blk's base modulation vectors."""
+        ring, l = self._ring(blk)
+        ring.acquire(l)
+        if 0 <= nxt < self.L + self.Ls:
+            r2, l2 = self._ring(nxt)
+            r2.prefetch(l2)
+
+    def _release(self, blk):
+        ring, l = self._ring(blk)
+        ring.release(l)
+
+    def _block_mods(self, ws, blk):
+        D, w = self.D, self.w
+        if blk < self.L:
+            lib.gemv_act(ws["temb"], w["mod_w"][blk].view(2 * 6 * D, D), w["mod_b"][blk].view(-1),
+                         ws["mods"][:, blk * 12 * D:(blk + 1) * 12 * D], act=1)
+            self._mod_lora_fwd(ws, ws["temb"], ("dbl", (2 * blk, 2 * blk + 1)))
+        else:
+            l = blk - self.L
+            lib.gemv_act(ws["temb"], w["s_mod_w"][l], w["s_mod_b"][l], ws["smods"][:, l * 3 * D:(l + 1) * 3 * D], act=1)
+            self._mod_lora_fwd(ws, ws["temb"], ("sgl", (l,)))
 
     def _linear_table(self) -> dict:
         D = self.D
@@ -285,21 +335,29 @@ class FluxB200(FusedMMDiTBase):
             lib.add_bf16(ws["temb"], ws["gemb"], ws["temb"])
         self._mlp2(pooled_projections.to(BF).contiguous(), "p", ws["pemb"], ws["e1"])
         lib.add_bf16(ws["temb"], ws["pemb"], ws["temb"])
-        lib.gemv_act(ws["temb"], w["mod_w"].view(L * 2 * 6 * D, D), w["mod_b"].view(-1), ws["mods"], act=1)
-        if Ls:
-            lib.gemv_act(ws["temb"], w["s_mod_w"].view(Ls * 3 * D, D), w["s_mod_b"].view(-1), ws["smods"], act=1)
+        sh = self._sharded
+        if sh is None:  # all modulation linears of a kind in one launch; sharded weights produce them block by block
+            lib.gemv_act(ws["temb"], w["mod_w"].view(L * 2 * 6 * D, D), w["mod_b"].view(-1), ws["mods"], act=1)
+            if Ls:
+                lib.gemv_act(ws["temb"], w["s_mod_w"].view(Ls * 3 * D, D), w["s_mod_b"].view(-1), ws["smods"], act=1)
+            self._mod_lora_fwd(ws, ws["temb"])
         lib.gemv_act(ws["temb"], w["norm_out_w"], w["norm_out_b"], ws["fmod"], act=1)
-        self._mod_lora_fwd(ws, ws["temb"])
         # --- embedders
         self._embed_fwd(ws, "x_in", 0, hidden_states.to(BF).reshape(B * Limg, self.C_in), X0[Mt:])
         self._embed_fwd(ws, "ctx_in", 1, encoder_hidden_states.to(BF).reshape(Mt, self.J), X0[:Mt])
         # --- blocks
         nb = L + Ls
         xi = lambda i: ws["X"][i] if train else ws["X"][i & 1]
-        for l in range(L):
-            self._double_fwd(ws, l, xi(l), xi(l + 1), ws["dbl"][l if train else 0], self._mods(ws, l))
-        for l in range(Ls):
-            self._single_fwd(ws, l, xi(L + l), xi(L + l + 1), ws["sgl"][l if train else 0])
+        for blk in range(nb):
+            if sh is not None:
+                self._acquire(ws, blk, blk + 1)
+                self._block_mods(ws, blk)
+            if blk < L:
+                self._double_fwd(ws, blk, xi(blk), xi(blk + 1), ws["dbl"][blk if train else 0], self._mods(ws, blk))
+            else:
+                self._single_fwd(ws, blk - L, xi(blk), xi(blk + 1), ws["sgl"][(blk - L) if train else 0])
+            if sh is not None:
+                self._release(blk)
         Xl = xi(nb)
         ws["Xlast"] = Xl
         lib.ln_modulate_fwd(Xl[Mt:], ws["hn"], ws["fmod"][:, D:], ws["fmod"][:, :D], Limg, ws["fstats"][0], ws["fstats"][1])
@@ -327,10 +385,14 @@ class FluxB200(FusedMMDiTBase):
         for blk in range(nb - 1, -1, -1):
             dXn = ws["dX"][blk & 1]
             prev = self._last_gate(ws, blk - 1) if blk > 0 else None
+            if self._sharded is not None:
+                self._acquire(ws, blk, blk - 1)
             if blk >= L:
                 self._single_bwd(ws, blk - L, ws["X"][blk], dX, dXn, ws["sgl"][blk - L], prev)
             else:
                 self._double_bwd(ws, blk, ws["X"][blk], dX, dXn, ws["dbl"][blk], self._mods(ws, blk), prev)
+            if self._sharded is not None:
+                self._release(blk)
             dX = dXn
         self._mod_lora_bwd(ws)
         self._embed_bwd(ws, "x_in", 0, dX)

@@ -133,3 +133,67 @@ def test_sharded_frozen_weights_match_replicated(tmp_path):
         assert r["loss"] and r["grads"] and r["fwd"], r
         assert 0.5 <= r["shard_fraction"] < 0.51, "each of 2 ranks keeps half of the block weights (plus alignment padding)"
         assert r["lora_only_state"]
+
+
+def _worker_sharded_flux(rank, world, port, out):
+    """The same sharding for FLUX: one two-slot ring for the double blocks, one for the single blocks; the walk crosses from one
+    ring to the other in the forward and back in the backward."""
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "qwen-image-finetune_b200"))
+    import emu_lib
+    from qflux_b200 import lib
+    emu_lib.install(lib)
+    from qflux_b200.flux_model import FluxB200, FluxB200Config
+    from qflux_b200.train_step import FluxKontextStep
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def build():
+        torch.manual_seed(11)
+        m = FluxB200(FluxB200Config(num_layers=3, num_single_layers=3, attention_head_dim=128, num_attention_heads=2, joint_attention_dim=64,
+                                    pooled_projection_dim=64, guidance_embeds=True), device="cpu", _host_only=True)
+        for k, t in m.w.items():
+            if k.endswith("_w") and t.ndim >= 2 and "qknorm" not in k:
+                t.copy_((torch.randn(t.shape) * 0.05).bfloat16())
+            elif k.endswith("_b"):
+                t.copy_((torch.randn(t.shape) * 0.02).bfloat16())
+        m.add_adapter(4, 4, target_modules=r".*(attn\.to_q|attn\.to_out\.0|norm1\.linear|single_transformer_blocks\.[0-9]+\.(norm\.linear|proj_mlp|proj_out)|ff\.net\.2)",
+                      b_std=0.05)
+        return m
+
+    full, sh = build(), build().shard_frozen_weights()
+    g = torch.Generator().manual_seed(200 + rank)
+    rn = lambda *s: torch.randn(*s, generator=g).bfloat16()
+    B, hw, T = 1, 4, 8
+    L = hw * hw
+    emb = dict(image_latents=rn(B, L, 64), control_latents=rn(B, L, 64), pooled_prompt_embeds=rn(B, 64), prompt_embeds=rn(B, T, 64),
+               text_ids=torch.zeros(T, 3), image_ids=FluxKontextStep.latent_image_ids(hw, hw, "cpu", 0.0),
+               control_ids=FluxKontextStep.latent_image_ids(hw, hw, "cpu", 1.0))
+    noise, t = rn(B, L, 64), torch.tensor([0.5])
+    res = {}
+    for name, m in (("full", full), ("sharded", sh)):
+        step = FluxKontextStep(m, max_grad_norm=0.0)
+        loss = step._run(*step._prepare(emb, noise, t))
+        res[name] = (float(loss), m.G32.clone())
+        step._run(*step._prepare(emb, noise, t))  # the second step starts from the rings as the backward left them
+        assert torch.equal(m.G32, res[name][1])
+    per_rank = sh._sharded.shard.numel() + sh._sharded_s.shard.numel()
+    total = sum(full.w[k].numel() for k in type(full)._PER_LAYER + type(full)._PER_SINGLE)
+    ok = dict(loss=res["full"][0] == res["sharded"][0], grads=torch.equal(res["full"][1], res["sharded"][1]) and float(res["full"][1].norm()) > 0,
+              shard_fraction=per_rank / total, lora_only_state=all("lora" in k or "transformer_blocks" not in k for k in sh.state_dict()))
+    allr = [None] * world
+    dist.all_gather_object(allr, ok)
+    if rank == 0:
+        torch.save(allr, out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_frozen_weights_flux(tmp_path):
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker_sharded_flux, args=(2, _free_port(), out), nprocs=2, join=True)
+    for r in torch.load(out):
+        assert r["loss"] and r["grads"], r
+        assert 0.5 <= r["shard_fraction"] < 0.51
+        assert r["lora_only_state"]

@@ -17,6 +17,50 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
+def flux_case(dev, rank):
+    """FLUX: double-block ring + single-block ring, peer-copy gather, against the replicated model."""
+    from qflux_b200.flux_model import FluxB200, FluxB200Config
+    from qflux_b200.train_step import FluxKontextStep
+
+    def build():
+        g = torch.Generator(device=dev).manual_seed(9)
+        m = FluxB200(FluxB200Config(num_layers=3, num_single_layers=4, attention_head_dim=128, num_attention_heads=8, joint_attention_dim=512,
+                                    pooled_projection_dim=256, guidance_embeds=True), device=dev)
+        for k, t in m.w.items():
+            if k.endswith("_w") and t.ndim >= 2 and "qknorm" not in k:
+                t.copy_((torch.randn(t.shape, device=dev, generator=g) * 0.03).bfloat16())
+            elif k.endswith("_b"):
+                t.copy_((torch.randn(t.shape, device=dev, generator=g) * 0.02).bfloat16())
+        m.add_adapter(16, 16, target_modules=r".*(attn\.to_[qkv]|attn\.to_out\.0|norm1\.linear|single_transformer_blocks\.[0-9]+\.(norm\.linear|proj_mlp|proj_out)|ff\.net\.2)",
+                      b_std=0.05)
+        return m
+
+    full, sh = build(), build().shard_frozen_weights(gather="peer")
+    g = torch.Generator(device=dev).manual_seed(300 + rank)
+    rn = lambda *s: torch.randn(*s, device=dev, generator=g).bfloat16()
+    B, hw, T = 2, 16, 40
+    L = hw * hw
+    emb = dict(image_latents=rn(B, L, 64), control_latents=rn(B, L, 64), pooled_prompt_embeds=rn(B, 256), prompt_embeds=rn(B, T, 512),
+               text_ids=torch.zeros(T, 3), image_ids=FluxKontextStep.latent_image_ids(hw, hw, dev, 0.0),
+               control_ids=FluxKontextStep.latent_image_ids(hw, hw, dev, 1.0))
+    noise, t = rn(B, L, 64), torch.tensor([0.5, 0.25])
+
+    def run(m):
+        step = FluxKontextStep(m, max_grad_norm=0.0)
+        for _ in range(3):
+            loss = step._run(*step._prepare(emb, noise, t))
+        torch.cuda.synchronize()
+        return float(loss), m.G32.clone()
+
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    (lf, gf), (lf2, gf2), (ls, gs) = run(full), run(full), run(sh)
+    r = dict(loss_rel=abs(ls - lf) / abs(lf), grad_rel=rel(gs, gf), self_grad_rel=rel(gf2, gf), grad_norm=float(gf.norm()), gather=sh._sharded.gather)
+    r["pass"] = r["loss_rel"] < 1e-5 and r["grad_rel"] < max(1e-4, 10 * r["self_grad_rel"]) and r["gather"] == "peer"
+    sh._sharded.close()
+    sh._sharded_s.close()
+    return r
+
+
 def main():
     from qflux_b200.qwen_model import QwenB200Config, QwenImageB200
     from qflux_b200.train_step import QwenImageEditStep
@@ -62,6 +106,8 @@ def main():
     tol = max(1e-4, 10 * ok["self_grad_rel"])
     ok["pass"] = ok["loss_rel"] < 1e-5 and ok["grad_rel"] < tol and ok["nccl_loss_rel"] < 1e-5 and ok["nccl_grad_rel"] < tol and ok["gather"] == "peer"
     sh._sharded.close()
+    ok["flux"] = flux_case(dev, rank)
+    ok["pass"] = ok["pass"] and ok["flux"]["pass"]
     allr = [None] * world
     dist.all_gather_object(allr, ok)
     if rank == 0:
