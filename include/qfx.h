@@ -60,12 +60,18 @@ typedef struct {
   const void* resid; int64_t ldr;/* QFX_EPI_RESID_GATE */
   const void* gate;  int64_t ldg; int rows_per_batch;
   const void* aux;   int64_t ldaux; /* QFX_EPI_DGELU: u */
+  /* Ragged row groups (pad-to-max multi-resolution batches, transformer_qwen_custom.py:444-553): when row_tiles != NULL only the
+   * n_row_tiles 256-row bands starting at rows row_tiles[i] (device int32, disjoint, ascending) are computed; the other rows of
+   * `out`/`out2` are NOT written (the caller zero-fills them, qfx_zero_rows).  NULL: all M rows. */
+  const int* row_tiles; int n_row_tiles;
 } qfx_gemm_problem;
 
 /* lora_group_n > 0 (trans_b = 0 only): output columns [g*lora_group_n, (g+1)*lora_group_n) use A2 columns
  * a2_col0 + g*64*kb2 .. (fused q|k|v projection with one LoRA pair per third).  block_n: 0 = auto, else 64/128/192/256. */
 int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, int K, int trans_b, int epilogue, float alpha,
                   int lora_group_n, int block_n, void* stream);
+/* out[rows lo..hi) [:, 0:ncols) = 0 for the n_ranges {lo, hi} pairs in `ranges` (device int32): the padding rows a ragged GEMM skips. */
+int qfx_zero_rows(void* out, int64_t ld, int ncols, const int* ranges, int n_ranges, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------------------------------

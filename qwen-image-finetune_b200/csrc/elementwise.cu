@@ -931,3 +931,24 @@ extern "C" int qfx_grad_finalize(const float* g, int64_t n, float pre_scale, flo
   clip_cast_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(g, n, pre_scale, sumsq, max_norm, (bf16*)out_bf16);
   LAUNCH_OK();
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Zero-fill of the padding rows a ragged GEMM skips (qfx_gemm_problem.row_tiles): keeps "every padded row of a gradient buffer is
+// exactly zero", which the LoRA weight-gradient and modulation-gradient reductions over all rows rely on.
+__global__ void zero_rows_kernel(bf16* __restrict__ out, int64_t ld, int ncols, const int* __restrict__ ranges, int n_ranges) {
+  const int vec_per_row = ncols >> 3;
+  for (int r = 0; r < n_ranges; ++r) {
+    const int lo = ranges[2 * r], hi = ranges[2 * r + 1];
+    const int64_t total = (int64_t)(hi - lo) * vec_per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int row = lo + (int)(i / vec_per_row), c = (int)(i % vec_per_row);
+      *reinterpret_cast<uint4*>(out + (int64_t)row * ld + 8 * c) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+extern "C" int qfx_zero_rows(void* out, int64_t ld, int ncols, const int* ranges, int n_ranges, void* stream) {
+  QFX_CHECK_ARG(out && ranges && n_ranges > 0 && ncols % 8 == 0 && ld % 8 == 0, "qfx_zero_rows: bad arguments (ncols=%d)", ncols);
+  zero_rows_kernel<<<2 * qfx::num_sms(), 256, 0, (cudaStream_t)stream>>>((bf16*)out, ld, ncols, ranges, n_ranges);
+  LAUNCH_OK();
+}

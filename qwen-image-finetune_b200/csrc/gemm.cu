@@ -29,6 +29,7 @@ struct GemmProb {
   const bf16* resid;
   const bf16* gate;
   const bf16* aux;
+  const int* row_tiles;  // ragged rows: start row of each computed 256-row band (NULL: dense)
   int64_t ldo, ldo2, ldr, ldg, ldaux;
 };
 
@@ -231,7 +232,9 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
     int n_blk = tile / P.tiles_m_total;
     int mm = tile - n_blk * P.tiles_m_total;
     prob = mm >= P.tiles_m0 ? 1 : 0;
-    m0 = (prob ? mm - P.tiles_m0 : mm) * BM;
+    const int local = prob ? mm - P.tiles_m0 : mm;
+    const int* rt = P.p[prob].row_tiles;
+    m0 = rt ? __ldg(rt + (local >> 1)) + (local & 1) * BM : local * BM;
     n0 = n_blk * BN;
   };
 
@@ -399,7 +402,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm2_kernel
       mm = tile - n_blk * P.tiles_m_total;
     }
     prob = mm >= P.tiles_m0 ? 1 : 0;
-    m0 = (prob ? mm - P.tiles_m0 : mm) * 256 + (int)rank * BM;
+    const int local = prob ? mm - P.tiles_m0 : mm;
+    const int* rt = P.p[prob].row_tiles;
+    m0 = (rt ? __ldg(rt + local) : local * 256) + (int)rank * BM;
     n0 = n_blk * BN;
   };
   // Work units of this CTA pair, in order: whole tiles cluster_id, cluster_id + n_clusters, ... below tail_first, then (split-K of
@@ -752,11 +757,14 @@ extern "C" int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, in
     d.gate = (const bf16*)s.gate;
     d.aux = (const bf16*)s.aux;
     d.ldo = s.ldo; d.ldo2 = s.ldo2; d.ldr = s.ldr; d.ldg = s.ldg; d.ldaux = s.ldaux;
+    d.row_tiles = s.row_tiles;
+    QFX_CHECK_ARG(!s.row_tiles || s.n_row_tiles > 0, "qfx_gemm_bf16: row_tiles without n_row_tiles");
     if (epilogue == QFX_EPI_GELU) QFX_CHECK_ARG(s.out2 && s.ldo2 % 8 == 0, "qfx_gemm_bf16: GELU epilogue needs out2");
     if (epilogue == QFX_EPI_RESID_GATE) QFX_CHECK_ARG(s.resid && s.gate && s.ldr % 8 == 0 && s.ldg % 8 == 0, "qfx_gemm_bf16: RESID_GATE epilogue needs resid+gate");
     if (epilogue == QFX_EPI_ADD) QFX_CHECK_ARG(s.resid && s.ldr % 8 == 0, "qfx_gemm_bf16: ADD epilogue needs resid");
     if (epilogue == QFX_EPI_DGELU) QFX_CHECK_ARG(s.aux && s.ldaux % 8 == 0, "qfx_gemm_bf16: DGELU epilogue needs aux");
     int tm = two_cta ? (s.M + 255) / 256 : (s.M + BM - 1) / BM;
+    if (s.row_tiles) tm = two_cta ? s.n_row_tiles : 2 * s.n_row_tiles;
     if (i == 0) P.tiles_m0 = tm;
     tiles_m_total += tm;
   }

@@ -277,8 +277,9 @@ class FluxB200(FusedMMDiTBase):
             lb = self._lora_bwd(ws, l, "s_out", s, dYs, self._rows(ws, save["cat"], s), D)
             ka = dict(A2=lb[0], B2=lb[1][:, :D], kb2=1) if lb is not None else {}
             km = dict(A2=lb[0], B2=lb[1][:, D:], kb2=1) if lb is not None else {}
-            pa.append(lib.gemm_problem(dYs, Wo[:, :D], self._rows(ws, ws["dO"], s), **ka))
-            pm.append(lib.gemm_problem(dYs, Wo[:, D:], self._rows(ws, ws["dbig"], s), aux=self._rows(ws, u, s), **km))
+            pa.append(lib.gemm_problem(dYs, Wo[:, :D], self._rows(ws, ws["dO"], s), row_bands=self._bands(ws, s), **ka))
+            pm.append(lib.gemm_problem(dYs, Wo[:, D:], self._rows(ws, ws["dbig"], s), aux=self._rows(ws, u, s),
+                                       row_bands=self._bands(ws, s), **km))
         lib.gemm(pa, D, D, trans_b=True)
         lib.gemm(pm, 4 * D, D, trans_b=True, epilogue=lib.EPI_DGELU)
         self._attn_bwd_core(ws, qkv, O, save["lse"], lambda s: (w["s_qknorm_w"][l, 0], w["s_qknorm_w"][l, 1]))
@@ -300,7 +301,7 @@ class FluxB200(FusedMMDiTBase):
         lib.gemv_act(tmp, w[pre + "2_w"], w[pre + "2_b"], out, act=1)
 
     def _forward_impl(self, hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
-                      kv_len=None, train: bool = False):
+                      kv_len=None, train: bool = False, valid_rows=None):
         """img_ids [L, 3] (shared) or [B, L, 3] together with kv_len (int32 [B] on the device: T + valid image tokens) for a
         pad-to-max multi-resolution batch — per-sample RoPE tables and key masks (transformer_flux_custom.py:494-616)."""
         lib.require_cuda(hidden_states, encoder_hidden_states, pooled_projections, timestep, kv_len)
@@ -322,6 +323,7 @@ class FluxB200(FusedMMDiTBase):
         else:
             ws["rope"] = flux_rope_table(torch.cat((ti, ii), dim=0), self.config.axes_dims_rope)
         ws["kv_len"] = kv_len
+        self._plan_bands(ws, valid_rows if kv_len is not None else None)  # host copy of kv_len - T (None: every row is computed)
         assert ws["rope"].shape[-3] == ws["S"]
         X0 = ws["X"][0]
         # --- conditioning: temb = MLP_t(sin(1000 t)) [+ MLP_g(sin(1000 g))] + MLP_p(pooled)   (bf16 products, like the model)

@@ -66,6 +66,7 @@ class GemmProblem(C.Structure):
         ("resid", C.c_void_p), ("ldr", C.c_int64),
         ("gate", C.c_void_p), ("ldg", C.c_int64), ("rows_per_batch", C.c_int),
         ("aux", C.c_void_p), ("ldaux", C.c_int64),
+        ("row_tiles", C.c_void_p), ("n_row_tiles", C.c_int),
     ]
 
 
@@ -82,17 +83,80 @@ def _ld(t):
     return 0 if t is None else t.stride(0)
 
 
+class RowBands:
+    """Which rows of a pad-to-max row group a ragged GEMM computes: `tiles` = device int32 start rows of the disjoint 256-row bands
+    that cover every valid row; `dead` = device int32 [n_dead, 2] row ranges outside the bands (zero-filled before the GEMM)."""
+
+    def __init__(self, tiles, dead, device):
+        self.n, self.n_dead = len(tiles), len(dead)
+        self.tiles = torch.tensor(tiles, dtype=torch.int32, device=device)
+        self.dead = torch.tensor(dead, dtype=torch.int32, device=device).reshape(-1, 2) if dead else None
+        self.host_tiles, self.host_dead = list(tiles), [tuple(d) for d in dead]
+
+    @staticmethod
+    def plan(valid, rows_per_sample, band=256):
+        """valid[b] = valid rows of sample b (sample b owns rows [b*R, (b+1)*R)).  Returns (band start rows, dead ranges) or None when
+        nothing can be skipped.  Bands never overlap: an interval whose last band would run into the next interval is merged with it."""
+        R, M = rows_per_sample, rows_per_sample * len(valid)
+        iv = []
+        for b, v in enumerate(valid):
+            if v > 0:
+                lo, hi = b * R, b * R + int(v)
+                if iv and iv[-1][1] >= lo:
+                    iv[-1][1] = hi
+                else:
+                    iv.append([lo, hi])
+        tiles, dead, cur = [], [], 0
+        i = 0
+        while i < len(iv):
+            lo, hi = iv[i]
+            while True:
+                end = lo + -(-(hi - lo) // band) * band
+                if i + 1 < len(iv) and iv[i + 1][0] < end:  # the last band would cross into the next interval: treat the gap as valid
+                    hi = iv[i + 1][1]
+                    i += 1
+                else:
+                    break
+            if lo > cur:
+                dead.append((cur, lo))
+            tiles += list(range(lo, end, band))
+            cur = min(end, M)
+            i += 1
+        if cur < M:
+            dead.append((cur, M))
+        return (tiles, dead) if dead else None
+
+
 def gemm_problem(A, B, out, *, A2=None, B2=None, kb2=0, a2_col0=0, bias=None, out2=None, resid=None, gate=None,
-                 rows_per_batch=0, aux=None) -> GemmProblem:
+                 rows_per_batch=0, aux=None, row_bands=None) -> GemmProblem:
     require_cuda(A, B, out, A2, B2, bias, out2, resid, gate, aux)
     for t in (A, B, out, A2, B2, out2, resid, gate, aux):
         assert t is None or (t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1), "bf16 row-major 2-D expected"
-    return GemmProblem(_dp(A), _ld(A), _dp(B), _ld(B), A.shape[0], _dp(A2), _ld(A2), _dp(B2), _ld(B2), kb2, a2_col0,
-                       _dp(bias), _dp(out), _ld(out), _dp(out2), _ld(out2), _dp(resid), _ld(resid), _dp(gate), _ld(gate),
-                       rows_per_batch, _dp(aux), _ld(aux))
+    p = GemmProblem(_dp(A), _ld(A), _dp(B), _ld(B), A.shape[0], _dp(A2), _ld(A2), _dp(B2), _ld(B2), kb2, a2_col0,
+                    _dp(bias), _dp(out), _ld(out), _dp(out2), _ld(out2), _dp(resid), _ld(resid), _dp(gate), _ld(gate),
+                    rows_per_batch, _dp(aux), _ld(aux), 0 if row_bands is None else row_bands.tiles.data_ptr(),
+                    0 if row_bands is None else row_bands.n)
+    p.bands, p.outs = row_bands, (out, out2)  # kept alive / used by gemm() for the zero fill
+    return p
+
+
+_zero_rows = None
+
+
+def zero_rows(out, ncols, ranges, n_ranges):
+    global _zero_rows
+    if _zero_rows is None:
+        _zero_rows = _sig("qfx_zero_rows", C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p)
+    check(_zero_rows(ptr(out), out.stride(0), ncols, ptr(ranges), n_ranges, cur_stream()), "qfx_zero_rows")
 
 
 def gemm(problems, N, K, *, trans_b=False, epilogue=EPI_BIAS, alpha=1.0, lora_group_n=0, block_n=0):
+    for p in problems:  # ragged row groups: the rows outside the computed bands become zeros
+        b = getattr(p, "bands", None)
+        if b is not None and b.n_dead:
+            for o in p.outs:
+                if o is not None:
+                    zero_rows(o, N, b.dead, b.n_dead)
     arr = (GemmProblem * len(problems))(*problems)
     check(_lib.qfx_gemm_bf16(arr, len(problems), N, K, int(trans_b), epilogue, float(alpha), lora_group_n, block_n,
                              cur_stream()), "qfx_gemm_bf16")

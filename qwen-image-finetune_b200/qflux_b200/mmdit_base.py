@@ -11,6 +11,7 @@ Layout conventions:
 from __future__ import annotations
 
 import math
+import os
 import re
 
 import torch
@@ -96,6 +97,7 @@ class FusedMMDiTBase(nn.Module):
         self._rope_cache = {}
         self.gradient_checkpointing = False  # accepted for interface compatibility; HBM holds the activations
         self._sharded = None     # sharding.ShardedBlocks once shard_frozen_weights() has run
+        self._bands_cache = {}   # (valid image rows per sample, Limg) -> lib.RowBands (ragged GEMM row bands)
 
     @property
     def device(self):
@@ -463,6 +465,24 @@ class FusedMMDiTBase(nn.Module):
     def _rpb(self, ws, s):
         return ws["Limg"] if s == 0 else ws["T"]
 
+    def _plan_bands(self, ws, valid_img_rows):
+        """Pad-to-max multi-resolution batch: the block GEMMs compute only the 256-row bands that hold valid image rows of a
+        sample (lib.RowBands) and zero-fill the rest.  valid_img_rows: host list, one count per sample (None: dense batch).
+        The tables are uploaded once per shape combination (never inside a captured step)."""
+        ws["bands"] = None
+        if valid_img_rows is None or os.environ.get("QFX_NO_RAGGED_GEMM"):
+            return
+        key = (tuple(int(v) for v in valid_img_rows), ws["Limg"])
+        if key not in self._bands_cache:
+            if len(self._bands_cache) >= 64:
+                self._bands_cache.pop(next(iter(self._bands_cache)))
+            plan = lib.RowBands.plan(key[0], ws["Limg"])
+            self._bands_cache[key] = None if plan is None else lib.RowBands(plan[0], plan[1], self.dev)
+        ws["bands"] = self._bands_cache[key]
+
+    def _bands(self, ws, s):
+        return ws.get("bands") if s == 0 else None
+
     def _site(self, l, grp, s):
         return self.sites.get((l, grp, s))
 
@@ -520,7 +540,7 @@ class FusedMMDiTBase(nn.Module):
                 else:
                     kw[k] = self._rows(ws, v, s)
             W, b = self._wb(l, grp, s)
-            probs.append(lib.gemm_problem(A, W, self._rows(ws, dst, s), bias=b, **kw))
+            probs.append(lib.gemm_problem(A, W, self._rows(ws, dst, s), bias=b, row_bands=self._bands(ws, s), **kw))
         fused3 = any(p.kb2 for p in probs) and self._site_n(l, grp) == 3
         lib.gemm(probs, N, K, epilogue=epilogue, lora_group_n=(N // 3 if fused3 else 0))
 
@@ -574,7 +594,7 @@ class FusedMMDiTBase(nn.Module):
                 kw["aux"] = self._rows(ws, aux, s)
             if resid is not None:
                 kw["resid"] = self._rows(ws, resid, s)
-            probs.append(lib.gemm_problem(dYs, self._wb(l, grp, s)[0], self._rows(ws, dXout, s), **kw))
+            probs.append(lib.gemm_problem(dYs, self._wb(l, grp, s)[0], self._rows(ws, dXout, s), row_bands=self._bands(ws, s), **kw))
         lib.gemm(probs, N, K, trans_b=True, epilogue=epilogue)
 
     # ------------------------------------------------------------------------------------------------ double-stream block

@@ -229,7 +229,9 @@ class QwenImageB200(FusedMMDiTBase):
         if any(sh != per_sample[0] for sh in per_sample):
             assert len(per_sample) == B
             ws["rope"], ws["kv_len"] = self._rope_multi(per_sample, T, Limg)
+            self._plan_bands(ws, [sum(f * h * w for f, h, w in sh) for sh in per_sample])
         else:
+            self._plan_bands(ws, None)
             rope = self._rope(per_sample[0], T)
             assert rope.shape[0] == ws["S"], f"img_shapes {per_sample[0]} do not add up to {Limg} image tokens"
             ws["rope"], ws["kv_len"] = rope, None

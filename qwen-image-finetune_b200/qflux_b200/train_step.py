@@ -332,7 +332,7 @@ class FluxKontextStep(_Accumulation):
         norm = 1.0 / (C * (float(sum(lt)) + 1e-12)) if self.loss_kind == "attention_mask" else 1.0 / (B * L * C)
         guidance = torch.ones(B, device=dev) if m.config.guidance_embeds else None
         return (x0, ctrl, pe, pooled, embeddings["text_ids"].to(dev), ids.to(dev, non_blocking=True), noise, t, guidance,
-                w.to(dev).contiguous(), norm, (Lt, Lc, Ltot, kv_len))
+                w.to(dev).contiguous(), norm, (Lt, Lc, Ltot, kv_len, tuple(a + b for a, b in zip(lt, lc))))
 
     def _run(self, x0, ctrl, pe, pooled, text_ids, ids, noise, t, guidance, w, norm, var=None):
         m = self.dit
@@ -342,10 +342,10 @@ class FluxKontextStep(_Accumulation):
             lib.flow_noisy_input(x0, noise, ctrl, t.float().contiguous(), packed)
             pred = m._forward_impl(packed, pe, pooled, t, ids, text_ids, guidance, train=True)
         else:
-            Lt, Lc, Ltot, kv_len = var
+            Lt, Lc, Ltot, kv_len, valid_rows = var  # valid_rows: host copy of kv_len - T (plans the ragged GEMM row bands; part of the graph key)
             packed = torch.empty(B, Ltot, C, device=m.dev, dtype=BF)
             lib.flow_noisy_input_var(x0, noise, ctrl, t.float().contiguous(), Lt, Lc, packed)
-            pred = m._forward_impl(packed, pe, pooled, t, ids, text_ids, guidance, kv_len, train=True)
+            pred = m._forward_impl(packed, pe, pooled, t, ids, text_ids, guidance, kv_len, train=True, valid_rows=valid_rows)
         ws = m._ws
         lib.flow_loss(pred, x0, noise, w, norm, ws["loss"], ws["dpred"])
         if not self._accumulating:

@@ -23,9 +23,9 @@ def _f(t):
 
 
 def gemm_problem(A, B, out, *, A2=None, B2=None, kb2=0, a2_col0=0, bias=None, out2=None, resid=None, gate=None,
-                 rows_per_batch=0, aux=None):
+                 rows_per_batch=0, aux=None, row_bands=None):
     return types.SimpleNamespace(A=A, B=B, out=out, A2=A2, B2=B2, kb2=kb2, a2_col0=a2_col0, bias=bias, out2=out2, resid=resid,
-                                 gate=gate, rows_per_batch=rows_per_batch, aux=aux)
+                                 gate=gate, rows_per_batch=rows_per_batch, aux=aux, row_bands=row_bands)
 
 
 def _gelu_grad(u):
@@ -68,6 +68,11 @@ def gemm(problems, N, K, *, trans_b=False, epilogue=EPI_BIAS, alpha=1.0, lora_gr
             p.out.copy_(((acc * alpha).to(BF).float() * _gelu_grad(p.aux.float())).to(BF))
         else:
             raise ValueError(epilogue)
+        if p.row_bands is not None:  # ragged row group: rows outside the computed bands are zero-filled (qfx_zero_rows)
+            for lo, hi in p.row_bands.host_dead:
+                p.out[lo:hi] = 0
+                if p.out2 is not None:
+                    p.out2[lo:hi] = 0
 
 
 def ln_modulate_fwd(x, y, shift, scale, rows_per_batch, mean=None, rstd=None, eps=1e-6):
