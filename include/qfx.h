@@ -143,10 +143,12 @@ int qfx_qk_norm_rope_fwd_pair(const void* qkv, int64_t ldqkv, const void* wq, co
                               int64_t rope_bstride, void* Q, void* K, void* V, int tokens, int tokens_per_sample, int s_offset, int S,
                               int H, float eps, int round_mid, int split, const void* wq1, const void* wk1, int tokens_per_sample1,
                               int s_offset1, void* stream);
-int qfx_qk_norm_rope_bwd_pair(const void* dQ, const void* dK, const void* dV, const void* qkv, int64_t ldqkv, const void* wq,
+/* clear_dq != 0: every dQ element is set to 0 after it has been read, so the fp32 accumulator is ready for the next attention backward
+ * without a separate 118 MB fill (the two row groups together must cover all S positions of every sample). */
+int qfx_qk_norm_rope_bwd_pair(void* dQ, const void* dK, const void* dV, const void* qkv, int64_t ldqkv, const void* wq,
                               const void* wk, const float* rope, int64_t rope_bstride, void* dqkv, int64_t lddqkv, int tokens,
                               int tokens_per_sample, int s_offset, int S, int H, float eps, int round_mid, int split, const void* wq1,
-                              const void* wk1, int tokens_per_sample1, int s_offset1, void* stream);
+                              const void* wk1, int tokens_per_sample1, int s_offset1, int clear_dq, void* stream);
 int qfx_attn_delta_pair(const void* O, int64_t ldo, const void* dO, int64_t lddo, float* delta, void* dO_joint, int tokens,
                         int tokens_per_sample, int s_offset, int S, int H, int split, int tokens_per_sample1, int s_offset1,
                         void* stream);

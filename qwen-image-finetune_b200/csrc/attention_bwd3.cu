@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(B3_THREADS, 1) attn_bwd3_kernel(const __grid_c
   const int b = bh / P.H;
   const int kv_len = P.kv_len ? P.kv_len[b] : P.S;
   const int txt_len = P.txt_len ? P.txt_len[b] : P.split;
-  const int n_q = (P.S + 127) / 128;
+  // query tiles that hold only padding rows of a pad-to-max batch (positions >= kv_len[b]) carry dO = 0: nothing to add, skip them
+  const int n_q = ((kv_len < P.S ? kv_len : P.S) + 127) / 128;
   // a fully masked key tile (beyond kv_len, or entirely inside the text padding) contributes nothing: write zeros and leave
   const bool active = kv0 < kv_len && !(kv0 >= txt_len && kv0 + 128 <= P.split);
   // Query tiles are visited in a per-key-tile ROTATED order: the 19 key-tile CTAs of a head run concurrently, and with a common order all

@@ -52,6 +52,21 @@ __device__ __forceinline__ void mask_scores(uint32_t* r, int col0, int valid, in
   }
 }
 
+// A query tile that holds only padding rows of a pad-to-max batch (every query position >= kv_len[b], all of them image rows): the
+// output rows become zeros (they feed row-wise kernels and must stay finite) and no attention math runs.
+__device__ __forceinline__ bool attn_fwd_skip_padding_tile(const AttnFwdParams& P, int q0, int b, int h, int bh, int kv_len) {
+  if (q0 < kv_len || q0 < P.split) return false;
+  for (int idx = threadIdx.x; idx < ATT_BQ * 16; idx += blockDim.x) {
+    const int sq = q0 + (idx >> 4), c = idx & 15;
+    if (sq < P.S) {
+      bf16* dst = P.out1 + ((int64_t)b * P.rows1 + (sq - P.split)) * P.ld1 + h * ATT_D + c * 8;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+      if (P.lse && c == 0) P.lse[(int64_t)bh * P.S + sq] = 0.f;
+    }
+  }
+  return true;
+}
+
 __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // 128B-swizzle atoms need 1024 B alignment (no slack left to round up)
   const uint32_t smem_base = smem_u32(smem_raw);
@@ -80,6 +95,7 @@ __global__ void __launch_bounds__(320, 1) attn_fwd_kernel(const __grid_constant_
   const int kv_len = P.kv_len ? P.kv_len[b] : P.S;
   const int txt_len = P.txt_len ? P.txt_len[b] : P.split;  // >= 1; keys [txt_len, split) are text padding
   const int n_tiles = (kv_len + ATT_BK - 1) / ATT_BK;
+  if (attn_fwd_skip_padding_tile(P, q0, b, h, bh, kv_len)) return;
 
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
@@ -333,6 +349,7 @@ __global__ void __launch_bounds__(192, 2) attn_fwd64_kernel(const __grid_constan
   const int kv_len = P.kv_len ? P.kv_len[b] : P.S;
   const int txt_len = P.txt_len ? P.txt_len[b] : P.split;
   const int n_tiles = (kv_len + 63) / 64;
+  if (attn_fwd_skip_padding_tile(P, q0, b, h, bh, kv_len)) return;
 
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);

@@ -359,14 +359,15 @@ __global__ void __launch_bounds__(256) qk_norm_rope_fwd_kernel(const bf16* __res
 
 // Backward: dQ/dK/dV[B,H,S,128] (bf16) + saved pre-norm qkv  ->  dqkv[tok, 3D].
 template <bool ROUND_MID>
-__global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(const float* __restrict__ dQ, const bf16* __restrict__ dK,
+__global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(float* __restrict__ dQ, const bf16* __restrict__ dK,
                                                                const bf16* __restrict__ dV, const bf16* __restrict__ qkv,
                                                                int64_t ldqkv, const bf16* __restrict__ wq,
                                                                const bf16* __restrict__ wk, const float2* __restrict__ rope,
                                                                int64_t rope_bstride, bf16* __restrict__ dqkv, int64_t lddqkv,
                                                                int tokens, int tokens_per_sample, int s_offset, int S, int H,
                                                                float eps, int split, const bf16* __restrict__ wq1,
-                                                               const bf16* __restrict__ wk1, int tokens_per_sample1, int s_offset1) {
+                                                               const bf16* __restrict__ wk1, int tokens_per_sample1, int s_offset1,
+                                                               int clear_dq) {
   const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (gw >= tokens * H) return;
@@ -394,6 +395,7 @@ __global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(const float* __re
       go[0] = bf16_lo(graw.x); go[1] = bf16_hi(graw.x); go[2] = bf16_lo(graw.y); go[3] = bf16_hi(graw.y);
     } else {  // dQ is the fp32 TMA-reduce accumulator of the attention backward; autograd would hold it in bf16
       const float4 gq = *reinterpret_cast<const float4*>(dQ + src);
+      if (clear_dq) *reinterpret_cast<float4*>(dQ + src) = make_float4(0.f, 0.f, 0.f, 0.f);  // accumulator ready for the next backward
       go[0] = round_bf16(gq.x); go[1] = round_bf16(gq.y); go[2] = round_bf16(gq.z); go[3] = round_bf16(gq.w);
     }
     // rotate back by the conjugate angle (RoPE is orthogonal)
@@ -809,23 +811,23 @@ extern "C" int qfx_qk_norm_rope_fwd(const void* qkv, int64_t ldqkv, const void* 
                                    round_mid, tokens, nullptr, nullptr, 1, 0, stream);
 }
 
-extern "C" int qfx_qk_norm_rope_bwd_pair(const void* dQ, const void* dK, const void* dV, const void* qkv, int64_t ldqkv,
+extern "C" int qfx_qk_norm_rope_bwd_pair(void* dQ, const void* dK, const void* dV, const void* qkv, int64_t ldqkv,
                                          const void* wq, const void* wk, const float* rope, int64_t rope_bstride, void* dqkv,
                                          int64_t lddqkv, int tokens, int tokens_per_sample, int s_offset, int S, int H, float eps,
                                          int round_mid, int split, const void* wq1, const void* wk1, int tokens_per_sample1,
-                                         int s_offset1, void* stream) {
+                                         int s_offset1, int clear_dq, void* stream) {
   QFX_CHECK_ARG(split >= tokens || (wq1 && wk1 && tokens_per_sample1 > 0), "qfx_qk_norm_rope_bwd_pair: second group incomplete");
   const int blocks = (tokens * H + 7) / 8;
   if (round_mid)
     qk_norm_rope_bwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-        (const float*)dQ, (const bf16*)dK, (const bf16*)dV, (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk,
+        (float*)dQ, (const bf16*)dK, (const bf16*)dV, (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk,
         (const float2*)rope, rope_bstride, (bf16*)dqkv, lddqkv, tokens, tokens_per_sample, s_offset, S, H, eps, split,
-        (const bf16*)wq1, (const bf16*)wk1, tokens_per_sample1, s_offset1);
+        (const bf16*)wq1, (const bf16*)wk1, tokens_per_sample1, s_offset1, clear_dq);
   else
     qk_norm_rope_bwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-        (const float*)dQ, (const bf16*)dK, (const bf16*)dV, (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk,
+        (float*)dQ, (const bf16*)dK, (const bf16*)dV, (const bf16*)qkv, ldqkv, (const bf16*)wq, (const bf16*)wk,
         (const float2*)rope, rope_bstride, (bf16*)dqkv, lddqkv, tokens, tokens_per_sample, s_offset, S, H, eps, split,
-        (const bf16*)wq1, (const bf16*)wk1, tokens_per_sample1, s_offset1);
+        (const bf16*)wq1, (const bf16*)wk1, tokens_per_sample1, s_offset1, clear_dq);
   LAUNCH_OK();
 }
 
@@ -833,8 +835,8 @@ extern "C" int qfx_qk_norm_rope_bwd(const void* dQ, const void* dK, const void* 
                                     const void* wq, const void* wk, const float* rope, int64_t rope_bstride, void* dqkv,
                                     int64_t lddqkv, int tokens, int tokens_per_sample, int s_offset, int S, int H, float eps,
                                     int round_mid, void* stream) {
-  return qfx_qk_norm_rope_bwd_pair(dQ, dK, dV, qkv, ldqkv, wq, wk, rope, rope_bstride, dqkv, lddqkv, tokens, tokens_per_sample,
-                                   s_offset, S, H, eps, round_mid, tokens, nullptr, nullptr, 1, 0, stream);
+  return qfx_qk_norm_rope_bwd_pair(const_cast<void*>(dQ), dK, dV, qkv, ldqkv, wq, wk, rope, rope_bstride, dqkv, lddqkv, tokens,
+                                   tokens_per_sample, s_offset, S, H, eps, round_mid, tokens, nullptr, nullptr, 1, 0, 0, stream);
 }
 
 extern "C" int qfx_gemv_act(const void* x, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* y, int64_t ldy,

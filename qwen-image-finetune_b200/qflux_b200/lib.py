@@ -197,7 +197,7 @@ _ln_bwd2 = _sig("qfx_ln_modulate_bwd_pair", _vp, _i64, _vp, _i64, _vp, _vp, _vp,
 _qknr_fwd2 = _sig("qfx_qk_norm_rope_fwd_pair", _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _vp,
                   _i, _i, _vp)
 _qknr_bwd2 = _sig("qfx_qk_norm_rope_bwd_pair", _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _f, _i, _i,
-                  _vp, _vp, _i, _i, _vp)
+                  _vp, _vp, _i, _i, _i, _vp)
 _delta2 = _sig("qfx_attn_delta_pair", _vp, _i64, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp)
 
 
@@ -231,13 +231,14 @@ def qk_norm_rope_fwd_pair(qkv, g0, g1, split, rope, Q, K, V, eps=1e-6, round_mid
           "qfx_qk_norm_rope_fwd_pair")
 
 
-def qk_norm_rope_bwd_pair(dQ, dK, dV, qkv, g0, g1, split, rope, dqkv, eps=1e-6, round_mid=True):
+def qk_norm_rope_bwd_pair(dQ, dK, dV, qkv, g0, g1, split, rope, dqkv, eps=1e-6, round_mid=True, clear_dq=False):
+    """clear_dq: dQ (the fp32 accumulator of the attention backward) is zeroed as it is read."""
     require_cuda(dQ, dK, dV, qkv, g0[0], g0[1], g1[0], g1[1], rope, dqkv)
     B, H, S, _ = dK.shape
     bstride = 0 if rope.dim() == 3 else S
     check(_qknr_bwd2(ptr(dQ), ptr(dK), ptr(dV), ptr(qkv), qkv.stride(0), ptr(g0[0]), ptr(g0[1]), ptr(rope), bstride, ptr(dqkv),
                      dqkv.stride(0), qkv.shape[0], g0[2], g0[3], S, H, eps, int(round_mid), split, ptr(g1[0]), ptr(g1[1]), g1[2], g1[3],
-                     cur_stream()), "qfx_qk_norm_rope_bwd_pair")
+                     int(clear_dq), cur_stream()), "qfx_qk_norm_rope_bwd_pair")
 
 
 def attn_delta_pair(O, dO, delta, g0, g1, split, dO_joint=None):

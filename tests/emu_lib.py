@@ -324,9 +324,11 @@ def qk_norm_rope_fwd_pair(qkv, g0, g1, split, rope, Q, K, V, eps=1e-6, round_mid
         qk_norm_rope_fwd(qkv[sl], wq, wk, rope, Q, K, V, tps, so, eps=eps, round_mid=round_mid)
 
 
-def qk_norm_rope_bwd_pair(dQ, dK, dV, qkv, g0, g1, split, rope, dqkv, eps=1e-6, round_mid=True):
+def qk_norm_rope_bwd_pair(dQ, dK, dV, qkv, g0, g1, split, rope, dqkv, eps=1e-6, round_mid=True, clear_dq=False):
     for (wq, wk, tps, so), sl in ((g0, slice(0, split)), (g1, slice(split, None))):
         qk_norm_rope_bwd(dQ, dK, dV, qkv[sl], wq, wk, rope, dqkv[sl], tps, so, eps=eps, round_mid=round_mid)
+    if clear_dq:
+        dQ.zero_()
 
 
 def attn_delta_pair(O, dO, delta, g0, g1, split, dO_joint=None):

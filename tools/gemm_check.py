@@ -126,7 +126,82 @@ def perf(trans_b, bn, M0=8192, M1=1408, N=3072, K=3072):
                 err=err)
 
 
+def ragged(bn, trans_b=False, R=1600, valid=(1600, 400, 1024, 900), N=768, K=512, perf=False):
+    """Ragged row groups (qfx_gemm_problem.row_tiles): a grouped launch whose first problem is a pad-to-max image stream (sample b owns rows
+    [b*R, (b+1)*R), valid[b] of them real) and whose second is a dense text stream.  Rows inside the computed 256-row bands must equal the
+    dense result, every other row of the outputs must be exactly zero; covers BIAS, GELU (two outputs) and RESID_GATE / DGELU."""
+    from qflux_b200 import lib
+    M0, M1, Bsz = R * len(valid), 300, len(valid)
+    plan = lib.RowBands.plan(list(valid), R)
+    bands = lib.RowBands(plan[0], plan[1], "cuda")
+    live = torch.zeros(M0, dtype=torch.bool, device="cuda")
+    for t in bands.host_tiles:
+        live[t:t + 256] = True
+    for lo, hi in bands.host_dead:
+        assert not live[lo:hi].any()
+    A = [_mk(M0, K, seed=1), _mk(M1, K, seed=2)]
+    W = [(_mk(K, N, seed=3 + i, scale=0.1) if trans_b else _mk(N, K, seed=3 + i, scale=0.1)) for i in range(2)]
+    b = [None, None] if trans_b else [_mk(N, seed=5), _mk(N, seed=6)]
+    mm = lambda i: A[i].float() @ (W[i].float() if trans_b else W[i].float().t()) + (0 if trans_b else b[i].float())
+    res, worst = {}, 0.0
+
+    def run(epi, **extra):
+        outs = [torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16) for M in (M0, M1)]
+        out2 = [torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16) for M in (M0, M1)] if epi in (lib.EPI_GELU, lib.EPI_RESID_GATE) else [None, None]
+        probs = [lib.gemm_problem(A[i], W[i], outs[i], bias=b[i], out2=out2[i], row_bands=bands if i == 0 else None,
+                                  **{k: v[i] for k, v in extra.items()}) for i in range(2)]
+        lib.gemm(probs, N, K, trans_b=trans_b, epilogue=epi, block_n=bn)
+        torch.cuda.synchronize()
+        return outs, out2
+
+    def check(name, got, ref):
+        nonlocal worst
+        e_live = rel_l2(got[0][live].float(), ref[0][live])
+        dead_max = float(got[0][~live].float().abs().max()) if (~live).any() else 0.0
+        e_txt = rel_l2(got[1].float(), ref[1])
+        res[name] = (round(e_live, 6), dead_max, round(e_txt, 6))
+        worst = max(worst, e_live, e_txt, 1.0 if dead_max != 0.0 else 0.0)
+
+    if not trans_b:
+        o, _ = run(lib.EPI_BIAS)
+        check("bias", o, [mm(0), mm(1)])
+        o, u = run(lib.EPI_GELU)
+        check("gelu", o, [torch.nn.functional.gelu(mm(i), approximate="tanh") for i in range(2)])
+        check("gelu_u", u, [mm(0), mm(1)])
+        resid = [_mk(M0, N, seed=8), _mk(M1, N, seed=9)]
+        gate = [_mk(Bsz, N, seed=10), _mk(3, N, seed=11)]
+        o, y = run(lib.EPI_RESID_GATE, resid=resid, gate=gate, rows_per_batch=[R, M1 // 3])
+        check("resid_gate", o, [resid[i].float() + gate[i].float().repeat_interleave([R, M1 // 3][i], 0) * mm(i) for i in range(2)])
+        check("resid_gate_y", y, [mm(0), mm(1)])
+    else:
+        o, _ = run(lib.EPI_BIAS)
+        check("dgrad", o, [mm(0), mm(1)])
+        aux = [_mk(M0, N, seed=12), _mk(M1, N, seed=13)]
+        o, _ = run(lib.EPI_DGELU, aux=aux)
+        check("dgelu", o, [mm(i) * _gelu_grad(aux[i]) for i in range(2)])
+    out = dict(err=worst, cases=res, bands=bands.n, dead_ranges=bands.host_dead)
+    if perf:  # the benchmark's multi-resolution mix at the MLP-up shape: ragged vs dense launch
+        Rp, vp, Np, Kp = 1600, (1600, 400, 1024, 1024), 12288, 3072
+        plan = lib.RowBands.plan(list(vp), Rp)
+        bp = lib.RowBands(plan[0], plan[1], "cuda")
+        Ab, Wb = _mk(4 * Rp, Kp, seed=1), _mk(Np, Kp, seed=2, scale=0.05)
+        ob, ub = torch.empty(4 * Rp, Np, device="cuda", dtype=torch.bfloat16), torch.empty(4 * Rp, Np, device="cuda", dtype=torch.bfloat16)
+        flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
+        for nm, rb in (("dense_ms", None), ("ragged_ms", bp)):
+            pr = [lib.gemm_problem(Ab, Wb, ob, bias=None, out2=ub, row_bands=rb)]
+            out[nm] = time_cuda(lambda: lib.gemm(pr, Np, Kp, epilogue=lib.EPI_GELU), iters=10, flush=flush)
+        out["live_fraction"] = bp.n * 256 / (4 * Rp)
+    return out
+
+
 CASES = {}
+CASES["ragged_nt_bn256"] = lambda: ragged(256)
+CASES["ragged_nt_bn128"] = lambda: ragged(128)
+CASES["ragged_nn_bn192"] = lambda: ragged(192, trans_b=True)
+CASES["cta2_ragged_nt"] = lambda: ragged(1256)
+CASES["cta2_ragged_nn"] = lambda: ragged(1256, trans_b=True)
+CASES["cta2_ragged_nt_splitk"] = lambda: ragged(1256, N=2048, K=4096)
+CASES["cta2_ragged_perf"] = lambda: ragged(1256, perf=True)
 for bn in (64, 128, 192, 256):
     CASES[f"basic_nt_bn{bn}"] = (lambda bn=bn: basic(False, bn))
     CASES[f"basic_nn_bn{bn}"] = (lambda bn=bn: basic(True, bn))

@@ -317,14 +317,15 @@ def flux_step_parity(H=2, L=2, Ls=2, J=64, Pp=64, B=2, hw=4, T=8, r=4,
     return res
 
 
-def qwen_multires(H=2, L=2, J=128):
-    """pad-to-max multi-resolution batch (per-sample RoPE, text + image key masks, AttentionMask loss) vs un-padded oracle runs."""
+def qwen_multires(H=2, L=2, J=128, shapes=None, expect_bands=False):
+    """pad-to-max multi-resolution batch (per-sample RoPE, text + image key masks, AttentionMask loss) vs un-padded oracle runs.
+    expect_bands: the shapes are large enough that the block GEMMs run on ragged row bands (lib.RowBands) and zero-fill the rest."""
     from oracle import mmdit_oracle as mo
     from qflux_b200.train_step import QwenImageEditStep
     orc, m = build_pair(H, L, J, 4, ("to_q", "to_k", "to_v", "to_out.0"))
     g = torch.Generator(device="cuda").manual_seed(11)
     rn = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()
-    shapes = [[(1, 16, 12), (1, 16, 12)], [(1, 8, 10), (1, 8, 10)], [(1, 12, 12), (1, 12, 12)]]
+    shapes = shapes or [[(1, 16, 12), (1, 16, 12)], [(1, 8, 10), (1, 8, 10)], [(1, 12, 12), (1, 12, 12)]]
     lt = [sh[0][1] * sh[0][2] for sh in shapes]
     lc = lt
     B, T, txt = 3, 40, [40, 23, 31]
@@ -360,17 +361,21 @@ def qwen_multires(H=2, L=2, J=128):
     den = sum((v.double() ** 2).sum() for v in go.values())
     res["grad_vs_fp32"] = float((num / den).sqrt())
     res["err"] = max(res["pred_vs_fp32"], res["grad_vs_fp32"])
+    bands = m._ws.get("bands")
+    res["bands"] = None if bands is None else dict(n=bands.n, dead=bands.host_dead)
+    if expect_bands:
+        assert bands is not None and bands.n_dead > 0, "the ragged GEMM path was not taken"
     return res
 
 
-def flux_multires(H=2, L=2, Ls=2, J=64, Pp=64):
+def flux_multires(H=2, L=2, Ls=2, J=64, Pp=64, shapes=None, expect_bands=False):
     """FLUX pad-to-max multi-resolution recipe (flux_kontext_trainer.py:579-796): per-sample ids / RoPE, key mask, masked loss —
     against one un-padded oracle run per sample."""
     from qflux_b200.train_step import FluxKontextStep
     orc, m = build_flux_pair(H, L, Ls, J, Pp, 4, r".*(attn\.to_[qkv]|to_out\.0|proj_mlp|single_transformer_blocks\.[0-9]+\.proj_out)")
     g = torch.Generator(device="cuda").manual_seed(21)
     rn = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()
-    shapes = [[(1, 16, 12), (1, 16, 12)], [(1, 8, 10), (1, 10, 8)], [(1, 12, 8), (1, 6, 8), (1, 8, 12)]]
+    shapes = shapes or [[(1, 16, 12), (1, 16, 12)], [(1, 8, 10), (1, 10, 8)], [(1, 12, 8), (1, 6, 8), (1, 8, 12)]]
     B, T = 3, 24
     lt = [sh[0][1] * sh[0][2] for sh in shapes]
     lc = [sum(h * w for (_, h, w) in sh[1:]) for sh in shapes]
@@ -406,6 +411,10 @@ def flux_multires(H=2, L=2, Ls=2, J=64, Pp=64):
     den = sum((v.double() ** 2).sum() for v in go.values())
     res["grad_vs_fp32"] = float((num / den).sqrt())
     res["err"] = max(res["pred_vs_fp32"], res["grad_vs_fp32"])
+    bands = m._ws.get("bands")
+    res["bands"] = None if bands is None else dict(n=bands.n, dead=bands.host_dead)
+    if expect_bands:
+        assert bands is not None and bands.n_dead > 0, "the ragged GEMM path was not taken"
     return res
 
 
@@ -461,6 +470,11 @@ CASES = {
     "flux_tiny_mlp_out_targets": lambda: flux_step_parity(
         r=8, targets=r".*(single_transformer_blocks\.[0-9]+\.(proj_mlp|proj_out)|ff\.net\.2|ff_context\.net\.(0\.proj|2)|attn\.to_out\.0)"),
     "flux_multires": flux_multires,
+    # the same recipes with image sizes whose padding spans whole 256-row GEMM bands: ragged row bands + zero fill on the product path
+    "qwen_multires_bands": lambda: qwen_multires(shapes=[[(1, 32, 24), (1, 32, 24)], [(1, 12, 10), (1, 12, 10)], [(1, 20, 20), (1, 20, 20)]],
+                                                 expect_bands=True),
+    "flux_multires_bands": lambda: flux_multires(shapes=[[(1, 32, 24), (1, 32, 24)], [(1, 8, 10), (1, 10, 8)], [(1, 20, 16), (1, 12, 8), (1, 16, 20)]],
+                                                 expect_bands=True),
     "sampler_tiny": sampler_tiny,
     # BASELINE config 3 target set (configs/face_seg_flux_kontext_fp16.yaml:11): every block Linear, the AdaLN linears, x_embedder
     "flux_tiny_yaml_targets": lambda: flux_step_parity(r=8, targets=FLUX_YAML_TARGETS),
