@@ -628,14 +628,15 @@ class FusedMMDiTBase(nn.Module):
         lib.attn_delta_pair(O, ws["dO"], ws["delta"], (T, 0), (Limg, T), Mt, ws["dOj"])
         if not have:
             lib.qk_norm_rope_fwd_pair(qkv, g_txt, g_img, Mt, ws["rope"], Qs, Ks, Vs, round_mid=self.round_mid)
-        if not ws.get("dQ_clean"):  # first use (or an interrupted backward): afterwards the consumer below re-zeroes what it reads, which
+        refill = bool(os.environ.get("QFX_DQ_FILL"))  # A/B switch: the old separate fill per block
+        if refill or not ws.get("dQ_clean"):  # first use (or an interrupted backward): afterwards the consumer below re-zeroes what it reads, which
             ws["dQ"].zero_()        # replaces a 118 MB fill per block (70 us at the benchmark shape) by stores in a kernel that streams dQ anyway
         ws["dQ_clean"] = False
         lib.attn_bwd(Qs, Ks, Vs, ws["dOj"], lse, ws["delta"], ws["dQ"], ws["dK"], ws["dV"], kv_len=ws.get("kv_len"),
                      txt_len=ws.get("txt_len"), split=T)
         lib.qk_norm_rope_bwd_pair(ws["dQ"], ws["dK"], ws["dV"], qkv, g_txt, g_img, Mt, ws["rope"], ws["dqkv"], round_mid=self.round_mid,
-                                  clear_dq=True)
-        ws["dQ_clean"] = True
+                                  clear_dq=not refill)
+        ws["dQ_clean"] = not refill
 
     def _double_bwd(self, ws, l, Xin, dX, dXn, save, mods, prev_gate):
         """dX: grad wrt the block output (ws['dY'] already holds dX * gate2).  Writes the grad wrt the block input to dXn
