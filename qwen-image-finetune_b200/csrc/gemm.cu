@@ -582,10 +582,12 @@ template <int BN, bool TRANS_B, int EPI>
 static int launch(const GemmParams& P, cudaStream_t stream) {
   using C = GemmCfg<BN>;
   auto kern = gemm_kernel<BN, TRANS_B, EPI>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};  // function attributes are per device
+  int dev = 0;
+  QFX_CUDA(cudaGetDevice(&dev));
+  if (!attr_done[dev & 63]) {
     QFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_done = true;
+    attr_done[dev & 63] = true;
   }
   int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
   kern<<<grid, 256, C::SMEM_BYTES, stream>>>(P);
@@ -593,14 +595,41 @@ static int launch(const GemmParams& P, cudaStream_t stream) {
   return 0;
 }
 
+// Split-K scratch of the CTA-pair kernel: ONE workspace + arrival counters per device, shared by every template instantiation,
+// allocated on the first launch that needs it on that device (the only allocation this library makes after load; it happens during
+// the eager warm-up step, never inside a captured graph).  GEMMs of one device are issued from one stream at a time (include/qfx.h).
+static int tail_workspace(float** ws, int** cnt) {
+  constexpr int MAX_DEV = 64;
+  static float* g_ws[MAX_DEV] = {};
+  static int* g_cnt[MAX_DEV] = {};
+  int dev = 0;
+  QFX_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAX_DEV) {
+    set_error("qfx_gemm_bf16: device ordinal %d out of range", dev);
+    return -1;
+  }
+  if (g_ws[dev] == nullptr) {
+    const size_t bytes = (size_t)(num_sms() / 2) * 256 * (256 + WS_PAD) * sizeof(float);
+    QFX_CUDA(cudaMalloc(&g_ws[dev], bytes));
+    QFX_CUDA(cudaMemset(g_ws[dev], 0, bytes));
+    QFX_CUDA(cudaMalloc(&g_cnt[dev], num_sms() * sizeof(int)));
+    QFX_CUDA(cudaMemset(g_cnt[dev], 0, num_sms() * sizeof(int)));
+  }
+  *ws = g_ws[dev];
+  *cnt = g_cnt[dev];
+  return 0;
+}
+
 template <int BN, bool TRANS_B, int EPI>
 static int launch2(const GemmParams& P, cudaStream_t stream) {
   using C = Gemm2Cfg<BN>;
   auto kern = gemm2_kernel<BN, TRANS_B, EPI>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};  // function attributes are per device
+  int dev = 0;
+  QFX_CUDA(cudaGetDevice(&dev));
+  if (!attr_done[dev & 63]) {
     QFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_done = true;
+    attr_done[dev & 63] = true;
   }
   int clusters = num_sms() / 2;
   if (P.total_tiles < clusters) clusters = P.total_tiles;
@@ -626,15 +655,9 @@ static int launch2(const GemmParams& P, cudaStream_t stream) {
     int S = clusters / R;
     if (S > nkb / 8) S = nkb / 8;  // at least 8 k-blocks per range
     if (S >= 2) {
-      static float* ws = nullptr;
-      static int* cnt = nullptr;
-      if (ws == nullptr) {
-        const size_t bytes = (size_t)(num_sms() / 2) * 256 * (256 + WS_PAD) * sizeof(float);
-        QFX_CUDA(cudaMalloc(&ws, bytes));
-        QFX_CUDA(cudaMemset(ws, 0, bytes));
-        QFX_CUDA(cudaMalloc(&cnt, num_sms() * sizeof(int)));
-        QFX_CUDA(cudaMemset(cnt, 0, num_sms() * sizeof(int)));
-      }
+      float* ws = nullptr;
+      int* cnt = nullptr;
+      if (tail_workspace(&ws, &cnt)) return -1;
       // (zeroing the rows inside the kernel after the final read was measured at ~100 us per GEMM; a memset of the 3 MB in use is ~2)
       QFX_CUDA(cudaMemsetAsync(ws, 0, (size_t)R * 256 * (BN + WS_PAD) * sizeof(float), stream));
       Q.tail_first = P.total_tiles - R;

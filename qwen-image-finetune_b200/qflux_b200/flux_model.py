@@ -309,6 +309,7 @@ class FluxB200(FusedMMDiTBase):
         T = encoder_hidden_states.shape[1]
         D, L, Ls, w = self.D, self.L, self.Ls, self.w
         ws = self._workspace(B, T, Limg, train)
+        self._fwd_gen += 1
         Mt = ws["Mt"]
         if txt_ids.ndim == 3:
             txt_ids = txt_ids[0]

@@ -98,6 +98,7 @@ class FusedMMDiTBase(nn.Module):
         self.gradient_checkpointing = False  # accepted for interface compatibility; HBM holds the activations
         self._sharded = None     # sharding.ShardedBlocks once shard_frozen_weights() has run
         self._bands_cache = {}   # (valid image rows per sample, Limg) -> lib.RowBands (ragged GEMM row bands)
+        self._fwd_gen = 0        # bumped by every forward: autograd nodes of an older forward refuse to run (their activations are gone)
 
     @property
     def device(self):
@@ -628,15 +629,18 @@ class FusedMMDiTBase(nn.Module):
         lib.attn_delta_pair(O, ws["dO"], ws["delta"], (T, 0), (Limg, T), Mt, ws["dOj"])
         if not have:
             lib.qk_norm_rope_fwd_pair(qkv, g_txt, g_img, Mt, ws["rope"], Qs, Ks, Vs, round_mid=self.round_mid)
-        refill = bool(os.environ.get("QFX_DQ_FILL"))  # A/B switch: the old separate fill per block
-        if refill or not ws.get("dQ_clean"):  # first use (or an interrupted backward): afterwards the consumer below re-zeroes what it reads, which
-            ws["dQ"].zero_()        # replaces a 118 MB fill per block (70 us at the benchmark shape) by stores in a kernel that streams dQ anyway
+        # dQ (fp32, 118 MB at the benchmark shape) is zero-filled right before the kernel that reduces into it.  Letting the consumer
+        # below re-zero what it reads (QFX_DQ_CLEAR_IN_CONSUMER=1) removes the 70 us fill but makes the step 5 % SLOWER (same box:
+        # 344.7 vs 326.4 ms): the fill doubles as an L2 warm-up for the red.global.add traffic, which otherwise misses to DRAM.
+        consumer_clears = bool(os.environ.get("QFX_DQ_CLEAR_IN_CONSUMER"))
+        if not (consumer_clears and ws.get("dQ_clean")):
+            ws["dQ"].zero_()
         ws["dQ_clean"] = False
         lib.attn_bwd(Qs, Ks, Vs, ws["dOj"], lse, ws["delta"], ws["dQ"], ws["dK"], ws["dV"], kv_len=ws.get("kv_len"),
                      txt_len=ws.get("txt_len"), split=T)
         lib.qk_norm_rope_bwd_pair(ws["dQ"], ws["dK"], ws["dV"], qkv, g_txt, g_img, Mt, ws["rope"], ws["dqkv"], round_mid=self.round_mid,
-                                  clear_dq=not refill)
-        ws["dQ_clean"] = not refill
+                                  clear_dq=consumer_clears)
+        ws["dQ_clean"] = consumer_clears
 
     def _double_bwd(self, ws, l, Xin, dX, dXn, save, mods, prev_gate):
         """dX: grad wrt the block output (ws['dY'] already holds dX * gate2).  Writes the grad wrt the block input to dXn
@@ -750,11 +754,16 @@ class ModelFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, fwd_args, *params):
         ctx.model = model
-        return model._forward_impl(*fwd_args, train=True).clone()
+        out = model._forward_impl(*fwd_args, train=True).clone()
+        ctx.gen = model._fwd_gen  # the activations live in the model's single workspace: a later forward invalidates this graph
+        return out
 
     @staticmethod
     def backward(ctx, dpred):
         m = ctx.model
+        if ctx.gen != m._fwd_gen:
+            raise RuntimeError("qflux_b200: backward() of a forward whose activations were overwritten by a later forward of the same "
+                               "model (one workspace per model: call backward before the next forward)")
         m.G32.zero_()
         m._backward_impl(dpred.to(BF).reshape(-1, m.C_out).contiguous())
         views = m.lora_grad_views(m.G32.to(BF))

@@ -223,6 +223,7 @@ class QwenImageB200(FusedMMDiTBase):
         T = encoder_hidden_states.shape[1]
         D, L, w = self.D, self.L, self.w
         ws = self._workspace(B, T, Limg, train)
+        self._fwd_gen += 1
         Mt = ws["Mt"]
         nested = isinstance(img_shapes[0], (list, tuple)) and isinstance(img_shapes[0][0], (list, tuple))
         per_sample = [list(map(tuple, sh)) for sh in img_shapes] if nested else [list(map(tuple, img_shapes))] * B

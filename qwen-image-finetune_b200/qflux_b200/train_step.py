@@ -115,7 +115,8 @@ class _Accumulation:
 
     def _fused_micro_step(self, args, optimizer):
         self._accumulating = self._micro > 0  # read by _run: keep the gradient of the earlier micro-steps
-        loss = self._run_maybe_graphed(args)
+        loss = self._run_maybe_graphed(args).clone()  # the workspace scalar is overwritten by the next step
+        self.dit._fwd_gen += 1                         # (a graph replay does not pass through _forward_impl)
         self._accumulating = False
         self._micro += 1
         if self._micro >= self.gradient_accumulation_steps:
@@ -151,11 +152,14 @@ class _StepFn(torch.autograd.Function):
     def forward(ctx, step, args, *params):
         loss = step._run(*args)
         ctx.step = step
+        ctx.gen = step.dit._fwd_gen
         return loss.clone().reshape(())
 
     @staticmethod
     def backward(ctx, g):
         m = ctx.step.dit
+        if ctx.gen != m._fwd_gen:
+            raise RuntimeError("qflux_b200: backward() of a loss whose fused gradients were overwritten by a later forward of the same model")
         views = m.lora_grad_views((m.G32 * g).to(BF))
         grads = tuple(views[k] for k in m._lora_params)
         return (None, None) + grads

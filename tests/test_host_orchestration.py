@@ -472,3 +472,29 @@ def test_gradient_accumulation_equals_one_big_batch(emu):
     num = sum(((a - b) ** 2).sum() for a, b in zip(res["big"][1], res["accum"][1]))
     den = sum((a ** 2).sum() for a in res["big"][1])
     assert float((num / den).sqrt()) < 1e-3
+
+
+def test_backward_of_a_stale_forward_is_refused(emu):
+    """One activation workspace per model: a second forward overwrites what the first forward's backward would read, so that backward
+    raises instead of producing gradients from the wrong activations; train_step's loss is a private copy."""
+    from qflux_b200.train_step import QwenImageEditStep
+    orc, m = _pair(2, 1, 128, 4, ("to_q", "to_k", "to_v", "to_out.0"))
+    x = _inputs(1, 4, 24, 128)
+    packed = torch.cat([x["image_latents"], x["control_latents"]], 1)
+    kw = dict(timestep=torch.tensor([0.625]), encoder_hidden_states_mask=x["prompt_embeds_mask"], img_shapes=x["img_shapes"], txt_seq_lens=[24],
+              encoder_hidden_states=x["prompt_embeds"])
+    p1 = m(hidden_states=packed, **kw)[0]
+    p2 = m(hidden_states=packed * 0.5, **kw)[0]
+    with pytest.raises(RuntimeError, match="overwritten by a later forward"):
+        p1.float().pow(2).mean().backward()
+    p2.float().pow(2).mean().backward()  # the most recent forward is fine
+    step = QwenImageEditStep(m)
+    emb = {k: x[k] for k in ("image_latents", "control_latents", "prompt_embeds", "img_shapes")}
+    l1 = step.compute_loss(emb, noise=x["image_latents"], u=torch.tensor([0.5]))
+    step.compute_loss(emb, noise=x["image_latents"], u=torch.tensor([0.25]))
+    with pytest.raises(RuntimeError, match="overwritten by a later forward"):
+        l1.backward()
+    a = step.train_step(emb, noise=x["image_latents"], u=torch.tensor([0.5]))
+    a0 = float(a)
+    step.train_step(emb, noise=x["image_latents"], u=torch.tensor([0.25]))
+    assert float(a) == a0, "train_step must return its own copy of the loss, not the workspace scalar"
