@@ -41,6 +41,7 @@ struct AttnBwd3Params {
   const int* txt_len;
   int split, S, H;
   float scale, scale_log2;
+  int rev;         // 1: heads are visited in descending order, i.e. most recently zero-filled dQ lines (still in L2) first (A/B)
   int rotate;      // 1: rotate the query-tile order per key tile (default), 0: all key tiles walk query tiles 0..n-1 (A/B)
   long long* dbg;  // optional clock64 stamps of CTA (1, 0): [iteration][16] (tools/attn_timeline3.py)
 };
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(B3_THREADS, 1) attn_bwd3_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv0 = blockIdx.x * 128;
-  const int bh = blockIdx.y;
+  const int bh = P.rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int b = bh / P.H;
   const int kv_len = P.kv_len ? P.kv_len[b] : P.S;
   const int txt_len = P.txt_len ? P.txt_len[b] : P.split;
@@ -477,6 +478,7 @@ int attn_bwd_pipelined(const void* Q, const void* K, const void* V, const void* 
   static const bool no_rotate = getenv("QFX_ATTN_BWD3_NO_ROTATE") != nullptr;
   P.rotate = no_rotate ? 0 : 1;
   if (getenv("QFX_ATTN_BWD3_NO_RED")) P.rotate = 2;  // EXPERIMENT ONLY (wrong dQ): how much of the kernel time is the dQ red traffic?
+  P.rev = getenv("QFX_ATTN_BWD3_REV") ? atoi(getenv("QFX_ATTN_BWD3_REV")) : 0;
   static const bool lane_issue = getenv("QFX_ATTN_BWD3_LANE_ISSUE") != nullptr;  // A/B: single-lane issue region (lane-serialising loops)
   static bool attr_done = false;
   if (!attr_done) {
