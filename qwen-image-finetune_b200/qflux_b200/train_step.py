@@ -92,7 +92,10 @@ class _Accumulation:
                 self.use_cuda_graph = False
                 lib.LAUNCHES = n0
                 return self._run(*args)
-            ent = dict(graph=g, static=static, loss=loss, launches=lib.LAUNCHES - n0, ws=m._ws)
+            # `keep`: per-shape tables the captured kernels point at (RoPE, key lengths, ragged row bands) live in bounded caches of the model —
+            # the graph must keep them alive after they are evicted there
+            ent = dict(graph=g, static=static, loss=loss, launches=lib.LAUNCHES - n0, ws=m._ws,
+                       keep=tuple(m._ws.get(k) for k in ("rope", "kv_len", "txt_len", "bands")))
             lib.LAUNCHES = n0  # capture launches nothing
             self._graphs[key] = ent
         self._copy_args(ent["static"], args)
