@@ -413,7 +413,7 @@ class FluxB200(FusedMMDiTBase):
         if torch.is_grad_enabled() and self._lora_params:
             out = ModelFn.apply(self, args, *self._lora_params.values())
         else:
-            out = self._forward_impl(*args, train=False).clone()
+            out = self._infer(args).clone()
         if kv_len is not None:  # padded image rows come back as exact zeros (transformer_flux_custom.py:724-735)
             T = encoder_hidden_states.shape[1]
             valid = torch.arange(out.shape[1], device=out.device)[None, :] < (kv_len[:, None] - T)

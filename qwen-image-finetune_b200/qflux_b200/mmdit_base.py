@@ -94,10 +94,12 @@ class FusedMMDiTBase(nn.Module):
         self.adapter_name, self.peft_config = "default", {}
         self.G32 = self.G16 = None
         self._ws = self._ws_key = None
+        self._train_ws, self._infer_ws = None, {}   # cached workspaces (see _get_workspace)
         self._rope_cache = {}
         self.gradient_checkpointing = False  # accepted for interface compatibility; HBM holds the activations
         self._sharded = None     # sharding.ShardedBlocks once shard_frozen_weights() has run
         self._bands_cache = {}   # (valid image rows per sample, Limg) -> lib.RowBands (ragged GEMM row bands)
+        self._infer_graphs, self.use_cuda_graph_inference = {}, True  # captured no-grad forwards, by input signature (see _infer)
         self._fwd_gen = 0        # bumped by every forward: autograd nodes of an older forward refuse to run (their activations are gone)
 
     @property
@@ -295,6 +297,7 @@ class FusedMMDiTBase(nn.Module):
         self._gnorm_sq = torch.zeros(1, device=self.dev, dtype=torch.float32)
         self._gscratch = torch.zeros(5 * self.D * PAD, device=self.dev, dtype=torch.float32)
         self._ws = self._ws_key = None  # per-block saved tensors depend on which sites exist
+        self._train_ws, self._infer_ws, self._infer_graphs = None, {}, {}
         return self
 
     def _register_lora(self, full: str, pA: nn.Parameter, pB: nn.Parameter):
@@ -483,6 +486,51 @@ class FusedMMDiTBase(nn.Module):
 
     def _bands(self, ws, s):
         return ws.get("bands") if s == 0 else None
+
+    # ------------------------------------------------------------------------------------------------ inference forward
+    # A no-grad forward of 60 blocks is ~650 launches issued through ctypes: 40-65 ms of host time against 25 ms (B=1) to 95 ms (B=4) of
+    # device time, and the validation sampler calls it 40 times per image (20 Euler steps x true CFG).  Like the training step, the second
+    # forward of a given input signature is captured into a CUDA graph and later ones replay it (inputs copied into static buffers).
+    MAX_INFER_GRAPHS = 8
+
+    def _infer(self, args):
+        """`_forward_impl(*args, train=False)` -> prediction [B, Limg, C_out] (a view of workspace memory: callers clone it)."""
+        cuda = self.dev.type == "cuda" and torch.cuda.is_available()
+        if not cuda or not self.use_cuda_graph_inference or self._sharded is not None:
+            return self._forward_impl(*args, train=False)
+        key = _graph_sig(args)
+        ent = self._infer_graphs.get(key)
+        if ent is None:
+            if len(self._infer_graphs) >= self.MAX_INFER_GRAPHS:  # a caller that changes shapes every call stays eager
+                return self._forward_impl(*args, train=False)
+            self._infer_graphs[key] = "warm"
+            return self._forward_impl(*args, train=False)
+        if ent != "warm" and ent["ws"] is not self._ws and not self._activate_ws(ent["ws"], ent["ws_key"]):
+            ent = "warm"  # the workspace this graph was recorded on has been dropped: record again
+        if ent == "warm":
+            static = _graph_clone(args)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = lib.LAUNCHES
+            try:
+                with torch.cuda.graph(g):
+                    out = self._forward_impl(*static, train=False)
+            except Exception as e:
+                import warnings
+                warnings.warn(f"qflux_b200: CUDA-graph capture of the inference forward failed ({type(e).__name__}: {e}); running eagerly")
+                torch.cuda.synchronize()
+                self.use_cuda_graph_inference = False
+                lib.LAUNCHES = n0
+                return self._forward_impl(*args, train=False)
+            ent = dict(graph=g, static=static, out=out, launches=lib.LAUNCHES - n0, ws=self._ws, ws_key=self._ws_key,
+                       keep=tuple(self._ws.get(k) for k in ("rope", "kv_len", "txt_len", "bands")))
+            lib.LAUNCHES = n0
+            self._infer_graphs[key] = ent
+        _graph_copy(ent["static"], args)
+        ent["graph"].replay()
+        lib.LAUNCHES += ent["launches"]
+        self._fwd_gen += 1
+        return ent["out"]
 
     def _site(self, l, grp, s):
         return self.sites.get((l, grp, s))
@@ -737,14 +785,57 @@ class FusedMMDiTBase(nn.Module):
         return ws
 
     def _get_workspace(self, key, build):
+        """key = (B, T, Limg, train).  One training workspace (tens of GB of saved activations) and up to three inference workspaces
+        (a few hundred MB each: validation alternates between the prompt and the negative prompt, whose text lengths may differ) stay
+        allocated, so switching between them neither re-allocates nor invalidates the CUDA graphs captured on them."""
         if self._ws_key == key:
             return self._ws
-        self._ws = None
-        if torch.cuda.is_available():
-            torch.cuda.empty_cache()
-        self._ws = build()
-        self._ws_key = key
-        return self._ws
+        train = bool(key[-1])
+        cached = self._train_ws if train else self._infer_ws.get(key)
+        if cached is not None and (not train or cached[0] == key):
+            ws = cached[1] if train else cached
+        else:
+            if train:
+                self._ws = self._train_ws = None  # a new training shape: the old saved activations go first
+                if torch.cuda.is_available():
+                    torch.cuda.empty_cache()
+            ws = build()
+            if train:
+                self._train_ws = (key, ws)
+            else:
+                if len(self._infer_ws) >= 3:
+                    self._infer_ws.pop(next(iter(self._infer_ws)))
+                self._infer_ws[key] = ws
+        self._ws, self._ws_key = ws, key
+        return ws
+
+    def _activate_ws(self, ws, key) -> bool:
+        """Make a workspace a captured graph was recorded on current again; False if the model no longer holds it."""
+        held = (self._train_ws is not None and self._train_ws[1] is ws) or any(w is ws for w in self._infer_ws.values())
+        if held:
+            self._ws, self._ws_key = ws, key
+        return held
+
+
+def _graph_sig(a):
+    if torch.is_tensor(a):
+        return ("t", tuple(a.shape), str(a.dtype))
+    if isinstance(a, (tuple, list)):
+        return tuple(_graph_sig(x) for x in a)
+    return repr(a)
+
+
+def _graph_clone(args):
+    return tuple(a.clone() if torch.is_tensor(a) else (_graph_clone(a) if isinstance(a, tuple) else a) for a in args)
+
+
+def _graph_copy(static, args):
+    for s_, a in zip(static, args):
+        if torch.is_tensor(s_):
+            if s_.data_ptr() != a.data_ptr():
+                s_.copy_(a, non_blocking=True)
+        elif isinstance(s_, tuple):
+            _graph_copy(s_, a)
 
 
 class ModelFn(torch.autograd.Function):

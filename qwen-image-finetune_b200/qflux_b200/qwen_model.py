@@ -316,7 +316,7 @@ class QwenImageB200(FusedMMDiTBase):
         if torch.is_grad_enabled() and self._lora_params:
             out = ModelFn.apply(self, args, *self._lora_params.values())
         else:
-            out = self._forward_impl(*args, train=False).clone()
+            out = self._infer(args).clone()
         kv = self._ws.get("kv_len")
         if kv is not None:  # padded image rows of a multi-resolution batch are returned as exact zeros (test_qwen_custom.py:672-692)
             T = encoder_hidden_states.shape[1]

@@ -75,8 +75,8 @@ class _Accumulation:
         if ent is None:  # first step of this shape: eager (allocates the workspace, RoPE tables, split-K scratch, sets kernel attributes)
             self._graphs[key] = "warm"
             return self._run(*args)
-        if ent != "warm" and ent["ws"] is not m._ws:  # the model re-allocated its workspace (another shape ran in between): stale pointers
-            ent = "warm"
+        if ent != "warm" and ent["ws"] is not m._ws and not m._activate_ws(ent["ws"], ent["ws_key"]):
+            ent = "warm"  # the model dropped the workspace this graph was recorded on (another training shape ran in between): record again
         if ent == "warm":
             static = self._clone_args(args)
             torch.cuda.synchronize()
@@ -94,7 +94,7 @@ class _Accumulation:
                 return self._run(*args)
             # `keep`: per-shape tables the captured kernels point at (RoPE, key lengths, ragged row bands) live in bounded caches of the model —
             # the graph must keep them alive after they are evicted there
-            ent = dict(graph=g, static=static, loss=loss, launches=lib.LAUNCHES - n0, ws=m._ws,
+            ent = dict(graph=g, static=static, loss=loss, launches=lib.LAUNCHES - n0, ws=m._ws, ws_key=m._ws_key,
                        keep=tuple(m._ws.get(k) for k in ("rope", "kv_len", "txt_len", "bands")))
             lib.LAUNCHES = n0  # capture launches nothing
             self._graphs[key] = ent

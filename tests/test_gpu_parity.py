@@ -87,6 +87,12 @@ def test_cuda_graph_replay_equals_eager_step():
     assert r["err"] < 1e-4, r
 
 
+def test_inference_forward_graph_replay_is_bit_exact():
+    """No-grad forwards replay a CUDA graph per input signature (prompt / negative prompt alternate, a training step interleaves)."""
+    r = _cases("model_check")["infer_graph_replay"]()
+    assert r["err"] == 0.0 and r["graphs"] == 2, r
+
+
 def test_five_optimizer_steps_track_the_oracle():
     """fused step + fused clip/AdamW vs fp32 oracle + clip_grad_norm_ + torch.optim.AdamW: loss trajectory within 1e-2 (relative)."""
     r = _cases("model_check")["train_trajectory_5steps"]()

@@ -241,6 +241,50 @@ def graph_replay():
     return res
 
 
+def infer_graph_replay():
+    """The no-grad forward replays a CUDA graph from its third call of a shape on: outputs must equal the eager forward bit for bit (no
+    atomics on that path), for two alternating prompt lengths (true CFG: prompt / negative prompt), interleaved with a training step
+    that uses another workspace, and for the whole sampling loop."""
+    from qflux_b200.sampler import sample_qwen
+    from qflux_b200.train_step import QwenImageEditStep
+    orc, m = build_pair(2, 2, 128, 4, ("to_q", "to_k", "to_v", "to_out.0"))
+    x = inputs(2, 4, 24, 128)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()
+    packed = torch.cat([x["image_latents"], x["control_latents"]], 1)
+    shapes = x["img_shapes"]
+
+    def call(pe, hs, t):
+        with torch.no_grad():
+            return m(hidden_states=hs, timestep=torch.tensor([t, t], device="cuda"), encoder_hidden_states=pe,
+                     encoder_hidden_states_mask=torch.ones(2, pe.shape[1], dtype=torch.int64, device="cuda"), img_shapes=shapes)[0].clone()
+    pe_a, pe_b = x["prompt_embeds"], rn(2, 17, 128) * 3
+    m.use_cuda_graph_inference = False
+    ref = [call(pe_a, packed, 0.5), call(pe_b, packed, 0.5), call(pe_a, packed * 0.5, 0.25), call(pe_b, packed * 0.5, 0.25)]
+    m.use_cuda_graph_inference = True
+    worst = 0.0
+    step = QwenImageEditStep(m)
+    emb = {k: x[k] for k in ("image_latents", "control_latents", "prompt_embeds", "img_shapes")}
+    for rep in range(4):  # 1st: warm, 2nd: capture + replay, then replays; a training step in between re-points the model's workspace
+        got = [call(pe_a, packed, 0.5), call(pe_b, packed, 0.5), call(pe_a, packed * 0.5, 0.25), call(pe_b, packed * 0.5, 0.25)]
+        worst = max(worst, max(float((a.float() - b.float()).abs().max()) for a, b in zip(got, ref)))
+        if rep == 2:
+            step.train_step(emb, noise=x["noise"], u=x["u"])
+    n_graphs = sum(isinstance(v, dict) for v in m._infer_graphs.values())
+    assert n_graphs == 2, f"expected two captured inference graphs, got {n_graphs}"
+    # the sampling loop end to end, graphed vs eager
+    e = dict(latents=rn(2, 16, 64), control_latents=x["control_latents"], prompt_embeds=pe_a, prompt_embeds_mask=torch.ones(2, 24, dtype=torch.int64, device="cuda"),
+             negative_prompt_embeds=pe_b, negative_prompt_embeds_mask=torch.ones(2, 17, dtype=torch.int64, device="cuda"), img_shapes=shapes,
+             num_inference_steps=4, true_cfg_scale=3.0)
+    out_g = sample_qwen(m, e)
+    m.use_cuda_graph_inference = False
+    out_e = sample_qwen(m, e)
+    m.use_cuda_graph_inference = True
+    res = dict(forward_max_abs=worst, sampler_max_abs=float((out_g.float() - out_e.float()).abs().max()), graphs=n_graphs)
+    res["err"] = max(res["forward_max_abs"], res["sampler_max_abs"])
+    return res
+
+
 FLUX_YAML_TARGETS = (
     r"(.*x_embedder|.*transformer_blocks\.[0-9]+\.(norm|norm1)\.linear|.*transformer_blocks\.[0-9]+\.attn\.(to_k|to_q|to_v|to_add_out)"
     r"|.*transformer_blocks\.[0-9]+\.attn\.to_out\.0|.*single_transformer_blocks\.[0-9]+\.attn\.to_out"
@@ -482,6 +526,7 @@ CASES = {
     "step_tiny_mlp_down_targets": lambda: step_parity(targets=("to_k", "img_mlp.net.2", "txt_mlp.net.0.proj", "txt_mlp.net.2")),
     "flux_full_width_1p1": lambda: flux_step_parity(H=24, L=1, Ls=1, J=4096, Pp=768, B=1, hw=32, T=512, r=16),
     "bench_point_6blk": bench_point_6blk,
+    "infer_graph_replay": infer_graph_replay,
     "train_trajectory_5steps": train_trajectory,
     "graph_replay": graph_replay,
 }
