@@ -85,6 +85,10 @@ class QwenImageB200(FusedMMDiTBase):
         self._init_common(device, _host_only)
         assert cfg.attention_head_dim == 128, "the sm_100a attention kernels are specialised for head_dim 128"
         self.config = cfg
+        # Multi-resolution batches with PADDED TEXT: "aligned" rotates a sample's image tokens where they sit ([T, T + L_b)), which makes
+        # a padded batch equal the per-sample runs; "reference" reproduces transformer_qwen_custom.py:199-208, which lays the image table
+        # down right after the sample's un-padded text length.  The two agree when no text is padded.
+        self.rope_placement = "aligned"
         self.pos_embed = _QwenPosEmbed(cfg.axes_dims_rope)
         D = cfg.num_attention_heads * cfg.attention_head_dim
         self.D, self.H, self.L, self.J = D, cfg.num_attention_heads, cfg.num_layers, cfg.joint_attention_dim
@@ -196,28 +200,32 @@ class QwenImageB200(FusedMMDiTBase):
         return f
 
     # ------------------------------------------------------------------------------------------------ forward
-    def _rope_multi(self, img_shapes, T, Limg):
+    def _rope_multi(self, img_shapes, T, Limg, txt_lens=None):
         """Per-sample tables [B, T+Limg, 64, 2] for a pad-to-max multi-resolution batch; padded rows get the identity rotation
-        (cos 1, sin 0 — transformer_flux_custom.py:148-154), their keys are masked anyway.  Returns (table, kv_len int32 [B])."""
-        key = ("multi", tuple(tuple(tuple(s) for s in sh) for sh in img_shapes), T, Limg)
+        (cos 1, sin 0 — transformer_flux_custom.py:148-154), their keys are masked anyway.  Returns (table, kv_len int32 [B]).
+        txt_lens (host ints, `rope_placement="reference"` only): sample b's table is built for ITS text length and laid down from joint
+        position 0 — text angles on [0, n_b), image angles on [n_b, n_b + L_b) — which is where the reference's
+        `_apply_rope_per_sample` puts them (transformer_qwen_custom.py:199-208), text padding or not."""
+        key = ("multi", tuple(tuple(tuple(s) for s in sh) for sh in img_shapes), T, Limg, None if txt_lens is None else tuple(txt_lens))
         if key not in self._rope_cache:
             if len(self._rope_cache) >= 64:  # bucketed multi-resolution training meets a bounded set of shape combinations; stay bounded anyway
                 self._rope_cache.pop(next(iter(self._rope_cache)))
             tabs, lens = [], []
-            for sh in img_shapes:
-                t = qwen_rope_table(sh, T, self.config.axes_dims_rope)
+            for b, sh in enumerate(img_shapes):
+                t = qwen_rope_table(sh, T if txt_lens is None else int(txt_lens[b]), self.config.axes_dims_rope)
                 pad = torch.zeros(T + Limg - t.shape[0], t.shape[1], 2)
                 pad[..., 0] = 1.0
                 tabs.append(torch.cat([t, pad], 0))
-                lens.append(t.shape[0])
+                lens.append(T + sum(f * h * w for f, h, w in sh))  # keys live at their joint positions whatever the rotation placement
             self._rope_cache[key] = (torch.stack(tabs).contiguous().to(self.dev),
                                      torch.tensor(lens, dtype=torch.int32).to(self.dev))
         return self._rope_cache[key]
 
-    def _forward_impl(self, hidden_states, encoder_hidden_states, timestep, img_shapes, txt_len=None, train: bool = False):
+    def _forward_impl(self, hidden_states, encoder_hidden_states, timestep, img_shapes, txt_len=None, txt_seq_lens=None, *,
+                      train: bool = False):
         """img_shapes: one list of (frame, h, w) per sample.  When the samples differ (multi-resolution, pad-to-max) every
         sample gets its own RoPE table and key mask (transformer_qwen_custom.py:444-553); `txt_len` (int32 [B] on the device)
-        additionally masks text padding."""
+        additionally masks text padding; `txt_seq_lens` (host ints) selects the reference's RoPE placement (see _rope_multi)."""
         lib.require_cuda(hidden_states, encoder_hidden_states, timestep, txt_len)
         B, Limg, _ = hidden_states.shape
         T = encoder_hidden_states.shape[1]
@@ -229,7 +237,7 @@ class QwenImageB200(FusedMMDiTBase):
         per_sample = [list(map(tuple, sh)) for sh in img_shapes] if nested else [list(map(tuple, img_shapes))] * B
         if any(sh != per_sample[0] for sh in per_sample):
             assert len(per_sample) == B
-            ws["rope"], ws["kv_len"] = self._rope_multi(per_sample, T, Limg)
+            ws["rope"], ws["kv_len"] = self._rope_multi(per_sample, T, Limg, txt_seq_lens)
             self._plan_bands(ws, [sum(f * h * w for f, h, w in sh) for sh in per_sample])
         else:
             self._plan_bands(ws, None)
@@ -313,6 +321,10 @@ class QwenImageB200(FusedMMDiTBase):
         args = (hidden_states, encoder_hidden_states, timestep, img_shapes)
         if multi:
             args = args + (txt_len,)
+            if self.rope_placement == "reference":
+                if txt_seq_lens is None:
+                    raise ValueError("rope_placement='reference' needs txt_seq_lens (one text length per sample), as the reference's forward takes it")
+                args = args + (tuple(int(n) for n in txt_seq_lens),)
         if torch.is_grad_enabled() and self._lora_params:
             out = ModelFn.apply(self, args, *self._lora_params.values())
         else:

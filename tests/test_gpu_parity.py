@@ -93,6 +93,17 @@ def test_inference_forward_graph_replay_is_bit_exact():
     assert r["err"] == 0.0 and r["graphs"] == 2, r
 
 
+def test_gradient_accumulation_on_the_cuda_path():
+    r = _cases("model_check")["grad_accum"]()
+    assert r["grad"] < 2e-2 and r["params_after_3_steps"] < 2e-3, r
+
+
+def test_reference_rope_placement_switch():
+    """a11: both RoPE placements of the custom multi-resolution model (the aligned one and the reference's) match the oracle's."""
+    r = _cases("model_check")["qwen_reference_rope_placement"]()
+    assert r["err"] < 2e-2, r
+
+
 def test_five_optimizer_steps_track_the_oracle():
     """fused step + fused clip/AdamW vs fp32 oracle + clip_grad_norm_ + torch.optim.AdamW: loss trajectory within 1e-2 (relative)."""
     r = _cases("model_check")["train_trajectory_5steps"]()

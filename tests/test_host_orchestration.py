@@ -289,6 +289,20 @@ def test_qwen_multi_resolution_matches_per_sample_oracle(emu):
         ref = orc(hidden_states=packed.float(), timestep=sig, encoder_hidden_states=pe.float(), img_shapes=shapes, txt_seq_lens=txt,
                   attention_mask=am)[0]
     assert ((out.float() - ref).norm() / ref.norm()).item() < 1e-2 and ref[1, 16:].abs().max() == 0
+    # the reference's own RoPE placement with padded text (transformer_qwen_custom.py:199-208: image table laid down right after the
+    # un-padded text length) is available behind a switch and differs from the aligned placement exactly when text is padded
+    with torch.no_grad():
+        ref_r = orc(hidden_states=packed.float(), timestep=sig, encoder_hidden_states=pe.float(), img_shapes=shapes, txt_seq_lens=txt,
+                    attention_mask=am, img_offset="reference")[0]
+        m.rope_placement = "reference"
+        out_r = m(hidden_states=packed, timestep=sig, encoder_hidden_states=pe, encoder_hidden_states_mask=mask, img_shapes=shapes,
+                  txt_seq_lens=txt)[0]
+        with pytest.raises(ValueError, match="txt_seq_lens"):
+            m(hidden_states=packed, timestep=sig, encoder_hidden_states=pe, encoder_hidden_states_mask=mask, img_shapes=shapes)
+        m.rope_placement = "aligned"
+    assert ((out_r.float() - ref_r).norm() / ref_r.norm()).item() < 1e-2
+    assert ((ref_r[1] - ref[1]).norm() / ref[1].norm()).item() > 2e-2, "sample 1 has padded text: the two placements must differ there"
+    assert ((out_r[0].float() - out[0].float()).norm() / out[0].float().norm()).item() < 1e-2, "sample 0 has no text padding: same result"
 
 
 def test_flux_multi_resolution_matches_per_sample_oracle(emu):

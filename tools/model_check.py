@@ -241,6 +241,78 @@ def graph_replay():
     return res
 
 
+def grad_accum():
+    """`gradient_accumulation_steps=2` on the CUDA path (graphs on: the accumulating and the non-accumulating micro-step are two different
+    captured graphs): two B=1 micro-steps must give the gradient and the parameter update of one B=2 step (accelerator.accumulate
+    semantics, base_trainer.py:518-533), repeated so that the replays are exercised too."""
+    from qflux_b200.optim import FusedLoraAdamW
+    from qflux_b200.train_step import QwenImageEditStep
+    keys = ("image_latents", "control_latents", "prompt_embeds")
+    x = inputs(2, 8, 24, 128)
+    out = {}
+    for mode in ("big", "accum"):
+        orc, m = build_pair(2, 2, 128, 4, ("to_q", "to_k", "to_v", "to_out.0"))
+        opt = FusedLoraAdamW(m, lr=1e-2, weight_decay=0.0)
+        gs = []
+        if mode == "big":
+            step = QwenImageEditStep(m, "mse", max_grad_norm=0.0)
+            for it in range(3):
+                step.train_step({**{k: x[k] for k in keys}, "img_shapes": x["img_shapes"]}, opt, noise=x["noise"], u=x["u"])
+                gs.append(m.G32.clone())
+        else:
+            step = QwenImageEditStep(m, "mse", max_grad_norm=0.0, gradient_accumulation_steps=2)
+            for it in range(3):
+                for b in range(2):
+                    emb = {**{k: x[k][b:b + 1] for k in keys}, "img_shapes": x["img_shapes"][b:b + 1]}
+                    step.train_step(emb, opt, noise=x["noise"][b:b + 1], u=x["u"][b:b + 1])
+                gs.append(m.G32.clone() / 2)  # the accumulator holds the SUM over micro-steps; the optimizer divides
+            assert opt.step_count == 3
+            n_graphs = sum(isinstance(v, dict) for v in step._graphs.values())
+            assert n_graphs == 2, f"expected one graph per micro-step kind, got {n_graphs}"
+        out[mode] = (gs, [p.detach().float().clone() for p in m.parameters()])
+    res = dict(grad=max(rel_l2(a, b) for a, b in zip(out["accum"][0], out["big"][0])))
+    num = sum(((a - b) ** 2).sum() for a, b in zip(out["big"][1], out["accum"][1]))
+    den = sum((a ** 2).sum() for a in out["big"][1])
+    res["params_after_3_steps"] = float((num / den).sqrt())
+    res["err"] = max(res["grad"], res["params_after_3_steps"])
+    return res
+
+
+def qwen_reference_rope_placement():
+    """`rope_placement="reference"` on the CUDA path vs the oracle's restatement of transformer_qwen_custom.py:199-208 with padded text."""
+    orc, m = build_pair(2, 2, 128, 4, ("to_q", "to_k", "to_v", "to_out.0"))
+    g = torch.Generator(device="cuda").manual_seed(13)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()
+    shapes = [[(1, 8, 8), (1, 8, 8)], [(1, 4, 8), (1, 4, 8)]]
+    T, txt = 24, [24, 13]
+    pe = rn(2, T, 128) * 3
+    pe[1, 13:] = 0
+    mask = torch.zeros(2, T, dtype=torch.int64, device="cuda")
+    mask[0], mask[1, :13] = 1, 1
+    packed = torch.zeros(2, 128, 64, dtype=torch.bfloat16, device="cuda")
+    packed[0], packed[1, :64] = rn(128, 64), rn(64, 64)
+    sig = torch.tensor([0.5, 0.25], device="cuda")
+    am = torch.zeros(2, T + 128, dtype=torch.bool, device="cuda")
+    am[0], am[1, :13], am[1, T:T + 64] = True, True, True
+    res = {}
+    with torch.no_grad():
+        for place in ("aligned", "reference"):
+            ref = orc(hidden_states=packed.float(), timestep=sig, encoder_hidden_states=pe.float(), img_shapes=shapes, txt_seq_lens=txt,
+                      attention_mask=am, img_offset=place)[0]
+            m.rope_placement = place
+            out = m(hidden_states=packed, timestep=sig, encoder_hidden_states=pe, encoder_hidden_states_mask=mask, img_shapes=shapes,
+                    txt_seq_lens=txt)[0]
+            res[place] = rel_l2(out.float(), ref)
+            res[place + "_pad_rows_max"] = float(out[1, 64:].abs().max())
+            if place == "aligned":
+                ref_a = ref
+        res["placements_differ"] = rel_l2(ref[1], ref_a[1])
+    m.rope_placement = "aligned"
+    assert res["placements_differ"] > 2e-2
+    res["err"] = max(res["aligned"], res["reference"], res["aligned_pad_rows_max"], res["reference_pad_rows_max"])
+    return res
+
+
 def infer_graph_replay():
     """The no-grad forward replays a CUDA graph from its third call of a shape on: outputs must equal the eager forward bit for bit (no
     atomics on that path), for two alternating prompt lengths (true CFG: prompt / negative prompt), interleaved with a training step
@@ -527,6 +599,8 @@ CASES = {
     "flux_full_width_1p1": lambda: flux_step_parity(H=24, L=1, Ls=1, J=4096, Pp=768, B=1, hw=32, T=512, r=16),
     "bench_point_6blk": bench_point_6blk,
     "infer_graph_replay": infer_graph_replay,
+    "grad_accum": grad_accum,
+    "qwen_reference_rope_placement": qwen_reference_rope_placement,
     "train_trajectory_5steps": train_trajectory,
     "graph_replay": graph_replay,
 }
