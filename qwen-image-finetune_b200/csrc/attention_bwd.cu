@@ -365,9 +365,6 @@ extern "C" void qfx_attn_bwd_set_debug(long long* buf) { g_qfx_attn_bwd_dbg = bu
 /* All of Q, K, V, dO, dK, dV: [B, H, S, 128] bf16; dQ_accum: [B, H, S, 128] fp32, MUST be zeroed by the caller (it is the
  * target of TMA reduce-adds from every key tile).  lse: log2-domain logsumexp from qfx_attn_fwd; delta = rowsum(dO*O). */
 namespace qfx {
-int attn_bwd_transposed(const void* Q, const void* K, const void* V, const void* dO, const float* lse, const float* delta, float* dQ,
-                        void* dK, void* dV, const int* kv_len, const int* txt_len, int split, int B, int H, int S, float softmax_scale,
-                        cudaStream_t stream);  // attention_bwd2.cu
 int attn_bwd_pipelined(const void* Q, const void* K, const void* V, const void* dO, const float* lse, const float* delta, float* dQ,
                        void* dK, void* dV, const int* kv_len, const int* txt_len, int split, int B, int H, int S, float softmax_scale,
                        cudaStream_t stream);  // attention_bwd3.cu
@@ -378,16 +375,13 @@ extern "C" int qfx_attn_bwd(const void* Q, const void* K, const void* V, const v
                             int S, float softmax_scale, void* stream) {
   extern long long* g_qfx_attn_bwd_dbg;
   QFX_CHECK_ARG(B > 0 && H > 0 && S > 0 && dQ_accum && dK && dV && lse && delta, "qfx_attn_bwd: bad arguments");
-  // default: the software-pipelined transposed kernel (attention_bwd3.cu).  A/B switches: QFX_ATTN_BWD1=1 the round-1 serial-chain
-  // kernel below, QFX_ATTN_BWD2=1 the 64-query transposed kernel (attention_bwd2.cu)
-  static const bool transposed = getenv("QFX_ATTN_BWD2") != nullptr;
+  // default: the software-pipelined transposed kernel (attention_bwd3.cu).  A/B switch: QFX_ATTN_BWD1=1 runs the round-1 serial-chain
+  // kernel below (the same-box comparison in profiles/r02_bench_b_*.json).  The 64-query transposed variant of round 1 lives on as
+  // tools/experiments/attention_bwd_transposed_64q.cu — it never beat either and is no longer part of the library.
   static const bool serial = getenv("QFX_ATTN_BWD1") != nullptr;
-  if (!transposed && !serial)
+  if (!serial)
     return qfx::attn_bwd_pipelined(Q, K, V, dO, lse, delta, dQ_accum, dK, dV, kv_len, txt_len, split, B, H, S, softmax_scale,
                                    (cudaStream_t)stream);
-  if (transposed)
-    return qfx::attn_bwd_transposed(Q, K, V, dO, lse, delta, dQ_accum, dK, dV, kv_len, txt_len, split, B, H, S, softmax_scale,
-                                    (cudaStream_t)stream);
   AttnBwdParams P;
   memset(&P, 0, sizeof(P));
   int rc;

@@ -540,10 +540,6 @@ int make_qkv_tmap(CUtensorMap* m, const void* base, int BH, int S) {
   return make_tmap_bf16(m, base, 3, dims, strides, box);
 }
 
-int attn_fwd_two_tiles(const void* Q, const void* K, const void* V, void* out0, int64_t ld0, int rows0, void* out1, int64_t ld1,
-                       int rows1, int split, float* lse, const int* kv_len, const int* txt_len, int B, int H, int S, float softmax_scale,
-                       cudaStream_t stream);  // attention_fwd2.cu
-
 }  // namespace qfx
 
 using namespace qfx;
@@ -554,12 +550,8 @@ extern "C" int qfx_attn_fwd(const void* Q, const void* K, const void* V, void* o
                             int64_t ld1, int rows1, int split, float* lse, const int* kv_len, const int* txt_len, int B, int H,
                             int S, float softmax_scale, void* stream) {
   QFX_CHECK_ARG(B > 0 && H > 0 && S > 0 && out0 && (split >= S || out1), "qfx_attn_fwd: bad arguments");
-  // default: the 64-key-tile kernel below (two CTAs per SM).  A/B switches: QFX_ATTN_FWD2=1 two query tiles per CTA ping-ponging on
-  // 128-key tiles (attention_fwd2.cu: measured slower, see its header), QFX_ATTN_FWD128=1 the first 128-key-tile kernel
-  static const bool two_tiles = getenv("QFX_ATTN_FWD2") != nullptr;
-  if (two_tiles)
-    return qfx::attn_fwd_two_tiles(Q, K, V, out0, ld0, rows0, out1, ld1, rows1, split, lse, kv_len, txt_len, B, H, S, softmax_scale,
-                                   (cudaStream_t)stream);
+  // default: the 64-key-tile kernel (two CTAs per SM).  A/B switch: QFX_ATTN_FWD128=1 the first 128-key-tile kernel.  The two-query-tiles-
+  // per-CTA ping-pong design (341 us vs 266) is kept for the record as tools/experiments/attention_fwd_two_tiles.cu, outside the library.
   AttnFwdParams P;
   memset(&P, 0, sizeof(P));
   int rc;

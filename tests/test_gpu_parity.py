@@ -121,20 +121,6 @@ def test_smoke_entry():
     g.smoke()
 
 
-@pytest.mark.parametrize("name", ["attn_bwd_300", "attn_bwd_tail", "attn_bwd_ragged", "attn_bwd_txtgap"])
-def test_attention_backward_transposed_variant(name):
-    """The opt-in transposed backward (csrc/attention_bwd2.cu, QFX_ATTN_BWD2=1): same parity bar as the default kernel.  The switch is
-    read once per process, so the case runs in a subprocess."""
-    import json
-    import subprocess
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "ops_check.py"), "--case", name], capture_output=True, text=True,
-                       timeout=300, env=dict(os.environ, QFX_ATTN_BWD2="1"))
-    res = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
-    assert r.returncode == 0 and res, r.stdout[-500:] + r.stderr[-500:]
-    assert json.loads(res[-1][7:])["err"] < 5e-3
-
-
 def test_cache_loader_cuda_path(tmp_path):
     """CachedEmbeddingLoader on the device: pinned ping-pong staging + side-stream upload must hand out complete, un-clobbered batches."""
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

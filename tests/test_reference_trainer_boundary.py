@@ -285,3 +285,33 @@ def test_sampler_schedule_matches_reference_prepare_predict_timesteps(ref):
             from qflux_b200.sampler import _euler_step
             got = _euler_step(x, v, sig, 0)
             assert torch.equal(want, got)
+
+
+def test_loader_reads_a_cache_written_by_the_reference(ref, tmp_path):
+    """f3: the cache directory is produced by the reference's own `EmbeddingCacheManager.save_cache_embedding` (data/cache_manager.py:
+    46-93) and read back two ways — by the reference's `load_cache` and by `CachedEmbeddingLoader` — which must agree sample by sample
+    (values, fp16 storage, pixel `img_shapes` converted to latent-patch units, pad-to-max collate like `pad_to_max_shape`)."""
+    from qflux.data.cache_manager import EmbeddingCacheManager
+    from qflux.utils.tools import pad_to_max_shape
+    from qflux_b200.cache_loader import CachedEmbeddingLoader
+    mgr = EmbeddingCacheManager(str(tmp_path))
+    g = torch.Generator().manual_seed(5)
+    sizes, hashes = [(512, 512), (320, 640), (640, 384)], []
+    for i, (H, W) in enumerate(sizes):
+        L, T = (H // 16) * (W // 16), 6 + 5 * i
+        data = dict(image_latents=torch.randn(L, 64, generator=g), control_latents=torch.randn(L, 64, generator=g),
+                    prompt_embeds=torch.randn(T, 48, generator=g))
+        fh = dict(main_hash=f"m{i:03d}", image_hash=f"i{i:03d}", control_hash=f"c{i:03d}", prompt_hash=f"p{i:03d}")
+        mgr.save_cache_embedding(data, dict(image_latents="image_hash", control_latents="control_hash", prompt_embeds="prompt_hash"), fh,
+                                 img_shapes=[[3, H, W], [3, H, W]])
+        hashes.append(fh)
+    assert EmbeddingCacheManager.exist(str(tmp_path))
+    ours = list(CachedEmbeddingLoader(str(tmp_path), batch_size=3, device="cpu", shuffle=False, drop_last=False))
+    assert len(ours) == 1
+    b = ours[0]
+    theirs = [mgr.load_cache({"file_hashes": fh}) for fh in hashes]  # the reference's reader, one sample at a time
+    for key in ("image_latents", "control_latents", "prompt_embeds"):
+        want = pad_to_max_shape([t[key] for t in theirs])  # the reference's collate (utils/tools.py:399-425)
+        assert b[key].dtype == torch.float16 and torch.equal(b[key], want), key
+    assert b["img_shapes"] == [[(1, H // 16, W // 16)] * 2 for H, W in sizes]
+    assert b["prompt_embeds_mask"].sum(1).tolist() == [6, 11, 16]
