@@ -449,7 +449,7 @@ def run_b200(args):
             "kernel": f"gemm2_kernel<256,false,GELU> (CTA pair, cta_group::2): grouped img+txt MLP-up [{B * Limg_launch}+{B * T},3072]x[12288,3072] "
                       "with the step's epilogue (GELU output + pre-activation, two [M,4D] bf16 stores)",
             "achieved": g_tf, "peak": burst, "unit": "TFLOP/s", "frac": g_tf / burst, "kernel_ms": g_ms, "flop_per_launch": g_fl,
-            "traffic": (traffic or {}).get("gemm2_mlp_up_gelu", {}).get("dram_bytes"),
+            "traffic": (traffic or {}).get("gemm2_mlp_up_gelu", {}).get("dram_bytes") if name == "qwen_edit" else None,  # measured at that shape only
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture listed in "
                               "profiles/r02_ncu_traffic.json" if traffic else None,
             "peak_source": f"{which} MEASURED_PEAKS.json bf16_tflops (burst; kernels timed alone, L2 flushed between launches)",
