@@ -27,7 +27,7 @@ int qfx_version(void);
  * Fused LoRA projection GEMM (tcgen05 + TMA).  Replaces one `peft.tuners.lora.Linear.forward` call
  * (injected at base_trainer.py:929-941; y = base(x) + lora_B(lora_A(x)) * alpha/r) or its autograd backward, for
  * up to QFX_MAX_PROBLEMS row-groups that share N, K (e.g. the image and text streams of one MMDiT block:
- * transformer_qwenimage.py:286-293).
+ * transformer_qwenimage.py:286-293; or the three q|k|v slices of both streams of a LoRA backward, six small problems in one launch).
  *
  *   trans_b = 0 :  out[M,N] = epi( alpha * ( A[M,K] . B[N,K]^T  +  A2[M,64*kb2] . B2[N,64*kb2]^T ) + bias )
  *   trans_b = 1 :  out[M,N] = epi( alpha * ( A[M,K] . B[K,N]    +  A2[M,64*kb2] . B2[64*kb2,N]   ) )      (dgrad)
@@ -35,7 +35,7 @@ int qfx_version(void);
  * The LoRA factor pair (A2,B2) is appended to the K loop of the SAME tensor-core contraction (rank padded to a
  * multiple of 64 with zeros by the caller), so one accumulator in TMEM receives base + low-rank update.
  */
-#define QFX_MAX_PROBLEMS 2
+#define QFX_MAX_PROBLEMS 6
 
 enum qfx_epilogue {
   QFX_EPI_BIAS = 0,       /* out = alpha*acc + bias                                                  (nn.Linear)            */

@@ -33,10 +33,11 @@ struct GemmProb {
   int64_t ldo, ldo2, ldr, ldg, ldaux;
 };
 
-struct GemmParams {
+struct GemmParams {  // passed by value as a __grid_constant__ kernel parameter: must stay below the 4 KB parameter space
   GemmProb p[QFX_MAX_PROBLEMS];
   int nprob, N, K, lora_group_n;
-  int tiles_m0, tiles_m_total, tiles_n, total_tiles;
+  int tiles_m_end[QFX_MAX_PROBLEMS];  // running sum of the problems' m-tile counts (problem i owns m-tiles [end[i-1], end[i]))
+  int tiles_m_total, tiles_n, total_tiles;
   float alpha;
   // split-K of the last, partial wave of the CTA-pair kernel (tail_split > 1): tiles >= tail_first are cut into tail_split
   // K ranges that run on otherwise idle CTA pairs; partial sums meet in tail_ws (fp32, zeroed by a memset node in front of the
@@ -48,6 +49,8 @@ struct GemmParams {
   float* tail_ws;
   int* tail_cnt;
 };
+
+static_assert(sizeof(GemmParams) <= 4000, "GemmParams must fit the kernel parameter space");
 
 template <int BN>
 struct GemmCfg {
@@ -231,8 +234,10 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
   auto decode = [&](int tile, int& prob, int& m0, int& n0) {
     int n_blk = tile / P.tiles_m_total;
     int mm = tile - n_blk * P.tiles_m_total;
-    prob = mm >= P.tiles_m0 ? 1 : 0;
-    const int local = prob ? mm - P.tiles_m0 : mm;
+    prob = 0;
+#pragma unroll
+    for (int i = 0; i < QFX_MAX_PROBLEMS - 1; ++i) prob += (i + 1 < P.nprob && mm >= P.tiles_m_end[i]) ? 1 : 0;
+    const int local = prob ? mm - P.tiles_m_end[prob - 1] : mm;
     const int* rt = P.p[prob].row_tiles;
     m0 = rt ? __ldg(rt + (local >> 1)) + (local & 1) * BM : local * BM;
     n0 = n_blk * BN;
@@ -401,8 +406,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm2_kernel
       n_blk = tile / P.tiles_m_total;
       mm = tile - n_blk * P.tiles_m_total;
     }
-    prob = mm >= P.tiles_m0 ? 1 : 0;
-    const int local = prob ? mm - P.tiles_m0 : mm;
+    prob = 0;
+#pragma unroll
+    for (int i = 0; i < QFX_MAX_PROBLEMS - 1; ++i) prob += (i + 1 < P.nprob && mm >= P.tiles_m_end[i]) ? 1 : 0;
+    const int local = prob ? mm - P.tiles_m_end[prob - 1] : mm;
     const int* rt = P.p[prob].row_tiles;
     m0 = (rt ? __ldg(rt + local) : local * 256) + (int)rank * BM;
     n0 = n_blk * BN;
@@ -788,8 +795,8 @@ extern "C" int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, in
     if (epilogue == QFX_EPI_DGELU) QFX_CHECK_ARG(s.aux && s.ldaux % 8 == 0, "qfx_gemm_bf16: DGELU epilogue needs aux");
     int tm = two_cta ? (s.M + 255) / 256 : (s.M + BM - 1) / BM;
     if (s.row_tiles) tm = two_cta ? s.n_row_tiles : 2 * s.n_row_tiles;
-    if (i == 0) P.tiles_m0 = tm;
     tiles_m_total += tm;
+    P.tiles_m_end[i] = tiles_m_total;
   }
   P.tiles_m_total = tiles_m_total;
   P.total_tiles = tiles_m_total * P.tiles_n;

@@ -272,9 +272,10 @@ class FluxB200(FusedMMDiTBase):
         # d[attn | mlp] = dY . W_out (+ U . A_lora)   (dY = dX * gate is already in ws['dY']); the two column ranges of the
         # concatenated input go to different consumers (attention backward / GELU backward), so they are two contractions
         pa, pm = [], []
+        lbs = self._lora_bwd_pair(ws, l, "s_out", ws["dY"], save["cat"], D)
         for s in (0, 1):
             dYs = self._rows(ws, ws["dY"], s)
-            lb = self._lora_bwd(ws, l, "s_out", s, dYs, self._rows(ws, save["cat"], s), D)
+            lb = lbs[s]
             ka = dict(A2=lb[0], B2=lb[1][:, :D], kb2=1) if lb is not None else {}
             km = dict(A2=lb[0], B2=lb[1][:, D:], kb2=1) if lb is not None else {}
             pa.append(lib.gemm_problem(dYs, Wo[:, :D], self._rows(ws, ws["dO"], s), row_bands=self._bands(ws, s), **ka))

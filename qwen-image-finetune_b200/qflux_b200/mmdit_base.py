@@ -559,6 +559,23 @@ class FusedMMDiTBase(nn.Module):
         lib.gemm([lib.gemm_problem(X, site.A_pad, Tb)], site.n * PAD, X.shape[1], alpha=self.lora_scaling)
         return site, Tb
 
+    def _lora_T_pair(self, ws, l, grp, src):
+        """`_lora_T` for the image and the text stream of one weight group in ONE launch (two problems): these [M, 64 g] projections
+        are latency-bound on 8-75 CTAs each, so running them side by side halves their cost.  Returns {s: (site, T)}."""
+        res, probs = {}, []
+        for s in (0, 1):
+            site = self._site(l, grp, s)
+            res[s] = (site, None if site is None else ws["loraT"][(l, grp, s)])
+            if site is not None:
+                probs.append((site.n, lib.gemm_problem(self._rows(ws, src, s), site.A_pad, res[s][1])))
+        K = src.shape[1]
+        if len(probs) == 2 and probs[0][0] == probs[1][0]:
+            lib.gemm([p for _, p in probs], probs[0][0] * PAD, K, alpha=self.lora_scaling)
+        else:
+            for n, p in probs:
+                lib.gemm([p], n * PAD, K, alpha=self.lora_scaling)
+        return res
+
     def _embed_fwd(self, ws, key, s, X, dst):
         """Input embedder `key` (x_embedder / context_embedder / img_in / txt_in) with its optional fused LoRA pair."""
         W, b = self._wb(-1, key, s)
@@ -575,9 +592,10 @@ class FusedMMDiTBase(nn.Module):
     def _grouped(self, ws, l, grp, src, dst, N, K, epilogue, **epi):
         """One grouped GEMM over (image, text) rows of block l for weight group `grp` with optional fused LoRA."""
         probs = []
+        lora = self._lora_T_pair(ws, l, grp, src)
         for s in (0, 1):
             A = self._rows(ws, src, s)
-            site, Tb = self._lora_T(ws, l, grp, s, A)
+            site, Tb = lora[s]
             kw = {}
             if site is not None:
                 kw = dict(A2=Tb, B2=site.B_pad, kb2=1)
@@ -600,19 +618,18 @@ class FusedMMDiTBase(nn.Module):
                 return site.n
         return 0
 
-    def _lora_bwd(self, ws, l, grp, s, dY, Xsaved, n_out_each):
-        """LoRA part of a linear's backward for one site: U = s*dY.B (for the fused dgrad) and the weight gradients.
-        dY [M_s, n_slots*out]; Xsaved [M_s, in] is the linear's input (for dA)."""
+    def _lora_U_problems(self, ws, l, grp, s, dY, n_out_each):
+        """GEMM problems of U_g = scaling * dY_g . B_g for the slots g of one site (U feeds the fused dgrad and dA)."""
         site = self._site(l, grp, s)
-        if site is None:
-            return None
+        U = self._rows(ws, ws["U"], s)[:, : site.n * PAD]
+        return [lib.gemm_problem(dY[:, g * n_out_each:(g + 1) * n_out_each], site.B_pad[g * n_out_each:(g + 1) * n_out_each],
+                                 U[:, g * PAD:(g + 1) * PAD]) for g in range(site.n)]
+
+    def _lora_wgrads(self, ws, l, grp, s, dY, Xsaved, n_out_each):
+        """Weight gradients of one site on the tensor cores: dB_g[out, r] += dY_g^T T_g (grouped-diagonal), dA_g[r, in] += U_g^T X."""
+        site = self._site(l, grp, s)
         r, Tb = site.r, ws["loraT"][(l, grp, s)]
         U = self._rows(ws, ws["U"], s)[:, : site.n * PAD]
-        for g in range(site.n):
-            dYg = dY[:, g * n_out_each:(g + 1) * n_out_each]
-            Bg = site.B_pad[g * n_out_each:(g + 1) * n_out_each]
-            lib.gemm([lib.gemm_problem(dYg, Bg, U[:, g * PAD:(g + 1) * PAD])], PAD, n_out_each, trans_b=True, alpha=self.lora_scaling)
-        # weight gradients on the tensor cores: dB_g[out, r] += dY_g^T T_g  (grouped-diagonal), dA_g[r, in] += U_g^T X
         gB, gA = [], []
         for g in range(site.n):
             if g in site.members:
@@ -630,12 +647,35 @@ class FusedMMDiTBase(nn.Module):
                 lib.lora_wgrad(Xsaved, U[:, g * PAD:(g + 1) * PAD], gA[g], 1, Xsaved.shape[1], r)
         return U, site.A_pad, site.n
 
+    def _lora_bwd(self, ws, l, grp, s, dY, Xsaved, n_out_each):
+        """LoRA part of a linear's backward for one site: U = s*dY.B (for the fused dgrad) and the weight gradients.
+        dY [M_s, n_slots*out]; Xsaved [M_s, in] is the linear's input (for dA)."""
+        if self._site(l, grp, s) is None:
+            return None
+        lib.gemm(self._lora_U_problems(ws, l, grp, s, dY, n_out_each), PAD, n_out_each, trans_b=True, alpha=self.lora_scaling)
+        return self._lora_wgrads(ws, l, grp, s, dY, Xsaved, n_out_each)
+
+    def _lora_bwd_pair(self, ws, l, grp, dY, Xsaved, n_out_each):
+        """`_lora_bwd` for both streams of a weight group with ALL their U projections (up to 3 slots x 2 streams) in one launch.
+        dY / Xsaved are stream-major [M, .] buffers.  Returns {s: (U, A_pad, n) | None}."""
+        probs = []
+        for s in (0, 1):
+            if self._site(l, grp, s) is not None:
+                probs += self._lora_U_problems(ws, l, grp, s, self._rows(ws, dY, s), n_out_each)
+        if probs:
+            lib.gemm(probs, PAD, n_out_each, trans_b=True, alpha=self.lora_scaling)
+        return {s: (self._lora_wgrads(ws, l, grp, s, self._rows(ws, dY, s), self._rows(ws, Xsaved, s), n_out_each)
+                    if self._site(l, grp, s) is not None else None) for s in (0, 1)}
+
     def _dgrad_grouped(self, ws, l, grp, dY, dXout, N, K, n_out_each, Xsaved, epilogue=lib.EPI_BIAS, aux=None, resid=None):
         """dX = dY . W (+ U . A) for both streams of weight group `grp` (W stored [out, in] = [K_red, N])."""
         probs = []
+        if Xsaved is None:
+            assert self._site(l, grp, 0) is None and self._site(l, grp, 1) is None, "a LoRA site needs the saved input of its linear"
+        lbs = self._lora_bwd_pair(ws, l, grp, dY, Xsaved, n_out_each) if Xsaved is not None else {0: None, 1: None}
         for s in (0, 1):
             dYs = self._rows(ws, dY, s)
-            lb = self._lora_bwd(ws, l, grp, s, dYs, self._rows(ws, Xsaved, s) if Xsaved is not None else None, n_out_each)
+            lb = lbs[s]
             kw = {}
             if lb is not None:
                 kw = dict(A2=lb[0], B2=lb[1], kb2=lb[2])

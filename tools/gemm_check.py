@@ -108,6 +108,40 @@ def grouped(trans_b, bn, N=768, K=512, M0=700, M1=130):
     return dict(err=max(rel_l2(o0.float(), r0), rel_l2(o1.float(), f(A1, W1))))
 
 
+def many(trans_b, bn, Ms=(700, 130, 256, 1, 385, 64), N=64, K=768, timing=False):
+    """Up to QFX_MAX_PROBLEMS = 6 row groups in one launch (the U = s dY B projections of the three q|k|v slots of both streams of a LoRA
+    backward): every problem has its own A, B and output, slices of wider buffers like the real call; one of them carries a LoRA k-block."""
+    from qflux_b200 import lib
+    wide = [_mk(M, 3 * K, seed=10 + i) for i, M in enumerate(Ms)]          # dY [M, 3*out]: problem i reads column slice i % 3
+    A = [w[:, (i % 3) * K:(i % 3 + 1) * K] for i, w in enumerate(wide)]
+    W = [(_mk(K, N, seed=30 + i, scale=0.1) if trans_b else _mk(N, K, seed=30 + i, scale=0.1)) for i in range(len(Ms))]
+    outw = [torch.zeros(M, 3 * N, device="cuda", dtype=torch.bfloat16) for M in Ms]
+    out = [o[:, (i % 3) * N:(i % 3 + 1) * N] for i, o in enumerate(outw)]
+    A2, B2 = _mk(Ms[0], 64, seed=50), (_mk(64, N, seed=51) if trans_b else _mk(N, 64, seed=51))
+    probs = [lib.gemm_problem(A[i], W[i], out[i], **(dict(A2=A2, B2=B2, kb2=1) if i == 0 else {})) for i in range(len(Ms))]
+    lib.gemm(probs, N, K, trans_b=trans_b, alpha=0.5 if N == 64 else 1.0, block_n=bn)
+    torch.cuda.synchronize()
+    f = (lambda a, w: a.float() @ w.float()) if trans_b else (lambda a, w: a.float() @ w.float().t())
+    alpha = 0.5 if N == 64 else 1.0
+    errs = []
+    for i in range(len(Ms)):
+        ref = alpha * (f(A[i], W[i]) + (f(A2, B2) if i == 0 else 0))
+        errs.append(rel_l2(out[i].float(), ref))
+        others = torch.cat([outw[i][:, :(i % 3) * N], outw[i][:, (i % 3 + 1) * N:]], 1)
+        assert float(others.abs().max()) == 0.0, "a problem wrote outside its column slice"
+    res = dict(err=max(errs))
+    if timing:  # six launches vs one, at the LoRA backward shape of the benchmark (image 8192 rows, text 1408 rows, out = 3072)
+        Mi, Mt, Ko = 8192, 1408, 3072
+        dY = [_mk(Mi, 3 * Ko, seed=1), _mk(Mt, 3 * Ko, seed=2)]
+        Bp = [_mk(3 * Ko, 64, seed=3, scale=0.1), _mk(3 * Ko, 64, seed=4, scale=0.1)]
+        U = [torch.zeros(Mi, 192, device="cuda", dtype=torch.bfloat16), torch.zeros(Mt, 192, device="cuda", dtype=torch.bfloat16)]
+        pr = [lib.gemm_problem(dY[s][:, g * Ko:(g + 1) * Ko], Bp[s][g * Ko:(g + 1) * Ko], U[s][:, g * 64:(g + 1) * 64]) for s in range(2) for g in range(3)]
+        flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
+        res["one_launch_ms"] = time_cuda(lambda: lib.gemm(pr, 64, Ko, trans_b=True), flush=flush)
+        res["six_launches_ms"] = time_cuda(lambda: [lib.gemm([q], 64, Ko, trans_b=True) for q in pr], flush=flush)
+    return res
+
+
 def perf(trans_b, bn, M0=8192, M1=1408, N=3072, K=3072):
     from qflux_b200 import lib
     A0, A1 = _mk(M0, K, seed=1), _mk(M1, K, seed=2)
@@ -195,6 +229,12 @@ def ragged(bn, trans_b=False, R=1600, valid=(1600, 400, 1024, 900), N=768, K=512
 
 
 CASES = {}
+CASES["many6_nn_bn64"] = lambda: many(True, 64)
+CASES["many6_nt_bn64"] = lambda: many(False, 64)
+CASES["many5_nt_bn192"] = lambda: many(False, 192, Ms=(300, 130, 256, 129, 64), N=192)
+CASES["cta2_many6_nn"] = lambda: many(True, 1256, N=256, K=512)
+CASES["cta2_many4_nt_splitk"] = lambda: many(False, 1256, Ms=(2304, 256, 130, 700), N=2048, K=4096)
+CASES["many6_timing"] = lambda: many(True, 64, timing=True)
 CASES["ragged_nt_bn256"] = lambda: ragged(256)
 CASES["ragged_nt_bn128"] = lambda: ragged(128)
 CASES["ragged_nn_bn192"] = lambda: ragged(192, trans_b=True)
