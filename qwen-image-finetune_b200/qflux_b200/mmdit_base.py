@@ -452,6 +452,10 @@ class FusedMMDiTBase(nn.Module):
             # multiply-adds straight into the gradient accumulator they are one pass over it per sample
             GA = self.G32[ms["ga"]: ms["ga"] + n * r * D].view(n, r, D)
             GB = self.G32[ms["gb"]: ms["gb"] + n * C * r].view(n, C, r)
+            if os.environ.get("QFX_MOD_EINSUM"):  # A/B switch: the einsum formulation
+                GA.add_(torch.einsum("nbr,bd->nrd", u, x))
+                GB.add_(torch.einsum("bnc,nbr->ncr", dm, t) * self.lora_scaling)
+                continue
             for b in range(dm.shape[0]):
                 GB.addcmul_(dm[b].unsqueeze(-1), t[:, b].unsqueeze(1), value=self.lora_scaling)
                 GA.addcmul_(u[:, b].unsqueeze(-1), x[b].view(1, 1, D))
@@ -722,8 +726,8 @@ class FusedMMDiTBase(nn.Module):
         if not have:
             lib.qk_norm_rope_fwd_pair(qkv, g_txt, g_img, Mt, ws["rope"], Qs, Ks, Vs, round_mid=self.round_mid)
         # dQ (fp32, 118 MB at the benchmark shape) is zero-filled right before the kernel that reduces into it.  Letting the consumer
-        # below re-zero what it reads (QFX_DQ_CLEAR_IN_CONSUMER=1) removes the 70 us fill but makes the step 5 % SLOWER (same box:
-        # 344.7 vs 326.4 ms): the fill doubles as an L2 warm-up for the red.global.add traffic, which otherwise misses to DRAM.
+        # below re-zero what it reads (QFX_DQ_CLEAR_IN_CONSUMER=1) removes the fill but makes the step 5 % SLOWER (same box: 344.7 vs
+        # 326.4 ms): the red.global.add traffic then lands on lines that left L2 a whole block earlier.
         consumer_clears = bool(os.environ.get("QFX_DQ_CLEAR_IN_CONSUMER"))
         if not (consumer_clears and ws.get("dQ_clean")):
             ws["dQ"].zero_()
