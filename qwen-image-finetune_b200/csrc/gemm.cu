@@ -658,7 +658,8 @@ static int launch2(const GemmParams& P, cudaStream_t stream) {
   // disables it (A/B).  The workspace is process-wide: GEMMs are issued from one stream at a time.
   static const bool no_split = getenv("QFX_GEMM_NO_SPLITK") != nullptr;
   const int nkb = P.K / BK, R = P.total_tiles % clusters;
-  if (!no_split && P.total_tiles > clusters && R > 0 && nkb >= 64) {
+  static const int min_kb = getenv("QFX_GEMM_SPLITK_MIN_KB") ? atoi(getenv("QFX_GEMM_SPLITK_MIN_KB")) : 64;  // A/B: 48 lets K = 3072 split too
+  if (!no_split && P.total_tiles > clusters && R > 0 && nkb >= min_kb) {
     int S = clusters / R;
     if (S > nkb / 8) S = nkb / 8;  // at least 8 k-blocks per range
     if (S >= 2) {
