@@ -48,6 +48,8 @@ class _Accumulation:
     micro-steps add into the same flat fp32 LoRA gradient; the exchange + clip + optimizer step run on the last one with the mean over
     micro-steps and ranks (accelerate divides the loss by the number of accumulation steps)."""
 
+    MAX_GRAPHS = 16
+
     def _init_accumulation(self, steps: int, use_cuda_graph: bool = True):
         self.gradient_accumulation_steps, self._micro = max(1, int(steps)), 0
         self.use_cuda_graph, self._graphs = bool(use_cuda_graph), {}
@@ -71,8 +73,12 @@ class _Accumulation:
         if not self.use_cuda_graph or m._sharded is not None or not torch.cuda.is_available() or not m.dev.type == "cuda":
             return self._run(*args)
         key = (self._sig(args), self._accumulating)
-        ent = self._graphs.get(key)
+        ent = self._graphs.pop(key, None)
+        if ent is not None:
+            self._graphs[key] = ent  # most recently used last
         if ent is None:  # first step of this shape: eager (allocates the workspace, RoPE tables, split-K scratch, sets kernel attributes)
+            while len(self._graphs) >= self.MAX_GRAPHS:  # bucketed multi-resolution training: keep the most recent shape combinations only
+                self._graphs.pop(next(iter(self._graphs)))   # (every captured graph owns a private memory pool)
             self._graphs[key] = "warm"
             return self._run(*args)
         if ent != "warm" and ent["ws"] is not m._ws and not m._activate_ws(ent["ws"], ent["ws_key"]):
