@@ -43,7 +43,13 @@ enum qfx_epilogue {
   QFX_EPI_RESID_GATE = 2, /* out = resid + gate[row / rows_per_batch, :] * (acc + bias)   (transformer_qwenimage.py:473,480);
                              out2 (optional) = acc + bias, the un-gated branch output (needed for d gate)                  */
   QFX_EPI_DGELU = 3,      /* out = acc * gelu_tanh'(aux)                                   (autograd of net.0's GELU)        */
-  QFX_EPI_ADD = 4         /* out = resid + alpha*acc   (trans_b=1: sum of two dgrads, FLUX single block qkv + proj_mlp)      */
+  QFX_EPI_ADD = 4,        /* out = resid + alpha*acc   (trans_b=1: sum of two dgrads, FLUX single block qkv + proj_mlp)      */
+  QFX_EPI_ATTN_DO = 5     /* trans_b=1, N = H*128: g = bf16(alpha*acc) is the gradient wrt the attention output of token
+                             (b, s) = (row / rows_per_batch, s_offset + row % rows_per_batch).  Written HEAD-major into
+                             out = dO_joint [B, H, S, 128] (ldo unused) — the layout qfx_attn_bwd reads — and, if out2 != NULL,
+                             token-major to out2; delta[(b*H + h)*S + s] = sum_d g[h*128 + d] * aux[row, h*128 + d] with aux = the
+                             attention output O (token-major).  Replaces qfx_attn_delta after the out-projection dgrad
+                             (autograd of transformer_qwenimage.py:348-352 feeding SDPA's backward).                            */
 };
 
 typedef struct {
@@ -64,6 +70,7 @@ typedef struct {
    * n_row_tiles 256-row bands starting at rows row_tiles[i] (device int32, disjoint, ascending) are computed; the other rows of
    * `out`/`out2` are NOT written (the caller zero-fills them, qfx_zero_rows).  NULL: all M rows. */
   const int* row_tiles; int n_row_tiles;
+  float* delta; int attn_S, attn_H, s_offset; /* QFX_EPI_ATTN_DO */
 } qfx_gemm_problem;
 
 /* lora_group_n > 0 (trans_b = 0 only): output columns [g*lora_group_n, (g+1)*lora_group_n) use A2 columns

@@ -31,11 +31,14 @@ struct GemmProb {
   const bf16* aux;
   const int* row_tiles;  // ragged rows: start row of each computed 256-row band (NULL: dense)
   int64_t ldo, ldo2, ldr, ldg, ldaux;
+  int s_offset, pad_;    // ATTN_DO epilogue: joint position of this row group's first token
 };
 
 struct GemmParams {  // passed by value as a __grid_constant__ kernel parameter: must stay below the 4 KB parameter space
   GemmProb p[QFX_MAX_PROBLEMS];
   int nprob, N, K, lora_group_n;
+  float* delta;          // ATTN_DO epilogue (shared by the row groups): rowsum(dO * O) per (b, h, s), and the [B, H, S, 128] geometry
+  int attn_S, attn_H;
   int tiles_m_end[QFX_MAX_PROBLEMS];  // running sum of the problems' m-tile counts (problem i owns m-tiles [end[i-1], end[i]))
   int tiles_m_total, tiles_n, total_tiles;
   float alpha;
@@ -50,7 +53,7 @@ struct GemmParams {  // passed by value as a __grid_constant__ kernel parameter:
   int* tail_cnt;
 };
 
-static_assert(sizeof(GemmParams) <= 4000, "GemmParams must fit the kernel parameter space");
+static_assert(sizeof(GemmParams) <= 4090, "GemmParams must fit the kernel parameter space");
 
 template <int BN>
 struct GemmCfg {
@@ -74,6 +77,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmProb& q, const GemmParam
                                               float* ws_row = nullptr) {
     const bf16* gate_row = nullptr;
     if (EPI == QFX_EPI_RESID_GATE && row_ok) gate_row = q.gate + (int64_t)(row / q.rows_per_batch) * q.ldg;
+    // ATTN_DO: this row is token (ab, as) of the joint sequence; dacc carries sum_d dO*O across the four 32-column chunks of a head
+    int ab = 0, as = 0;
+    float dacc = 0.f;
+    if (EPI == QFX_EPI_ATTN_DO) {
+      ab = row / q.rows_per_batch;
+      as = q.s_offset + row - ab * q.rows_per_batch;
+    }
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t r[32];
@@ -161,6 +171,36 @@ __device__ __forceinline__ void epilogue_tile(const GemmProb& q, const GemmParam
             }
           }
         }
+      } else if (EPI == QFX_EPI_ATTN_DO) {
+        if (row_ok) {
+          const uint4* os = reinterpret_cast<const uint4*>(q.aux + (int64_t)row * q.ldaux + n);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint4 oo = os[v];
+            const uint32_t* ow = reinterpret_cast<const uint32_t*>(&oo);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * v + e;
+              const float g0 = round_bf16(__uint_as_float(r[2 * i]) * P.alpha), g1 = round_bf16(__uint_as_float(r[2 * i + 1]) * P.alpha);
+              o[i] = pack_bf16(g0, g1);
+              dacc += g0 * bf16_lo(ow[e]) + g1 * bf16_hi(ow[e]);
+            }
+          }
+          const int h = n >> 7, cc = n & 127;
+          const int64_t pos = ((int64_t)ab * P.attn_H + h) * P.attn_S + as;
+          uint4* dj = reinterpret_cast<uint4*>(q.out + pos * 128 + cc);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) dj[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+          if (cc == 96) {  // last chunk of this head
+            P.delta[pos] = dacc;
+            dacc = 0.f;
+          }
+          if (q.out2 != nullptr) {
+            uint4* dst2 = reinterpret_cast<uint4*>(q.out2 + (int64_t)row * q.ldo2 + n);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) dst2[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+          }
+        }
       } else if (EPI == QFX_EPI_DGELU) {
         if (row_ok) {
           const uint4* us = reinterpret_cast<const uint4*>(q.aux + (int64_t)row * q.ldaux + n);
@@ -178,7 +218,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmProb& q, const GemmParam
           }
         }
       }
-      if (row_ok) {
+      if (row_ok && EPI != QFX_EPI_ATTN_DO) {
         uint4* dst = reinterpret_cast<uint4*>(q.out + (int64_t)row * q.ldo + n);
 #pragma unroll
         for (int v = 0; v < 4; ++v) st_out(dst + v, make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]), P.stream_out);
@@ -692,6 +732,7 @@ static int dispatch2(const GemmParams& P, int trans_b, int epi, cudaStream_t s) 
       case QFX_EPI_BIAS: return launch2<BN, true, QFX_EPI_BIAS>(P, s);
       case QFX_EPI_DGELU: return launch2<BN, true, QFX_EPI_DGELU>(P, s);
       case QFX_EPI_ADD: return launch2<BN, true, QFX_EPI_ADD>(P, s);
+      case QFX_EPI_ATTN_DO: return launch2<BN, true, QFX_EPI_ATTN_DO>(P, s);
     }
   }
   set_error("qfx_gemm_bf16: unsupported (trans_b=%d, epilogue=%d)", trans_b, epi);
@@ -711,6 +752,9 @@ static int dispatch(const GemmParams& P, int trans_b, int epi, cudaStream_t s) {
       case QFX_EPI_BIAS: return launch<BN, true, QFX_EPI_BIAS>(P, s);
       case QFX_EPI_DGELU: return launch<BN, true, QFX_EPI_DGELU>(P, s);
       case QFX_EPI_ADD: return launch<BN, true, QFX_EPI_ADD>(P, s);
+      case QFX_EPI_ATTN_DO:
+        if (BN % 128 == 0) return launch<(BN % 128 == 0 ? BN : 128), true, QFX_EPI_ATTN_DO>(P, s);
+        break;
     }
   }
   set_error("qfx_gemm_bf16: unsupported (trans_b=%d, epilogue=%d)", trans_b, epi);
@@ -733,7 +777,9 @@ extern "C" int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, in
   const bool two_cta = block_n >= 1000;
   if (two_cta) block_n -= 1000;
   int bn = block_n;
+  if (bn == 0 && epilogue == QFX_EPI_ATTN_DO) bn = N % 256 == 0 ? 256 : 128;  // a tile must hold whole heads
   if (bn == 0) bn = N % 256 == 0 ? 256 : N % 192 == 0 ? 192 : N % 128 == 0 ? 128 : 64;
+  QFX_CHECK_ARG(epilogue != QFX_EPI_ATTN_DO || (trans_b && N % 128 == 0 && bn % 128 == 0), "qfx_gemm_bf16: ATTN_DO needs trans_b=1, N %% 128 == 0");
   QFX_CHECK_ARG((bn == 64 || bn == 128 || bn == 192 || bn == 256) && N % bn == 0, "qfx_gemm_bf16: N=%d block_n=%d", N, bn);
   QFX_CHECK_ARG(!two_cta || bn == 128 || bn == 256, "qfx_gemm_bf16: the 2-CTA kernel takes block_n 128 or 256");
   QFX_CHECK_ARG(!(trans_b && lora_group_n), "qfx_gemm_bf16: lora_group_n only with trans_b=0");
@@ -794,6 +840,15 @@ extern "C" int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, in
     if (epilogue == QFX_EPI_RESID_GATE) QFX_CHECK_ARG(s.resid && s.gate && s.ldr % 8 == 0 && s.ldg % 8 == 0, "qfx_gemm_bf16: RESID_GATE epilogue needs resid+gate");
     if (epilogue == QFX_EPI_ADD) QFX_CHECK_ARG(s.resid && s.ldr % 8 == 0, "qfx_gemm_bf16: ADD epilogue needs resid");
     if (epilogue == QFX_EPI_DGELU) QFX_CHECK_ARG(s.aux && s.ldaux % 8 == 0, "qfx_gemm_bf16: DGELU epilogue needs aux");
+    if (epilogue == QFX_EPI_ATTN_DO)
+      QFX_CHECK_ARG(s.aux && s.ldaux % 8 == 0 && s.delta && s.attn_H * 128 == N && s.attn_S > 0 && s.rows_per_batch > 0 && !s.row_tiles,
+                    "qfx_gemm_bf16: ATTN_DO epilogue needs aux (O), delta, attn_H*128 == N, attn_S, rows_per_batch (dense rows only)");
+    d.s_offset = s.s_offset;
+    if (epilogue == QFX_EPI_ATTN_DO) {
+      QFX_CHECK_ARG(i == 0 || (s.delta == P.delta && s.attn_S == P.attn_S && s.attn_H == P.attn_H),
+                    "qfx_gemm_bf16: ATTN_DO row groups must share delta / attn_S / attn_H");
+      P.delta = s.delta; P.attn_S = s.attn_S; P.attn_H = s.attn_H;
+    }
     int tm = two_cta ? (s.M + 255) / 256 : (s.M + BM - 1) / BM;
     if (s.row_tiles) tm = two_cta ? s.n_row_tiles : 2 * s.n_row_tiles;
     tiles_m_total += tm;

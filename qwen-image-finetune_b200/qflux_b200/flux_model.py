@@ -278,10 +278,10 @@ class FluxB200(FusedMMDiTBase):
             lb = lbs[s]
             ka = dict(A2=lb[0], B2=lb[1][:, :D], kb2=1) if lb is not None else {}
             km = dict(A2=lb[0], B2=lb[1][:, D:], kb2=1) if lb is not None else {}
-            pa.append(lib.gemm_problem(dYs, Wo[:, :D], self._rows(ws, ws["dO"], s), row_bands=self._bands(ws, s), **ka))
+            pa.append((dYs, Wo[:, :D], ka))
             pm.append(lib.gemm_problem(dYs, Wo[:, D:], self._rows(ws, ws["dbig"], s), aux=self._rows(ws, u, s),
                                        row_bands=self._bands(ws, s), **km))
-        lib.gemm(pa, D, D, trans_b=True)
+        self._dgrad_attn_out(ws, pa, O, D, D)  # d attn: straight into the attention backward's layout (+ delta)
         lib.gemm(pm, 4 * D, D, trans_b=True, epilogue=lib.EPI_DGELU)
         self._attn_bwd_core(ws, qkv, O, save["lse"], lambda s: (w["s_qknorm_w"][l, 0], w["s_qknorm_w"][l, 1]))
         if self._site(l, "s_qkv", 0) or self._site(l, "s_mlp", 0):  # LoRA input = modulated norm output (recomputed)

@@ -49,7 +49,7 @@ def cur_stream():
 
 
 # ---------------------------------------------------------------------------------------------------- GEMM
-EPI_BIAS, EPI_GELU, EPI_RESID_GATE, EPI_DGELU, EPI_ADD = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_GELU, EPI_RESID_GATE, EPI_DGELU, EPI_ADD, EPI_ATTN_DO = 0, 1, 2, 3, 4, 5
 
 
 class GemmProblem(C.Structure):
@@ -67,6 +67,7 @@ class GemmProblem(C.Structure):
         ("gate", C.c_void_p), ("ldg", C.c_int64), ("rows_per_batch", C.c_int),
         ("aux", C.c_void_p), ("ldaux", C.c_int64),
         ("row_tiles", C.c_void_p), ("n_row_tiles", C.c_int),
+        ("delta", C.c_void_p), ("attn_S", C.c_int), ("attn_H", C.c_int), ("s_offset", C.c_int),
     ]
 
 
@@ -128,14 +129,18 @@ class RowBands:
 
 
 def gemm_problem(A, B, out, *, A2=None, B2=None, kb2=0, a2_col0=0, bias=None, out2=None, resid=None, gate=None,
-                 rows_per_batch=0, aux=None, row_bands=None) -> GemmProblem:
-    require_cuda(A, B, out, A2, B2, bias, out2, resid, gate, aux)
-    for t in (A, B, out, A2, B2, out2, resid, gate, aux):
+                 rows_per_batch=0, aux=None, row_bands=None, delta=None, s_offset=0) -> GemmProblem:
+    """delta (fp32 [B, H, S]) + s_offset select the EPI_ATTN_DO outputs: `out` is then the head-major dO_joint [B, H, S, 128]."""
+    require_cuda(A, B, out, A2, B2, bias, out2, resid, gate, aux, delta)
+    for t in (A, B, A2, B2, out2, resid, gate, aux) + (() if delta is not None else (out,)):
         assert t is None or (t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1), "bf16 row-major 2-D expected"
     p = GemmProblem(_dp(A), _ld(A), _dp(B), _ld(B), A.shape[0], _dp(A2), _ld(A2), _dp(B2), _ld(B2), kb2, a2_col0,
                     _dp(bias), _dp(out), _ld(out), _dp(out2), _ld(out2), _dp(resid), _ld(resid), _dp(gate), _ld(gate),
                     rows_per_batch, _dp(aux), _ld(aux), 0 if row_bands is None else row_bands.tiles.data_ptr(),
-                    0 if row_bands is None else row_bands.n)
+                    0 if row_bands is None else row_bands.n, _dp(delta), 0, 0, s_offset)
+    if delta is not None:  # out = dO_joint [B, H, S, 128] (contiguous), delta [B, H, S]
+        assert out.dim() == 4 and out.is_contiguous() and out.shape[3] == 128 and tuple(delta.shape) == tuple(out.shape[:3]) and row_bands is None
+        p.ldo, p.attn_S, p.attn_H = 0, out.shape[2], out.shape[1]
     p.bands, p.outs = row_bands, (out, out2)  # kept alive / used by gemm() for the zero fill
     return p
 

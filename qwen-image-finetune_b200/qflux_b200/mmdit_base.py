@@ -694,6 +694,23 @@ class FusedMMDiTBase(nn.Module):
             probs.append(lib.gemm_problem(dYs, self._wb(l, grp, s)[0], self._rows(ws, dXout, s), row_bands=self._bands(ws, s), **kw))
         lib.gemm(probs, N, K, trans_b=True, epilogue=epilogue)
 
+    def _dgrad_attn_out(self, ws, probs_in, O, N, K):
+        """Out-projection dgrad whose epilogue hands the result straight to the attention backward (EPI_ATTN_DO): dO goes head-major
+        into ws['dOj'] and delta = rowsum(dO * O) into ws['delta'] — no token-major dO, no separate attn_delta pass.
+        probs_in: per stream (dY rows, W, lora kw).  Runs dense (no row bands): every (b, s) of dOj / delta must be defined."""
+        T, Limg = ws["T"], ws["Limg"]
+        if os.environ.get("QFX_NO_FUSED_DO"):  # A/B switch: the round-1 sequence (token-major dO, then the attn_delta pass)
+            if "dO" not in ws:
+                ws["dO"] = torch.empty(ws["Mt"] + ws["Mi"], N, device=self.dev, dtype=BF)
+            lib.gemm([lib.gemm_problem(dYs, W, self._rows(ws, ws["dO"], s), **kw) for s, (dYs, W, kw) in enumerate(probs_in)], N, K, trans_b=True)
+            lib.attn_delta_pair(O, ws["dO"], ws["delta"], (T, 0), (Limg, T), ws["Mt"], ws["dOj"])
+            return
+        probs = []
+        for s, (dYs, W, kw) in enumerate(probs_in):
+            probs.append(lib.gemm_problem(dYs, W, ws["dOj"], aux=self._rows(ws, O, s), delta=ws["delta"], rows_per_batch=self._rpb(ws, s),
+                                          s_offset=T if s == 0 else 0, **kw))
+        lib.gemm(probs, N, K, trans_b=True, epilogue=lib.EPI_ATTN_DO)
+
     # ------------------------------------------------------------------------------------------------ double-stream block
     # mods(j): j-th D-wide chunk (shift1, scale1, gate1, shift2, scale2, gate2) -> (img view, txt view), each [B, D]
     def _double_fwd(self, ws, l, Xin, Xout, save, mods):
@@ -716,13 +733,13 @@ class FusedMMDiTBase(nn.Module):
         self._grouped(ws, l, "down", h, Xout, D, 4 * D, lib.EPI_RESID_GATE, resid=xmid, gate=mods(5), out2=save.get("y_mlp"))
 
     def _attn_bwd_core(self, ws, qkv, O, lse, wq_wk, save=None):
-        """dO (token-major, ws['dO']) -> dqkv (ws['dqkv']); wq_wk(s) -> (wq, wk) norm weights of stream s.
+        """dO (head-major ws['dOj'] + ws['delta'], written by the out-projection dgrad: _dgrad_attn_out) -> dqkv (ws['dqkv']);
+        wq_wk(s) -> (wq, wk) norm weights of stream s.
         The normalised / rotated Q, K, V come from the block's saved tensors when present, else they are regenerated."""
         T, Limg, Mt = ws["T"], ws["Limg"], ws["Mt"]
         have = save is not None and "Q" in save
         Qs, Ks, Vs = (save["Q"], save["K"], save["V"]) if have else (ws["Q"], ws["K"], ws["V"])
         g_txt, g_img = (*wq_wk(1), T, 0), (*wq_wk(0), Limg, T)  # (wq, wk, tokens per sample, joint offset) of the two row groups
-        lib.attn_delta_pair(O, ws["dO"], ws["delta"], (T, 0), (Limg, T), Mt, ws["dOj"])
         if not have:
             lib.qk_norm_rope_fwd_pair(qkv, g_txt, g_img, Mt, ws["rope"], Qs, Ks, Vs, round_mid=self.round_mid)
         # dQ (fp32, 118 MB at the benchmark shape) is zero-filled right before the kernel that reduces into it.  Letting the consumer
@@ -765,7 +782,9 @@ class FusedMMDiTBase(nn.Module):
             if dm(s, 2) is not None:  # d gate1 = sum_t dXmid * attn_out   (dX holds dXmid now)
                 lib.mod_grad(self._rows(ws, dX, s), self._rpb(ws, s), m=self._rows(ws, save["y_attn"], s), prod_out=dm(s, 2))
         # ---- attention output projection (LoRA input = O), attention, q|k|v projection (LoRA input = xm1, recomputed)
-        self._dgrad_grouped(ws, l, "out", ws["dY"], ws["dO"], D, D, D, O)
+        lbs = self._lora_bwd_pair(ws, l, "out", ws["dY"], O, D)
+        self._dgrad_attn_out(ws, [(self._rows(ws, ws["dY"], s), self._wb(l, "out", s)[0],
+                                   dict(A2=lbs[s][0], B2=lbs[s][1], kb2=lbs[s][2]) if lbs[s] is not None else {}) for s in (0, 1)], O, D, D)
         self._attn_bwd_core(ws, qkv, O, save["lse"], lambda s: (w["qknorm_w"][l, 2 * s], w["qknorm_w"][l, 2 * s + 1]), save)
         xm1 = save.get("xm1")
         if xm1 is None:
@@ -823,7 +842,7 @@ class FusedMMDiTBase(nn.Module):
         self._alloc_lora_T(ws)
         if train:
             ws["dX"] = e(2, M, D)
-            ws["dY"], ws["dbig"], ws["dqkv"], ws["dxm"], ws["dO"] = e(M, D), e(M, 4 * D), e(M, 3 * D), e(M, D), e(M, D)
+            ws["dY"], ws["dbig"], ws["dqkv"], ws["dxm"] = e(M, D), e(M, 4 * D), e(M, 3 * D), e(M, D)
             ws["dOj"], ws["dK"], ws["dV"] = e(B, H, S, 128), e(B, H, S, 128), e(B, H, S, 128)
             ws["dQ"] = e(B, H, S, 128, dt=torch.float32)
             ws["delta"] = e(B, H, S, dt=torch.float32)

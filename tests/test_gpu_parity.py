@@ -32,6 +32,8 @@ GEMM = ["basic_nt_bn64", "basic_nn_bn64", "basic_nt_bn128", "basic_nn_bn128", "b
         "cta2_splitk_lora_nn", "cta2_splitk_grouped_nn",
         # ragged row groups of a pad-to-max multi-resolution batch: computed bands equal the dense result, the other rows are exact zeros
         # up to six row groups per launch (LoRA backward: three q|k|v slots of both streams)
+        # out-projection dgrad whose epilogue writes dO head-major + delta = rowsum(dO * O) for the attention backward
+        "attn_do_bn256", "attn_do_bn128_h3", "cta2_attn_do", "cta2_attn_do_splitk",
         "many6_nn_bn64", "many6_nt_bn64", "many5_nt_bn192", "cta2_many6_nn", "cta2_many4_nt_splitk",
         "ragged_nt_bn256", "ragged_nt_bn128", "ragged_nn_bn192", "cta2_ragged_nt", "cta2_ragged_nn", "cta2_ragged_nt_splitk"]
 OPS = ["wgrad_tc", "ln_mod_3072", "ln_mod_256", "mod_grad_3072", "mod_grad_256_ragged", "fused_adamw", "rms_rows", "qk_norm_rope", "qk_norm_rope_h2", "gemv", "flow", "wgrad", "attn_small",

@@ -142,6 +142,32 @@ def many(trans_b, bn, Ms=(700, 130, 256, 1, 385, 64), N=64, K=768, timing=False)
     return res
 
 
+def attn_do(bn, H=2, Bsz=3, T=40, L=260, K=512, lora=True):
+    """QFX_EPI_ATTN_DO: the out-projection dgrad writes dO head-major into dO_joint [B, H, S, 128] and delta = rowsum(dO * O) — checked
+    against the plain dgrad (fp32 matmul, bf16-rounded) followed by the attn_delta semantics.  Two row groups (image: positions T.., text: 0..)."""
+    from qflux_b200 import lib
+    N, S = H * 128, T + L
+    Mi, Mt = Bsz * L, Bsz * T
+    dY = [_mk(Mi, K, seed=1), _mk(Mt, K, seed=2)]
+    W = [_mk(K, N, seed=3, scale=0.1), _mk(K, N, seed=4, scale=0.1)]
+    O = [_mk(Mi, N, seed=5), _mk(Mt, N, seed=6)]
+    A2, B2 = _mk(Mi, 64, seed=7), _mk(64, N, seed=8, scale=0.1)
+    dOj = torch.full((Bsz, H, S, 128), 9.0, device="cuda", dtype=torch.bfloat16)
+    delta = torch.full((Bsz, H, S), 9.0, device="cuda")
+    tok = [torch.zeros(Mi, N, device="cuda", dtype=torch.bfloat16), None]
+    probs = [lib.gemm_problem(dY[s], W[s], dOj, aux=O[s], delta=delta, rows_per_batch=(L, T)[s], s_offset=(T, 0)[s], out2=tok[s],
+                              **(dict(A2=A2, B2=B2, kb2=1) if (lora and s == 0) else {})) for s in range(2)]
+    lib.gemm(probs, N, K, trans_b=True, epilogue=lib.EPI_ATTN_DO, block_n=bn)
+    torch.cuda.synchronize()
+    ref = [dY[s].float() @ W[s].float() + ((A2.float() @ B2.float()) if (lora and s == 0) else 0) for s in range(2)]
+    g = [r.bfloat16() for r in ref]
+    want_j = torch.cat([g[1].view(Bsz, T, H, 128), g[0].view(Bsz, L, H, 128)], 1).permute(0, 2, 1, 3).float()
+    want_d = torch.cat([(g[1].float() * O[1].float()).view(Bsz, T, H, 128).sum(-1), (g[0].float() * O[0].float()).view(Bsz, L, H, 128).sum(-1)], 1).permute(0, 2, 1)
+    res = dict(dOj=rel_l2(dOj.float(), want_j), delta=rel_l2(delta, want_d), token_major=rel_l2(tok[0].float(), g[0].float()))
+    res["err"] = max(res.values())
+    return res
+
+
 def perf(trans_b, bn, M0=8192, M1=1408, N=3072, K=3072):
     from qflux_b200 import lib
     A0, A1 = _mk(M0, K, seed=1), _mk(M1, K, seed=2)
@@ -229,6 +255,10 @@ def ragged(bn, trans_b=False, R=1600, valid=(1600, 400, 1024, 900), N=768, K=512
 
 
 CASES = {}
+CASES["attn_do_bn256"] = lambda: attn_do(256)
+CASES["attn_do_bn128_h3"] = lambda: attn_do(0, H=3)
+CASES["cta2_attn_do"] = lambda: attn_do(1256, H=4, K=1024)
+CASES["cta2_attn_do_splitk"] = lambda: attn_do(1256, H=16, Bsz=4, T=40, L=600, K=4096)
 CASES["many6_nn_bn64"] = lambda: many(True, 64)
 CASES["many6_nt_bn64"] = lambda: many(False, 64)
 CASES["many5_nt_bn192"] = lambda: many(False, 192, Ms=(300, 130, 256, 129, 64), N=192)
