@@ -44,18 +44,12 @@ enum qfx_epilogue {
                              out2 (optional) = acc + bias, the un-gated branch output (needed for d gate)                  */
   QFX_EPI_DGELU = 3,      /* out = acc * gelu_tanh'(aux)                                   (autograd of net.0's GELU)        */
   QFX_EPI_ADD = 4,        /* out = resid + alpha*acc   (trans_b=1: sum of two dgrads, FLUX single block qkv + proj_mlp)      */
-  QFX_EPI_ATTN_DO = 5,    /* trans_b=1, N = H*128: g = bf16(alpha*acc) is the gradient wrt the attention output of token
+  QFX_EPI_ATTN_DO = 5     /* trans_b=1, N = H*128: g = bf16(alpha*acc) is the gradient wrt the attention output of token
                              (b, s) = (row / rows_per_batch, s_offset + row % rows_per_batch).  Written HEAD-major into
                              out = dO_joint [B, H, S, 128] (ldo unused) — the layout qfx_attn_bwd reads — and, if out2 != NULL,
                              token-major to out2; delta[(b*H + h)*S + s] = sum_d g[h*128 + d] * aux[row, h*128 + d] with aux = the
                              attention output O (token-major).  Replaces qfx_attn_delta after the out-projection dgrad
                              (autograd of transformer_qwenimage.py:348-352 feeding SDPA's backward).                            */
-  QFX_EPI_QKV_HEADS = 6   /* trans_b=0, N = 3*H*128 (fused q|k|v projection): besides out = acc + bias (token-major, what the
-                             backward of the norm needs; may be NULL at inference) the epilogue applies the per-head RMSNorm
-                             (norm_q / norm_k, eps) and RoPE (rope[(b*rope_bstride + s)*64 + i] = (cos, sin) of pair i) to q and k
-                             and writes q, k, v HEAD-major into head_q / head_k / head_v [B, H, S, 128] at
-                             (b, s) = (row / rows_per_batch, s_offset + row % rows_per_batch) — the work of
-                             qfx_qk_norm_rope_fwd without its 2 x 177 MB pass (transformer_qwenimage.py:296-326).                */
 };
 
 typedef struct {
@@ -76,11 +70,7 @@ typedef struct {
    * n_row_tiles 256-row bands starting at rows row_tiles[i] (device int32, disjoint, ascending) are computed; the other rows of
    * `out`/`out2` are NOT written (the caller zero-fills them, qfx_zero_rows).  NULL: all M rows. */
   const int* row_tiles; int n_row_tiles;
-  float* delta; int attn_S, attn_H, s_offset; /* QFX_EPI_ATTN_DO; attn_S / attn_H / s_offset also QFX_EPI_QKV_HEADS */
-  /* QFX_EPI_QKV_HEADS (head_*, rope, rope_bstride, eps, round_mid must be the same in every row group of a launch) */
-  const void* norm_q; const void* norm_k;   /* [128] bf16 RMSNorm weights of this row group's stream */
-  void* head_q; void* head_k; void* head_v; /* [B, H, S, 128] bf16 */
-  const float* rope; int64_t rope_bstride; float eps; int round_mid; /* round_mid: bf16 rounding between x*rstd and *weight (diffusers RMSNorm) */
+  float* delta; int attn_S, attn_H, s_offset; /* QFX_EPI_ATTN_DO */
 } qfx_gemm_problem;
 
 /* lora_group_n > 0 (trans_b = 0 only): output columns [g*lora_group_n, (g+1)*lora_group_n) use A2 columns

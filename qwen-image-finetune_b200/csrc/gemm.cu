@@ -39,11 +39,6 @@ struct GemmParams {  // passed by value as a __grid_constant__ kernel parameter:
   int nprob, N, K, lora_group_n;
   float* delta;          // ATTN_DO epilogue (shared by the row groups): rowsum(dO * O) per (b, h, s), and the [B, H, S, 128] geometry
   int attn_S, attn_H;
-  bf16 *head_q, *head_k, *head_v;  // QKV_HEADS epilogue: head-major outputs, RoPE table, RMSNorm epsilon / rounding mode
-  const float* rope;               // (this row group's norm weights travel in GemmProb.resid = norm_q, GemmProb.gate = norm_k)
-  int64_t rope_bstride;
-  float eps;
-  int round_mid;
   int tiles_m_end[QFX_MAX_PROBLEMS];  // running sum of the problems' m-tile counts (problem i owns m-tiles [end[i-1], end[i]))
   int tiles_m_total, tiles_n, total_tiles;
   float alpha;
@@ -231,94 +226,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmProb& q, const GemmParam
     }
 }
 
-// Epilogue of the fused q|k|v projection (QFX_EPI_QKV_HEADS): thread = token row; a 128-column span of the tile is one head of q, k or v.
-// Pass A stores x = bf16(acc + bias) token-major (the norm's backward reads it) and sums x^2; pass B re-reads the accumulator, normalises,
-// rotates and stores the head-major row.  The rounding points are those of qk_norm_rope_fwd_kernel (elementwise.cu).
-template <int BN>
-__device__ __forceinline__ void epilogue_qkv_heads(const GemmProb& q, const GemmParams& P, uint32_t t_row, int row, bool row_ok, int n0,
-                                                   float* ws_row) {
-  static_assert(BN % 128 == 0, "a tile must hold whole heads");
-  const int D = P.attn_H * 128;
-  const int ab = row / q.rows_per_batch, as = q.s_offset + row - ab * q.rows_per_batch;
-  auto load_chunk = [&](int c, uint32_t* r) {
-    if (ws_row == nullptr) {
-      tmem_ld32(t_row + c, r);
-      tmem_ld_wait();
-    } else {
-#pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        const float4 f = __ldcg(reinterpret_cast<const float4*>(ws_row + c) + v);
-        r[4 * v] = __float_as_uint(f.x); r[4 * v + 1] = __float_as_uint(f.y);
-        r[4 * v + 2] = __float_as_uint(f.z); r[4 * v + 3] = __float_as_uint(f.w);
-      }
-    }
-  };
-  auto biased = [&](int n, const uint32_t* r, uint32_t* x) {  // x = bf16(acc + bias), 32 columns packed into 16 words
-    uint4 bias4[4];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) bias4[v] = q.bias ? __ldg(reinterpret_cast<const uint4*>(q.bias + n) + v) : make_uint4(0, 0, 0, 0);
-    const uint32_t* bw = reinterpret_cast<const uint32_t*>(bias4);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = pack_bf16(__uint_as_float(r[2 * i]) + bf16_lo(bw[i]), __uint_as_float(r[2 * i + 1]) + bf16_hi(bw[i]));
-  };
-#pragma unroll 1
-  for (int hb = 0; hb < BN; hb += 128) {
-    const int nh = n0 + hb;                      // first column of this head span
-    const int part = nh / D;                     // 0 = q, 1 = k, 2 = v
-    const int h = (nh - part * D) >> 7;
-    const int64_t pos = (((int64_t)ab * P.attn_H + h) * P.attn_S + as) * 128;
-    bf16* hd = (part == 0 ? P.head_q : part == 1 ? P.head_k : P.head_v) + pos;
-    float ss = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < 128; c += 32) {          // pass A
-      uint32_t r[32], x[16];
-      load_chunk(hb + c, r);
-      biased(nh + c, r, x);
-      if (row_ok) {
-        if (q.out != nullptr) {
-          uint4* dst = reinterpret_cast<uint4*>(q.out + (int64_t)row * q.ldo + nh + c);
-#pragma unroll
-          for (int v = 0; v < 4; ++v) st_out(dst + v, make_uint4(x[4 * v], x[4 * v + 1], x[4 * v + 2], x[4 * v + 3]), P.stream_out);
-        }
-        if (part == 2) {
-          uint4* dv = reinterpret_cast<uint4*>(hd + c);
-#pragma unroll
-          for (int v = 0; v < 4; ++v) dv[v] = make_uint4(x[4 * v], x[4 * v + 1], x[4 * v + 2], x[4 * v + 3]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) ss += bf16_lo(x[i]) * bf16_lo(x[i]) + bf16_hi(x[i]) * bf16_hi(x[i]);
-    }
-    if (part == 2) continue;
-    const float rs = rsqrtf(ss * (1.f / 128) + P.eps);
-    const bf16* wn = part == 0 ? q.resid : q.gate;  // norm_q / norm_k of this row group
-    const float* cs_row = P.rope + ((int64_t)ab * P.rope_bstride + as) * 128;  // 64 (cos, sin) pairs
-#pragma unroll 1
-    for (int c = 0; c < 128; c += 32) {          // pass B
-      uint32_t r[32], x[16], o[16];
-      load_chunk(hb + c, r);
-      biased(nh + c, r, x);
-      uint4 w4[4];
-#pragma unroll
-      for (int v = 0; v < 4; ++v) w4[v] = __ldg(reinterpret_cast<const uint4*>(wn + c) + v);
-      const uint32_t* ww = reinterpret_cast<const uint32_t*>(w4);
-      if (row_ok) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {            // pair (2i, 2i+1) of this chunk = rotary pair c/2 + i
-          const float2 cs = *reinterpret_cast<const float2*>(cs_row + c + 2 * i);
-          const float f0 = bf16_lo(x[i]), f1 = bf16_hi(x[i]);
-          const float a = P.round_mid ? round_bf16(round_bf16(f0 * rs) * bf16_lo(ww[i])) : round_bf16(f0 * rs * bf16_lo(ww[i]));
-          const float b = P.round_mid ? round_bf16(round_bf16(f1 * rs) * bf16_hi(ww[i])) : round_bf16(f1 * rs * bf16_hi(ww[i]));
-          o[i] = pack_bf16(a * cs.x - b * cs.y, a * cs.y + b * cs.x);
-        }
-        uint4* dq = reinterpret_cast<uint4*>(hd + c);
-#pragma unroll
-        for (int v = 0; v < 4; ++v) dq[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
-      }
-    }
-  }
-}
-
 template <int BN, bool TRANS_B, int EPI>
 __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ GemmParams P) {
   using C = GemmCfg<BN>;
@@ -462,8 +369,7 @@ __global__ void __launch_bounds__(256, 1) gemm_kernel(const __grid_constant__ Ge
       const int row = m0 + q4 * 32 + lane;
       const bool row_ok = row < q.M;
       const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * BN;
-      if constexpr (EPI == QFX_EPI_QKV_HEADS) epilogue_qkv_heads<(BN % 128 == 0 ? BN : 128)>(q, P, t_row, row, row_ok, n0, nullptr);
-      else epilogue_tile<BN, EPI>(q, P, t_row, row, row_ok, n0);
+      epilogue_tile<BN, EPI>(q, P, t_row, row, row_ok, n0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -663,8 +569,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm2_kernel
       const uint32_t t_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * BN;
       float* ws_row = nullptr;
       if (!u.split) {
-        if constexpr (EPI == QFX_EPI_QKV_HEADS) epilogue_qkv_heads<BN>(q, P, t_row, row, row_ok, n0, nullptr);
-        else epilogue_tile<BN, EPI>(q, P, t_row, row, row_ok, n0);
+        epilogue_tile<BN, EPI>(q, P, t_row, row, row_ok, n0);
       } else {  // partial sum over [kb_lo, kb_hi): add it into the workspace row of this (tile, CTA half)
         const int slot = (u.tile - P.tail_first) * 2 + (int)rank;
         ws_row = P.tail_ws + ((int64_t)slot * BM + q4 * 32 + lane) * (BN + WS_PAD);  // padded rows: a power-of-two row stride camps on L2 slices
@@ -696,8 +601,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) gemm2_kernel
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (tail_last) {
           __threadfence();
-          if constexpr (EPI == QFX_EPI_QKV_HEADS) epilogue_qkv_heads<BN>(q, P, 0u, row, row_ok, n0, ws_row);
-          else epilogue_tile<BN, EPI>(q, P, 0u, row, row_ok, n0, ws_row);
+          epilogue_tile<BN, EPI>(q, P, 0u, row, row_ok, n0, ws_row);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // tail_last is re-used only after everyone has read it
       }
@@ -822,7 +726,6 @@ static int dispatch2(const GemmParams& P, int trans_b, int epi, cudaStream_t s) 
       case QFX_EPI_BIAS: return launch2<BN, false, QFX_EPI_BIAS>(P, s);
       case QFX_EPI_GELU: return launch2<BN, false, QFX_EPI_GELU>(P, s);
       case QFX_EPI_RESID_GATE: return launch2<BN, false, QFX_EPI_RESID_GATE>(P, s);
-      case QFX_EPI_QKV_HEADS: return launch2<BN, false, QFX_EPI_QKV_HEADS>(P, s);
     }
   } else {
     switch (epi) {
@@ -843,9 +746,6 @@ static int dispatch(const GemmParams& P, int trans_b, int epi, cudaStream_t s) {
       case QFX_EPI_BIAS: return launch<BN, false, QFX_EPI_BIAS>(P, s);
       case QFX_EPI_GELU: return launch<BN, false, QFX_EPI_GELU>(P, s);
       case QFX_EPI_RESID_GATE: return launch<BN, false, QFX_EPI_RESID_GATE>(P, s);
-      case QFX_EPI_QKV_HEADS:
-        if (BN % 128 == 0) return launch<(BN % 128 == 0 ? BN : 128), false, QFX_EPI_QKV_HEADS>(P, s);
-        break;
     }
   } else {
     switch (epi) {
@@ -877,9 +777,7 @@ extern "C" int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, in
   const bool two_cta = block_n >= 1000;
   if (two_cta) block_n -= 1000;
   int bn = block_n;
-  if (bn == 0 && (epilogue == QFX_EPI_ATTN_DO || epilogue == QFX_EPI_QKV_HEADS)) bn = N % 256 == 0 ? 256 : 128;  // a tile must hold whole heads
-  QFX_CHECK_ARG(epilogue != QFX_EPI_QKV_HEADS || (!trans_b && N % 384 == 0 && bn % 128 == 0 && (N / 3) % bn == 0),
-                "qfx_gemm_bf16: QKV_HEADS needs trans_b=0, N = 3*H*128 and tiles that do not straddle q|k|v");
+  if (bn == 0 && epilogue == QFX_EPI_ATTN_DO) bn = N % 256 == 0 ? 256 : 128;  // a tile must hold whole heads
   if (bn == 0) bn = N % 256 == 0 ? 256 : N % 192 == 0 ? 192 : N % 128 == 0 ? 128 : 64;
   QFX_CHECK_ARG(epilogue != QFX_EPI_ATTN_DO || (trans_b && N % 128 == 0 && bn % 128 == 0), "qfx_gemm_bf16: ATTN_DO needs trans_b=1, N %% 128 == 0");
   QFX_CHECK_ARG((bn == 64 || bn == 128 || bn == 192 || bn == 256) && N % bn == 0, "qfx_gemm_bf16: N=%d block_n=%d", N, bn);
@@ -905,7 +803,7 @@ extern "C" int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, in
   for (int i = 0; i < nprob; ++i) {
     const qfx_gemm_problem& s = probs[i];
     GemmProb& d = P.p[i];
-    QFX_CHECK_ARG(s.M > 0 && s.A && s.B && (s.out || epilogue == QFX_EPI_QKV_HEADS), "qfx_gemm_bf16: problem %d has null/empty operands", i);
+    QFX_CHECK_ARG(s.M > 0 && s.A && s.B && s.out, "qfx_gemm_bf16: problem %d has null/empty operands", i);
     QFX_CHECK_ARG(s.lda % 8 == 0 && s.ldb % 8 == 0 && s.ldo % 8 == 0, "qfx_gemm_bf16: leading dims must be multiples of 8");
     int rc = make_2d(&d.tmA, s.A, (uint64_t)K, (uint64_t)s.M, s.lda, BK, BM);
     if (rc) return rc;
@@ -946,16 +844,6 @@ extern "C" int qfx_gemm_bf16(const qfx_gemm_problem* probs, int nprob, int N, in
       QFX_CHECK_ARG(s.aux && s.ldaux % 8 == 0 && s.delta && s.attn_H * 128 == N && s.attn_S > 0 && s.rows_per_batch > 0 && !s.row_tiles,
                     "qfx_gemm_bf16: ATTN_DO epilogue needs aux (O), delta, attn_H*128 == N, attn_S, rows_per_batch (dense rows only)");
     d.s_offset = s.s_offset;
-    if (epilogue == QFX_EPI_QKV_HEADS) {
-      QFX_CHECK_ARG(s.norm_q && s.norm_k && s.head_q && s.head_k && s.head_v && s.rope && s.attn_H * 384 == N && s.attn_S > 0 &&
-                        s.rows_per_batch > 0 && !s.row_tiles && !s.resid && !s.gate,
-                    "qfx_gemm_bf16: QKV_HEADS epilogue needs norm_q/k, head_q/k/v, rope, attn_H*384 == N, attn_S, rows_per_batch (dense rows)");
-      QFX_CHECK_ARG(i == 0 || (s.head_q == (void*)P.head_q && s.rope == P.rope && s.attn_S == P.attn_S && s.attn_H == P.attn_H),
-                    "qfx_gemm_bf16: QKV_HEADS row groups must share the head-major outputs and the RoPE table");
-      d.resid = (const bf16*)s.norm_q; d.gate = (const bf16*)s.norm_k;
-      P.head_q = (bf16*)s.head_q; P.head_k = (bf16*)s.head_k; P.head_v = (bf16*)s.head_v; P.rope = s.rope;
-      P.rope_bstride = s.rope_bstride; P.eps = s.eps; P.round_mid = s.round_mid; P.attn_S = s.attn_S; P.attn_H = s.attn_H;
-    }
     if (epilogue == QFX_EPI_ATTN_DO) {
       QFX_CHECK_ARG(i == 0 || (s.delta == P.delta && s.attn_S == P.attn_S && s.attn_H == P.attn_H),
                     "qfx_gemm_bf16: ATTN_DO row groups must share delta / attn_S / attn_H");

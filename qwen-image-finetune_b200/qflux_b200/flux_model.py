@@ -251,9 +251,11 @@ class FluxB200(FusedMMDiTBase):
         T, Mt = ws["T"], ws["Mt"]
         st, qkv, O, h, u = save["stats"], save["qkv"], save["O"], save["h"], save["u"]
         self._ln_fwd2(ws, Xin, ws["xm"], self._smod(ws, l, 0), self._smod(ws, l, 1), st[0], st[1])
-        qn = w["s_qknorm_w"][l]
-        self._qkv_heads_fwd(ws, l, "s_qkv", ws["xm"], qkv, {0: (qn[0], qn[1]), 1: (qn[0], qn[1])}, ws["Q"], ws["K"], ws["V"], False)
+        self._grouped(ws, l, "s_qkv", ws["xm"], qkv, 3 * D, D, lib.EPI_BIAS)
         self._grouped(ws, l, "s_mlp", ws["xm"], h, 4 * D, D, lib.EPI_GELU, out2=u)
+        qn = w["s_qknorm_w"][l]
+        lib.qk_norm_rope_fwd_pair(qkv, (qn[0], qn[1], T, 0), (qn[0], qn[1], ws["Limg"], T), Mt, ws["rope"], ws["Q"], ws["K"], ws["V"],
+                                  round_mid=False)
         lib.attn_fwd(ws["Q"], ws["K"], ws["V"], O[:Mt], O[Mt:], T, save["lse"], kv_len=ws.get("kv_len"), txt_len=ws.get("txt_len"))
         # x = x + gate * proj_out(cat[attn, gelu(mlp)]): attention wrote columns [0, D) and the GELU epilogue [D, 5D) of save["cat"]
         self._grouped(ws, l, "s_out", save["cat"], Xout, D, 5 * D, lib.EPI_RESID_GATE, resid=Xin, gate=self._smod(ws, l, 2),

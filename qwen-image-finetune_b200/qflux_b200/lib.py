@@ -49,7 +49,7 @@ def cur_stream():
 
 
 # ---------------------------------------------------------------------------------------------------- GEMM
-EPI_BIAS, EPI_GELU, EPI_RESID_GATE, EPI_DGELU, EPI_ADD, EPI_ATTN_DO, EPI_QKV_HEADS = 0, 1, 2, 3, 4, 5, 6
+EPI_BIAS, EPI_GELU, EPI_RESID_GATE, EPI_DGELU, EPI_ADD, EPI_ATTN_DO = 0, 1, 2, 3, 4, 5
 
 
 class GemmProblem(C.Structure):
@@ -68,8 +68,6 @@ class GemmProblem(C.Structure):
         ("aux", C.c_void_p), ("ldaux", C.c_int64),
         ("row_tiles", C.c_void_p), ("n_row_tiles", C.c_int),
         ("delta", C.c_void_p), ("attn_S", C.c_int), ("attn_H", C.c_int), ("s_offset", C.c_int),
-        ("norm_q", C.c_void_p), ("norm_k", C.c_void_p), ("head_q", C.c_void_p), ("head_k", C.c_void_p), ("head_v", C.c_void_p),
-        ("rope", C.c_void_p), ("rope_bstride", C.c_int64), ("eps", C.c_float), ("round_mid", C.c_int),
     ]
 
 
@@ -131,28 +129,19 @@ class RowBands:
 
 
 def gemm_problem(A, B, out, *, A2=None, B2=None, kb2=0, a2_col0=0, bias=None, out2=None, resid=None, gate=None,
-                 rows_per_batch=0, aux=None, row_bands=None, delta=None, s_offset=0, heads=None) -> GemmProblem:
-    """delta (fp32 [B, H, S]) + s_offset select the EPI_ATTN_DO outputs: `out` is then the head-major dO_joint [B, H, S, 128].
-    heads = (norm_q, norm_k, Q, K, V, rope, eps, round_mid) + s_offset + rows_per_batch: the EPI_QKV_HEADS outputs (`out` may be None)."""
+                 rows_per_batch=0, aux=None, row_bands=None, delta=None, s_offset=0) -> GemmProblem:
+    """delta (fp32 [B, H, S]) + s_offset select the EPI_ATTN_DO outputs: `out` is then the head-major dO_joint [B, H, S, 128]."""
     require_cuda(A, B, out, A2, B2, bias, out2, resid, gate, aux, delta)
-    for t in (A, B, A2, B2, out2, resid, gate, aux) + (() if (delta is not None or out is None) else (out,)):
+    for t in (A, B, A2, B2, out2, resid, gate, aux) + (() if delta is not None else (out,)):
         assert t is None or (t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1), "bf16 row-major 2-D expected"
     p = GemmProblem(_dp(A), _ld(A), _dp(B), _ld(B), A.shape[0], _dp(A2), _ld(A2), _dp(B2), _ld(B2), kb2, a2_col0,
-                    _dp(bias), _dp(out), _ld(out) if out is not None and out.dim() == 2 else 0, _dp(out2), _ld(out2), _dp(resid), _ld(resid),
-                    _dp(gate), _ld(gate), rows_per_batch, _dp(aux), _ld(aux), 0 if row_bands is None else row_bands.tiles.data_ptr(),
+                    _dp(bias), _dp(out), _ld(out), _dp(out2), _ld(out2), _dp(resid), _ld(resid), _dp(gate), _ld(gate),
+                    rows_per_batch, _dp(aux), _ld(aux), 0 if row_bands is None else row_bands.tiles.data_ptr(),
                     0 if row_bands is None else row_bands.n, _dp(delta), 0, 0, s_offset)
-    if heads is not None:
-        nq, nk, Q, K, V, rope, eps, round_mid = heads
-        require_cuda(nq, nk, Q, K, V, rope)
-        assert Q.is_contiguous() and K.is_contiguous() and V.is_contiguous() and Q.shape == K.shape == V.shape and Q.shape[3] == 128
-        assert rope.dtype == torch.float32 and rope.is_contiguous() and row_bands is None
-        p.norm_q, p.norm_k, p.head_q, p.head_k, p.head_v, p.rope = (t.data_ptr() for t in (nq, nk, Q, K, V, rope))
-        p.rope_bstride = 0 if rope.dim() == 3 else Q.shape[2]
-        p.eps, p.round_mid, p.attn_S, p.attn_H = float(eps), int(round_mid), Q.shape[2], Q.shape[1]
     if delta is not None:  # out = dO_joint [B, H, S, 128] (contiguous), delta [B, H, S]
         assert out.dim() == 4 and out.is_contiguous() and out.shape[3] == 128 and tuple(delta.shape) == tuple(out.shape[:3]) and row_bands is None
         p.ldo, p.attn_S, p.attn_H = 0, out.shape[2], out.shape[1]
-    p.bands, p.outs, p.keep = row_bands, (out, out2), heads  # kept alive / used by gemm() for the zero fill
+    p.bands, p.outs = row_bands, (out, out2)  # kept alive / used by gemm() for the zero fill
     return p
 
 

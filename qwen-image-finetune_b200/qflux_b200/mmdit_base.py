@@ -619,26 +619,6 @@ class FusedMMDiTBase(nn.Module):
         fused3 = any(p.kb2 for p in probs) and self._site_n(l, grp) == 3
         lib.gemm(probs, N, K, epilogue=epilogue, lora_group_n=(N // 3 if fused3 else 0))
 
-    def _qkv_heads_fwd(self, ws, l, grp, src, qkv, norms, Qs, Ks, Vs, round_mid):
-        """q|k|v projection of both streams whose epilogue also does the per-head RMSNorm + RoPE and writes Q, K, V head-major
-        (EPI_QKV_HEADS) — one launch instead of GEMM + qk_norm_rope_fwd.  norms[s] = (norm_q, norm_k) weights of stream s.
-        Pad-to-max batches that run on ragged row bands keep the two-kernel sequence: the head-major rows of skipped bands would stay
-        unwritten, and attention multiplies masked keys' V rows by zero — which must not meet uninitialised memory."""
-        D, T, Limg, Mt = self.D, ws["T"], ws["Limg"], ws["Mt"]
-        if ws.get("bands") is not None or os.environ.get("QFX_NO_FUSED_QKNR"):
-            self._grouped(ws, l, grp, src, qkv, 3 * D, D, lib.EPI_BIAS)
-            lib.qk_norm_rope_fwd_pair(qkv, (*norms[1], T, 0), (*norms[0], Limg, T), Mt, ws["rope"], Qs, Ks, Vs, round_mid=round_mid)
-            return
-        lora, probs = self._lora_T_pair(ws, l, grp, src), []
-        for s in (0, 1):
-            site, Tb = lora[s]
-            kw = dict(A2=Tb, B2=site.B_pad, kb2=1) if site is not None else {}
-            W, b = self._wb(l, grp, s)
-            probs.append(lib.gemm_problem(self._rows(ws, src, s), W, self._rows(ws, qkv, s), bias=b, rows_per_batch=self._rpb(ws, s),
-                                          s_offset=T if s == 0 else 0, heads=(*norms[s], Qs, Ks, Vs, ws["rope"], 1e-6, round_mid), **kw))
-        fused3 = any(p.kb2 for p in probs) and self._site_n(l, grp) == 3
-        lib.gemm(probs, 3 * D, D, epilogue=lib.EPI_QKV_HEADS, lora_group_n=(D if fused3 else 0))
-
     def _site_n(self, l, grp):
         for s in (0, 1):
             site = self._site(l, grp, s)
@@ -742,8 +722,9 @@ class FusedMMDiTBase(nn.Module):
         Qs, Ks, Vs = save.get("Q", ws["Q"]), save.get("K", ws["K"]), save.get("V", ws["V"])
         # stream-major rows: text (stream 1) first, image (stream 0) behind it -> ONE launch per op covers both streams
         lib.ln_modulate_fwd_pair(Xin, xm1, (mods(0)[1], mods(1)[1], T), (mods(0)[0], mods(1)[0], Limg), Mt, st[0], st[1])
+        self._grouped(ws, l, "qkv", xm1, qkv, 3 * D, D, lib.EPI_BIAS)
         qn = w["qknorm_w"][l]
-        self._qkv_heads_fwd(ws, l, "qkv", xm1, qkv, {0: (qn[0], qn[1]), 1: (qn[2], qn[3])}, Qs, Ks, Vs, self.round_mid)
+        lib.qk_norm_rope_fwd_pair(qkv, (qn[2], qn[3], T, 0), (qn[0], qn[1], Limg, T), Mt, ws["rope"], Qs, Ks, Vs, round_mid=self.round_mid)
         lib.attn_fwd(Qs, Ks, Vs, O[:Mt], O[Mt:], T, save["lse"], kv_len=ws.get("kv_len"), txt_len=ws.get("txt_len"))
         self._grouped(ws, l, "out", O, xmid, D, D, lib.EPI_RESID_GATE, resid=Xin, gate=mods(2), out2=save.get("y_attn"))
         lib.ln_modulate_fwd_pair(xmid, ws["xm"], (mods(3)[1], mods(4)[1], T), (mods(3)[0], mods(4)[0], Limg), Mt, st[2], st[3])

@@ -15,7 +15,7 @@ import torch
 import torch.nn.functional as F
 
 BF = torch.bfloat16
-EPI_BIAS, EPI_GELU, EPI_RESID_GATE, EPI_DGELU, EPI_ADD, EPI_ATTN_DO, EPI_QKV_HEADS = 0, 1, 2, 3, 4, 5, 6
+EPI_BIAS, EPI_GELU, EPI_RESID_GATE, EPI_DGELU, EPI_ADD, EPI_ATTN_DO = 0, 1, 2, 3, 4, 5
 
 
 def _f(t):
@@ -23,10 +23,9 @@ def _f(t):
 
 
 def gemm_problem(A, B, out, *, A2=None, B2=None, kb2=0, a2_col0=0, bias=None, out2=None, resid=None, gate=None,
-                 rows_per_batch=0, aux=None, row_bands=None, delta=None, s_offset=0, heads=None):
+                 rows_per_batch=0, aux=None, row_bands=None, delta=None, s_offset=0):
     return types.SimpleNamespace(A=A, B=B, out=out, A2=A2, B2=B2, kb2=kb2, a2_col0=a2_col0, bias=bias, out2=out2, resid=resid,
-                                 gate=gate, rows_per_batch=rows_per_batch, aux=aux, row_bands=row_bands, delta=delta, s_offset=s_offset,
-                                 heads=heads)
+                                 gate=gate, rows_per_batch=rows_per_batch, aux=aux, row_bands=row_bands, delta=delta, s_offset=s_offset)
 
 
 def _gelu_grad(u):
@@ -67,12 +66,6 @@ def gemm(problems, N, K, *, trans_b=False, epilogue=EPI_BIAS, alpha=1.0, lora_gr
             p.out.copy_((p.resid.float() + (acc * alpha).to(BF).float()).to(BF))
         elif epilogue == EPI_DGELU:
             p.out.copy_(((acc * alpha).to(BF).float() * _gelu_grad(p.aux.float())).to(BF))
-        elif epilogue == EPI_QKV_HEADS:  # token-major qkv + per-head RMSNorm / RoPE / head-major layout (= qk_norm_rope_fwd on this row group)
-            x = (acc + b).to(BF)
-            if p.out is not None:
-                p.out.copy_(x)
-            nq, nk, Q, K, V, rope, eps, round_mid = p.heads
-            qk_norm_rope_fwd(x, nq, nk, rope, Q, K, V, p.rows_per_batch, p.s_offset, eps=eps, round_mid=round_mid)
         elif epilogue == EPI_ATTN_DO:  # g = grad wrt the attention output: head-major scatter + delta = rowsum(g * O)
             g = (acc * alpha).to(BF)
             Bsz, H, S, _ = p.out.shape

@@ -33,8 +33,6 @@ GEMM = ["basic_nt_bn64", "basic_nn_bn64", "basic_nt_bn128", "basic_nn_bn128", "b
         # ragged row groups of a pad-to-max multi-resolution batch: computed bands equal the dense result, the other rows are exact zeros
         # up to six row groups per launch (LoRA backward: three q|k|v slots of both streams)
         # out-projection dgrad whose epilogue writes dO head-major + delta = rowsum(dO * O) for the attention backward
-        # fused q|k|v projection: token-major qkv + per-head RMSNorm + RoPE + head-major Q/K/V in the GEMM epilogue
-        "qkv_heads_bn256", "qkv_heads_bn128_norm_flux", "cta2_qkv_heads",
         "attn_do_bn256", "attn_do_bn128_h3", "cta2_attn_do", "cta2_attn_do_splitk",
         "many6_nn_bn64", "many6_nt_bn64", "many5_nt_bn192", "cta2_many6_nn", "cta2_many4_nt_splitk",
         "ragged_nt_bn256", "ragged_nt_bn128", "ragged_nn_bn192", "cta2_ragged_nt", "cta2_ragged_nn", "cta2_ragged_nt_splitk"]

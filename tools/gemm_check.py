@@ -168,63 +168,6 @@ def attn_do(bn, H=2, Bsz=3, T=40, L=260, K=512, lora=True):
     return res
 
 
-def qkv_heads(bn, H=2, Bsz=3, T=40, L=260, K=512, round_mid=True, per_sample_rope=False, lora=True, timing=False):
-    """QFX_EPI_QKV_HEADS: the fused q|k|v projection writes token-major qkv AND the normalised / rotated head-major Q, K, V — against the
-    two-kernel sequence it replaces (EPI_BIAS GEMM + qfx_qk_norm_rope_fwd, itself checked against the oracle in ops_check.qk_norm_rope).
-    The only legitimate difference is the summation order of the 128 squares of a head (one thread vs a warp shuffle tree)."""
-    from qflux_b200 import lib
-    D, S = H * 128, T + L
-    N = 3 * D
-    Mi, Mt = Bsz * L, Bsz * T
-    g = torch.Generator(device="cuda").manual_seed(5)
-    ang = torch.rand((Bsz, S, 64) if per_sample_rope else (S, 64), device="cuda", generator=g) * 6.28
-    rope = torch.stack([ang.cos(), ang.sin()], -1).contiguous()
-    X = [_mk(Mi, K, seed=1), _mk(Mt, K, seed=2)]
-    W = [_mk(N, K, seed=3, scale=0.1), _mk(N, K, seed=4, scale=0.1)]
-    b = [_mk(N, seed=5), _mk(N, seed=6)]
-    A2, B2 = _mk(Mi, 192, seed=7), _mk(N, 64, seed=8, scale=0.1)
-    nq = [_mk(128, seed=9, scale=0.2) + 1, _mk(128, seed=10, scale=0.2) + 1]
-    nk = [_mk(128, seed=11, scale=0.2) + 1, _mk(128, seed=12, scale=0.2) + 1]
-    lkw = lambda s: dict(A2=A2, B2=B2, kb2=1) if (lora and s == 0) else {}
-    gn = D if lora else 0
-    # reference: two kernels
-    qkv_r = [torch.zeros(Mi, N, device="cuda", dtype=torch.bfloat16), torch.zeros(Mt, N, device="cuda", dtype=torch.bfloat16)]
-    lib.gemm([lib.gemm_problem(X[s], W[s], qkv_r[s], bias=b[s], **lkw(s)) for s in range(2)], N, K, lora_group_n=gn, block_n=bn)
-    Qr, Kr, Vr = (torch.zeros(Bsz, H, S, 128, device="cuda", dtype=torch.bfloat16) for _ in range(3))
-    for s, (n, off) in enumerate(((L, T), (T, 0))):
-        lib.qk_norm_rope_fwd(qkv_r[s], nq[s], nk[s], rope, Qr, Kr, Vr, n, off, round_mid=round_mid)
-    # fused
-    qkv = [torch.zeros_like(t) for t in qkv_r]
-    Q, Kh, V = (torch.full((Bsz, H, S, 128), 7.0, device="cuda", dtype=torch.bfloat16) for _ in range(3))
-    probs = [lib.gemm_problem(X[s], W[s], qkv[s], bias=b[s], rows_per_batch=(L, T)[s], s_offset=(T, 0)[s],
-                              heads=(nq[s], nk[s], Q, Kh, V, rope, 1e-6, round_mid), **lkw(s)) for s in range(2)]
-    lib.gemm(probs, N, K, epilogue=lib.EPI_QKV_HEADS, lora_group_n=gn, block_n=bn)
-    torch.cuda.synchronize()
-    res = dict(qkv_equal=float(sum((a != c).sum() for a, c in zip(qkv, qkv_r))), Q=rel_l2(Q.float(), Qr.float()), K=rel_l2(Kh.float(), Kr.float()),
-               V_equal=float((V != Vr).sum()), q_mismatch_frac=float((Q != Qr).float().mean()))
-    res["err"] = max(res["Q"], res["K"], 1.0 if (res["qkv_equal"] or res["V_equal"]) else 0.0)
-    if timing:
-        Hh, Bb, Tt, Ll, Kk = 24, 4, 352, 2048, 3072
-        Dd, Ss = Hh * 128, Tt + Ll
-        Xb, Wb = [_mk(Bb * Ll, Kk, seed=1), _mk(Bb * Tt, Kk, seed=2)], [_mk(3 * Dd, Kk, seed=3, scale=0.02), _mk(3 * Dd, Kk, seed=4, scale=0.02)]
-        ob = [torch.empty(Bb * Ll, 3 * Dd, device="cuda", dtype=torch.bfloat16), torch.empty(Bb * Tt, 3 * Dd, device="cuda", dtype=torch.bfloat16)]
-        Qb, Kb, Vb = (torch.empty(Bb, Hh, Ss, 128, device="cuda", dtype=torch.bfloat16) for _ in range(3))
-        angb = torch.rand(Ss, 64, device="cuda", generator=g) * 6.28
-        rb = torch.stack([angb.cos(), angb.sin()], -1).contiguous()
-        w1 = _mk(128, seed=9, scale=0.2) + 1
-        flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
-        pf = [lib.gemm_problem(Xb[s], Wb[s], ob[s], rows_per_batch=(Ll, Tt)[s], s_offset=(Tt, 0)[s], heads=(w1, w1, Qb, Kb, Vb, rb, 1e-6, True)) for s in range(2)]
-        pu = [lib.gemm_problem(Xb[s], Wb[s], ob[s]) for s in range(2)]
-        qkv_all = torch.cat(ob[::-1], 0)
-
-        def two():
-            lib.gemm(pu, 3 * Dd, Kk)
-            lib.qk_norm_rope_fwd_pair(qkv_all, (w1, w1, Tt, 0), (w1, w1, Ll, Tt), Bb * Tt, rb, Qb, Kb, Vb)
-        res["fused_ms"] = time_cuda(lambda: lib.gemm(pf, 3 * Dd, Kk, epilogue=lib.EPI_QKV_HEADS), iters=10, flush=flush)
-        res["gemm_plus_qknr_ms"] = time_cuda(two, iters=10, flush=flush)
-    return res
-
-
 def perf(trans_b, bn, M0=8192, M1=1408, N=3072, K=3072):
     from qflux_b200 import lib
     A0, A1 = _mk(M0, K, seed=1), _mk(M1, K, seed=2)
@@ -312,10 +255,6 @@ def ragged(bn, trans_b=False, R=1600, valid=(1600, 400, 1024, 900), N=768, K=512
 
 
 CASES = {}
-CASES["qkv_heads_bn256"] = lambda: qkv_heads(256)
-CASES["qkv_heads_bn128_norm_flux"] = lambda: qkv_heads(128, H=3, round_mid=False, lora=False)
-CASES["cta2_qkv_heads"] = lambda: qkv_heads(1256, H=4, K=1024, per_sample_rope=True)
-CASES["cta2_qkv_heads_timing"] = lambda: qkv_heads(1256, H=4, K=1024, timing=True)
 CASES["attn_do_bn256"] = lambda: attn_do(256)
 CASES["attn_do_bn128_h3"] = lambda: attn_do(0, H=3)
 CASES["cta2_attn_do"] = lambda: attn_do(1256, H=4, K=1024)
