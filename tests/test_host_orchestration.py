@@ -512,3 +512,40 @@ def test_backward_of_a_stale_forward_is_refused(emu):
     a0 = float(a)
     step.train_step(emb, noise=x["image_latents"], u=torch.tensor([0.25]))
     assert float(a) == a0, "train_step must return its own copy of the loss, not the workspace scalar"
+
+
+def test_row_band_plan_properties():
+    """lib.RowBands.plan (ragged GEMM rows of a pad-to-max batch): bands are disjoint 256-row spans, every valid row is inside a band, the
+    dead ranges are exactly the complement inside [0, M), and nothing is planned when nothing can be skipped."""
+    from hypothesis import given, settings, strategies as st
+    from qflux_b200.lib import RowBands
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(1, 6).flatmap(lambda B: st.tuples(st.just(B), st.integers(1, 2000))).flatmap(
+        lambda br: st.tuples(st.just(br[1]), st.lists(st.integers(0, br[1]), min_size=br[0], max_size=br[0]))))
+    def check(rv):
+        R, valid = rv
+        M = R * len(valid)
+        plan = RowBands.plan(valid, R)
+        covered = [False] * M
+        if plan is None:  # nothing to skip: the bands of the dense tiling would cover every row
+            live = set()
+            for b, v in enumerate(valid):
+                live.update(range(b * R, b * R + v))
+            # a plan is only omitted when there is no dead range, i.e. the 256-row bands over the merged valid intervals reach M
+            assert M - len(live) < 256 * len(valid) + 256
+            return
+        tiles, dead = plan
+        assert tiles == sorted(tiles) and all(b - a >= 256 for a, b in zip(tiles, tiles[1:])), "bands overlap"
+        for t in tiles:
+            for r in range(t, min(t + 256, M)):
+                covered[r] = True
+        for b, v in enumerate(valid):
+            assert all(covered[b * R: b * R + v]), "a valid row is outside every band"
+        dead_rows = set()
+        for lo, hi in dead:
+            assert 0 <= lo < hi <= M
+            dead_rows.update(range(lo, hi))
+        assert dead_rows == {r for r in range(M) if not covered[r]}, "dead ranges must be the complement of the bands"
+        assert dead, "a plan without dead ranges should have been None"
+    check()
