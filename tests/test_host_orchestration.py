@@ -549,3 +549,39 @@ def test_row_band_plan_properties():
         assert dead_rows == {r for r in range(M) if not covered[r]}, "dead ranges must be the complement of the bands"
         assert dead, "a plan without dead ranges should have been None"
     check()
+
+
+def test_multi_resolution_row_bands_equal_pad_to_max(emu, monkeypatch):
+    """Host-side plumbing of the ragged GEMM row bands (emulated kernels zero-fill the skipped rows like qfx_zero_rows): a pad-to-max batch
+    whose padding spans whole 256-row bands must give the loss and LoRA gradients of the dense pad-to-max run — the padded rows carry
+    exact zeros through every gradient buffer either way."""
+    from qflux_b200.train_step import QwenImageEditStep
+    g = torch.Generator().manual_seed(17)
+    rn = lambda *s: torch.randn(*s, generator=g).bfloat16()
+    shapes = [[(1, 24, 16), (1, 24, 16)], [(1, 8, 8), (1, 8, 8)], [(1, 16, 16), (1, 16, 16)]]
+    lt = [sh[0][1] * sh[0][2] for sh in shapes]
+    B, T, txt, Lt = 3, 8, [8, 5, 7], max(lt)
+    x0, ctrl, pe, noise = rn(B, Lt, 64), rn(B, Lt, 64), rn(B, T, 128) * 3, rn(B, Lt, 64)
+    mask = torch.zeros(B, T, dtype=torch.int64)
+    for b in range(B):
+        x0[b, lt[b]:] = 0; ctrl[b, lt[b]:] = 0; noise[b, lt[b]:] = 0; pe[b, txt[b]:] = 0; mask[b, :txt[b]] = 1
+    emb = dict(image_latents=x0, control_latents=ctrl, prompt_embeds=pe, prompt_embeds_mask=mask, img_shapes=shapes)
+    u = torch.tensor([0.5, 0.25, 0.75])
+    out = {}
+    for mode in ("bands", "dense"):
+        if mode == "dense":
+            monkeypatch.setenv("QFX_NO_RAGGED_GEMM", "1")
+        orc, m = _pair(2, 2, 128, 4, ("to_q", "to_k", "to_v", "to_out.0", "img_mlp.net.2"))
+        step = QwenImageEditStep(m, "attention_mask")
+        loss = step.compute_loss(emb, noise=noise, u=u)
+        loss.backward()
+        bands = m._ws.get("bands")
+        assert (bands is not None and bands.n_dead > 0) == (mode == "bands")
+        out[mode] = (float(loss), m.G32.clone(), m._ws["pred"].float().clone())
+    assert out["bands"][0] == out["dense"][0]
+    assert ((out["bands"][1] - out["dense"][1]).norm() / out["dense"][1].norm()).item() < 1e-6
+    valid = torch.zeros(B, Lt, dtype=torch.bool)
+    for b in range(B):
+        valid[b, :lt[b]] = True
+    pb, pd = (o[2].view(B, 2 * Lt, 64)[:, :Lt][valid] for o in (out["bands"], out["dense"]))
+    assert torch.equal(pb, pd)
