@@ -11,6 +11,12 @@ straight into PINNED staging buffers (two, ping-pong) and uploaded with non-bloc
 waits on the file system or on pageable-memory copies; `img_shapes` come back converted to the latent-patch units the step
 classes take (convert_img_shapes_to_latent, trainer/qwen_image_edit_trainer.py:557-577).  Masks needed by the multi-resolution
 recipes (`prompt_embeds_mask`) are derived from the un-padded lengths, not stored.
+
+Packed shards (`pack_cache`): the reference's layout costs one `torch.load` (un-pickling) and one small file per sample and key.
+`pack_cache(cache_root)` rewrites it once into `<cache_root>/packed/<key>.<n>.bin` — the fp16 payloads back to back, sample by sample —
+plus `packed/index.json` (per sample: shard, element offset and shape per key, `img_shapes`); the loader then maps the shards
+(`numpy.memmap`) and copies each sample straight from the page cache into the pinned staging buffer.  The reference-format cache stays
+the source of truth (the loader falls back to it when no pack is present; `pack_cache` is idempotent and keyed on the metadata list).
 """
 from __future__ import annotations
 
@@ -26,6 +32,45 @@ import torch
 def img_shapes_to_latent(shapes_px, vae_scale: int = 8, patch: int = 2):
     """[(C, H, W), ...] pixel shapes of one sample -> [(1, H/16, W/16), ...] latent-patch shapes."""
     return [(1, int(s[1]) // vae_scale // patch, int(s[2]) // vae_scale // patch) for s in shapes_px]
+
+
+PACK_DIR, PACK_VERSION = "packed", 1
+
+
+def pack_cache(cache_root: str, keys=("image_latents", "control_latents", "prompt_embeds"), shard_bytes: int = 1 << 30) -> str:
+    """Rewrite a reference-format cache into packed fp16 shards (see the module docstring).  Returns the pack directory."""
+    import numpy as np
+    root = str(cache_root)
+    metas = sorted(glob.glob(os.path.join(root, "metadata", "*.json")))
+    if not metas:
+        raise FileNotFoundError(f"no cache metadata under {root}/metadata")
+    out_dir = os.path.join(root, PACK_DIR)
+    os.makedirs(out_dir, exist_ok=True)
+    files, shard_of, fill = {}, {k: 0 for k in keys}, {k: 0 for k in keys}
+    open_shard = lambda k: open(os.path.join(out_dir, f"{k}.{shard_of[k]}.bin"), "wb")
+    for k in keys:
+        files[k] = open_shard(k)
+    samples = []
+    for mp in metas:
+        with open(mp) as f:
+            meta = json.load(f)
+        entry = {"meta": os.path.basename(mp), "img_shapes": meta.get("img_shapes")}
+        for k in keys:
+            t = torch.load(os.path.join(root, k, f"{meta[k]}.pt"), map_location="cpu", weights_only=False).to(torch.float16).contiguous()
+            nbytes = t.numel() * 2
+            if fill[k] and fill[k] + nbytes > shard_bytes:
+                files[k].close()
+                shard_of[k], fill[k] = shard_of[k] + 1, 0
+                files[k] = open_shard(k)
+            entry[k] = {"shard": shard_of[k], "offset": fill[k] // 2, "shape": list(t.shape)}
+            files[k].write(np.ascontiguousarray(t.numpy()).tobytes())
+            fill[k] += nbytes
+        samples.append(entry)
+    for f in files.values():
+        f.close()
+    with open(os.path.join(out_dir, "index.json"), "w") as f:
+        json.dump({"version": PACK_VERSION, "dtype": "float16", "keys": list(keys), "samples": samples}, f)
+    return out_dir
 
 
 def pad_stack(tensors, out=None):
@@ -46,10 +91,13 @@ def pad_stack(tensors, out=None):
 class CachedEmbeddingLoader:
     def __init__(self, cache_root: str, batch_size: int, keys=("image_latents", "control_latents", "prompt_embeds"),
                  device="cuda", shuffle: bool = True, seed: int = 1234, drop_last: bool = True, prefetch: int = 2,
-                 rank: int = 0, world_size: int = 1):
+                 rank: int = 0, world_size: int = 1, packed="auto"):
+        """packed: "auto" uses `<cache_root>/packed` when `pack_cache` has written it for exactly these samples and keys, True requires
+        it, False always reads the reference's per-sample files."""
         self.root, self.bs, self.keys, self.device = str(cache_root), batch_size, tuple(keys), torch.device(device)
         self.shuffle, self.seed, self.drop_last, self.prefetch = shuffle, seed, drop_last, prefetch
         metas = sorted(glob.glob(os.path.join(self.root, "metadata", "*.json")))
+        self._pack = self._open_pack(metas, packed)
         if not metas:
             raise FileNotFoundError(f"no cache metadata under {self.root}/metadata (EmbeddingCacheManager.exist would be False)")
         # data parallel: disjoint strided shards.  Every rank must yield the SAME number of batches (a rank with one batch more would
@@ -72,7 +120,40 @@ class CachedEmbeddingLoader:
         return n // self.bs if self.drop_last else -(-n // self.bs)
 
     # ---------------------------------------------------------------------------------------------------- host side
+    def _open_pack(self, metas, packed):
+        """{metadata file name: index entry} + lazily mapped shards, or None when the reference-format files are to be read."""
+        idx_path = os.path.join(self.root, PACK_DIR, "index.json")
+        if packed is False or not os.path.exists(idx_path):
+            if packed is True:
+                raise FileNotFoundError(f"{idx_path} is missing: run qflux_b200.cache_loader.pack_cache({self.root!r}) first")
+            return None
+        with open(idx_path) as f:
+            idx = json.load(f)
+        by_meta = {e["meta"]: e for e in idx["samples"]}
+        ok = idx.get("version") == PACK_VERSION and set(self.keys) <= set(idx["keys"]) and all(os.path.basename(m) in by_meta for m in metas)
+        if not ok:
+            if packed is True:
+                raise ValueError(f"{idx_path} does not cover this cache (stale pack, or other keys): re-run pack_cache")
+            return None
+        return {"by_meta": by_meta, "maps": {}}
+
+    def _packed_tensor(self, key, ent):
+        import numpy as np
+        name = (key, ent["shard"])
+        if name not in self._pack["maps"]:
+            self._pack["maps"][name] = np.memmap(os.path.join(self.root, PACK_DIR, f"{key}.{ent['shard']}.bin"), dtype=np.float16, mode="r")
+        n = 1
+        for d in ent["shape"]:
+            n *= d
+        return torch.from_numpy(np.asarray(self._pack["maps"][name][ent["offset"]: ent["offset"] + n])).view(ent["shape"])
+
     def _load_sample(self, meta_path):
+        if self._pack is not None:
+            e = self._pack["by_meta"][os.path.basename(meta_path)]
+            out = {k: self._packed_tensor(k, e[k]) for k in self.keys}
+            if e.get("img_shapes") is not None:
+                out["img_shapes"] = img_shapes_to_latent(e["img_shapes"])
+            return out
         with open(meta_path) as f:
             meta = json.load(f)
         out = {}

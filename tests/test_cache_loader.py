@@ -83,3 +83,34 @@ def test_loader_feeds_the_multi_resolution_step(tmp_path):
         assert torch.isfinite(loss).all() and m._ws["kv_len"].tolist() == [5 + 2 * 1024 + 3, 8 + 2 * 800]
     finally:
         restore()
+
+
+def test_packed_shards_reproduce_the_per_sample_cache(tmp_path):
+    """`pack_cache` rewrites the reference-format cache into fp16 shards + an index; the loader must hand out exactly the same batches
+    from the pack (memory-mapped) as from the per-sample `.pt` files, across shard boundaries, and must ignore a stale pack."""
+    import warnings
+    from qflux_b200.cache_loader import CachedEmbeddingLoader, pack_cache
+    truth = _write_cache(str(tmp_path), n=7)
+    plain = list(CachedEmbeddingLoader(str(tmp_path), batch_size=3, device="cpu", shuffle=True, seed=5, drop_last=False, packed=False))
+    out_dir = pack_cache(str(tmp_path), shard_bytes=200_000)  # small shards: several files per key
+    assert len([f for f in os.listdir(out_dir) if f.startswith("image_latents.")]) > 1
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # torch.from_numpy on a read-only memmap
+        ld = CachedEmbeddingLoader(str(tmp_path), batch_size=3, device="cpu", shuffle=True, seed=5, drop_last=False, packed=True)
+        packed = list(ld)
+    assert ld._pack is not None and len(packed) == len(plain) == 3
+    for a, b in zip(plain, packed):
+        assert a["img_shapes"] == b["img_shapes"]
+        for k in ("image_latents", "control_latents", "prompt_embeds", "prompt_embeds_mask"):
+            assert a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
+    # a sample added after packing: "auto" falls back to the per-sample files, packed=True refuses
+    g = torch.Generator().manual_seed(9)
+    for k, shape in (("image_latents", (1, 64, 64)), ("control_latents", (1, 64, 64)), ("prompt_embeds", (1, 4, 32))):
+        torch.save(torch.randn(*shape, generator=g).to(torch.float16), os.path.join(str(tmp_path), k, "new.pt"))
+    with open(os.path.join(str(tmp_path), "metadata", "zzz_new.json"), "w") as f:
+        json.dump({"version": "1.0", "img_shapes": [[3, 128, 128], [3, 128, 128]], "image_latents": "new", "control_latents": "new",
+                   "prompt_embeds": "new"}, f)
+    assert CachedEmbeddingLoader(str(tmp_path), 1, device="cpu", packed="auto")._pack is None
+    import pytest
+    with pytest.raises(ValueError, match="re-run pack_cache"):
+        CachedEmbeddingLoader(str(tmp_path), 1, device="cpu", packed=True)

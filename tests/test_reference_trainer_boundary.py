@@ -315,3 +315,8 @@ def test_loader_reads_a_cache_written_by_the_reference(ref, tmp_path):
         assert b[key].dtype == torch.float16 and torch.equal(b[key], want), key
     assert b["img_shapes"] == [[(1, H // 16, W // 16)] * 2 for H, W in sizes]
     assert b["prompt_embeds_mask"].sum(1).tolist() == [6, 11, 16]
+    # ... and the same batch again from the packed shards written off that cache
+    from qflux_b200.cache_loader import pack_cache
+    pack_cache(str(tmp_path))
+    p = list(CachedEmbeddingLoader(str(tmp_path), batch_size=3, device="cpu", shuffle=False, drop_last=False, packed=True))[0]
+    assert all(torch.equal(p[k], b[k]) for k in ("image_latents", "control_latents", "prompt_embeds", "prompt_embeds_mask")) and p["img_shapes"] == b["img_shapes"]
