@@ -7,7 +7,7 @@
           flux_kontext       (configs[2]) : FLUX-Kontext LoRA r=32 with the YAML target regex, 19+38 blocks, T=512, batch 2 / GPU
           qwen_plus_sharded  (configs[3]) : Qwen-Image-Edit-2509, target + 2 controls (3 x 1024 image tokens, frame offsets 0,1,2), T=448,
                                             batch 4 / GPU, frozen block weights sharded 1/N per rank when N > 1
-          qwen_multires      (configs[4]) : Qwen-Image-Edit LoRA r=16, every batch mixes {320^2, 512^2, 640^2} samples (pad-to-max recipe,
+          qwen_multires      (configs[4]) : Qwen-Image-Edit LoRA r=16, every batch mixes {320^2, 512^2, 640^2} samples (pad-to-max layout, block GEMMs on ragged row bands,
                                             AttentionMaskMseLoss), batch 4 / GPU
 
 b200 arm     : one "step" = noisy-input -> fused MMDiT forward -> flow-matching loss -> fused backward -> NCCL all-reduce of the flat
