@@ -585,3 +585,32 @@ def test_multi_resolution_row_bands_equal_pad_to_max(emu, monkeypatch):
         valid[b, :lt[b]] = True
     pb, pd = (o[2].view(B, 2 * Lt, 64)[:, :Lt][valid] for o in (out["bands"], out["dense"]))
     assert torch.equal(pb, pd)
+
+
+def test_workspaces_are_kept_per_shape(emu):
+    """One training workspace and up to three inference workspaces stay allocated: alternating prompt lengths (true CFG) or a validation
+    pass between training steps must hand back the SAME buffers, because CUDA graphs captured on them hold raw pointers."""
+    from qflux_b200.train_step import QwenImageEditStep
+    orc, m = _pair(2, 1, 128, 4, ("to_q", "to_k", "to_v", "to_out.0"))
+    x = _inputs(1, 4, 24, 128)
+    packed = torch.cat([x["image_latents"], x["control_latents"]], 1)
+
+    def infer(T):
+        pe = x["prompt_embeds"][:, :T]
+        with torch.no_grad():
+            m(hidden_states=packed, timestep=torch.tensor([0.5]), encoder_hidden_states=pe, img_shapes=x["img_shapes"],
+              encoder_hidden_states_mask=torch.ones(1, T, dtype=torch.int64))
+        return m._ws
+    a, b = infer(24), infer(17)
+    assert a is not b and infer(24) is a and infer(17) is b and len(m._infer_ws) == 2
+    step = QwenImageEditStep(m)
+    emb = {k: x[k] for k in ("image_latents", "control_latents", "prompt_embeds", "img_shapes")}
+    step.train_step(emb, noise=x["image_latents"], u=torch.tensor([0.5]))
+    train_ws = m._ws
+    assert m._train_ws[1] is train_ws and train_ws is not a
+    assert infer(24) is a                     # validation in between ...
+    step.train_step(emb, noise=x["image_latents"], u=torch.tensor([0.5]))
+    assert m._ws is train_ws                  # ... and training resumes on the buffers it had
+    for T in (9, 10, 11):                     # a fourth inference shape evicts the oldest one only
+        infer(T)
+    assert len(m._infer_ws) == 3 and m._activate_ws(train_ws, m._train_ws[0]) and not m._activate_ws(a, (1, 24, 32, False))
