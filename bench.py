@@ -514,6 +514,9 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
+        # step 1 of a shape runs eagerly (allocations, kernel attributes), step 2 captures the CUDA graph, step 3 is the first replay:
+        # fewer than three warm-up steps would put the capture inside the timed region (the reported "warmup" is what was really done)
+        args.warmup = max(args.warmup, 3)
         run_b200(args)
 
 
