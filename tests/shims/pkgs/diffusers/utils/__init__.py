@@ -33,3 +33,13 @@ def unscale_lora_layers(model, weight=None):
 def convert_state_dict_to_diffusers(state_dict, original_type=None, **kwargs):
     """PEFT-format keys (`...lora_A.weight`) are already the diffusers LoRA format: identity for that input."""
     return state_dict
+
+
+def is_torch_xla_available():
+    """diffusers.utils.import_utils.is_torch_xla_available: no XLA here."""
+    return False
+
+
+def replace_example_docstring(example_docstring):
+    """diffusers.utils.doc_utils.replace_example_docstring: decorator that splices an example into the docstring — a no-op for the tests."""
+    return lambda fn: fn

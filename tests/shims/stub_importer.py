@@ -53,6 +53,11 @@ class _ShimLoader(importlib.machinery.SourceFileLoader):
 
     def exec_module(self, module):
         super().exec_module(module)
+        if hasattr(module, "__path__"):
+            # sub-modules must come back through _Finder (importlib re-populates an empty search path with the directory, and the default
+            # path finder would then load them WITHOUT the placeholder fallback below: `from pkg.sub import Missing` would yield a stub
+            # module instead of a class)
+            module.__path__ = []
         own = module.__dict__.get("__getattr__")
 
         def fallback(name, _own=own, _mod=module):
@@ -86,7 +91,7 @@ class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         base = os.path.join(PKGS, *fullname.split("."))
         if os.path.isdir(base) and os.path.exists(os.path.join(base, "__init__.py")):
             f = os.path.join(base, "__init__.py")
-            return importlib.util.spec_from_file_location(fullname, f, loader=_ShimLoader(fullname, f), submodule_search_locations=[base])
+            return importlib.util.spec_from_file_location(fullname, f, loader=_ShimLoader(fullname, f), submodule_search_locations=[])
         if os.path.exists(base + ".py"):
             return importlib.util.spec_from_file_location(fullname, base + ".py", loader=_ShimLoader(fullname, base + ".py"))
         if fullname.split(".")[0] in REAL and path is None:

@@ -320,3 +320,13 @@ def test_loader_reads_a_cache_written_by_the_reference(ref, tmp_path):
     pack_cache(str(tmp_path))
     p = list(CachedEmbeddingLoader(str(tmp_path), batch_size=3, device="cpu", shuffle=False, drop_last=False, packed=True))[0]
     assert all(torch.equal(p[k], b[k]) for k in ("image_latents", "control_latents", "prompt_embeds", "prompt_embeds_mask")) and p["img_shapes"] == b["img_shapes"]
+
+
+def test_dreamomni2_trainer_rides_the_flux_kontext_path(ref):
+    """§8 f4: the reference's DreamOmni2 trainer only changes what happens BEFORE the embeddings exist (VLM prompt optimisation); its loss
+    recipes are FluxKontextLoraTrainer's own, i.e. exactly what FluxKontextStep / patch_trainer replace."""
+    from qflux.trainer.dreamomni2_trainer import DreamOmni2Trainer
+    from qflux.trainer.flux_kontext_trainer import FluxKontextLoraTrainer
+    assert issubclass(DreamOmni2Trainer, FluxKontextLoraTrainer)
+    for name in ("_compute_loss", "_compute_loss_shared_mode", "_compute_loss_multi_resolution_mode"):
+        assert getattr(DreamOmni2Trainer, name) is getattr(FluxKontextLoraTrainer, name), name
