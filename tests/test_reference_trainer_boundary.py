@@ -330,3 +330,7 @@ def test_dreamomni2_trainer_rides_the_flux_kontext_path(ref):
     assert issubclass(DreamOmni2Trainer, FluxKontextLoraTrainer)
     for name in ("_compute_loss", "_compute_loss_shared_mode", "_compute_loss_multi_resolution_mode"):
         assert getattr(DreamOmni2Trainer, name) is getattr(FluxKontextLoraTrainer, name), name
+    # likewise BASELINE config 4's trainer: Edit-Plus only changes how the (several) control images are encoded and concatenated
+    from qflux.trainer.qwen_image_edit_plus_trainer import QwenImageEditPlusTrainer
+    from qflux.trainer.qwen_image_edit_trainer import QwenImageEditTrainer
+    assert issubclass(QwenImageEditPlusTrainer, QwenImageEditTrainer) and QwenImageEditPlusTrainer._compute_loss is QwenImageEditTrainer._compute_loss
