@@ -405,6 +405,10 @@ class FluxB200(FusedMMDiTBase):
     # ------------------------------------------------------------------------------------------------ public API
     def forward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None, timestep=None, img_ids=None,
                 txt_ids=None, guidance=None, joint_attention_kwargs=None, return_dict=False, attention_mask=None):
+        if torch.is_inference_mode_enabled():  # see QwenImageB200.forward: nothing of the model's state may become an inference tensor
+            with torch.inference_mode(False), torch.no_grad():
+                return self.forward(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
+                                    joint_attention_kwargs, return_dict, attention_mask)
         kv_len = None
         if attention_mask is not None:  # [B, T + L] validity mask of a pad-to-max batch (prefix-valid per sample, tools.py:319-396)
             kv_len = attention_mask.to(self.dev).sum(dim=1).to(torch.int32)

@@ -328,6 +328,49 @@ class FusedMMDiTBase(nn.Module):
     def active_adapters(self):
         return [self.adapter_name] if self._lora_params else []
 
+    def cache_context(self, name: str):
+        """diffusers `CacheMixin.cache_context` (a context manager that names the active branch for cache hooks): the reference's
+        validation loop wraps every forward in it (qwen_image_edit_trainer.py:1236,1255).  No cache hooks here: a no-op context."""
+        import contextlib
+        return contextlib.nullcontext()
+
+    @torch.no_grad()
+    def merge_adapter(self, adapter_names=None):
+        """PEFT `merge_adapter` (`BaseTrainer.merge_lora`, base_trainer.py:413-416): W <- W + scaling * B A for every adapted Linear, after
+        which the adapter contributes nothing until `unmerge_adapter()`.  The factors are parked (the kernels always add the low-rank
+        term, so a merged adapter is represented by lora_B = 0); the bf16 rounding of W + delta is PEFT's own."""
+        if self._sharded is not None:
+            raise lib.QfxError("merge_adapter: the frozen weights are sharded; merge on a replicated model")
+        if not self._lora_params or getattr(self, "_merged", None):
+            return
+        views, parked = self._weight_views(), {}
+        for k, pB in self._lora_params.items():
+            if ".lora_B." not in k:
+                continue
+            mod = k.rsplit(".lora_B.", 1)[0]
+            pA = self._lora_params[k.replace(".lora_B.", ".lora_A.")]
+            W = views[mod + ".weight"]
+            delta = (pB.float() @ pA.float()) * self.lora_scaling
+            W.copy_((W.float() + delta).to(BF))
+            parked[k] = pB.detach().clone()
+            pB.zero_()
+        self._merged = parked
+
+    @torch.no_grad()
+    def unmerge_adapter(self):
+        """PEFT `unmerge_adapter`: subtract the merged delta again and restore lora_B."""
+        parked = getattr(self, "_merged", None)
+        if not parked:
+            return
+        views = self._weight_views()
+        for k, B0 in parked.items():
+            mod = k.rsplit(".lora_B.", 1)[0]
+            pA = self._lora_params[k.replace(".lora_B.", ".lora_A.")]
+            W = views[mod + ".weight"]
+            W.copy_((W.float() - (B0.float() @ pA.float()) * self.lora_scaling).to(BF))
+            self._lora_params[k].copy_(B0)
+        self._merged = None
+
     def load_lora_adapter(self, pretrained_model_name_or_path_or_dict, prefix="transformer", adapter_name="default", **kwargs):
         """`transformer.load_lora_adapter(path, adapter_name=...)` (base_trainer.py:983): a diffusers-format LoRA file
         (`pytorch_lora_weights.safetensors`, keys `transformer.<module>.lora_A.weight`, what `save_lora` writes).  The rank is read from

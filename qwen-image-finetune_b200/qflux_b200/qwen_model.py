@@ -313,6 +313,12 @@ class QwenImageB200(FusedMMDiTBase):
                 img_shapes=None, txt_seq_lens=None, guidance=None, attention_kwargs=None, return_dict=False):
         """Same signature as the reference model.  With grad enabled and an adapter attached the result carries
         autograd history to the LoRA parameters (custom Function around the fused backward)."""
+        if torch.is_inference_mode_enabled():
+            # the reference's validation loop runs under torch.inference_mode() (qwen_image_edit_trainer.py:1219): workspaces and cached
+            # tables allocated there would be inference tensors, which later no_grad / training calls may not update in place
+            with torch.inference_mode(False), torch.no_grad():
+                return self.forward(hidden_states, encoder_hidden_states, encoder_hidden_states_mask, timestep, img_shapes, txt_seq_lens,
+                                    guidance, attention_kwargs, return_dict)
         nested = isinstance(img_shapes[0], (list, tuple)) and isinstance(img_shapes[0][0], (list, tuple))
         multi = nested and any(list(map(tuple, sh)) != list(map(tuple, img_shapes[0])) for sh in img_shapes)
         txt_len = None

@@ -334,3 +334,71 @@ def test_dreamomni2_trainer_rides_the_flux_kontext_path(ref):
     from qflux.trainer.qwen_image_edit_plus_trainer import QwenImageEditPlusTrainer
     from qflux.trainer.qwen_image_edit_trainer import QwenImageEditTrainer
     assert issubclass(QwenImageEditPlusTrainer, QwenImageEditTrainer) and QwenImageEditPlusTrainer._compute_loss is QwenImageEditTrainer._compute_loss
+
+
+def test_reference_validation_loop_runs_on_the_fused_model(ref, emu):
+    """§8 f2 pinned to the reference's own loop: `QwenImageEditTrainer.sampling_from_embeddings` (qwen_image_edit_trainer.py:1116-1289 —
+    shifted schedule, `dit.cache_context`, true CFG with norm rescale, `scheduler.step`) is run UNMODIFIED with `self.dit` = the fused
+    model and must produce the latents of `qflux_b200.sampler.sample_qwen` on the same model, and — within bf16 tolerance — those of the
+    same loop driving the reference's own transformer."""
+    import contextlib
+    import io
+    import ref_common as rc
+    from diffusers.schedulers.scheduling_flow_match_euler_discrete import FlowMatchEulerDiscreteScheduler
+    from qflux.trainer.base_trainer import BaseTrainer
+    from qflux.trainer.qwen_image_edit_trainer import QwenImageEditTrainer
+    from qflux_b200 import from_reference
+    from qflux_b200.sampler import sample_qwen
+    spec = rc.CASES["qwen_hd128"]
+    ref_dit, _ = ref.build_reference(spec)
+    fused = from_reference(ref_dit, _host_only=True)
+    x = rc.rand_inputs(spec)
+    B, L = x["image_latents"].shape[:2]
+    T = x["prompt_embeds"].shape[1]
+    g = torch.Generator().manual_seed(77)
+    sched = dict(num_train_timesteps=1000, shift=1.0, use_dynamic_shifting=True, base_shift=0.5, max_shift=0.9, base_image_seq_len=256,
+                 max_image_seq_len=8192, shift_terminal=0.02)
+    emb = dict(num_inference_steps=4, true_cfg_scale=3.0, guidance=1.0, height=512, width=512, negative_prompt="bad",
+               control_latents=x["control_latents"].bfloat16(), prompt_embeds=x["prompt_embeds"].bfloat16(),
+               prompt_embeds_mask=torch.ones(B, T, dtype=torch.int64), img_shapes=x["img_shapes"],
+               negative_prompt_embeds=(torch.randn(B, T - 3, x["prompt_embeds"].shape[2], generator=g) * 3).bfloat16(),
+               negative_prompt_embeds_mask=torch.ones(B, T - 3, dtype=torch.int64), latents=torch.randn(B, L, 64, generator=g).bfloat16())
+
+    def reference_loop(dit, dtype):
+        tr = types.SimpleNamespace(dit=dit, vae_scale_factor=8, weight_dtype=dtype, scheduler=None,
+                                   sampling_scheduler=FlowMatchEulerDiscreteScheduler(**sched))
+        tr.prepare_predict_timesteps = lambda *a, **k: BaseTrainer.prepare_predict_timesteps(tr, *a, **k)
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            return QwenImageEditTrainer.sampling_from_embeddings(tr, dict(emb))
+    via_reference_loop = reference_loop(fused, torch.bfloat16)
+    ours = sample_qwen(fused, dict(emb), scheduler_kwargs=dict(base_seq_len=256, max_seq_len=8192, base_shift=0.5, max_shift=0.9, shift_terminal=0.02))
+    assert via_reference_loop.shape == ours.shape == (B, L, 64)
+    assert ((via_reference_loop.float() - ours.float()).norm() / ours.float().norm()).item() < 2e-3, "sampler.py must be the reference's loop"
+    want = reference_loop(ref_dit.float(), torch.float32)  # the reference's loop on the reference's own fp32 transformer
+    assert ((ours.float() - want).norm() / want.norm()).item() < 3e-2
+
+
+def test_merge_adapter_like_peft(ref, emu):
+    """`BaseTrainer.merge_lora` -> `dit.merge_adapter()` (base_trainer.py:413-416): after merging, the adapter-free forward of the
+    merged weights equals the adapted forward; `unmerge_adapter()` brings the factors back."""
+    import ref_common as rc
+    from qflux.trainer.base_trainer import BaseTrainer
+    from qflux_b200 import from_reference
+    spec = rc.CASES["qwen_hd128"]
+    ref_dit, _ = ref.build_reference(spec)
+    m = from_reference(ref_dit, _host_only=True)
+    x = rc.rand_inputs(spec)
+    packed = torch.cat([x["image_latents"], x["control_latents"]], 1).bfloat16()
+    kw = dict(hidden_states=packed, timestep=torch.tensor([0.5] * packed.shape[0]), encoder_hidden_states=x["prompt_embeds"].bfloat16(),
+              encoder_hidden_states_mask=torch.ones(packed.shape[0], x["prompt_embeds"].shape[1], dtype=torch.int64), img_shapes=x["img_shapes"])
+    with torch.no_grad():
+        before = m(**kw)[0].float()
+        B_norm = sum(float(p.float().norm()) for k, p in m._lora_params.items() if ".lora_B." in k)
+        BaseTrainer.merge_lora(types.SimpleNamespace(dit=m))
+        assert all(float(p.abs().max()) == 0 for k, p in m._lora_params.items() if ".lora_B." in k) and B_norm > 0
+        merged = m(**kw)[0].float()
+        m.unmerge_adapter()
+        after = m(**kw)[0].float()
+    assert ((merged - before).norm() / before.norm()).item() < 1e-2
+    assert ((after - before).norm() / before.norm()).item() < 1e-2
+    assert abs(sum(float(p.float().norm()) for k, p in m._lora_params.items() if ".lora_B." in k) - B_norm) < 1e-6
