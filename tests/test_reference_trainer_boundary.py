@@ -402,3 +402,47 @@ def test_merge_adapter_like_peft(ref, emu):
     assert ((merged - before).norm() / before.norm()).item() < 1e-2
     assert ((after - before).norm() / before.norm()).item() < 1e-2
     assert abs(sum(float(p.float().norm()) for k, p in m._lora_params.items() if ".lora_B." in k) - B_norm) < 1e-6
+
+
+def test_reference_flux_validation_loop_runs_on_the_fused_model(ref, emu):
+    """The FLUX-Kontext counterpart: `FluxKontextLoraTrainer.sampling_from_embeddings` (flux_kontext_trainer.py:902-976; plain CFG, no norm
+    rescale) unmodified on the fused FLUX model vs `sample_flux`, and vs the same loop on the reference's own transformer."""
+    import contextlib
+    import io
+    import ref_common as rc
+    from diffusers.schedulers.scheduling_flow_match_euler_discrete import FlowMatchEulerDiscreteScheduler
+    from qflux.trainer.base_trainer import BaseTrainer
+    from qflux.trainer.flux_kontext_trainer import FluxKontextLoraTrainer
+    from qflux_b200 import from_reference
+    from qflux_b200.sampler import sample_flux
+    from qflux_b200.train_step import FluxKontextStep
+    spec = rc.CASES["flux_hd128"]
+    ref_dit, _ = ref.build_reference(spec)
+    fused = from_reference(ref_dit, _host_only=True)
+    x = rc.rand_inputs(spec)
+    B, L = x["image_latents"].shape[:2]
+    T, J = x["prompt_embeds"].shape[1:]
+    hw = int(L ** 0.5)
+    g = torch.Generator().manual_seed(78)
+    sched = dict(num_train_timesteps=1000, shift=3.0, use_dynamic_shifting=True, base_shift=0.5, max_shift=1.15, base_image_seq_len=256,
+                 max_image_seq_len=4096)
+    emb = dict(num_inference_steps=4, true_cfg_scale=2.5, guidance=3.5, control_latents=x["control_latents"].bfloat16(),
+               control_ids=FluxKontextStep.latent_image_ids(hw, hw, "cpu", 1.0), latent_ids=FluxKontextStep.latent_image_ids(hw, hw, "cpu", 0.0),
+               latents=torch.randn(B, L, 64, generator=g).bfloat16(), pooled_prompt_embeds=x["pooled_prompt_embeds"].bfloat16(),
+               prompt_embeds=x["prompt_embeds"].bfloat16(), text_ids=torch.zeros(T, 3),
+               negative_pooled_prompt_embeds=torch.randn(B, x["pooled_prompt_embeds"].shape[1], generator=g).bfloat16(),
+               negative_prompt_embeds=torch.randn(B, T, J, generator=g).bfloat16(), negative_text_ids=torch.zeros(T, 3))
+
+    def reference_loop(dit, dtype):
+        tr = types.SimpleNamespace(dit=dit, weight_dtype=dtype, scheduler=None, sampling_scheduler=FlowMatchEulerDiscreteScheduler(**sched))
+        tr.prepare_predict_timesteps = lambda *a, **k: BaseTrainer.prepare_predict_timesteps(tr, *a, **k)
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            return FluxKontextLoraTrainer.sampling_from_embeddings(tr, dict(emb))
+    via_reference_loop = reference_loop(fused, torch.bfloat16)
+    ours = sample_flux(fused, dict(emb), scheduler_kwargs=dict(base_seq_len=256, max_seq_len=4096, base_shift=0.5, max_shift=1.15))
+    assert via_reference_loop.shape == ours.shape == (B, L, 64)
+    assert ((via_reference_loop.float() - ours.float()).norm() / ours.float().norm()).item() < 2e-3, "sampler.py must be the reference's loop"
+    # against the reference's own transformer in bf16 (an fp32 run is not comparable over several steps: a bf16 FLUX model multiplies the
+    # timestep by 1000 IN bf16, transformer_flux.py:707-710, so its time embedding differs from the fp32 model's at most sigmas)
+    want = reference_loop(ref_dit.bfloat16(), torch.bfloat16).float()
+    assert ((ours.float() - want).norm() / want.norm()).item() < 5e-2
