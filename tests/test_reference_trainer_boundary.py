@@ -446,3 +446,51 @@ def test_reference_flux_validation_loop_runs_on_the_fused_model(ref, emu):
     # timestep by 1000 IN bf16, transformer_flux.py:707-710, so its time embedding differs from the fp32 model's at most sigmas)
     want = reference_loop(ref_dit.bfloat16(), torch.bfloat16).float()
     assert ((ours.float() - want).norm() / want.norm()).item() < 5e-2
+
+
+def test_reference_fit_setup_runs_on_the_patched_trainer(ref, emu):
+    """The reference's own fit-stage plumbing around the hot path, unmodified, on a trainer whose `dit` is the fused model:
+    `setup_model_device_train_mode("fit")` (qwen_image_edit_trainer.py:286-330: requires_grad_ / train / LoRA filter by name),
+    `configure_optimizers()` (base_trainer.py:884-916: class_path optimizer over the trainable parameters) and the DDP branch of
+    `accelerator_prepare()` (:318-388: gradient checkpointing switch, AttnProcsLayers(get_lora_layers(dit)), dit.to(device));
+    then one loop-body iteration must move exactly the LoRA parameters."""
+    import contextlib
+    import io
+    import ref_common as rc
+    from accelerate import Accelerator
+    from qflux.losses import MseLoss
+    from qflux.trainer.base_trainer import BaseTrainer
+    from qflux.trainer.qwen_image_edit_trainer import QwenImageEditTrainer
+    from qflux_b200 import patch_trainer
+    spec = rc.CASES["qwen_hd128"]
+    x = rc.rand_inputs(spec)
+    dit, _ = ref.build_reference(spec)
+    tr = ref._trainer(QwenImageEditTrainer, dit, MseLoss(reduction="mean"))
+    tr.config = _cfg()
+    tr.config.train.gradient_checkpointing = True
+    tr.config.resume = None
+    tr.config.validation = types.SimpleNamespace(enabled=True)
+    tr.config.optimizer = types.SimpleNamespace(class_path="torch.optim.AdamW", init_args=dict(lr=1e-2, weight_decay=0.0))
+    tr.config.lr_scheduler = types.SimpleNamespace(scheduler_type="constant", warmup_steps=0)
+    tr.config.train.max_train_steps = 10
+    tr.config.logging = types.SimpleNamespace(output_dir="/tmp")
+    tr.adapter_name, tr.cache_exist, tr.use_cache = "default", True, True
+    tr.vae, tr.text_encoder = torch.nn.Linear(2, 2), torch.nn.Linear(2, 2)
+    tr.is_fsdp_enabled = lambda: False
+    patch_trainer(tr, _host_only=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        QwenImageEditTrainer.setup_model_device_train_mode(tr, stage="fit")
+        BaseTrainer.configure_optimizers(tr)
+        BaseTrainer.accelerator_prepare(tr, train_dataloader=[1, 2, 3])
+    names = [n for n, p in tr.dit.named_parameters() if p.requires_grad]
+    assert names and all("lora" in n for n in names) and len(names) == len(list(tr.dit.parameters()))
+    assert isinstance(tr.optimizer, torch.optim.AdamW) or isinstance(getattr(tr.optimizer, "optimizer", None), torch.optim.AdamW)
+    before = {n: p.detach().clone() for n, p in tr.dit.named_parameters()}
+    e = {k: v for k, v in x.items() if k != "u"}
+    with tr.accelerator.accumulate(tr.dit):
+        loss = tr._compute_loss(e)
+        tr.accelerator.backward(loss)
+        tr.clip_gradients()
+        tr.optimizer.step()
+        tr.optimizer.zero_grad()
+    assert torch.isfinite(loss) and all(not torch.equal(p, before[n]) for n, p in tr.dit.named_parameters() if ".lora_A." in n)
