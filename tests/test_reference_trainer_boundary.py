@@ -482,6 +482,10 @@ def test_reference_fit_setup_runs_on_the_patched_trainer(ref, emu):
         QwenImageEditTrainer.setup_model_device_train_mode(tr, stage="fit")
         BaseTrainer.configure_optimizers(tr)
         BaseTrainer.accelerator_prepare(tr, train_dataloader=[1, 2, 3])
+    from qflux.utils.model_summary import print_model_summary_table
+    with contextlib.redirect_stdout(io.StringIO()):
+        info = print_model_summary_table(tr.dit)  # fit() logs this table right before the loop (base_trainer.py:634-640)
+    assert info["rows"] and info["columns"]
     names = [n for n, p in tr.dit.named_parameters() if p.requires_grad]
     assert names and all("lora" in n for n in names) and len(names) == len(list(tr.dit.parameters()))
     assert isinstance(tr.optimizer, torch.optim.AdamW) or isinstance(getattr(tr.optimizer, "optimizer", None), torch.optim.AdamW)
