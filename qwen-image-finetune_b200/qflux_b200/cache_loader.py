@@ -91,13 +91,18 @@ def pad_stack(tensors, out=None):
 class CachedEmbeddingLoader:
     def __init__(self, cache_root: str, batch_size: int, keys=("image_latents", "control_latents", "prompt_embeds"),
                  device="cuda", shuffle: bool = True, seed: int = 1234, drop_last: bool = True, prefetch: int = 2,
-                 rank: int = 0, world_size: int = 1, packed="auto"):
-        """packed: "auto" uses `<cache_root>/packed` when `pack_cache` has written it for exactly these samples and keys, True requires
+                 rank: int = 0, world_size: int = 1, packed="auto", reference_batch_format: bool = False):
+        """reference_batch_format: yield what the reference's own DataLoader yields for a cached sample — `img_shapes` in PIXEL units
+        (C, H, W) and `cached = [True] * B` — so that the loader can feed `BaseTrainer.train_epoch` unchanged (its `training_step` ->
+        `prepare_cached_embeddings` converts the shapes itself, base_trainer.py:457-466); the default hands out latent-patch shapes,
+        the form the step classes take directly.
+        packed: "auto" uses `<cache_root>/packed` when `pack_cache` has written it for exactly these samples and keys, True requires
         it, False always reads the reference's per-sample files."""
         self.root, self.bs, self.keys, self.device = str(cache_root), batch_size, tuple(keys), torch.device(device)
         self.shuffle, self.seed, self.drop_last, self.prefetch = shuffle, seed, drop_last, prefetch
         metas = sorted(glob.glob(os.path.join(self.root, "metadata", "*.json")))
         self._pack = self._open_pack(metas, packed)
+        self.reference_batch_format = bool(reference_batch_format)
         if not metas:
             raise FileNotFoundError(f"no cache metadata under {self.root}/metadata (EmbeddingCacheManager.exist would be False)")
         # data parallel: disjoint strided shards.  Every rank must yield the SAME number of batches (a rank with one batch more would
@@ -152,7 +157,7 @@ class CachedEmbeddingLoader:
             e = self._pack["by_meta"][os.path.basename(meta_path)]
             out = {k: self._packed_tensor(k, e[k]) for k in self.keys}
             if e.get("img_shapes") is not None:
-                out["img_shapes"] = img_shapes_to_latent(e["img_shapes"])
+                out["img_shapes"] = self._shapes(e["img_shapes"])
             return out
         with open(meta_path) as f:
             meta = json.load(f)
@@ -160,8 +165,11 @@ class CachedEmbeddingLoader:
         for k in self.keys:
             out[k] = torch.load(os.path.join(self.root, k, f"{meta[k]}.pt"), map_location="cpu", weights_only=False)
         if "img_shapes" in meta:
-            out["img_shapes"] = img_shapes_to_latent(meta["img_shapes"])
+            out["img_shapes"] = self._shapes(meta["img_shapes"])
         return out
+
+    def _shapes(self, shapes_px):
+        return [tuple(int(v) for v in s) for s in shapes_px] if self.reference_batch_format else img_shapes_to_latent(shapes_px)
 
     def _collate(self, samples, stage):
         batch = {}
@@ -174,6 +182,8 @@ class CachedEmbeddingLoader:
             batch["prompt_embeds_mask"] = (torch.arange(batch["prompt_embeds"].shape[1])[None, :] < lens[:, None]).to(torch.int64)
         if "img_shapes" in samples[0]:
             batch["img_shapes"] = [s["img_shapes"] for s in samples]
+        if self.reference_batch_format:
+            batch["cached"] = [True] * len(samples)
         return batch
 
     def _order(self):

@@ -34,5 +34,9 @@ class Accelerator:
     def wait_for_everyone(self):
         pass
 
+    def gather(self, tensor):
+        """Accelerator.gather on one process: the tensor itself, with a leading process dimension for 0-d inputs."""
+        return tensor.reshape(1) if tensor.dim() == 0 else tensor
+
     def prepare(self, *objs):
         return objs if len(objs) != 1 else objs[0]

@@ -498,3 +498,49 @@ def test_reference_fit_setup_runs_on_the_patched_trainer(ref, emu):
         tr.optimizer.step()
         tr.optimizer.zero_grad()
     assert torch.isfinite(loss) and all(not torch.equal(p, before[n]) for n, p in tr.dit.named_parameters() if ".lora_A." in n)
+
+
+def test_reference_train_epoch_runs_end_to_end(ref, emu, tmp_path):
+    """The whole inner loop as the reference ships it: `BaseTrainer.train_epoch` (base_trainer.py:508-560) -> `training_step` ->
+    `prepare_cached_embeddings` (pixel -> latent img_shapes) -> the patched `_compute_loss` -> `accelerator.backward` -> `clip_gradients`
+    -> `optimizer.step` -> `lr_scheduler.step`, fed by `CachedEmbeddingLoader(reference_batch_format=True)` reading a cache that the
+    reference's `EmbeddingCacheManager` wrote.  The loss must be finite every step and go down over the epoch."""
+    import contextlib
+    import io
+    import ref_common as rc
+    from qflux.data.cache_manager import EmbeddingCacheManager
+    from qflux.losses import MseLoss
+    from qflux.trainer.base_trainer import BaseTrainer
+    from qflux.trainer.qwen_image_edit_trainer import QwenImageEditTrainer
+    from qflux_b200 import patch_trainer
+    from qflux_b200.cache_loader import CachedEmbeddingLoader
+    spec = rc.CASES["qwen_hd128"]
+    J = rc.QWEN_HD128["joint_attention_dim"]
+    mgr, g = EmbeddingCacheManager(str(tmp_path)), torch.Generator().manual_seed(3)
+    for i in range(4):  # the same two samples twice: a small problem the LoRA can actually fit within one epoch
+        gi = torch.Generator().manual_seed(40 + i % 2)
+        data = dict(image_latents=torch.randn(16, 64, generator=gi), control_latents=torch.randn(16, 64, generator=gi),
+                    prompt_embeds=torch.randn(6, J, generator=gi) * 3)
+        fh = dict(main_hash=f"m{i}", image_hash=f"i{i}", control_hash=f"c{i}", prompt_hash=f"p{i}")
+        mgr.save_cache_embedding(data, dict(image_latents="image_hash", control_latents="control_hash", prompt_embeds="prompt_hash"), fh,
+                                 img_shapes=[[3, 64, 64], [3, 64, 64]])
+    dit, _ = ref.build_reference(spec)
+    tr = ref._trainer(QwenImageEditTrainer, dit, MseLoss(reduction="mean"))
+    tr.config, tr.adapter_name = _cfg(), "default"
+    tr.config.train.max_grad_norm = 1.0
+    patch_trainer(tr, _host_only=True)
+    tr.optimizer = torch.optim.AdamW([p for p in tr.dit.parameters() if p.requires_grad], lr=2e-2, weight_decay=0.0)
+    tr.lr_scheduler = torch.optim.lr_scheduler.ConstantLR(tr.optimizer, factor=1.0, total_iters=0)
+    losses = []
+    tr.training_interrupted, tr.batch_size, tr.global_step, tr.running_loss, tr.train_loss = False, 2, 0, 0.0, 0.0
+    tr.fps_logger = types.SimpleNamespace(update=lambda **k: None, pause=lambda: None, resume=lambda: None, total_fps=lambda: 0.0)
+    tr.update_progressbar = lambda logs: losses.append(logs["loss"])
+    tr.save_checkpoint = lambda *a, **k: None
+    tr.should_run_validation = lambda step: False
+    torch.manual_seed(0)
+    for epoch in range(6):
+        loader = CachedEmbeddingLoader(str(tmp_path), batch_size=2, device="cpu", shuffle=False, reference_batch_format=True)
+        with contextlib.redirect_stdout(io.StringIO()):
+            BaseTrainer.train_epoch(tr, epoch, loader)
+    assert len(losses) == 12 and all(l == l and abs(l) < 1e4 for l in losses), losses
+    assert sum(losses[-4:]) < sum(losses[:4]), losses
