@@ -8,6 +8,8 @@ __version__ = "0.0.0"
 
 
 class Accelerator:
+    """accelerate.Accelerator on ONE process without mixed precision: the methods the reference's step body and checkpointing touch
+    (accumulate, backward, clip_grad_norm_, unwrap_model, prepare, gather, wait_for_everyone) with their single-process semantics."""
     def __init__(self, *args, gradient_accumulation_steps=1, **kwargs):
         self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
         self.gradient_accumulation_steps = gradient_accumulation_steps

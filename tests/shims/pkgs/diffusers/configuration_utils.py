@@ -4,6 +4,7 @@ import inspect
 
 
 class FrozenDict(dict):
+    """diffusers.configuration_utils.FrozenDict: the config mapping with attribute access (read-only in diffusers; reads are all the tests need)."""
     def __getattr__(self, k):
         try:
             return self[k]
@@ -12,9 +13,11 @@ class FrozenDict(dict):
 
 
 class ConfigMixin:
+    """diffusers.ConfigMixin: `self.config` = the __init__ arguments captured by @register_to_config."""
     config_name = "config.json"
 
     def register_to_config(self, **kwargs):
+        """diffusers.configuration_utils.register_to_config: record the bound __init__ arguments (defaults included) in `self.config`."""
         kwargs.pop("kwargs", None)
         prev = dict(getattr(self, "_internal_dict", {}))
         self._internal_dict = FrozenDict({**prev, **kwargs})

@@ -3,14 +3,18 @@ import torch.nn as nn
 
 
 class FromOriginalModelMixin:
+    """diffusers FromOriginalModelMixin (single-file checkpoint loading): not used by the tests, present as a base class."""
     pass
 
 
 class FluxTransformer2DLoadersMixin:
+    """diffusers FluxTransformer2DLoadersMixin (IP-adapter weight loading): not used by the tests, present as a base class."""
     pass
 
 
 class AttnProcsLayers(nn.Module):
+    """diffusers.loaders.AttnProcsLayers: an nn.Module holding the given {name: module} dict as a ModuleList — what the reference wraps
+    `get_lora_layers(dit)` in before `accelerator.prepare` (base_trainer.py:384)."""
     def __init__(self, state_dict):
         super().__init__()
         self.layers = nn.ModuleList(state_dict.values())

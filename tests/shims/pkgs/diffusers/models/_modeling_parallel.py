@@ -4,6 +4,7 @@ from dataclasses import dataclass
 
 @dataclass
 class ContextParallelInput:
+    """diffusers context-parallel plan record (class-level `_cp_plan` metadata of the vendored models; never executed here)."""
     split_dim: int = 0
     expected_dims: int | None = None
     split_output: bool = False
@@ -11,5 +12,6 @@ class ContextParallelInput:
 
 @dataclass
 class ContextParallelOutput:
+    """diffusers context-parallel plan record (see ContextParallelInput)."""
     gather_dim: int = 0
     expected_dims: int | None = None

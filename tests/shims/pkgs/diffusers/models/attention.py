@@ -33,6 +33,7 @@ class FeedForward(nn.Module):
 
 
 class AttentionModuleMixin:
+    """diffusers AttentionModuleMixin: processor get / set on an attention module (what the vendored FLUX attention class inherits)."""
     _default_processor_cls = None
     _available_processors = []
     fused_projections = False
@@ -45,6 +46,7 @@ class AttentionModuleMixin:
 
 
 class AttentionMixin:
+    """diffusers AttentionMixin: model-level `attn_processors` / `set_attn_processor` walking the attention sub-modules."""
     @property
     def attn_processors(self):
         return {n + ".processor": m.processor for n, m in self.named_modules() if hasattr(m, "processor")}

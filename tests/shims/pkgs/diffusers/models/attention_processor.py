@@ -9,6 +9,9 @@ from .normalization import RMSNorm
 
 
 class Attention(nn.Module):
+    """diffusers.models.attention_processor.Attention as a PARAMETER CONTAINER: to_q/k/v (+ add_q/k/v_proj, to_add_out, to_out = [Linear, Dropout]
+    unless pre_only), norm_q / norm_k (+ norm_added_*) as RMSNorm(dim_head) for qk_norm="rms_norm"; forward delegates to the processor the
+    vendored model files install (their processors hold all of the arithmetic)."""
     def __init__(self, query_dim, cross_attention_dim=None, heads=8, kv_heads=None, dim_head=64, dropout=0.0, bias=False,
                  qk_norm=None, added_kv_proj_dim=None, added_proj_bias=True, out_bias=True, eps=1e-5, processor=None, out_dim=None,
                  out_context_dim=None, context_pre_only=None, pre_only=False, elementwise_affine=True):

@@ -25,6 +25,7 @@ def get_timestep_embedding(timesteps, embedding_dim, flip_sin_to_cos=False, down
 
 
 class Timesteps(nn.Module):
+    """diffusers Timesteps: get_timestep_embedding with the stored (num_channels, flip_sin_to_cos, downscale_freq_shift, scale)."""
     def __init__(self, num_channels: int, flip_sin_to_cos: bool, downscale_freq_shift: float, scale: int = 1):
         super().__init__()
         self.num_channels, self.flip_sin_to_cos = num_channels, flip_sin_to_cos
@@ -50,6 +51,7 @@ class TimestepEmbedding(nn.Module):
 
 
 class PixArtAlphaTextProjection(nn.Module):
+    """diffusers PixArtAlphaTextProjection: linear_1 -> act (gelu_tanh | silu) -> linear_2."""
     def __init__(self, in_features, hidden_size, out_features=None, act_fn="gelu_tanh"):
         super().__init__()
         out_features = hidden_size if out_features is None else out_features

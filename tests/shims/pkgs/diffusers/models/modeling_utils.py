@@ -6,6 +6,8 @@ import torch.nn as nn
 
 
 class ModelMixin(nn.Module):
+    """diffusers ModelMixin: an nn.Module with `device` / `dtype` of its first parameter and the gradient-checkpointing switches (the
+    loading / saving machinery is not needed: the tests build models from configs)."""
     _supports_gradient_checkpointing = False
 
     @property

@@ -56,6 +56,7 @@ class AdaLayerNormZero(nn.Module):
 
 
 class AdaLayerNormZeroSingle(nn.Module):
+    """emb = Linear(D, 3D)(SiLU(emb)) -> (shift_msa, scale_msa, gate_msa); x = LayerNorm(x; eps 1e-6, no affine) * (1 + scale_msa) + shift_msa."""
     def __init__(self, embedding_dim: int, norm_type="layer_norm", bias=True):
         super().__init__()
         assert norm_type == "layer_norm"

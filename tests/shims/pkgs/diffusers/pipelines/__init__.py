@@ -13,6 +13,8 @@ class _AnyClassAttr(type):
 
 
 class LoraSavingPipeline(metaclass=_AnyClassAttr):
+    """Stands in for every `*Pipeline` class the trainers name as `pipeline_class`: `save_lora_weights(dir, transformer_lora_layers, ...)`
+    writes `pytorch_lora_weights.safetensors` with the `transformer.` key prefix, like diffusers' LoraBaseMixin.write_lora_layers."""
     transformer_name = "transformer"
 
     @classmethod

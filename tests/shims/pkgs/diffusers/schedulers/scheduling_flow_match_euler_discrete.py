@@ -10,11 +10,16 @@ from ..configuration_utils import ConfigMixin, register_to_config
 
 
 class FlowMatchEulerDiscreteSchedulerOutput:
+    """Output record of `step` (prev_sample)."""
     def __init__(self, prev_sample):
         self.prev_sample = prev_sample
 
 
 class FlowMatchEulerDiscreteScheduler(ConfigMixin):
+    """diffusers.FlowMatchEulerDiscreteScheduler: init table sigmas = linspace(1, 1/N, N) (static shift applied only without dynamic
+    shifting); set_timesteps(sigmas=, mu=) -> exponential time shift e^mu / (e^mu + (1/t - 1)^sigma), sigma = 1, optional stretch to `shift_terminal`,
+    timesteps = sigmas * N, a final 0 appended; step: prev = sample.float() + (sigma_next - sigma) * model_output, cast to the
+    model_output dtype; scale_noise: sigma * noise + (1 - sigma) * sample."""
     order = 1
 
     @register_to_config

@@ -19,6 +19,8 @@ def compute_density_for_timestep_sampling(weighting_scheme, batch_size, logit_me
 
 
 def compute_loss_weighting_for_sd3(weighting_scheme, sigmas=None):
+    """diffusers.training_utils.compute_loss_weighting_for_sd3: "sigma_sqrt" -> sigma^-2, "cosmap" -> 2 / (pi * (1 - 2 sigma + 2 sigma^2)),
+    anything else (the reference passes "none") -> ones."""
     if weighting_scheme == "sigma_sqrt":
         return (sigmas ** -2.0).float()
     if weighting_scheme == "cosmap":

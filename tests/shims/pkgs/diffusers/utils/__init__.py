@@ -23,6 +23,7 @@ def scale_lora_layers(model, weight):
 
 
 def unscale_lora_layers(model, weight=None):
+    """peft.tuners.tuners_utils counterpart of scale_lora_layers: divide the scaling back (no-op for weight None / 1.0)."""
     if weight is None or weight == 1.0:
         return
     for m in model.modules():

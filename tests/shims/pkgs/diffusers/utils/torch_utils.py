@@ -1,8 +1,10 @@
 def maybe_allow_in_graph(cls):
+    """diffusers.utils.torch_utils.maybe_allow_in_graph: a torch.compile hint; identity decorator here."""
     return cls
 
 
 def is_compiled_module(module):
+    """diffusers.utils.torch_utils.is_compiled_module: whether the module is a torch.compile OptimizedModule (never, in the tests)."""
     return hasattr(module, "_orig_mod")
 
 

@@ -8,6 +8,8 @@ import torch.nn as nn
 
 @dataclass
 class LoraConfig:
+    """peft.LoraConfig: the fields BaseTrainer.add_lora_adapter sets (r, lora_alpha, init_lora_weights, target_modules) + peft's defaults
+    for the ones the injection reads (lora_dropout 0, bias "none"); scaling = lora_alpha / r (no rank-stabilised variant)."""
     r: int = 8
     target_modules: list | str | None = None
     lora_alpha: float = 8
@@ -28,6 +30,9 @@ class LoraLayer:
 
 
 class Linear(nn.Module, LoraLayer):
+    """peft.tuners.lora.Linear: wraps `base_layer`; forward = base_layer(x) + lora_B(lora_A(dropout(x))) * scaling with the low-rank branch
+    computed in the adapter weights' dtype and added to the base result (the bf16 rounding points of PEFT's eager forward);
+    lora_A init: "gaussian" -> normal with std 1/r, default -> kaiming_uniform(a=sqrt(5)); lora_B = 0."""
     def __init__(self, base_layer: nn.Linear, adapter_name: str, r: int, lora_alpha: float, lora_dropout: float = 0.0,
                  init_lora_weights=True):
         super().__init__()
